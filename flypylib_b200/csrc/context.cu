@@ -1,0 +1,113 @@
+// context.cu -- fpl_ctx lifetime, error string, arena.
+#include "common.cuh"
+
+namespace fpl {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int Arena::reserve(size_t bytes) {
+    if (bytes <= cap) return FPL_OK;
+    if (base) { cudaFree(base); base = nullptr; cap = 0; }
+    size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    cudaError_t e = cudaMalloc((void **)&base, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        base = nullptr;
+        return FPL_ENOMEM;
+    }
+    cap = want;
+    used = 0;
+    return FPL_OK;
+}
+
+void Arena::release() {
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; used = 0;
+}
+
+}  // namespace fpl
+
+extern "C" {
+
+int fpl_version(void) { return 1; }
+
+const char *fpl_last_error(void) { return fpl::g_err; }
+
+int fpl_device_count(int *count) {
+    FPL_REQUIRE(count != nullptr, "fpl_device_count: count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    *count = ok;
+    return FPL_OK;
+}
+
+int fpl_ctx_create(int device, fpl_ctx **out) {
+    FPL_REQUIRE(out != nullptr, "fpl_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fpl::set_error("fpl_ctx_create: no CUDA device visible (%s); this library has no CPU path",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return FPL_ENODEV;
+    }
+    FPL_REQUIRE(device >= 0 && device < n, "fpl_ctx_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    FPL_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        fpl::set_error("fpl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+        return FPL_ENODEV;
+    }
+    FPL_CUDA_CHECK(cudaSetDevice(device));
+    fpl_ctx *c = new fpl_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->h_pinned_bytes = 4096;
+    cudaError_t e2 = cudaMallocHost(&c->h_pinned, c->h_pinned_bytes);
+    if (e2 != cudaSuccess) {
+        delete c;
+        fpl::set_error("fpl_ctx_create: cudaMallocHost failed: %s", cudaGetErrorString(e2));
+        return FPL_ECUDA;
+    }
+    *out = c;
+    return FPL_OK;
+}
+
+int fpl_ctx_destroy(fpl_ctx *ctx) {
+    if (!ctx) return FPL_OK;
+    cudaSetDevice(ctx->device);
+    ctx->arena.release();
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return FPL_OK;
+}
+
+int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes) {
+    FPL_REQUIRE(ctx && bytes, "fpl_ctx_workspace_bytes: NULL argument");
+    *bytes = (int64_t)ctx->arena.cap;
+    return FPL_OK;
+}
+
+int fpl_ctx_launch_count(fpl_ctx *ctx, int64_t *launches) {
+    FPL_REQUIRE(ctx && launches, "fpl_ctx_launch_count: NULL argument");
+    *launches = ctx->launches;
+    return FPL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""Drop-in for the detection half of flypylib/fplobjdetect.py: ``voxel2obj``.
+
+Same signature, same ``{'locs','conf'}`` result (float64, (x,y,z) columns, emission order) as
+flypylib/fplobjdetect.py:132-257 -- but every array operation runs as sm_100a CUDA kernels behind
+the C ABI (include/fpl_b200.h, fpl_voxel2obj).  The host code below only derives the scalars the
+reference derives on the host: SciPy's Gaussian taps, NumPy's float32 percentile index arithmetic
+and the promotion of ``thd``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import fplutils
+
+
+def _gaussian_taps(sigma, truncate=2.0):
+    """Taps scipy.ndimage.gaussian_filter(.., sigma, truncate=2.0) uses
+    (scipy _filters.py gaussian_filter1d/_gaussian_kernel1d; reference call fplobjdetect.py:167-168)."""
+    sd = float(sigma)
+    if not sd > 1e-15:            # SciPy skips axes with sigma <= 1e-15
+        return None, -1
+    lw = int(truncate * sd + 0.5)
+    x = np.arange(-lw, lw + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[::-1], dtype=np.float64), lw
+
+
+def _percentile_plan(n, q=97):
+    """(rank_lo, rank_hi, gamma) of np.percentile(<float32 array of n values>, q), method 'linear'.
+
+    NumPy (>= 2.0) keeps the whole index computation in float32 for float32 data:
+    q/100 -> float32, virtual index (n-1)*q -> float32, floor, +1, gamma = vi - floor(vi).
+    The reference calls np.percentile(pred, 97) on the padded float32 map (fplobjdetect.py:183).
+    """
+    qf = np.true_divide(q, np.float32(100))
+    vi = np.asanyarray((n - 1) * qf)
+    prev = np.asanyarray(np.floor(vi))
+    nxt = np.asanyarray(prev + 1)
+    if vi >= n - 1:
+        prev = nxt = np.asanyarray(np.float32(-1))
+    if vi < 0:
+        prev = nxt = np.asanyarray(np.float32(0))
+    gamma = np.asanyarray(vi - prev, dtype=vi.dtype)
+    lo = int(prev.astype(np.intp))
+    hi = int(nxt.astype(np.intp))
+    if lo < 0:
+        lo += n
+    if hi < 0:
+        hi += n
+    return lo, hi, float(gamma)
+
+
+def _promote_thd(thd):
+    """Value of ``thd`` after np.maximum(<float32 scalar>, thd) style promotion, as a python float."""
+    t = np.maximum(np.float32(-np.inf), thd)
+    return float(t)
+
+
+def _make_params(shape, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd):
+    r = int(obj_min_dist)
+    if r != obj_min_dist:
+        raise TypeError("obj_min_dist must be an integer (the reference uses it as a pad width)")
+    Z, Y, X = (int(s) for s in shape)
+    buf = fplutils.to3d(buffer_sz)
+    weights, lw = _gaussian_taps(smoothing_sigma)
+    n_pad = (Z + 2 * r) * (Y + 2 * r) * (X + 2 * r)
+    lo, hi, gamma = _percentile_plan(n_pad, 97)
+    p = _lib.V2OParams()
+    p.obj_min_dist = r
+    p.lw = lw
+    p.h_weights = weights.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if weights is not None else None
+    p.thd = _promote_thd(thd)
+    p.rank_lo, p.rank_hi, p.gamma = lo, hi, gamma
+    for i in range(3):
+        b = buf[i]
+        if int(b) != b:
+            raise TypeError("buffer_sz must be integral")
+        p.buffer_xyz[i] = int(b)
+    off = tuple(volume_offset)          # the reference requires a tuple (fplobjdetect.py:252)
+    if len(off) != 3:
+        raise ValueError("volume_offset must have 3 entries (x,y,z)")
+    for i in range(3):
+        p.offset_xyz[i] = float(off[i])
+    return p, weights
+
+
+def _default_capacity(shape, r):
+    """Upper bound on detections: points are pairwise > r apart, so balls of radius r/2 are
+    disjoint; use a generous closed-form bound with slack."""
+    Z, Y, X = shape
+    rr = max(r, 1)
+    cell = max(1.0, rr / 2.0)
+    bound = (Z / cell + 2) * (Y / cell + 2) * (X / cell + 2)
+    return int(min(Z * Y * X, bound)) + 64
+
+
+def voxel2obj_device(pred_dev, obj_min_dist, smoothing_sigma, volume_offset=(0, 0, 0), buffer_sz=0,
+                     thd=0, capacity=None, return_stats=False):
+    """voxel2obj on a CUDA float32 tensor (Z,Y,X); returns the dict plus optional stats."""
+    import torch
+    if not (isinstance(pred_dev, torch.Tensor) and pred_dev.is_cuda):
+        raise TypeError("voxel2obj_device expects a CUDA tensor")
+    if pred_dev.dtype != torch.float32 or pred_dev.dim() != 3:
+        raise TypeError("voxel2obj_device expects a 3-D float32 tensor")
+    pred_dev = pred_dev.contiguous()
+    dev = pred_dev.device.index
+    ctx = _lib.context(dev)
+    shape = tuple(pred_dev.shape)
+    p, _keepalive = _make_params(shape, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+    cap = int(capacity) if capacity is not None else _default_capacity(shape, p.obj_min_dist)
+    with torch.cuda.device(dev):
+        dets = torch.empty((cap, 4), dtype=torch.float64, device=pred_dev.device)
+        count = ctypes.c_int64(0)
+        thresh = ctypes.c_double(0)
+        stats = (ctypes.c_int64 * 8)()
+        rc = _lib.lib().fpl_voxel2obj(ctx.handle, pred_dev.data_ptr(), shape[0], shape[1], shape[2],
+                                     ctypes.byref(p), dets.data_ptr(), cap, ctypes.byref(count),
+                                     ctypes.byref(thresh), stats, _lib.current_stream_ptr(dev))
+        _lib.check(rc, "fpl_voxel2obj")
+        rows = dets[:count.value].cpu().numpy()
+    out = {'locs': rows[:, :3].copy(), 'conf': rows[:, 3].copy()}
+    if return_stats:
+        return out, {'threshold': thresh.value, 'candidates': stats[0], 'rounds': stats[1],
+                     'ball_checks': stats[2], 'selected': stats[3]}
+    return out
+
+
+def voxel2obj(pred, obj_min_dist, smoothing_sigma,
+              volume_offset=(0, 0, 0), buffer_sz=0, thd=0,
+              seg=None, seg_dilate=None, seg_sz_thd=None,
+              seg_force=None):
+    """convert voxel-wise predictions to object predictions (flypylib/fplobjdetect.py:132-257).
+
+    Args / returns exactly as the reference: ``pred`` 3-D array of voxel-wise predictions (numpy,
+    or a CUDA torch tensor to skip the host->device copy), ``obj_min_dist`` suppression radius,
+    ``smoothing_sigma`` Gaussian sigma, ``volume_offset`` (x,y,z) shift, ``buffer_sz`` border in
+    which detections are dropped, ``thd`` lower bound on the threshold.  Returns
+    ``{'locs': (N,3) float64 (x,y,z), 'conf': (N,) float64}`` in the reference's emission order.
+
+    The segmentation-aware branch (seg*, :161-165,177-181,192-195,213-224) is out of scope.
+    """
+    import torch
+    if seg is not None or seg_dilate is not None or seg_sz_thd is not None or seg_force:
+        raise NotImplementedError("segmentation-aware suppression is not part of the B200 hot path")
+    if isinstance(pred, str):
+        raise NotImplementedError("h5 file input needs h5py, which is not available; pass an array")
+    if isinstance(pred, torch.Tensor):
+        dev = pred if pred.is_cuda else pred.cuda()
+        if dev.dtype != torch.float32:
+            raise TypeError("voxel2obj on device supports float32 probability maps only")
+    else:
+        a = np.asarray(pred)
+        if a.ndim != 3:
+            raise ValueError("pred must be 3-D")
+        if a.dtype != np.float32:
+            raise TypeError("the B200 voxel2obj path is the float32 path FplNetwork.infer produces; "
+                            "got dtype %s" % a.dtype)
+        _lib.context()          # raises when there is no GPU: no CPU fallback
+        dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return voxel2obj_device(dev, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)

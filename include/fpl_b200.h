@@ -1,0 +1,160 @@
+/* fpl_b200.h -- C ABI of the B200-native T-bar detection hot path (libfplb200.so).
+ *
+ * This is the drop-in boundary for ONE path of janelia-flyem/flypylib:
+ *
+ *     EM volume --[3-D CNN forward, tiled]--> probability map --[voxel2obj]--> point detections
+ *
+ * Every entry point states the reference interface it replaces (file:line relative to the
+ * reference tree).  The reference is pure Python; its "FFI" for this path is the Keras /
+ * SciPy / NumPy call sites, so the binding a maintainer adds is a ctypes stub.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars.  No torch / C++ types.
+ *   - every function returns 0 on success, a negative FPL_E* code on failure;
+ *     fpl_last_error() returns a thread-local human-readable message.
+ *   - pointers named d_* are DEVICE pointers (sm_100a B200 global memory) owned by the caller;
+ *     h_* are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - the library allocates only inside an explicit fpl_ctx (grow-only workspace arena,
+ *     packed weights); fpl_ctx_destroy frees everything.
+ *   - volumes are C-order (Z,Y,X); detections are rows (x, y, z, conf) of float64, exactly the
+ *     columns of the reference's obj_pred array (flypylib/fplobjdetect.py:211,233-257).
+ *   - there is NO CPU fallback: every compute entry point fails with FPL_ENODEV when no sm_100
+ *     device is present.
+ */
+#ifndef FPL_B200_H
+#define FPL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPL_OK        0
+#define FPL_EINVAL   -1   /* bad argument */
+#define FPL_ECUDA    -2   /* CUDA runtime / driver error (see fpl_last_error) */
+#define FPL_ENOMEM   -3   /* device allocation failed */
+#define FPL_ENODEV   -4   /* no sm_100 device */
+#define FPL_EOVERFLOW -5  /* caller-provided output capacity too small */
+#define FPL_ESTATE   -6   /* object used in the wrong state (e.g. network without weights) */
+
+typedef struct fpl_ctx fpl_ctx;
+typedef struct fpl_net fpl_net;
+
+/* ---------------------------------------------------------------------------------------------
+ * library / context
+ * ------------------------------------------------------------------------------------------- */
+int         fpl_version(void);                 /* ABI version, currently 1 */
+const char *fpl_last_error(void);
+int         fpl_device_count(int *count);      /* number of visible sm_100 devices */
+
+/* One context per (process, GPU).  Replaces nothing in the reference (Keras/TF session state). */
+int fpl_ctx_create(int device, fpl_ctx **out);
+int fpl_ctx_destroy(fpl_ctx *ctx);
+/* bytes currently held by the context's workspace arena */
+int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes);
+/* number of kernel launches issued by this context since creation (bench.py "gpu_launches") */
+int fpl_ctx_launch_count(fpl_ctx *ctx, int64_t *launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * voxel2obj: smoothing + percentile threshold + greedy NMS       (flypylib/fplobjdetect.py:132-257)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Parameters of one voxel2obj call.  Mirrors the reference signature
+ *   voxel2obj(pred, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+ * (fplobjdetect.py:132-135), seg=None branch.  The Gaussian taps are supplied by the host shim
+ * exactly as SciPy builds them (fplobjdetect.py:167-168 -> scipy _gaussian_kernel1d). */
+typedef struct fpl_v2o_params {
+    int32_t  obj_min_dist;      /* r: pad width, border width, suppression-ball radius            */
+    int32_t  lw;                /* Gaussian half width = int(2*sigma+0.5); -1: sigma==0, no filter */
+    const double *h_weights;    /* 2*lw+1 taps (host), correlate order                            */
+    double   thd;               /* thd as numpy would promote it against a float32 (see shim)     */
+    int64_t  rank_lo, rank_hi;  /* 0-based order statistics of the PADDED volume used by          */
+    float    gamma;             /*   np.percentile(.,97) and its float32 lerp weight (:183)       */
+    int32_t  buffer_xyz[3];     /* buffer_sz in (x,y,z) order as the reference applies it (:239-250) */
+    double   offset_xyz[3];     /* volume_offset (x,y,z) (:252-253)                               */
+} fpl_v2o_params;
+
+/* Stage A (fplobjdetect.py:158-175): interior (Z,Y,X) of  zero_border(gaussian_filter(pad(pred, r))).
+ * The r-wide border of the padded map is identically zero and is never materialised.
+ * d_smooth may not alias d_pred.  Uses ctx workspace: 1 x Z*Y*X floats. */
+int fpl_v2o_smooth(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,
+                   const fpl_v2o_params *p, float *d_smooth, void *stream);
+
+/* Stage B (fplobjdetect.py:183): threshold = max(percentile_97(padded map), thd).
+ * h_out[0] = threshold (as double), h_out[1] = value at rank_lo, h_out[2] = value at rank_hi,
+ * h_out[3] = number of NaNs seen.  Synchronises `stream`. */
+int fpl_v2o_threshold(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, int64_t X,
+                      const fpl_v2o_params *p, double *h_out, void *stream);
+
+/* Stage C (fplobjdetect.py:184-257): candidates > threshold, greedy NMS with ball suppression,
+ * emission order (conf desc, flat index asc), un-pad, buffer crop, offset.
+ * d_dets: capacity rows x 4 doubles (x,y,z,conf).  *h_count receives the number of rows.
+ * h_stats (optional, 8 int64): candidates, rounds, ball checks, selected before crop, ...
+ * Synchronises `stream`. */
+int fpl_v2o_detect(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, int64_t X,
+                   const fpl_v2o_params *p, double threshold, double *d_dets, int64_t capacity,
+                   int64_t *h_count, int64_t *h_stats, void *stream);
+
+/* A+B+C in one call: the replacement for fplobjdetect.voxel2obj(pred, ...) on a device-resident
+ * float32 probability map.  h_threshold (optional) receives the threshold used. */
+int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,
+                  const fpl_v2o_params *p, double *d_dets, int64_t capacity, int64_t *h_count,
+                  double *h_threshold, int64_t *h_stats, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * network: model builders + FplNetwork.infer         (flypylib/fplmodels.py, fplnetwork.py:99-189)
+ * ------------------------------------------------------------------------------------------- */
+
+/* architectures (flypylib/fplmodels.py:102-136, :138-172, :258-304) */
+#define FPL_ARCH_VGG_LIKE    1
+#define FPL_ARCH_VGG_LIKE2   2
+#define FPL_ARCH_UNET_LIKE2  3
+
+/* arithmetic of the conv stack */
+#define FPL_PREC_FP32  0   /* CUDA-core fp32 direct convolution (validation path)            */
+#define FPL_PREC_BF16  1   /* tcgen05 kind::f16 implicit GEMM, bf16 operands, fp32 accumulate */
+#define FPL_PREC_TF32  2   /* tcgen05 kind::tf32 implicit GEMM                                */
+
+/* Build a network object for `arch`; replaces the Keras graph construction in the builders and
+ * FplNetwork._set_infer (fplnetwork.py:99-110: the x rf_stride nearest up-sampling of the VGG
+ * output is part of the network). */
+int fpl_net_create(fpl_ctx *ctx, int arch, fpl_net **out);
+int fpl_net_destroy(fpl_net *net);
+
+/* receptive-field info the builders return: rf_size, rf_offset, rf_stride, infer_sz
+ * (fplmodels.py:136,172,304) */
+int fpl_net_info(const fpl_net *net, int32_t *rf_size, int32_t *rf_offset, int32_t *rf_stride,
+                 int32_t *infer_sz);
+
+/* Number of weight arrays in Keras get_weights() order and the element count of each
+ * (conv kernel (kd,kh,kw,Cin,Cout); BatchNormalization gamma,beta,moving_mean,moving_variance;
+ * last VGG conv kernel,bias).  Replaces Model.get_weights()/set_weights (fplnetwork.py:109-110). */
+int fpl_net_num_weights(const fpl_net *net, int32_t *n);
+int fpl_net_weight_size(const fpl_net *net, int32_t index, int64_t *elems);
+/* h_arrays[i] points to host float32 data of array i.  Folds BN into scale/bias and packs the
+ * kernels for the selected precision. */
+int fpl_net_set_weights(fpl_net *net, const float *const *h_arrays, int32_t n, int precision);
+
+/* Forward pass of a batch of tiles: replaces infer_network.predict (fplnetwork.py:175-176).
+ * d_tiles: n_tiles x in^3 float32 (channels = 1), in = tile input edge (any valid size for the
+ * architecture); d_out: n_tiles x out^3 float32 (VGG: already x4 up-sampled). */
+int fpl_net_out_size(const fpl_net *net, int32_t in_sz, int32_t *out_sz);
+int fpl_net_forward_tiles(fpl_net *net, const float *d_tiles, int32_t n_tiles, int32_t in_sz,
+                          float *d_out, void *stream);
+
+/* Whole-volume inference: replaces FplNetwork.infer(image) (fplnetwork.py:136-189): reference tile
+ * grid (origins k*(infer_sz-2*rf_offset)), zero padding of far-edge tiles, scatter of tile
+ * interiors, rf_offset-wide border left at 0.
+ * d_image: (Z,Y,X) float32 (already normalised, as the reference passes it) or uint8 with
+ * norm_mean/norm_std applied on the fly ((x-mean)/std, fplobjdetect.py:1106-1107);
+ * image_is_u8 selects.  z_tile_begin/z_tile_end restrict the call to a range of tile layers
+ * (multi-GPU z-slab sharding; pass 0,-1 for all).  d_pred: (Z,Y,X) float32, fully written. */
+int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
+                         float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
+                         int32_t z_tile_end, float *d_pred, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPL_B200_H */

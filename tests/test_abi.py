@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fpl_b200.h declares; the product
+refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import flypylib_b200
+from flypylib_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "fpl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fpl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert set(_lib.exported_symbols()) == set(names)
+
+
+def test_version_and_error_string():
+    l = _lib.lib()
+    assert l.fpl_version() == 1
+    assert isinstance(l.fpl_last_error(), bytes)
+
+
+def test_params_struct_layout_matches_header():
+    # offsets implied by the C declaration (natural alignment)
+    assert _lib.V2OParams.obj_min_dist.offset == 0
+    assert _lib.V2OParams.lw.offset == 4
+    assert _lib.V2OParams.h_weights.offset == 8
+    assert _lib.V2OParams.thd.offset == 16
+    assert _lib.V2OParams.rank_lo.offset == 24
+    assert _lib.V2OParams.rank_hi.offset == 32
+    assert _lib.V2OParams.gamma.offset == 40
+    assert _lib.V2OParams.buffer_xyz.offset == 44
+    assert _lib.V2OParams.offset_xyz.offset == 56
+    assert ctypes.sizeof(_lib.V2OParams) == 80
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from flypylib_b200 import fplobjdetect
+    with pytest.raises(_lib.FplError):
+        fplobjdetect.voxel2obj(np.zeros((8, 8, 8), np.float32), 2, 1.0)
+    h = ctypes.c_void_p()
+    rc = _lib.lib().fpl_ctx_create(0, ctypes.byref(h))
+    assert rc == -4  # FPL_ENODEV
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "flypylib_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

@@ -1,0 +1,121 @@
+"""GPU parity: CUDA voxel2obj (through the C ABI) against the oracle and the reference goldens.
+Bit-exact: smoothed map, threshold, detection coordinates, confidences and their order."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import voxel2obj_oracle as O
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxel2obj_golden.npz"))
+
+
+def _stages(pred, r, sigma, off, buf, thd, force_generic=False):
+    """smooth / threshold / detect through the staged ABI calls."""
+    import torch
+    from flypylib_b200 import _lib, fplobjdetect as P
+    dev = torch.device("cuda", 0)
+    ctx = _lib.context(0)
+    lib = _lib.lib()
+    lib.fpl_debug_force_generic_gauss.argtypes = [ctypes.c_int]
+    lib.fpl_debug_force_generic_gauss(1 if force_generic else 0)
+    try:
+        d_pred = torch.from_numpy(pred).to(dev)
+        d_s = torch.empty_like(d_pred)
+        p, keep = P._make_params(pred.shape, r, sigma, off, buf, thd)
+        Z, Y, X = pred.shape
+        st = _lib.current_stream_ptr(0)
+        _lib.check(lib.fpl_v2o_smooth(ctx.handle, d_pred.data_ptr(), Z, Y, X, ctypes.byref(p),
+                                      d_s.data_ptr(), st), "smooth")
+        hout = (ctypes.c_double * 4)()
+        _lib.check(lib.fpl_v2o_threshold(ctx.handle, d_s.data_ptr(), Z, Y, X, ctypes.byref(p), hout, st),
+                   "threshold")
+        cap = P._default_capacity(pred.shape, r)
+        dets = torch.empty((cap, 4), dtype=torch.float64, device=dev)
+        cnt = ctypes.c_int64()
+        stats = (ctypes.c_int64 * 8)()
+        _lib.check(lib.fpl_v2o_detect(ctx.handle, d_s.data_ptr(), Z, Y, X, ctypes.byref(p), hout[0],
+                                      dets.data_ptr(), cap, ctypes.byref(cnt), stats, st), "detect")
+        rows = dets[:cnt.value].cpu().numpy()
+        return d_s.cpu().numpy(), hout[0], rows, list(stats)
+    finally:
+        lib.fpl_debug_force_generic_gauss(0)
+
+
+@pytest.mark.parametrize("case", cases.VOXEL2OBJ_CASES, ids=[c[0] for c in cases.VOXEL2OBJ_CASES])
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+def test_stages_bit_exact_vs_oracle_and_golden(case, generic):
+    name, shape, seed, kind, r, sigma, thd, buf, off = case
+    pred = cases.prob_map(shape, seed, kind)
+    s_gpu, t_gpu, rows, stats = _stages(pred, r, sigma, off, buf, thd, force_generic=generic)
+    want, s_ref, t_ref = O.voxel2obj(pred, r, sigma, off, buf, thd, impl="c", return_intermediates=True)
+    interior = s_ref[r:r + shape[0], r:r + shape[1], r:r + shape[2]] if r > 0 else s_ref
+    assert np.array_equal(s_gpu.view(np.uint32), np.ascontiguousarray(interior).view(np.uint32)), \
+        "smoothed map not bit-exact"
+    assert t_gpu == float(t_ref)
+    assert np.array_equal(rows[:, :3], want["locs"])
+    assert np.array_equal(rows[:, 3], want["conf"])
+    # and against the reference's own output
+    assert np.array_equal(rows[:, :3], GOLD[name + "/locs"])
+    assert np.array_equal(rows[:, 3], GOLD[name + "/conf"])
+
+
+@pytest.mark.parametrize("case", cases.VOXEL2OBJ_CASES[:8], ids=[c[0] for c in cases.VOXEL2OBJ_CASES[:8]])
+def test_dropin_voxel2obj_matches_golden(case):
+    from flypylib_b200 import fplobjdetect
+    name, shape, seed, kind, r, sigma, thd, buf, off = case
+    pred = cases.prob_map(shape, seed, kind)
+    out = fplobjdetect.voxel2obj(pred, r, sigma, off, buf, thd)
+    assert out["locs"].dtype == np.float64 and out["conf"].dtype == np.float64
+    assert out["locs"].shape == GOLD[name + "/locs"].shape
+    assert np.array_equal(out["locs"], GOLD[name + "/locs"])
+    assert np.array_equal(out["conf"], GOLD[name + "/conf"])
+
+
+@pytest.mark.parametrize("shape,kind,seed", [((200, 190, 210), "blobs", 21), ((192, 192, 192), "uniform", 22),
+                                             ((256, 256, 256), "blobs", 23), ((180, 200, 170), "ties", 24)])
+def test_medium_volumes_vs_c_oracle(shape, kind, seed):
+    """Reference parameters (r=27, sigma=5) at sizes the C oracle finishes in seconds."""
+    from flypylib_b200 import fplobjdetect
+    pred = cases.prob_map(shape, seed, kind)
+    got, st = fplobjdetect.voxel2obj_device(__import__("torch").from_numpy(pred).cuda(), 27, 5, (0, 0, 0), 30, 0,
+                                            return_stats=True)
+    want, s, t = O.voxel2obj(pred, 27, 5, (0, 0, 0), 30, 0, impl="c", return_intermediates=True)
+    assert st["threshold"] == float(t)
+    assert np.array_equal(got["locs"], want["locs"])
+    assert np.array_equal(got["conf"], want["conf"])
+
+
+def test_nan_and_saturation_edge_cases():
+    from flypylib_b200 import fplobjdetect
+    a = cases.prob_map((40, 40, 40), 3, "blobs")
+    a[5, 6, 7] = np.nan
+    out = fplobjdetect.voxel2obj(a, 4, 1.0)
+    assert out["locs"].shape == (0, 3) and out["conf"].shape == (0,)
+    out = fplobjdetect.voxel2obj(cases.prob_map((32, 32, 32), 8, "saturated"), 4, 1.0)
+    assert out["locs"].shape == (0, 3)
+
+
+def test_large_volume_properties():
+    """512^3 with reference parameters: size-independent properties (no oracle at this size):
+    pairwise distance > r, confidences sorted, every detection above the threshold, idempotent."""
+    import torch
+    from flypylib_b200 import fplobjdetect
+    pred = cases.prob_map((512, 512, 512), 77, "blobs")
+    d = torch.from_numpy(pred).cuda()
+    out, st = fplobjdetect.voxel2obj_device(d, 27, 5, (0, 0, 0), 30, 0, return_stats=True)
+    out2 = fplobjdetect.voxel2obj_device(d, 27, 5, (0, 0, 0), 30, 0)
+    assert np.array_equal(out["locs"], out2["locs"]) and np.array_equal(out["conf"], out2["conf"])
+    conf = out["conf"]
+    assert conf.size > 100
+    assert np.all(np.diff(conf) <= 0)
+    assert np.all(conf > st["threshold"])
+    from scipy.spatial import cKDTree
+    pairs = cKDTree(out["locs"]).query_pairs(27.0)
+    assert len(pairs) == 0
+    lo = out["locs"].min(0); hi = out["locs"].max(0)
+    assert np.all(lo >= 30) and np.all(hi < 512 - 30)
