@@ -65,6 +65,7 @@ _SIGNATURES = {
     "fpl_net_num_weights": (ctypes.c_int, [vp, c_i32p]),
     "fpl_net_weight_size": (ctypes.c_int, [vp, ctypes.c_int32, c_i64p]),
     "fpl_net_set_weights": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.c_int32, ctypes.c_int]),
+    "fpl_net_set_tile_multiplier": (ctypes.c_int, [vp, ctypes.c_int32]),
     "fpl_net_out_size": (ctypes.c_int, [vp, ctypes.c_int32, c_i32p]),
     "fpl_net_forward_tiles": (ctypes.c_int, [vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]),
     "fpl_net_infer_volume": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,

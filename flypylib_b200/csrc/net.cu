@@ -1,0 +1,354 @@
+// net.cu -- graph construction, weight handling, volume tiler and the fpl_net_* C ABI.
+//
+// Replaces, for the inference hot path:
+//   flypylib/fplmodels.py:102-136,138-172,258-304   (graph definitions)
+//   flypylib/fplnetwork.py:99-110                    (_set_infer: up-sampling for strided nets, weights)
+//   flypylib/fplnetwork.py:136-189                   (infer: tile grid, zero padding, predict, scatter)
+#include "net.cuh"
+#include <math.h>
+
+namespace fpl {
+namespace net {
+
+static Op conv(int k, int cin, int cout) { Op o; o.kind = OP_CONV; o.k = k; o.cin = cin; o.cout = cout; return o; }
+static Op pool() { Op o; o.kind = OP_POOL; return o; }
+static Op save(int slot) { Op o; o.kind = OP_SAVE; o.slot = slot; return o; }
+static Op upcat(int slot, int crop) { Op o; o.kind = OP_UPCAT; o.slot = slot; o.crop = crop; return o; }
+static Op final_(int cin) { Op o; o.kind = OP_FINAL; o.k = 1; o.cin = cin; o.cout = 1; return o; }
+
+static int build_graph(fpl_net *n) {
+    std::vector<Op> &g = n->ops;
+    switch (n->arch) {
+        case FPL_ARCH_VGG_LIKE:      // fplmodels.py:102-136
+            g = {conv(3, 1, 48), conv(1, 48, 48), pool(), conv(3, 48, 48), conv(1, 48, 48), pool(),
+                 conv(3, 48, 48), conv(1, 48, 96), conv(1, 96, 96), final_(96)};
+            n->info = {18, 7, 4, 102, true};
+            break;
+        case FPL_ARCH_VGG_LIKE2:     // fplmodels.py:138-172
+            g = {conv(3, 1, 48), conv(3, 48, 48), pool(), conv(3, 48, 48), conv(3, 48, 48), pool(),
+                 conv(3, 48, 48), conv(1, 48, 96), conv(1, 96, 96), final_(96)};
+            n->info = {24, 10, 4, 100, true};
+            break;
+        case FPL_ARCH_UNET_LIKE2:    // fplmodels.py:258-304  (concat order: [up-sampled, skip])
+            g = {conv(3, 1, 32), conv(3, 32, 32), save(0), pool(), conv(3, 32, 64), conv(3, 64, 64), save(1),
+                 pool(), conv(1, 64, 128), upcat(1, 0), conv(3, 192, 64), conv(1, 64, 64), upcat(0, 6),
+                 conv(3, 96, 32), conv(1, 32, 32), final_(32)};
+            n->info = {24, 9, 1, 100, false};
+            break;
+        default:
+            set_error("fpl_net_create: unknown architecture %d", n->arch);
+            return FPL_EINVAL;
+    }
+    int ci = 0;
+    for (Op &o : g)
+        if (o.kind == OP_CONV || o.kind == OP_FINAL) {
+            o.conv_index = ci++;
+            ConvParams p; p.k = o.k; p.cin = o.cin; p.cout = o.cout;
+            n->convs.push_back(p);
+        }
+    return FPL_OK;
+}
+
+// Walk the graph on edge lengths only.  Returns the final edge (before up-sampling) or -1.
+static int walk_sizes(const fpl_net *n, int in_sz, std::vector<int> *sizes_out = nullptr) {
+    int d = in_sz;
+    int skip_d[4] = {0, 0, 0, 0};
+    for (const Op &o : n->ops) {
+        switch (o.kind) {
+            case OP_CONV: case OP_FINAL: d -= (o.k - 1); if (d <= 0) return -1; break;
+            case OP_POOL: if (d % 2) return -1; d /= 2; if (d <= 0) return -1; break;
+            case OP_SAVE: skip_d[o.slot] = d; break;
+            case OP_UPCAT: d *= 2; if (skip_d[o.slot] - 2 * o.crop != d) return -1; break;
+        }
+        if (sizes_out) sizes_out->push_back(d);
+    }
+    return d;
+}
+
+int out_size(const fpl_net *n, int in_sz) {
+    int d = walk_sizes(n, in_sz);
+    return d < 0 ? -1 : d * n->info.rf_stride;
+}
+
+static void free_device_weights(fpl_net *n) {
+    for (ConvParams &c : n->convs) {
+        if (c.d_kernel) cudaFree(c.d_kernel);
+        if (c.d_scale) cudaFree(c.d_scale);
+        if (c.d_bias) cudaFree(c.d_bias);
+        c.d_kernel = c.d_scale = c.d_bias = nullptr;
+    }
+    free_packed_umma(n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiler kernels
+// ------------------------------------------------------------------------------------------------
+struct TileGrid {
+    int nz, ny, nx;          // tiles per axis
+    int in_sz, out_sz, off;  // tile input edge, useful output edge (= stride of origins), rf_offset
+    long long Z, Y, X;
+};
+
+// tile t of the batch <- image[start : start+in_sz] (zero beyond the far edge), start = k*out_sz.
+// image either float32 or uint8 + (x-mean)/std in float32 (fplobjdetect.py:1106-1107).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_tiles_kernel(const T *__restrict__ img, float *__restrict__ tiles, TileGrid g, int tile0,
+                    int n_tiles, float mean, float stdv) {
+    const long long per_tile = (long long)g.in_sz * g.in_sz * g.in_sz;
+    const long long total = per_tile * n_tiles;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(i / per_tile);
+        long long rem = i - (long long)t * per_tile;
+        int x = (int)(rem % g.in_sz);
+        int y = (int)((rem / g.in_sz) % g.in_sz);
+        int z = (int)(rem / ((long long)g.in_sz * g.in_sz));
+        int tt = tile0 + t;
+        int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
+        long long gz = (long long)kz * g.out_sz + z, gy = (long long)ky * g.out_sz + y,
+                  gx = (long long)kx * g.out_sz + x;
+        float v = 0.f;
+        if (gz < g.Z && gy < g.Y && gx < g.X) {
+            T raw = img[(gz * g.Y + gy) * g.X + gx];
+            if (sizeof(T) == 1) v = __fdiv_rn(__fsub_rn((float)raw, mean), stdv);
+            else v = (float)raw;
+        }
+        tiles[i] = v;
+    }
+}
+
+// pred[off + k*out_sz + (0..ext)] <- tile output[0..ext), ext = min(out_sz, size - off - origin)
+__global__ void __launch_bounds__(256)
+scatter_tiles_kernel(const float *__restrict__ outs, float *__restrict__ pred, TileGrid g, int tile0,
+                     int n_tiles) {
+    const long long per_tile = (long long)g.out_sz * g.out_sz * g.out_sz;
+    const long long total = per_tile * n_tiles;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(i / per_tile);
+        long long rem = i - (long long)t * per_tile;
+        int x = (int)(rem % g.out_sz);
+        int y = (int)((rem / g.out_sz) % g.out_sz);
+        int z = (int)(rem / ((long long)g.out_sz * g.out_sz));
+        int tt = tile0 + t;
+        int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
+        long long gz = (long long)kz * g.out_sz + g.off + z, gy = (long long)ky * g.out_sz + g.off + y,
+                  gx = (long long)kx * g.out_sz + g.off + x;
+        if (gz < g.Z - g.off && gy < g.Y - g.off && gx < g.X - g.off)
+            pred[(gz * g.Y + gy) * g.X + gx] = outs[i];
+    }
+}
+
+static int tiles_along(long long size, int off, int out_sz) {
+    // np.mgrid[off : size-off : out_sz]  -> ceil((size - 2 off) / out_sz) origins, 0 if empty
+    long long span = size - 2LL * off;
+    if (span <= 0) return 0;
+    return (int)((span + out_sz - 1) / out_sz);
+}
+
+}  // namespace net
+}  // namespace fpl
+
+using namespace fpl::net;
+
+extern "C" {
+
+int fpl_net_create(fpl_ctx *ctx, int arch, fpl_net **out) {
+    FPL_REQUIRE(ctx && out, "fpl_net_create: NULL argument");
+    fpl_net *n = new fpl_net();
+    n->ctx = ctx;
+    n->arch = arch;
+    int rc = build_graph(n);
+    if (rc != FPL_OK) { delete n; return rc; }
+    *out = n;
+    return FPL_OK;
+}
+
+int fpl_net_destroy(fpl_net *net) {
+    if (!net) return FPL_OK;
+    cudaSetDevice(net->ctx->device);
+    free_device_weights(net);
+    delete net;
+    return FPL_OK;
+}
+
+int fpl_net_info(const fpl_net *net, int32_t *rf_size, int32_t *rf_offset, int32_t *rf_stride,
+                 int32_t *infer_sz) {
+    FPL_REQUIRE(net, "fpl_net_info: NULL net");
+    if (rf_size) *rf_size = net->info.rf_size;
+    if (rf_offset) *rf_offset = net->info.rf_offset;
+    if (rf_stride) *rf_stride = net->info.rf_stride;
+    if (infer_sz) *infer_sz = net->info.infer_sz;
+    return FPL_OK;
+}
+
+int fpl_net_num_weights(const fpl_net *net, int32_t *n) {
+    FPL_REQUIRE(net && n, "fpl_net_num_weights: NULL argument");
+    int c = 0;
+    for (const Op &o : net->ops) {
+        if (o.kind == OP_CONV) c += 5;
+        if (o.kind == OP_FINAL) c += net->info.final_bias ? 2 : 1;
+    }
+    *n = c;
+    return FPL_OK;
+}
+
+int fpl_net_weight_size(const fpl_net *net, int32_t index, int64_t *elems) {
+    FPL_REQUIRE(net && elems, "fpl_net_weight_size: NULL argument");
+    int c = 0;
+    for (const Op &o : net->ops) {
+        if (o.kind == OP_CONV) {
+            if (index == c) { *elems = (int64_t)o.k * o.k * o.k * o.cin * o.cout; return FPL_OK; }
+            if (index > c && index < c + 5) { *elems = o.cout; return FPL_OK; }
+            c += 5;
+        } else if (o.kind == OP_FINAL) {
+            if (index == c) { *elems = o.cin; return FPL_OK; }
+            if (net->info.final_bias && index == c + 1) { *elems = 1; return FPL_OK; }
+            c += net->info.final_bias ? 2 : 1;
+        }
+    }
+    fpl::set_error("fpl_net_weight_size: index %d out of range", index);
+    return FPL_EINVAL;
+}
+
+int fpl_net_set_tile_multiplier(fpl_net *net, int32_t m) {
+    FPL_REQUIRE(net && m >= 1, "fpl_net_set_tile_multiplier: bad argument");
+    FPL_REQUIRE(net->info.rf_stride != 1 || m == 1,
+                "tile multiplier > 1 is only valid for the VGG nets (U-Net output depends on the "
+                "reference tile grid, SURVEY 5.7)");
+    net->tile_mult = m;
+    return FPL_OK;
+}
+
+int fpl_net_set_weights(fpl_net *net, const float *const *h_arrays, int32_t n, int precision) {
+    FPL_REQUIRE(net && h_arrays, "fpl_net_set_weights: NULL argument");
+    FPL_REQUIRE(precision == FPL_PREC_FP32 || precision == FPL_PREC_BF16 || precision == FPL_PREC_TF32,
+                "fpl_net_set_weights: unknown precision %d", precision);
+    int32_t want = 0;
+    FPL_TRY(fpl_net_num_weights(net, &want));
+    FPL_REQUIRE(n == want, "fpl_net_set_weights: expected %d arrays (Keras get_weights order), got %d", want, n);
+    for (int i = 0; i < n; ++i) FPL_REQUIRE(h_arrays[i] != nullptr, "fpl_net_set_weights: array %d is NULL", i);
+    FPL_CUDA_CHECK(cudaSetDevice(net->ctx->device));
+    FPL_CUDA_CHECK(cudaDeviceSynchronize());
+    free_device_weights(net);
+    int w = 0;
+    for (const Op &o : net->ops) {
+        if (o.kind != OP_CONV && o.kind != OP_FINAL) continue;
+        ConvParams &c = net->convs[o.conv_index];
+        size_t ke = (size_t)o.k * o.k * o.k * o.cin * o.cout;
+        c.kernel.assign(h_arrays[w], h_arrays[w] + ke);
+        c.scale.assign(o.cout, 1.f);
+        c.bias.assign(o.cout, 0.f);
+        if (o.kind == OP_CONV) {
+            const float *gamma = h_arrays[w + 1], *beta = h_arrays[w + 2], *mean = h_arrays[w + 3],
+                        *var = h_arrays[w + 4];
+            for (int j = 0; j < o.cout; ++j) {   // BatchNormalization(eps=1e-3) inference, folded in double
+                double s = (double)gamma[j] / sqrt((double)var[j] + 1e-3);
+                c.scale[j] = (float)s;
+                c.bias[j] = (float)((double)beta[j] - (double)mean[j] * s);
+            }
+            w += 5;
+        } else {
+            if (net->info.final_bias) { c.bias[0] = h_arrays[w + 1][0]; w += 2; }
+            else w += 1;
+        }
+        FPL_CUDA_CHECK(cudaMalloc((void **)&c.d_kernel, ke * sizeof(float)));
+        FPL_CUDA_CHECK(cudaMalloc((void **)&c.d_scale, o.cout * sizeof(float)));
+        FPL_CUDA_CHECK(cudaMalloc((void **)&c.d_bias, o.cout * sizeof(float)));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_kernel, c.kernel.data(), ke * sizeof(float), cudaMemcpyHostToDevice));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_scale, c.scale.data(), o.cout * sizeof(float), cudaMemcpyHostToDevice));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_bias, c.bias.data(), o.cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    net->precision = precision;
+    if (precision != FPL_PREC_FP32) FPL_TRY(pack_weights_umma(net));
+    return FPL_OK;
+}
+
+int fpl_net_out_size(const fpl_net *net, int32_t in_sz, int32_t *out_sz) {
+    FPL_REQUIRE(net && out_sz, "fpl_net_out_size: NULL argument");
+    int o = out_size(net, in_sz);
+    FPL_REQUIRE(o > 0, "fpl_net_out_size: input edge %d is not valid for this architecture", in_sz);
+    *out_sz = o;
+    return FPL_OK;
+}
+
+int fpl_net_forward_tiles(fpl_net *net, const float *d_tiles, int32_t n_tiles, int32_t in_sz,
+                          float *d_out, void *stream) {
+    FPL_REQUIRE(net && d_tiles && d_out, "fpl_net_forward_tiles: NULL argument");
+    if (net->precision < 0) { fpl::set_error("fpl_net_forward_tiles: network has no weights"); return FPL_ESTATE; }
+    FPL_REQUIRE(n_tiles > 0, "fpl_net_forward_tiles: n_tiles must be > 0");
+    FPL_REQUIRE(out_size(net, in_sz) > 0, "fpl_net_forward_tiles: input edge %d invalid", in_sz);
+    FPL_CUDA_CHECK(cudaSetDevice(net->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net->precision == FPL_PREC_FP32) return forward_fp32(net, d_tiles, n_tiles, in_sz, d_out, st);
+    return forward_umma(net, d_tiles, n_tiles, in_sz, d_out, st);
+}
+
+int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
+                         float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
+                         int32_t z_tile_end, float *d_pred, void *stream) {
+    FPL_REQUIRE(net && d_image && d_pred, "fpl_net_infer_volume: NULL argument");
+    if (net->precision < 0) { fpl::set_error("network has not been trained"); return FPL_ESTATE; }
+    FPL_REQUIRE(Z > 0 && Y > 0 && X > 0, "fpl_net_infer_volume: empty image");
+    FPL_CUDA_CHECK(cudaSetDevice(net->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    fpl_ctx *ctx = net->ctx;
+    const int off = net->info.rf_offset;
+    const int ref_out = net->info.infer_sz - 2 * off;
+    TileGrid g;
+    g.off = off;
+    g.out_sz = ref_out * net->tile_mult;
+    g.in_sz = g.out_sz + 2 * off;
+    g.Z = Z; g.Y = Y; g.X = X;
+    g.nz = tiles_along(Z, off, g.out_sz);
+    g.ny = tiles_along(Y, off, g.out_sz);
+    g.nx = tiles_along(X, off, g.out_sz);
+    FPL_REQUIRE(out_size(net, g.in_sz) == g.out_sz, "internal: tile edge %d does not map to %d", g.in_sz, g.out_sz);
+    int zb = z_tile_begin < 0 ? 0 : z_tile_begin;
+    int ze = (z_tile_end < 0 || z_tile_end > g.nz) ? g.nz : z_tile_end;
+    // only this rank's rows of pred are cleared/written when a z-range is given
+    {
+        long long z0 = (zb == 0) ? 0 : (long long)zb * g.out_sz + off;
+        long long z1 = (ze == g.nz) ? Z : (long long)ze * g.out_sz + off;
+        if (z1 > Z) z1 = Z;
+        if (z1 > z0)
+            FPL_CUDA_CHECK(cudaMemsetAsync(d_pred + z0 * Y * X, 0, sizeof(float) * (size_t)(z1 - z0) * Y * X, st));
+    }
+    const long long n_tiles_total = (long long)(ze - zb) * g.ny * g.nx;
+    if (n_tiles_total <= 0) return FPL_OK;
+    // batch size: bounded by workspace (fp32 path works tile by tile anyway)
+    const size_t in_elems = (size_t)g.in_sz * g.in_sz * g.in_sz, out_elems = (size_t)g.out_sz * g.out_sz * g.out_sz;
+    int batch = net->precision == FPL_PREC_FP32 ? 4 : 8;
+    if (batch > n_tiles_total) batch = (int)n_tiles_total;
+    float *d_in = nullptr, *d_out = nullptr;
+    FPL_CUDA_CHECK(cudaMalloc((void **)&d_in, sizeof(float) * in_elems * batch));
+    cudaError_t e = cudaMalloc((void **)&d_out, sizeof(float) * out_elems * batch);
+    if (e != cudaSuccess) { cudaFree(d_in); FPL_CUDA_CHECK(e); }
+    int rc = FPL_OK;
+    const int tile_first = zb * g.ny * g.nx;
+    for (long long t0 = 0; t0 < n_tiles_total && rc == FPL_OK; t0 += batch) {
+        int nb = (int)((n_tiles_total - t0) < batch ? (n_tiles_total - t0) : batch);
+        int blocks = ctx->sm_count * 8;
+        if (image_is_u8)
+            gather_tiles_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)d_image, d_in, g,
+                                                                 tile_first + (int)t0, nb, norm_mean, norm_std);
+        else
+            gather_tiles_kernel<float><<<blocks, 256, 0, st>>>((const float *)d_image, d_in, g,
+                                                               tile_first + (int)t0, nb, 0.f, 1.f);
+        ctx->launches++;
+        if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, g.in_sz, d_out, st);
+        else rc = forward_umma(net, d_in, nb, g.in_sz, d_out, st);
+        if (rc != FPL_OK) break;
+        scatter_tiles_kernel<<<blocks, 256, 0, st>>>(d_out, d_pred, g, tile_first + (int)t0, nb);
+        ctx->launches++;
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_in); cudaFree(d_out);
+    if (rc != FPL_OK) return rc;
+    FPL_CUDA_CHECK(e2);
+    FPL_CUDA_CHECK(cudaGetLastError());
+    return FPL_OK;
+}
+
+}  // extern "C"

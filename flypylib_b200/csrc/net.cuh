@@ -1,0 +1,64 @@
+// net.cuh -- network description shared by the fp32 validation path and the tcgen05 path.
+#pragma once
+#include "common.cuh"
+#include <string>
+#include <vector>
+
+namespace fpl {
+namespace net {
+
+// One step of the (static) graph.  Mirrors the Keras functional graphs of
+// flypylib/fplmodels.py:102-136 / :138-172 / :258-304.
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_SAVE = 2, OP_UPCAT = 3, OP_FINAL = 4 };
+
+struct Op {
+    OpKind kind;
+    int k = 0, cin = 0, cout = 0;   // OP_CONV / OP_FINAL (cout == 1)
+    int slot = -1;                  // OP_SAVE: skip slot to store; OP_UPCAT: skip slot to read
+    int crop = 0;                   // OP_UPCAT: symmetric crop of the skip tensor
+    int conv_index = -1;            // index into ConvParams
+};
+
+struct ConvParams {                 // host copies (Keras order) + folded device copies
+    int k, cin, cout;
+    std::vector<float> kernel;      // (kd,kh,kw,cin,cout)
+    std::vector<float> scale, bias; // BN folded: y = conv*scale + bias   (final: scale=1, bias)
+    float *d_kernel = nullptr;      // fp32, same layout
+    float *d_scale = nullptr, *d_bias = nullptr;
+    // tcgen05 path
+    void *d_packed = nullptr;       // operand-B image for the UMMA kernel (BN scale folded in)
+    size_t packed_bytes = 0;
+};
+
+struct ArchInfo {
+    int rf_size, rf_offset, rf_stride, infer_sz;
+    bool final_bias;
+};
+
+}  // namespace net
+}  // namespace fpl
+
+struct fpl_net {
+    fpl_ctx *ctx = nullptr;
+    int arch = 0;
+    fpl::net::ArchInfo info{};
+    std::vector<fpl::net::Op> ops;
+    std::vector<fpl::net::ConvParams> convs;   // every OP_CONV and the OP_FINAL, in graph order
+    int precision = -1;                        // -1: no weights yet
+    int tile_mult = 1;                         // VGG only: tile edge = tile_mult*out_sz + 2*off
+};
+
+namespace fpl {
+namespace net {
+// fp32 validation path (conv_fp32.cu)
+int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out,
+                 cudaStream_t st);
+// tcgen05 path (conv_umma.cu)
+int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out,
+                 cudaStream_t st);
+int pack_weights_umma(fpl_net *net);
+void free_packed_umma(fpl_net *net);
+// output edge of a tile for input edge in_sz (after the x rf_stride up-sampling); -1 if invalid
+int out_size(const fpl_net *net, int in_sz);
+}  // namespace net
+}  // namespace fpl

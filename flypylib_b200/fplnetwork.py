@@ -1,0 +1,121 @@
+"""Drop-in for flypylib/fplnetwork.py on the inference path: ``FplNetwork`` with the same
+constructor, attributes and ``infer`` / ``make_infer_parallel`` methods (reference :46-189).
+
+``infer`` keeps the reference semantics exactly -- tile origins ``k*(infer_sz-2*rf_offset)``,
+zero-padded far-edge tiles, scatter of tile interiors, ``rf_offset``-wide border left at 0 -- but the
+tiles are gathered, evaluated and scattered on the GPU by ``fpl_net_infer_volume`` (no float64
+staging batch, no host loops).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import fplutils
+from . import fplmodels
+
+
+class FplNetwork:
+    """deep learning/CNN class wrapping a B200 network (reference: wraps a keras model)
+
+    supports full stack inference; training (fit_generator) is outside the B200 hot path.
+    """
+
+    def __init__(self, model):
+        self.model = model
+
+        self.train_network, rf_info, infer_sz, compile_args = self.model()
+        self.train_network.summary()
+        self.train_single = self.train_network
+
+        self.rf_size = fplutils.to3d(rf_info[0])
+        self.rf_offset = fplutils.to3d(rf_info[1])
+        self.rf_stride = fplutils.to3d(rf_info[2])
+
+        self.infer_network = None
+        self.n_gpu = 1
+
+        self.infer_sz = fplutils.to3d(infer_sz)
+
+        if compile_args is None:
+            compile_args = {'loss': 'binary_crossentropy',
+                            'optimizer': 'adam',
+                            'metrics': ['accuracy']}
+        self.train_network.compile(**compile_args)
+        self.compile_args = compile_args
+        self.tile_multiplier = 1
+
+    # ------------------------------------------------------------------------------------------
+    def _set_infer(self):
+        """fplnetwork.py:99-110: rebuild at infer_sz (+ UpSampling3D(rf_stride) when strided) and
+        copy the trained weights."""
+        net, _, _, _ = self.model(self.infer_sz)
+        net.upsample_output = True
+        net.set_precision(self.train_single.precision)
+        self.infer_network = net
+        self.infer_network.set_weights(self.train_single.get_weights())
+
+    def set_precision(self, precision):
+        """'bf16' (tcgen05, default), 'tf32' (tcgen05) or 'fp32' (CUDA-core validation path)."""
+        self.train_single.set_precision(precision)
+        if self.infer_network is not None:
+            self.infer_network.set_precision(precision)
+
+    def train(self, generator, steps_per_epoch, epochs, log_file, save_filepath):
+        raise NotImplementedError("training is not part of the B200 inference hot path (SURVEY 8a A8)")
+
+    def make_train_parallel(self, n_gpu, batch_size, input_shape):
+        raise NotImplementedError("training is not part of the B200 inference hot path (SURVEY 8a A8)")
+
+    def make_infer_parallel(self, n_gpu):
+        """fplnetwork.py:130-134.  The reference replicates the graph on n_gpu towers inside one
+        process; here n_gpu is the number of ranks (one process per GPU, torch.distributed) over which
+        ``infer`` shards the tile layers -- see multi_gpu.infer_volume_sharded."""
+        self._set_infer()
+        self.n_gpu = n_gpu
+
+    # ------------------------------------------------------------------------------------------
+    def infer_device(self, image_dev, normalize=None, out=None):
+        """``infer`` on a CUDA tensor (Z,Y,X): float32 (already normalised) or uint8 with
+        ``normalize=(mean, std)`` applied on the fly.  Returns a CUDA float32 tensor."""
+        import torch
+        assert self.infer_network is not None, 'network has not been trained'
+        assert self.infer_network.input_shape[1:-1] == self.infer_sz, \
+            'network input shape does not match expected infer_sz'
+        if image_dev.dim() != 3:
+            raise ValueError("image must be 3-D (Z,Y,X)")
+        is_u8 = image_dev.dtype == torch.uint8
+        if not is_u8 and image_dev.dtype != torch.float32:
+            image_dev = image_dev.float()
+        if is_u8 and normalize is None:
+            raise ValueError("uint8 input needs normalize=(mean, std)")
+        image_dev = image_dev.contiguous()
+        dev = image_dev.device.index
+        net = self.infer_network.device_net(dev)
+        lib = _lib.lib()
+        _lib.check(lib.fpl_net_set_tile_multiplier(net, int(self.tile_multiplier)), "fpl_net_set_tile_multiplier")
+        Z, Y, X = (int(s) for s in image_dev.shape)
+        pred = out if out is not None else torch.empty((Z, Y, X), dtype=torch.float32, device=image_dev.device)
+        mean, std = (float(normalize[0]), float(normalize[1])) if normalize is not None else (0.0, 1.0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fpl_net_infer_volume(net, image_dev.data_ptr(), 1 if is_u8 else 0, mean, std,
+                                                Z, Y, X, 0, -1, pred.data_ptr(),
+                                                _lib.current_stream_ptr(dev)), "fpl_net_infer_volume")
+        return pred
+
+    def infer(self, image):
+        """fplnetwork.py:136-189: probability map (float32, image.shape) of a 3-D image."""
+        import torch
+        if isinstance(image, str):
+            raise NotImplementedError("h5 file input needs h5py, which is not available; pass an array")
+        assert self.infer_network is not None, \
+            'network has not been trained'
+        assert self.infer_network.input_shape[1:-1] == self.infer_sz, \
+            'network input shape does not match expected infer_sz'
+        if isinstance(image, torch.Tensor):
+            dev = image if image.is_cuda else image.cuda()
+            return self.infer_device(dev)
+        image = np.asarray(image)
+        _lib.context()
+        dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).cuda()
+        return self.infer_device(dev).cpu().numpy()

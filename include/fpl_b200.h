@@ -136,6 +136,12 @@ int fpl_net_weight_size(const fpl_net *net, int32_t index, int64_t *elems);
  * kernels for the selected precision. */
 int fpl_net_set_weights(fpl_net *net, const float *const *h_arrays, int32_t n, int precision);
 
+/* VGG nets only: evaluate super-tiles of edge m*(infer_sz-2*rf_offset)+2*rf_offset in
+ * fpl_net_infer_volume.  Their origins stay on the reference grid and the nets are shift-equivariant
+ * by rf_stride, so the result equals the reference tiling with fewer halo FLOPs.
+ * m = 1 (default) is the reference grid itself; the U-Net must keep m = 1. */
+int fpl_net_set_tile_multiplier(fpl_net *net, int32_t m);
+
 /* Forward pass of a batch of tiles: replaces infer_network.predict (fplnetwork.py:175-176).
  * d_tiles: n_tiles x in^3 float32 (channels = 1), in = tile input edge (any valid size for the
  * architecture); d_out: n_tiles x out^3 float32 (VGG: already x4 up-sampled). */

@@ -49,23 +49,7 @@ def golden_voxel2obj(ref):
     np.savez_compressed(os.path.join(HERE, "voxel2obj_golden.npz"), **out)
 
 
-class _FakeNet:
-    """Stands in for the Keras model inside the reference FplNetwork.infer: output voxel =
-    mean of a (2*off+1)-cube would be costly; use centre-crop * 0.5 + tile-local ramp so that
-    any mistake in tile origin, padding or scatter shows up."""
-
-    def __init__(self, infer_sz, off, stride):
-        self.input_shape = (None,) + tuple(infer_sz) + (1,)
-        self.off = off
-        self.calls = []
-
-    def predict(self, x, batch_size=1):
-        self.calls.append((x.shape, str(x.dtype), batch_size))
-        o = self.off
-        core = x[:, o[0]:x.shape[1] - o[0], o[1]:x.shape[2] - o[1], o[2]:x.shape[3] - o[2], :]
-        zz, yy, xx = np.meshgrid(*[np.arange(n) for n in core.shape[1:4]], indexing="ij")
-        ramp = (zz * 1e-3 + yy * 1e-5 + xx * 1e-7)[None, ..., None]
-        return (core * 0.5 + ramp).astype(np.float32)
+_FakeNet = cases.FakeNet
 
 
 def golden_infer_tiler(ref):
