@@ -1,7 +1,748 @@
-// placeholder until the tcgen05 kernel lands
+// conv_umma.cu -- tcgen05 / TMEM / TMA implicit-GEMM execution of the network graph (FPL_PREC_BF16).
+//
+// Replaces infer_network.predict (flypylib/fplnetwork.py:175-176) for the graphs of
+// flypylib/fplmodels.py:102-136,138-172,258-304.
+//
+// Data layout in HBM ("C8-blocked"): activations are (tile, C/8, z, y, x, 8) bf16 -- one 16-byte
+// channel atom per voxel per channel group.  A K=16 MMA step consumes two atoms; the UMMA
+// K-major no-swizzle canonical layout (8 rows x 16 B core matrices) is then exactly "8 x-consecutive
+// voxels of one atom", so every one of the 27 taps of a 3x3x3 convolution is just a different start
+// address into ONE halo'd input plane staged in shared memory by a single TMA box load
+// (no im2col materialisation, no re-fetch per tap).
+//
+// conv kernel (one CTA per SM, persistent over work items = (tile, 16x16 xy patch, z chunk)):
+//   warp 0      TMA producer : weights once (cp.async.bulk, resident for the CTA's lifetime), then one
+//                              halo'd (18 x 18 x Cin) input plane per z step into a 3-plane ring
+//   warp 1      MMA issuer   : per output plane, 27 taps x Cin/16 K-steps x 2 M-tiles of
+//                              tcgen05.mma.cta_group::1.kind::f16 (M=128 = 8x16 voxels, N=Cout),
+//                              fp32 accumulators in TMEM (double buffered across planes)
+//   warps 2..5  epilogue     : tcgen05.ld -> + folded-BN bias -> ReLU -> bf16 -> C8-blocked store
+// Roofline: tensor pipe (dense contraction); see DESIGN.md for the FLOP count per tile.
 #include "net.cuh"
-namespace fpl { namespace net {
-int forward_umma(fpl_net *, const float *, int, int, float *, cudaStream_t) { set_error("tcgen05 path not built yet"); return FPL_ESTATE; }
-int pack_weights_umma(fpl_net *) { return FPL_OK; }
-void free_packed_umma(fpl_net *) {}
-}}
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace fpl {
+namespace net {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows
+// x 16 B stored contiguously; SBO = byte distance between 8-row groups (M/N direction), LBO = byte
+// distance between the two 16-byte K halves of one K=16 step.  Bit layout as in the PTX ISA
+// (start [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout type [61,64) = 0).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N at [17,23) (>>3), M at [24,29) (>>4)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the implicit-GEMM convolution kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kTX = 16, kTY = 16;            // output patch per CTA and z step (two M=128 tiles: x 0..7, 8..15)
+constexpr int kPlanes = 3;                   // input plane ring
+constexpr int kAccStages = 2;                // TMEM accumulator double buffering
+constexpr int kThreads = 192;
+
+struct ConvArgs {
+    const __nv_bfloat16 *w_packed;   // [tap][kstep][2][Cout][8] bf16, BN scale folded
+    const float *bias;               // [Cout] folded BN bias
+    __nv_bfloat16 *out;              // (tile, Cout/8, Dout, Dout, Dout, 8)
+    uint32_t w_bytes;
+    int n_tiles, din, dout, cin_atoms, cout;
+    int n_xt, n_yt, n_zc, zc_len;
+    int relu;
+    uint32_t tmem_cols;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) {
+    constexpr int SX = kTX + KS - 1, SY = kTY + KS - 1;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t atom_stride = SY * SX * 16;                      // bytes between channel atoms of a plane
+    const uint32_t plane_bytes = (uint32_t)a.cin_atoms * atom_stride;
+    const uint32_t w_region = (a.w_bytes + 127u) & ~127u;
+    uint8_t *s_w = smem_raw;
+    uint8_t *s_planes = smem_raw + w_region;
+    const uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_planes + kPlanes * plane_pitch);
+    uint64_t *plane_full = bars;                    // [kPlanes]
+    uint64_t *plane_empty = bars + kPlanes;         // [kPlanes]
+    uint64_t *acc_full = bars + 2 * kPlanes;        // [kAccStages]
+    uint64_t *acc_empty = acc_full + kAccStages;    // [kAccStages]
+    uint64_t *w_full = acc_empty + kAccStages;      // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ksteps = a.cin_atoms >> 1;
+    const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPlanes; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, a.w_bytes);
+            for (uint32_t off = 0; off < a.w_bytes; off += 32768u) {
+                uint32_t n = a.w_bytes - off < 32768u ? a.w_bytes - off : 32768u;
+                bulk_load_1d(s_w + off, reinterpret_cast<const uint8_t *>(a.w_packed) + off, n, w_full);
+            }
+            uint32_t pc = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int t = item;
+                const int zc = t % a.n_zc; t /= a.n_zc;
+                const int xt = t % a.n_xt; t /= a.n_xt;
+                const int yt = t % a.n_yt; t /= a.n_yt;
+                const int tile = t;
+                const int z0 = zc * a.zc_len;
+                const int nz = min(a.zc_len, a.dout - z0);
+                const int np = nz + KS - 1;
+                for (int p = 0; p < np; ++p, ++pc) {
+                    const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
+                    mbar_wait(&plane_empty[slot], ph ^ 1u);
+                    mbar_expect_tx(&plane_full[slot], plane_bytes);
+                    tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * kTX * 8, yt * kTY,
+                                z0 + p, tile * a.cin_atoms);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, a.cout);
+            const uint32_t w_addr = smem_u32(s_w);
+            const uint32_t planes_addr = smem_u32(s_planes);
+            const uint32_t b_lbo = (uint32_t)a.cout * 16u, b_sbo = 128u, b_step = (uint32_t)a.cout * 32u;
+            const uint32_t a_sbo = SX * 16u;
+            mbar_wait(w_full, 0);
+            uint32_t pc_base = 0, ac = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int zc = item % a.n_zc;
+                const int z0 = zc * a.zc_len;
+                const int nz = min(a.zc_len, a.dout - z0);
+                for (int zo = 0; zo < nz; ++zo, ++ac) {
+                    const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
+                    mbar_wait(&acc_empty[as], aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + as * (2u * (uint32_t)a.cout);
+                    uint32_t first = 1;
+#pragma unroll 1
+                    for (int kd = 0; kd < KS; ++kd) {
+                        const uint32_t pi = pc_base + zo + kd;
+                        const uint32_t slot = pi % kPlanes, ph = (pi / kPlanes) & 1u;
+                        mbar_wait(&plane_full[slot], ph);
+                        tc_fence_after();
+                        const uint32_t pbase = planes_addr + slot * plane_pitch;
+#pragma unroll 1
+                        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll 1
+                            for (int kw = 0; kw < KS; ++kw) {
+                                const uint32_t tap = (kd * KS + kh) * KS + kw;
+                                const uint32_t a_tap = pbase + (uint32_t)(kh * SX + kw) * 16u;
+                                const uint32_t b_tap = w_addr + tap * (uint32_t)ksteps * b_step;
+                                for (int s = 0; s < ksteps; ++s) {
+                                    const uint64_t bdesc = make_desc(b_tap + s * b_step, b_lbo, b_sbo);
+                                    const uint32_t a_s = a_tap + (uint32_t)(2 * s) * atom_stride;
+                                    umma_bf16(d0, make_desc(a_s, atom_stride, a_sbo), bdesc, idesc, first ? 0u : 1u);
+                                    umma_bf16(d0 + (uint32_t)a.cout, make_desc(a_s + 8u * 16u, atom_stride, a_sbo),
+                                              bdesc, idesc, first ? 0u : 1u);
+                                    first = 0;
+                                }
+                            }
+                        // plane (zo+kd) is dead once output zo has consumed it as kd==0 (or at item end)
+                        if (kd == 0 || zo == nz - 1) umma_commit(&plane_empty[slot]);
+                    }
+                    umma_commit(&acc_full[as]);
+                }
+                pc_base += nz + KS - 1;
+            }
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                // accumulator row = voxel inside the 8x16 M-tile
+        const int ly = row >> 3, lx = row & 7;
+        const int cg_out = a.cout >> 3;
+        uint32_t ac = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout - z0);
+            for (int zo = 0; zo < nz; ++zo, ++ac) {
+                const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+                const int z = z0 + zo;
+                const int y = yt * kTY + ly;
+#pragma unroll 1
+                for (int m = 0; m < 2; ++m) {
+                    const int x = xt * kTX + m * 8 + lx;
+                    const bool ok = (x < a.dout) && (y < a.dout);
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + as * (2u * (uint32_t)a.cout) +
+                                          (uint32_t)m * (uint32_t)a.cout;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < a.cout; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tcol + (uint32_t)c0, r);
+                        tmem_ld_wait();
+                        if (ok) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float v0 = __uint_as_float(r[h * 8 + 2 * j]) + __ldg(a.bias + c0 + h * 8 + 2 * j);
+                                    float v1 = __uint_as_float(r[h * 8 + 2 * j + 1]) + __ldg(a.bias + c0 + h * 8 + 2 * j + 1);
+                                    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                                    pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+                                }
+                                const int cg = (c0 >> 3) + h;
+                                size_t o = ((((size_t)tile * cg_out + cg) * a.dout + z) * a.dout + y) * a.dout + x;
+                                *reinterpret_cast<uint4 *>(a.out + o * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core kernels around the GEMMs (all bandwidth-bound, C8-blocked bf16)
+// ------------------------------------------------------------------------------------------------
+// first layer: Conv3D(Cout,(3,3,3)) on the single-channel float32 tile + folded BN + ReLU.
+// K = 27 is too thin for the tensor pipe; one thread = one output voxel, all Cout channels.
+template <int COUT>
+__global__ void __launch_bounds__(128)
+conv_first_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ scale,
+                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int n_tiles, int din) {
+    __shared__ float sw[27 * COUT];
+    __shared__ float sb[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i] * scale[i % COUT];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int dout = din - 2;
+    const int xb = (dout + 127) / 128;
+    long long bid = blockIdx.x;
+    const int x = (int)(bid % xb) * 128 + threadIdx.x; bid /= xb;
+    const int y = (int)(bid % dout); bid /= dout;
+    const int z = (int)(bid % dout); bid /= dout;
+    const int t = (int)bid;
+    if (x >= dout) return;
+    const float *tin = in + (size_t)t * din * din * din;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = sb[j];
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float v = __ldg(tin + ((size_t)(z + kd) * din + (y + kh)) * din + (x + kw));
+                const float *wp = sw + ((kd * 3 + kh) * 3 + kw) * COUT;
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+            }
+#pragma unroll
+    for (int cg = 0; cg < COUT / 8; ++cg) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(acc[cg * 8 + 2 * j], 0.f), fmaxf(acc[cg * 8 + 2 * j + 1], 0.f));
+            pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+        }
+        size_t o = ((((size_t)t * (COUT / 8) + cg) * dout + z) * dout + y) * dout + x;
+        *reinterpret_cast<uint4 *>(out + o * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a);
+    const __nv_bfloat162 *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+    __nv_bfloat162 *pr = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+
+// MaxPooling3D((2,2,2)); one thread = one output atom (8 channels of one voxel)
+__global__ void __launch_bounds__(256)
+pool_blocked_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_cg_total, int din) {
+    const int dout = din / 2;
+    const long long total = n_cg_total * dout * dout * dout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long v = i;
+        const int x = (int)(v % dout); v /= dout;
+        const int y = (int)(v % dout); v /= dout;
+        const int z = (int)(v % dout); v /= dout;       // v = tile*CG + cg
+        const uint4 *ip = in + ((size_t)v * din + 2 * z) * din * din;
+        uint4 m = __ldg(ip + (size_t)(2 * y) * din + 2 * x);
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x + 1));
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x));
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x + 1));
+        ip += (size_t)din * din;
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x));
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x + 1));
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x));
+        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x + 1));
+        out[i] = m;
+    }
+}
+
+// concatenate([UpSampling3D(2)(a), Cropping3D(crop)(skip)]): channel groups [0,cga) from a, rest from skip
+__global__ void __launch_bounds__(256)
+upcat_blocked_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *__restrict__ skip, int ds, int cgs,
+                     int crop, uint4 *__restrict__ out, int n_tiles) {
+    const int dout = 2 * da, cg_out = cga + cgs;
+    const long long total = (long long)n_tiles * cg_out * dout * dout * dout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long v = i;
+        const int x = (int)(v % dout); v /= dout;
+        const int y = (int)(v % dout); v /= dout;
+        const int z = (int)(v % dout); v /= dout;
+        const int cg = (int)(v % cg_out);
+        const int t = (int)(v / cg_out);
+        uint4 r;
+        if (cg < cga)
+            r = __ldg(a + ((((size_t)t * cga + cg) * da + z / 2) * da + y / 2) * da + x / 2);
+        else
+            r = __ldg(skip + ((((size_t)t * cgs + (cg - cga)) * ds + z + crop) * ds + y + crop) * ds + x + crop);
+        out[i] = r;
+    }
+}
+
+// final Conv3D(1,(1,1,1)) + sigmoid (+ nearest up-sampling by `stride`, fplnetwork.py:99-105) -> float32 tile
+__global__ void __launch_bounds__(256)
+final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, float bias, float *__restrict__ out,
+                     int n_tiles, int d, int cg_in, int stride) {
+    const long long vox = (long long)d * d * d;
+    const long long total = (long long)n_tiles * vox;
+    const int dout = d * stride;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / vox);
+        const long long v = i - (long long)t * vox;
+        float acc = bias;
+        for (int cg = 0; cg < cg_in; ++cg) {
+            uint4 q = __ldg(in + ((size_t)t * cg_in + cg) * vox + v);
+            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(p[j]);
+                acc = fmaf(f.x, __ldg(w + cg * 8 + 2 * j), acc);
+                acc = fmaf(f.y, __ldg(w + cg * 8 + 2 * j + 1), acc);
+            }
+        }
+        const float pr = 1.f / (1.f + expf(-acc));
+        const int x = (int)(v % d), y = (int)((v / d) % d), z = (int)(v / ((long long)d * d));
+        float *op = out + (size_t)t * dout * dout * dout;
+        for (int dz = 0; dz < stride; ++dz)
+            for (int dy = 0; dy < stride; ++dy)
+                for (int dx = 0; dx < stride; ++dx)
+                    op[((size_t)(z * stride + dz) * dout + (y * stride + dy)) * dout + (x * stride + dx)] = pr;
+    }
+}
+
+// Generic CUDA-core convolution on the blocked layout.  Used (a) for layers whose packed weights do
+// not fit next to the input ring in shared memory (until their streaming variant lands) and (b) by
+// the tests as an independent check of the tcgen05 kernel on identical bf16 inputs.
+template <int KS>
+__global__ void __launch_bounds__(256)
+conv_blocked_direct_kernel(const __nv_bfloat16 *__restrict__ in, const float *__restrict__ w,
+                           const float *__restrict__ scale, const float *__restrict__ bias,
+                           __nv_bfloat16 *__restrict__ out, int n_tiles, int din, int cin, int cout, int relu) {
+    const int dout = din - (KS - 1);
+    const int xb = (dout + 31) / 32;
+    long long bid = blockIdx.x;
+    const int x = (int)(bid % xb) * 32 + threadIdx.x; bid /= xb;
+    const int y = (int)(bid % dout); bid /= dout;
+    const int z = (int)(bid % dout); bid /= dout;
+    const int t = (int)bid;
+    const int cg = threadIdx.y;                  // output channel group
+    if (x >= dout) return;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int cgi = cin >> 3;
+    for (int kd = 0; kd < KS; ++kd)
+        for (int kh = 0; kh < KS; ++kh)
+            for (int kw = 0; kw < KS; ++kw) {
+                const float *wt = w + (size_t)((kd * KS + kh) * KS + kw) * cin * cout + cg * 8;
+                for (int ci = 0; ci < cgi; ++ci) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in) +
+                                          ((((size_t)t * cgi + ci) * din + z + kd) * din + y + kh) * din + x + kw);
+                    const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&q);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float av = __bfloat162float(e[k]);
+                        const float *wr = wt + (size_t)(ci * 8 + k) * cout;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            acc[j] = fmaf(av, __bfloat162float(__float2bfloat16_rn(__ldg(wr + j) * __ldg(scale + cg * 8 + j))), acc[j]);
+                    }
+                }
+            }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v0 = acc[2 * j] + bias[cg * 8 + 2 * j], v1 = acc[2 * j + 1] + bias[cg * 8 + 2 * j + 1];
+        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+        pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+    }
+    size_t o = ((((size_t)t * (cout >> 3) + cg) * dout + z) * dout + y) * dout + x;
+    *reinterpret_cast<uint4 *>(out + o * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static constexpr size_t kMaxDynSmem = 232448;   // 227 KB
+
+static size_t conv_smem_bytes(int ks, int cin, int cout) {
+    const int sx = kTX + ks - 1, sy = kTY + ks - 1;
+    size_t w = ((size_t)ks * ks * ks * cin * cout * 2 + 127) & ~size_t(127);
+    size_t plane = (((size_t)(cin / 8) * sy * sx * 16) + 127) & ~size_t(127);
+    return w + kPlanes * plane + 256;
+}
+
+static bool umma_supported(const ConvParams &c) {
+    if (c.cin % 16 || c.cout % 16 || c.cout > 128) return false;
+    if (c.k != 1 && c.k != 3) return false;
+    return conv_smem_bytes(c.k, c.cin, c.cout) <= kMaxDynSmem;
+}
+
+static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv through the CUDA-core kernel
+
+int pack_weights_umma(fpl_net *net) {
+    for (ConvParams &c : net->convs) {
+        if (c.cin % 16 || c.cout % 16) continue;         // first layer / final layer
+        const int taps = c.k * c.k * c.k, ksteps = c.cin / 16;
+        std::vector<__nv_bfloat16> pk((size_t)taps * c.cin * c.cout);
+        for (int t = 0; t < taps; ++t)
+            for (int s = 0; s < ksteps; ++s)
+                for (int h = 0; h < 2; ++h)
+                    for (int n = 0; n < c.cout; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int ci = 16 * s + 8 * h + e;
+                            const float v = c.kernel[((size_t)t * c.cin + ci) * c.cout + n] * c.scale[n];
+                            pk[((((size_t)t * ksteps + s) * 2 + h) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
+                        }
+        c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
+        FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, pk.data(), c.packed_bytes, cudaMemcpyHostToDevice));
+    }
+    return FPL_OK;
+}
+
+void free_packed_umma(fpl_net *net) {
+    for (ConvParams &c : net->convs) {
+        if (c.d_packed) cudaFree(c.d_packed);
+        c.d_packed = nullptr; c.packed_bytes = 0;
+    }
+}
+
+static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
+                            int n_tiles, int din, int relu, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
+    const int ks = c.k, dout = din - (ks - 1);
+    const int sx = kTX + ks - 1, sy = kTY + ks - 1;
+    const int cin_atoms = c.cin / 8;
+    CUtensorMap tmap;
+    cuuint64_t gdim[4] = {(cuuint64_t)din * 8, (cuuint64_t)din, (cuuint64_t)din, (cuuint64_t)n_tiles * cin_atoms};
+    cuuint64_t gstride[3] = {(cuuint64_t)din * 16, (cuuint64_t)din * din * 16, (cuuint64_t)din * din * din * 16};
+    cuuint32_t box[4] = {(cuuint32_t)sx * 8, (cuuint32_t)sy, 1, (cuuint32_t)cin_atoms};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FPL_ECUDA; }
+    ConvArgs a;
+    a.w_packed = (const __nv_bfloat16 *)c.d_packed;
+    a.bias = c.d_bias;
+    a.out = out;
+    a.w_bytes = (uint32_t)c.packed_bytes;
+    a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.cin_atoms = cin_atoms; a.cout = c.cout;
+    a.n_xt = (dout + kTX - 1) / kTX; a.n_yt = (dout + kTY - 1) / kTY;
+    // z chunking: aim for >= 4 work items per SM so the persistent CTAs stay balanced
+    const long long base_items = (long long)n_tiles * a.n_xt * a.n_yt;
+    int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
+    if (n_zc < 1) n_zc = 1;
+    int zc_len = (dout + n_zc - 1) / n_zc;
+    if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
+    a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
+    a.relu = relu;
+    const int acc_cols = kAccStages * 2 * c.cout;
+    a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+    const size_t smem = conv_smem_bytes(ks, c.cin, c.cout);
+    const long long n_items = base_items * a.n_zc;
+    int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
+    if (ks == 3) {
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_kernel<3><<<grid, kThreads, smem, st>>>(tmap, a);
+    } else {
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_kernel<1><<<grid, kThreads, smem, st>>>(tmap, a);
+    }
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
+}
+
+static int launch_conv_direct(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
+                              int n_tiles, int din, int relu, cudaStream_t st) {
+    const int dout = din - (c.k - 1);
+    const int xb = (dout + 31) / 32;
+    const long long blocks = (long long)n_tiles * dout * dout * xb;
+    FPL_REQUIRE(blocks < 2147483647LL && c.cout / 8 <= 32, "conv_blocked_direct: launch too large");
+    dim3 block(32, c.cout / 8);
+    if (c.k == 3)
+        conv_blocked_direct_kernel<3><<<(unsigned)blocks, block, 0, st>>>(in, c.d_kernel, c.d_scale, c.d_bias, out,
+                                                                         n_tiles, din, c.cin, c.cout, relu);
+    else
+        conv_blocked_direct_kernel<1><<<(unsigned)blocks, block, 0, st>>>(in, c.d_kernel, c.d_scale, c.d_bias, out,
+                                                                         n_tiles, din, c.cin, c.cout, relu);
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
+}
+
+// activation buffer pool (device), grow-only, owned by the net
+struct ActPool {
+    static constexpr int kBufs = 4;
+    void *buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap = 0;
+};
+static ActPool g_pool;       // one process = one GPU (one rank per device)
+
+static int pool_reserve(size_t bytes) {
+    if (bytes <= g_pool.cap) return FPL_OK;
+    for (int i = 0; i < ActPool::kBufs; ++i) { if (g_pool.buf[i]) cudaFree(g_pool.buf[i]); g_pool.buf[i] = nullptr; }
+    g_pool.cap = 0;
+    for (int i = 0; i < ActPool::kBufs; ++i) {
+        cudaError_t e = cudaMalloc(&g_pool.buf[i], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("forward_umma: activation pool allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return FPL_ENOMEM;
+        }
+    }
+    g_pool.cap = bytes;
+    return FPL_OK;
+}
+
+int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
+    fpl_ctx *ctx = net->ctx;
+    if (net->precision != FPL_PREC_BF16) {
+        set_error("forward_umma: only the bf16 tcgen05 path is built (precision %d requested)", net->precision);
+        return FPL_ESTATE;
+    }
+    // size the pool: largest activation tensor of the batch
+    size_t max_bytes = 0;
+    {
+        int d = in_sz, c = 1, sc[4] = {0, 0, 0, 0};
+        for (const Op &o : net->ops) {
+            if (o.kind == OP_CONV) { d -= o.k - 1; c = o.cout; }
+            else if (o.kind == OP_POOL) d /= 2;
+            else if (o.kind == OP_SAVE) sc[o.slot] = c;
+            else if (o.kind == OP_UPCAT) { d *= 2; c += sc[o.slot]; }
+            size_t b = (size_t)n_tiles * d * d * d * c * 2;
+            if (b > max_bytes) max_bytes = b;
+        }
+    }
+    if (max_bytes > g_pool.cap) {
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+        FPL_TRY(pool_reserve(max_bytes + 4096));
+    }
+    bool busy[ActPool::kBufs] = {false, false, false, false};
+    auto take = [&]() { for (int i = 0; i < ActPool::kBufs; ++i) if (!busy[i]) { busy[i] = true; return i; } return -1; };
+    int cur = -1;                 // buffer index holding the current activation (-1: the fp32 input tiles)
+    int skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
+    bool cur_is_skip = false;
+    int d = in_sz, c = 1;
+    const int stream_blocks = ctx->sm_count * 8;
+    for (const Op &o : net->ops) {
+        if (o.kind == OP_CONV) {
+            const ConvParams &cp = net->convs[o.conv_index];
+            const int nb = take();
+            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            __nv_bfloat16 *dst = (__nv_bfloat16 *)g_pool.buf[nb];
+            if (cp.cin == 1) {
+                const int dout = d - 2;
+                const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
+                FPL_REQUIRE(cp.k == 3 && blocks < 2147483647LL, "forward_umma: unsupported first layer");
+                if (cp.cout == 48)
+                    conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
+                else if (cp.cout == 32)
+                    conv_first_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
+                else { set_error("forward_umma: first layer Cout %d unsupported", cp.cout); return FPL_EINVAL; }
+                FPL_LAUNCH_CHECK(ctx);
+            } else {
+                const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_pool.buf[cur];
+                if (umma_supported(cp) && !g_force_direct) FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, 1, st));
+                else FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, 1, st));
+            }
+            if (cur >= 0 && !cur_is_skip) busy[cur] = false;
+            cur = nb; cur_is_skip = false;
+            d -= o.k - 1; c = o.cout;
+        } else if (o.kind == OP_POOL) {
+            const int nb = take();
+            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            pool_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], (uint4 *)g_pool.buf[nb],
+                                                              (long long)n_tiles * (c / 8), d);
+            FPL_LAUNCH_CHECK(ctx);
+            if (!cur_is_skip) busy[cur] = false;
+            cur = nb; cur_is_skip = false;
+            d /= 2;
+        } else if (o.kind == OP_SAVE) {
+            skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_c[o.slot] = c;
+            cur_is_skip = true;
+        } else if (o.kind == OP_UPCAT) {
+            const int nb = take();
+            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            upcat_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], d, c / 8,
+                                                               (const uint4 *)g_pool.buf[skip_buf[o.slot]],
+                                                               skip_d[o.slot], skip_c[o.slot] / 8, o.crop,
+                                                               (uint4 *)g_pool.buf[nb], n_tiles);
+            FPL_LAUNCH_CHECK(ctx);
+            if (!cur_is_skip) busy[cur] = false;
+            busy[skip_buf[o.slot]] = false;
+            cur = nb; cur_is_skip = false;
+            d *= 2; c += skip_c[o.slot];
+        } else if (o.kind == OP_FINAL) {
+            const ConvParams &cp = net->convs[o.conv_index];
+            final_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], cp.d_kernel, cp.bias[0],
+                                                               d_out, n_tiles, d, c / 8, net->info.rf_stride);
+            FPL_LAUNCH_CHECK(ctx);
+        }
+    }
+    return FPL_OK;
+}
+
+}  // namespace net
+}  // namespace fpl
+
+extern "C" int fpl_debug_force_direct_conv(int on) { fpl::net::g_force_direct = on; return FPL_OK; }
