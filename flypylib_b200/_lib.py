@@ -49,6 +49,8 @@ _SIGNATURES = {
     "fpl_ctx_destroy": (ctypes.c_int, [vp]),
     "fpl_ctx_workspace_bytes": (ctypes.c_int, [vp, c_i64p]),
     "fpl_ctx_launch_count": (ctypes.c_int, [vp, c_i64p]),
+    "fpl_ctx_profile_begin": (ctypes.c_int, [vp]),
+    "fpl_ctx_profile_end": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
     "fpl_v2o_smooth": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.POINTER(V2OParams), vp, vp]),
     "fpl_v2o_threshold": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -124,6 +126,16 @@ class Context:
         v = ctypes.c_int64()
         check(lib().fpl_ctx_workspace_bytes(self.handle, ctypes.byref(v)))
         return v.value
+
+    def profile_begin(self):
+        check(lib().fpl_ctx_profile_begin(self.handle), "fpl_ctx_profile_begin")
+
+    def profile_end(self):
+        """-> {family: (ms, work, count)}"""
+        ms = (ctypes.c_double * 8)(); work = (ctypes.c_double * 8)(); cnt = (ctypes.c_int64 * 8)()
+        check(lib().fpl_ctx_profile_end(self.handle, ms, work, cnt), "fpl_ctx_profile_end")
+        names = ["conv3", "conv1", "first", "netaux", "gauss", "select", "nms", "tiler"]
+        return {n: (ms[i], work[i], cnt[i]) for i, n in enumerate(names)}
 
     def close(self):
         if self.handle:

@@ -54,6 +54,13 @@ struct Arena {
 
 }  // namespace fpl
 
+namespace fpl {
+// per-kernel-family device timing (CUDA events on the launching stream), off by default
+enum ProfTag { PROF_CONV3 = 0, PROF_CONV1 = 1, PROF_FIRST = 2, PROF_NETAUX = 3, PROF_GAUSS = 4,
+               PROF_SELECT = 5, PROF_NMS = 6, PROF_TILER = 7, PROF_NTAGS = 8 };
+struct ProfRec { cudaEvent_t a, b; int tag; double work; };
+}  // namespace fpl
+
 struct fpl_ctx {
     int device = 0;
     int sm_count = 0;
@@ -61,7 +68,25 @@ struct fpl_ctx {
     int64_t launches = 0;
     void *h_pinned = nullptr;             // small pinned staging buffer (counters, thresholds)
     size_t h_pinned_bytes = 0;
+    bool profiling = false;
+    std::vector<fpl::ProfRec> prof;
+    std::vector<cudaEvent_t> prof_free;
 };
+
+namespace fpl {
+// RAII scope: records an event pair around the launches issued inside it when profiling is on.
+struct ProfScope {
+    fpl_ctx *ctx; cudaStream_t st; ProfRec rec; bool on;
+    ProfScope(fpl_ctx *c, cudaStream_t s, int tag, double work) : ctx(c), st(s), on(c->profiling) {
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t e; if (!ctx->prof_free.empty()) { e = ctx->prof_free.back(); ctx->prof_free.pop_back(); }
+                           else cudaEventCreate(&e); return e; };
+        rec.a = get(); rec.b = get(); rec.tag = tag; rec.work = work;
+        cudaEventRecord(rec.a, st);
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(rec.b, st); ctx->prof.push_back(rec); } }
+};
+}  // namespace fpl
 
 #define FPL_LAUNCH_CHECK(ctx)                                                             \
     do {                                                                                  \

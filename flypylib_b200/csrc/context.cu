@@ -93,6 +93,8 @@ int fpl_ctx_destroy(fpl_ctx *ctx) {
     if (!ctx) return FPL_OK;
     cudaSetDevice(ctx->device);
     ctx->arena.release();
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
     return FPL_OK;
@@ -101,6 +103,30 @@ int fpl_ctx_destroy(fpl_ctx *ctx) {
 int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes) {
     FPL_REQUIRE(ctx && bytes, "fpl_ctx_workspace_bytes: NULL argument");
     *bytes = (int64_t)ctx->arena.cap;
+    return FPL_OK;
+}
+
+int fpl_ctx_profile_begin(fpl_ctx *ctx) {
+    FPL_REQUIRE(ctx, "fpl_ctx_profile_begin: NULL ctx");
+    for (auto &r : ctx->prof) { ctx->prof_free.push_back(r.a); ctx->prof_free.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return FPL_OK;
+}
+
+int fpl_ctx_profile_end(fpl_ctx *ctx, double *ms_by_tag, double *work_by_tag, int64_t *count_by_tag) {
+    FPL_REQUIRE(ctx && ms_by_tag && work_by_tag && count_by_tag, "fpl_ctx_profile_end: NULL argument");
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    FPL_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < fpl::PROF_NTAGS; ++i) { ms_by_tag[i] = 0; work_by_tag[i] = 0; count_by_tag[i] = 0; }
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        ms_by_tag[r.tag] += ms; work_by_tag[r.tag] += r.work; count_by_tag[r.tag] += 1;
+        ctx->prof_free.push_back(r.a); ctx->prof_free.push_back(r.b);
+    }
+    ctx->prof.clear();
+    ctx->profiling = false;
     return FPL_OK;
 }
 

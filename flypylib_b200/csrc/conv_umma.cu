@@ -455,7 +455,7 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
 // not fit next to the input ring in shared memory (until their streaming variant lands) and (b) by
 // the tests as an independent check of the tcgen05 kernel on identical bf16 inputs.
 template <int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 conv_blocked_direct_kernel(const __nv_bfloat16 *__restrict__ in, const float *__restrict__ w,
                            const float *__restrict__ scale, const float *__restrict__ bias,
                            __nv_bfloat16 *__restrict__ out, int n_tiles, int din, int cin, int cout, int relu) {
@@ -601,6 +601,8 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const size_t smem = conv_smem_bytes(ks, c.cin, c.cout);
     const long long n_items = base_items * a.n_zc;
+    ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
+                   2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
     if (ks == 3) {
         FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -618,7 +620,7 @@ static int launch_conv_direct(fpl_ctx *ctx, const ConvParams &c, const __nv_bflo
     const int dout = din - (c.k - 1);
     const int xb = (dout + 31) / 32;
     const long long blocks = (long long)n_tiles * dout * dout * xb;
-    FPL_REQUIRE(blocks < 2147483647LL && c.cout / 8 <= 32, "conv_blocked_direct: launch too large");
+    FPL_REQUIRE(blocks < 2147483647LL && c.cout / 8 <= 16, "conv_blocked_direct: launch too large");
     dim3 block(32, c.cout / 8);
     if (c.k == 3)
         conv_blocked_direct_kernel<3><<<(unsigned)blocks, block, 0, st>>>(in, c.d_kernel, c.d_scale, c.d_bias, out,
@@ -694,6 +696,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 const int dout = d - 2;
                 const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
                 FPL_REQUIRE(cp.k == 3 && blocks < 2147483647LL, "forward_umma: unsupported first layer");
+                ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
                 if (cp.cout == 48)
                     conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
                 else if (cp.cout == 32)
@@ -711,6 +714,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         } else if (o.kind == OP_POOL) {
             const int nb = take();
             if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * c * 2.0 * d * d * d * 1.125);
             pool_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], (uint4 *)g_pool.buf[nb],
                                                               (long long)n_tiles * (c / 8), d);
             FPL_LAUNCH_CHECK(ctx);
@@ -723,6 +727,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         } else if (o.kind == OP_UPCAT) {
             const int nb = take();
             if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * (c + skip_c[o.slot]) * 2.0 * 8.0 * d * d * d * 2);
             upcat_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], d, c / 8,
                                                                (const uint4 *)g_pool.buf[skip_buf[o.slot]],
                                                                skip_d[o.slot], skip_c[o.slot] / 8, o.crop,
@@ -734,6 +739,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             d *= 2; c += skip_c[o.slot];
         } else if (o.kind == OP_FINAL) {
             const ConvParams &cp = net->convs[o.conv_index];
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * d * d * d * (c * 2.0 + 4.0 * net->info.rf_stride * net->info.rf_stride * net->info.rf_stride));
             final_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], cp.d_kernel, cp.bias[0],
                                                                d_out, n_tiles, d, c / 8, net->info.rf_stride);
             FPL_LAUNCH_CHECK(ctx);

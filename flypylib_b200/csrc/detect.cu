@@ -656,6 +656,7 @@ static int smooth_impl(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, 
         FPL_CUDA_CHECK(cudaMemcpyAsync(d_smooth, d_pred, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
         return FPL_OK;
     }
+    fpl::ProfScope prof(ctx, st, fpl::PROF_GAUSS, 3.0 * 8.0 * (double)n);
     Taps taps;
     memset(&taps, 0, sizeof(taps));
     for (int i = 0; i < 2 * p->lw + 1; ++i) taps.w[i] = p->h_weights[i];
@@ -693,6 +694,7 @@ static int threshold_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
     FPL_REQUIRE(p->rank_lo >= 0 && (unsigned long long)p->rank_lo < n_pad && p->rank_hi >= 0 &&
                 (unsigned long long)p->rank_hi < n_pad, "voxel2obj: percentile ranks out of range");
     const unsigned long long extra = n_pad - (unsigned long long)n;
+    fpl::ProfScope prof(ctx, st, fpl::PROF_SELECT, 3.0 * 4.0 * (double)n);
     FPL_TRY(select_rank(ctx, d_smooth, n, extra, (unsigned long long)p->rank_lo, d_states, st));
     SelectState *hi = d_states;
     if (p->rank_hi != p->rank_lo) {
@@ -765,6 +767,7 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
     FPL_CUDA_CHECK(cudaMemsetAsync(B.n_out, 0, 64, st));
 
     const int grid_stream = ctx->sm_count * 8;
+    fpl::ProfScope prof(ctx, st, fpl::PROF_NMS, 4.0 * (double)n);
     compact_candidates_kernel<<<grid_stream, 256, 0, st>>>(d_smooth, n, threshold, B.a_idx, B.a_val,
                                                           cand_cap, B.cnt);
     FPL_LAUNCH_CHECK(ctx);

@@ -330,17 +330,23 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     for (long long t0 = 0; t0 < n_tiles_total && rc == FPL_OK; t0 += batch) {
         int nb = (int)((n_tiles_total - t0) < batch ? (n_tiles_total - t0) : batch);
         int blocks = ctx->sm_count * 8;
+        {
+        fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * in_elems * (image_is_u8 ? 5.0 : 8.0));
         if (image_is_u8)
             gather_tiles_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)d_image, d_in, g,
                                                                  tile_first + (int)t0, nb, norm_mean, norm_std);
         else
             gather_tiles_kernel<float><<<blocks, 256, 0, st>>>((const float *)d_image, d_in, g,
                                                                tile_first + (int)t0, nb, 0.f, 1.f);
+        }
         ctx->launches++;
         if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, g.in_sz, d_out, st);
         else rc = forward_umma(net, d_in, nb, g.in_sz, d_out, st);
         if (rc != FPL_OK) break;
+        {
+        fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);
         scatter_tiles_kernel<<<blocks, 256, 0, st>>>(d_out, d_pred, g, tile_first + (int)t0, nb);
+        }
         ctx->launches++;
     }
     cudaError_t e2 = cudaStreamSynchronize(st);

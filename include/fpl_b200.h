@@ -56,6 +56,15 @@ int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes);
 /* number of kernel launches issued by this context since creation (bench.py "gpu_launches") */
 int fpl_ctx_launch_count(fpl_ctx *ctx, int64_t *launches);
 
+/* Device-side timing of kernel families with CUDA events recorded on the launching stream
+ * (bench.py roofline).  profile_end synchronises the device and returns, per family
+ * (0 conv3x3x3 tcgen05, 1 conv1x1x1 tcgen05, 2 first-layer conv, 3 pool/upsample/concat/final,
+ * 4 Gaussian passes, 5 radix select, 6 NMS (compaction, rounds, sort), 7 tile gather/scatter):
+ * summed milliseconds, summed algorithmic work (FLOP for 0-2, bytes otherwise) and launch-group
+ * count.  Arrays have 8 entries. */
+int fpl_ctx_profile_begin(fpl_ctx *ctx);
+int fpl_ctx_profile_end(fpl_ctx *ctx, double *ms_by_tag, double *work_by_tag, int64_t *count_by_tag);
+
 /* ---------------------------------------------------------------------------------------------
  * voxel2obj: smoothing + percentile threshold + greedy NMS       (flypylib/fplobjdetect.py:132-257)
  * ------------------------------------------------------------------------------------------- */
