@@ -110,6 +110,13 @@ int fpl_ctx_profile_begin(fpl_ctx *ctx) {
     FPL_REQUIRE(ctx, "fpl_ctx_profile_begin: NULL ctx");
     for (auto &r : ctx->prof) { ctx->prof_free.push_back(r.a); ctx->prof_free.push_back(r.b); }
     ctx->prof.clear();
+    // pre-create the event pool so that no cudaEventCreate happens inside a timed region
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    while (ctx->prof_free.size() < 8192) {
+        cudaEvent_t e;
+        FPL_CUDA_CHECK(cudaEventCreate(&e));
+        ctx->prof_free.push_back(e);
+    }
     ctx->profiling = true;
     return FPL_OK;
 }

@@ -102,6 +102,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+                 : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows
@@ -136,17 +143,18 @@ struct ConvArgs {
     uint32_t tmem_cols;
 };
 
-template <int KS>
+template <int KS, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) {
     constexpr int SX = kTX + KS - 1, SY = kTY + KS - 1;
+    constexpr int CIN_ATOMS = 2 * KSTEPS;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const uint32_t atom_stride = SY * SX * 16;                      // bytes between channel atoms of a plane
-    const uint32_t plane_bytes = (uint32_t)a.cin_atoms * atom_stride;
+    constexpr uint32_t atom_stride = SY * SX * 16;                  // bytes between channel atoms of a plane
+    constexpr uint32_t plane_bytes = CIN_ATOMS * atom_stride;
+    constexpr uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
     const uint32_t w_region = (a.w_bytes + 127u) & ~127u;
     uint8_t *s_w = smem_raw;
     uint8_t *s_planes = smem_raw + w_region;
-    const uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_planes + kPlanes * plane_pitch);
     uint64_t *plane_full = bars;                    // [kPlanes]
     uint64_t *plane_empty = bars + kPlanes;         // [kPlanes]
@@ -156,7 +164,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ksteps = a.cin_atoms >> 1;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
 
     if (threadIdx.x == 0) {
@@ -171,83 +178,92 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Roles run warp-uniformly (all 32 lanes walk the same loops on uniform values); only the
+    // asynchronous instructions themselves are issued by one elected lane.  This keeps descriptors in
+    // uniform registers and avoids per-instruction waterfall loops in SASS.
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        const bool leader = elect_one();
+        if (leader) {
             mbar_expect_tx(w_full, a.w_bytes);
             for (uint32_t off = 0; off < a.w_bytes; off += 32768u) {
                 uint32_t n = a.w_bytes - off < 32768u ? a.w_bytes - off : 32768u;
                 bulk_load_1d(s_w + off, reinterpret_cast<const uint8_t *>(a.w_packed) + off, n, w_full);
             }
-            uint32_t pc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int t = item;
-                const int zc = t % a.n_zc; t /= a.n_zc;
-                const int xt = t % a.n_xt; t /= a.n_xt;
-                const int yt = t % a.n_yt; t /= a.n_yt;
-                const int tile = t;
-                const int z0 = zc * a.zc_len;
-                const int nz = min(a.zc_len, a.dout - z0);
-                const int np = nz + KS - 1;
-                for (int p = 0; p < np; ++p, ++pc) {
-                    const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
-                    mbar_wait(&plane_empty[slot], ph ^ 1u);
+        }
+        uint32_t pc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout - z0);
+            const int np = nz + KS - 1;
+            for (int p = 0; p < np; ++p, ++pc) {
+                const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
+                mbar_wait(&plane_empty[slot], ph ^ 1u);
+                if (leader) {
                     mbar_expect_tx(&plane_full[slot], plane_bytes);
                     tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * kTX * 8, yt * kTY,
-                                z0 + p, tile * a.cin_atoms);
+                                z0 + p, tile * CIN_ATOMS);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, a.cout);
-            const uint32_t w_addr = smem_u32(s_w);
-            const uint32_t planes_addr = smem_u32(s_planes);
-            const uint32_t b_lbo = (uint32_t)a.cout * 16u, b_sbo = 128u, b_step = (uint32_t)a.cout * 32u;
-            const uint32_t a_sbo = SX * 16u;
-            mbar_wait(w_full, 0);
-            uint32_t pc_base = 0, ac = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int zc = item % a.n_zc;
-                const int z0 = zc * a.zc_len;
-                const int nz = min(a.zc_len, a.dout - z0);
-                for (int zo = 0; zo < nz; ++zo, ++ac) {
-                    const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
-                    mbar_wait(&acc_empty[as], aph ^ 1u);
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_bf16(128, a.cout);
+        // descriptor words in 16-byte units: lo = start | LBO << 16, hi = SBO | version 1 << 14
+        const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
+        const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((uint32_t)a.cout << 16);     // LBO = Cout*16 bytes
+        const uint32_t b_step16 = (uint32_t)a.cout * 2u;                           // Cout*32 bytes per K step
+        mbar_wait(w_full, 0);
+        uint32_t pc_base = 0, ac = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int zc = item % a.n_zc;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout - z0);
+            for (int zo = 0; zo < nz; ++zo, ++ac) {
+                const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
+                mbar_wait(&acc_empty[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + as * (2u * (uint32_t)a.cout);
+                const uint32_t d1 = d0 + (uint32_t)a.cout;
+#pragma unroll 1
+                for (int kd = 0; kd < KS; ++kd) {
+                    const uint32_t pi = pc_base + zo + kd;
+                    const uint32_t slot = pi % kPlanes, ph = (pi / kPlanes) & 1u;
+                    mbar_wait(&plane_full[slot], ph);
                     tc_fence_after();
-                    const uint32_t d0 = tmem_base + as * (2u * (uint32_t)a.cout);
-                    uint32_t first = 1;
-#pragma unroll 1
-                    for (int kd = 0; kd < KS; ++kd) {
-                        const uint32_t pi = pc_base + zo + kd;
-                        const uint32_t slot = pi % kPlanes, ph = (pi / kPlanes) & 1u;
-                        mbar_wait(&plane_full[slot], ph);
-                        tc_fence_after();
-                        const uint32_t pbase = planes_addr + slot * plane_pitch;
-#pragma unroll 1
+                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+                    uint32_t b_lo = b_lo0 + (uint32_t)(kd * KS * KS * KSTEPS) * b_step16;
+                    if (leader) {
+#pragma unroll
                         for (int kh = 0; kh < KS; ++kh)
-#pragma unroll 1
-                            for (int kw = 0; kw < KS; ++kw) {
-                                const uint32_t tap = (kd * KS + kh) * KS + kw;
-                                const uint32_t a_tap = pbase + (uint32_t)(kh * SX + kw) * 16u;
-                                const uint32_t b_tap = w_addr + tap * (uint32_t)ksteps * b_step;
-                                for (int s = 0; s < ksteps; ++s) {
-                                    const uint64_t bdesc = make_desc(b_tap + s * b_step, b_lbo, b_sbo);
-                                    const uint32_t a_s = a_tap + (uint32_t)(2 * s) * atom_stride;
-                                    umma_bf16(d0, make_desc(a_s, atom_stride, a_sbo), bdesc, idesc, first ? 0u : 1u);
-                                    umma_bf16(d0 + (uint32_t)a.cout, make_desc(a_s + 8u * 16u, atom_stride, a_sbo),
-                                              bdesc, idesc, first ? 0u : 1u);
-                                    first = 0;
+#pragma unroll
+                            for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                                for (int s = 0; s < KSTEPS; ++s) {
+                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
+                                    const uint32_t acc = (kd | kh | kw | s) ? 1u : 0u;
+                                    const uint64_t bdesc = desc64(b_lo, b_hi);
+                                    umma_bf16(d0, desc64(a_lo, a_hi), bdesc, idesc, acc);
+                                    umma_bf16(d1, desc64(a_lo + 8u, a_hi), bdesc, idesc, acc);
+                                    b_lo += b_step16;
                                 }
-                            }
                         // plane (zo+kd) is dead once output zo has consumed it as kd==0 (or at item end)
                         if (kd == 0 || zo == nz - 1) umma_commit(&plane_empty[slot]);
                     }
-                    umma_commit(&acc_full[as]);
+                    __syncwarp();
                 }
-                pc_base += nz + KS - 1;
+                if (leader) umma_commit(&acc_full[as]);
+                __syncwarp();
             }
+            pc_base += nz + KS - 1;
         }
     } else {
         // ===================================== epilogue =========================================
@@ -533,6 +549,9 @@ static size_t conv_smem_bytes(int ks, int cin, int cout) {
 static bool umma_supported(const ConvParams &c) {
     if (c.cin % 16 || c.cout % 16 || c.cout > 128) return false;
     if (c.k != 1 && c.k != 3) return false;
+    const int ksteps = c.cin / 16;
+    if (c.k == 3 && !(ksteps == 2 || ksteps == 3 || ksteps == 4)) return false;
+    if (c.k == 1 && !(ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6)) return false;
     return conv_smem_bytes(c.k, c.cin, c.cout) <= kMaxDynSmem;
 }
 
@@ -604,13 +623,22 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
                    2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
-    if (ks == 3) {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_umma_kernel<3><<<grid, kThreads, smem, st>>>(tmap, a);
-    } else {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_umma_kernel<1><<<grid, kThreads, smem, st>>>(tmap, a);
-    }
+    const int ksteps = c.cin / 16;
+#define FPL_LAUNCH_UMMA(KS_, KST_)                                                                               \
+    do {                                                                                                          \
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_>,                                          \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        conv_umma_kernel<KS_, KST_><<<grid, kThreads, smem, st>>>(tmap, a);                                       \
+    } while (0)
+    if (ks == 3 && ksteps == 3) FPL_LAUNCH_UMMA(3, 3);
+    else if (ks == 3 && ksteps == 2) FPL_LAUNCH_UMMA(3, 2);
+    else if (ks == 3 && ksteps == 4) FPL_LAUNCH_UMMA(3, 4);
+    else if (ks == 1 && ksteps == 2) FPL_LAUNCH_UMMA(1, 2);
+    else if (ks == 1 && ksteps == 3) FPL_LAUNCH_UMMA(1, 3);
+    else if (ks == 1 && ksteps == 4) FPL_LAUNCH_UMMA(1, 4);
+    else if (ks == 1 && ksteps == 6) FPL_LAUNCH_UMMA(1, 6);
+    else { set_error("conv_umma: no instantiation for k=%d Cin=%d", ks, c.cin); return FPL_EINVAL; }
+#undef FPL_LAUNCH_UMMA
     FPL_LAUNCH_CHECK(ctx);
     return FPL_OK;
 }

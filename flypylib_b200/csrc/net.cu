@@ -169,6 +169,8 @@ int fpl_net_destroy(fpl_net *net) {
     if (!net) return FPL_OK;
     cudaSetDevice(net->ctx->device);
     free_device_weights(net);
+    if (net->d_stage_in) cudaFree(net->d_stage_in);
+    if (net->d_stage_out) cudaFree(net->d_stage_out);
     delete net;
     return FPL_OK;
 }
@@ -321,10 +323,16 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     const size_t in_elems = (size_t)g.in_sz * g.in_sz * g.in_sz, out_elems = (size_t)g.out_sz * g.out_sz * g.out_sz;
     int batch = net->precision == FPL_PREC_FP32 ? 4 : 8;
     if (batch > n_tiles_total) batch = (int)n_tiles_total;
-    float *d_in = nullptr, *d_out = nullptr;
-    FPL_CUDA_CHECK(cudaMalloc((void **)&d_in, sizeof(float) * in_elems * batch));
-    cudaError_t e = cudaMalloc((void **)&d_out, sizeof(float) * out_elems * batch);
-    if (e != cudaSuccess) { cudaFree(d_in); FPL_CUDA_CHECK(e); }
+    if (net->stage_in_cap < in_elems * batch || net->stage_out_cap < out_elems * batch) {
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (net->d_stage_in) cudaFree(net->d_stage_in);
+        if (net->d_stage_out) cudaFree(net->d_stage_out);
+        net->d_stage_in = net->d_stage_out = nullptr; net->stage_in_cap = net->stage_out_cap = 0;
+        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_in, sizeof(float) * in_elems * batch));
+        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_out, sizeof(float) * out_elems * batch));
+        net->stage_in_cap = in_elems * batch; net->stage_out_cap = out_elems * batch;
+    }
+    float *d_in = net->d_stage_in, *d_out = net->d_stage_out;
     int rc = FPL_OK;
     const int tile_first = zb * g.ny * g.nx;
     for (long long t0 = 0; t0 < n_tiles_total && rc == FPL_OK; t0 += batch) {
@@ -349,10 +357,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         }
         ctx->launches++;
     }
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(d_in); cudaFree(d_out);
     if (rc != FPL_OK) return rc;
-    FPL_CUDA_CHECK(e2);
     FPL_CUDA_CHECK(cudaGetLastError());
     return FPL_OK;
 }

@@ -46,6 +46,8 @@ struct fpl_net {
     std::vector<fpl::net::ConvParams> convs;   // every OP_CONV and the OP_FINAL, in graph order
     int precision = -1;                        // -1: no weights yet
     int tile_mult = 1;                         // VGG only: tile edge = tile_mult*out_sz + 2*off
+    float *d_stage_in = nullptr, *d_stage_out = nullptr;   // tile staging of fpl_net_infer_volume (grow-only)
+    size_t stage_in_cap = 0, stage_out_cap = 0;
 };
 
 namespace fpl {
