@@ -130,7 +130,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int kTX = 16, kTY = 16;            // output patch per CTA and z step (two M=128 tiles: x 0..7, 8..15)
 constexpr int kPlanes = 3;                   // input plane ring
 constexpr int kAccStages = 2;                // TMEM accumulator double buffering
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct ConvArgs {
     const __nv_bfloat16 *w_packed;   // [tap][kstep][2][Cout][8] bf16, BN scale folded
@@ -142,6 +142,55 @@ struct ConvArgs {
     int relu;
     uint32_t tmem_cols;
 };
+
+// Epilogue of one M=128 accumulator tile (N = cout fp32 columns in TMEM):
+// TMEM -> registers -> + folded-BN bias (shared memory) -> ReLU -> bf16 -> C8-blocked global store.
+// Warp quadrant `q` owns TMEM lanes [32q, 32q+32); lane = accumulator row = voxel (y = row/8, x = row%8).
+// The next 16-column TMEM load is in flight while the previous one is converted and stored.
+__device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], int c0, const float *s_bias, int relu,
+                                                 __nv_bfloat16 *__restrict__ out, size_t vox, size_t cg_stride,
+                                                 bool ok) {
+    if (!ok) return;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v0 = __uint_as_float(r[h * 8 + 2 * j]) + s_bias[c0 + h * 8 + 2 * j];
+            float v1 = __uint_as_float(r[h * 8 + 2 * j + 1]) + s_bias[c0 + h * 8 + 2 * j + 1];
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+            pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+        }
+        *reinterpret_cast<uint4 *>(out + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, int cout, const float *s_bias,
+                                              int relu, __nv_bfloat16 *__restrict__ out, int tile, int dout, int z,
+                                              int y0, int x0) {
+    const int row = q * 32 + lane;
+    const int y = y0 + (row >> 3), x = x0 + (row & 7);
+    const bool ok = (x < dout) && (y < dout);
+    const size_t cg_stride = (size_t)dout * dout * dout;
+    const size_t vox = (size_t)tile * (cout >> 3) * cg_stride + ((size_t)z * dout + y) * dout + x;
+    const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16);
+    uint32_t ra[16], rb[16];
+    tmem_ld16(tcol, ra);
+#pragma unroll 1
+    for (int c0 = 0; c0 < cout; c0 += 32) {
+        tmem_ld_wait();
+        const bool more = c0 + 16 < cout;
+        if (more) tmem_ld16(tcol + (uint32_t)(c0 + 16), rb);
+        epilogue_store16(ra, c0, s_bias, relu, out, vox, cg_stride, ok);
+        if (more) {
+            tmem_ld_wait();
+            if (c0 + 32 < cout) tmem_ld16(tcol + (uint32_t)(c0 + 32), ra);
+            epilogue_store16(rb, c0 + 16, s_bias, relu, out, vox, cg_stride, ok);
+        }
+    }
+}
 
 template <int KS, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -162,16 +211,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     uint64_t *acc_empty = acc_full + kAccStages;    // [kAccStages]
     uint64_t *w_full = acc_empty + kAccStages;      // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
+    float *s_bias = reinterpret_cast<float *>(bars + 16);          // [cout]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPlanes; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
+    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) s_bias[i] = a.bias[i];
     if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -268,9 +319,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     } else {
         // ===================================== epilogue =========================================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;                // accumulator row = voxel inside the 8x16 M-tile
-        const int ly = row >> 3, lx = row & 7;
-        const int cg_out = a.cout >> 3;
+        const int m = (warp - 2) >> 2;                // which of the two M-tiles (x half) this warp drains
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
@@ -284,38 +333,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                 const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
                 mbar_wait(&acc_full[as], aph);
                 tc_fence_after();
-                const int z = z0 + zo;
-                const int y = yt * kTY + ly;
-#pragma unroll 1
-                for (int m = 0; m < 2; ++m) {
-                    const int x = xt * kTX + m * 8 + lx;
-                    const bool ok = (x < a.dout) && (y < a.dout);
-                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + as * (2u * (uint32_t)a.cout) +
-                                          (uint32_t)m * (uint32_t)a.cout;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < a.cout; c0 += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(tcol + (uint32_t)c0, r);
-                        tmem_ld_wait();
-                        if (ok) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float v0 = __uint_as_float(r[h * 8 + 2 * j]) + __ldg(a.bias + c0 + h * 8 + 2 * j);
-                                    float v1 = __uint_as_float(r[h * 8 + 2 * j + 1]) + __ldg(a.bias + c0 + h * 8 + 2 * j + 1);
-                                    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                                    pk[j] = *reinterpret_cast<uint32_t *>(&b2);
-                                }
-                                const int cg = (c0 >> 3) + h;
-                                size_t o = ((((size_t)tile * cg_out + cg) * a.dout + z) * a.dout + y) * a.dout + x;
-                                *reinterpret_cast<uint4 *>(a.out + o * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                        }
-                    }
-                }
+                epilogue_tile(tmem_base + as * (2u * (uint32_t)a.cout) + (uint32_t)m * (uint32_t)a.cout, q, lane, a.cout,
+                              s_bias, a.relu, a.out, tile, a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -325,6 +344,199 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer on the tensor pipe: Conv3D(Cout,(3,3,3)) of the single-channel float32 tile.
+// K = 27 taps padded to 32: builder warps write the im2col rows (bf16) of a 16x16 output patch straight
+// into shared memory in the UMMA canonical layout, two K=16 MMAs per M-tile do the contraction, the
+// common epilogue writes C8-blocked bf16.  The kernel is bound by its bf16 output stream (HBM/L2 write).
+//   warp 0      MMA issuer (+ TMEM alloc)      warps 1..4  epilogue      warps 5..8  im2col builders
+// ------------------------------------------------------------------------------------------------
+constexpr int kFirstThreads = 416;           // warp 0 MMA, warps 1..8 epilogue, warps 9..12 builders
+struct FirstArgs {
+    const float *in;                 // (tile, din, din, din) float32
+    const __nv_bfloat16 *w_packed;   // [2 ksteps][2][Cout][8], taps >= 27 zero, BN scale folded
+    const float *bias;
+    __nv_bfloat16 *out;
+    int n_tiles, din, dout, cout;
+    int n_xt, n_yt, n_zc, zc_len;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kFirstThreads, 1)
+conv_first_umma_kernel(const FirstArgs a) {
+    constexpr int SX = kTX + 2, SY = kTY + 2;
+    constexpr int kRing = 4;
+    constexpr int kPer = (SY * SX + 127) / 128;                // input elements per builder thread and plane
+    constexpr uint32_t kAStage = 2 * 4 * 128 * 16;            // 2 M-tiles x 4 atoms x 128 rows x 16 B
+    __shared__ __align__(128) uint8_t s_a[2 * kAStage];
+    __shared__ __align__(128) uint8_t s_w[2 * 2 * 128 * 16];   // up to Cout = 128
+    __shared__ float s_in[kRing][SY][SX];
+    __shared__ float s_bias[128];
+    __shared__ uint64_t bars[8];
+    __shared__ uint32_t tmem_slot;
+    uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
+        fence_barrier_init();
+    }
+    // weights -> smem (generic proxy), made visible to the tensor core with a proxy fence
+    for (int i = threadIdx.x; i < a.cout * 4; i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_w)[i] = __ldg(reinterpret_cast<const uint4 *>(a.w_packed) + i);
+    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) s_bias[i] = a.bias[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) tmem_alloc(&tmem_slot, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== MMA issuer =======================================
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_bf16(128, a.cout);
+        const uint32_t a_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B (rows contiguous)
+        const uint32_t a_lo0 = (smem_u32(s_a) >> 4) | ((2048u >> 4) << 16);    // LBO = 2048 B between atoms
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((uint32_t)a.cout << 16);
+        const uint32_t b_step16 = (uint32_t)a.cout * 2u;
+        uint32_t ac = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int zc = item % a.n_zc;
+            const int nz = min(a.zc_len, a.dout - zc * a.zc_len);
+            for (int zo = 0; zo < nz; ++zo, ++ac) {
+                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+                mbar_wait(&acc_empty[st], ph ^ 1u);
+                mbar_wait(&a_full[st], ph);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d0 = tmem_base + st * (2u * (uint32_t)a.cout);
+                    const uint32_t a_st = a_lo0 + st * (kAStage >> 4);
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const uint64_t bdesc = desc64(b_lo0 + s * b_step16, b_hi);
+                        umma_bf16(d0, desc64(a_st + s * (4096u >> 4), a_hi), bdesc, idesc, s ? 1u : 0u);
+                        umma_bf16(d0 + (uint32_t)a.cout, desc64(a_st + (8192u >> 4) + s * (4096u >> 4), a_hi), bdesc,
+                                  idesc, s ? 1u : 0u);
+                    }
+                    umma_commit(&a_empty[st]);
+                    umma_commit(&acc_full[st]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp <= 8) {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;
+        const int m = (warp - 1) >> 2;
+        uint32_t ac = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout - z0);
+            for (int zo = 0; zo < nz; ++zo, ++ac) {
+                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+                mbar_wait(&acc_full[st], ph);
+                tc_fence_after();
+                epilogue_tile(tmem_base + st * (2u * (uint32_t)a.cout) + (uint32_t)m * (uint32_t)a.cout, q, lane, a.cout,
+                              s_bias, 1, a.out, tile, a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[st]);
+            }
+        }
+    } else {
+        // ===================================== im2col builders ==================================
+        const int bt = threadIdx.x - 288;            // 0..127 = accumulator row
+        const int ly = bt >> 3, lx = bt & 7;
+        uint32_t ac = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout - z0);
+            const float *tin = a.in + (size_t)tile * a.din * a.din * a.din;
+            float pre[kPer];
+            auto fetch = [&](int zin) {            // this thread's share of input plane zin -> registers
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    const int i = bt + k * 128;
+                    const int yy = i / SX, xx = i - yy * SX;
+                    const int gy = yt * kTY + yy, gx = xt * kTX + xx;
+                    float v = 0.f;
+                    if (i < SY * SX && zin < a.din && gy < a.din && gx < a.din)
+                        v = __ldg(tin + ((size_t)zin * a.din + gy) * a.din + gx);
+                    pre[k] = v;
+                }
+            };
+            auto stash = [&](int zin) {            // registers -> ring slot zin % kRing
+                float *dst = &s_in[zin % kRing][0][0];
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    const int i = bt + k * 128;
+                    if (i < SY * SX) dst[i] = pre[k];
+                }
+            };
+            // all builders are past their last read of the ring (barrier at the end of the previous plane)
+            fetch(z0); stash(z0);
+            fetch(z0 + 1); stash(z0 + 1);
+            fetch(z0 + 2);
+            for (int zo = 0; zo < nz; ++zo, ++ac) {
+                stash(z0 + zo + 2);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (zo + 1 < nz) fetch(z0 + zo + 3);          // in flight while this plane is built
+                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+                mbar_wait(&a_empty[st], ph ^ 1u);
+                uint8_t *abase = s_a + st * kAStage;
+                const float *p0 = &s_in[(z0 + zo) % kRing][ly][lx];
+                const float *p1 = &s_in[(z0 + zo + 1) % kRing][ly][lx];
+                const float *p2 = &s_in[(z0 + zo + 2) % kRing][ly][lx];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    float v[32];
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            v[kh * 3 + kw] = p0[kh * SX + m * 8 + kw];
+                            v[9 + kh * 3 + kw] = p1[kh * SX + m * 8 + kw];
+                            v[18 + kh * 3 + kw] = p2[kh * SX + m * 8 + kw];
+                        }
+#pragma unroll
+                    for (int tp = 27; tp < 32; ++tp) v[tp] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[k * 8 + 2 * j], v[k * 8 + 2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+                        }
+                        *reinterpret_cast<uint4 *>(abase + m * 8192 + k * 2048 + bt * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[st]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // ring is free for the next item
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -543,7 +755,7 @@ static size_t conv_smem_bytes(int ks, int cin, int cout) {
     const int sx = kTX + ks - 1, sy = kTY + ks - 1;
     size_t w = ((size_t)ks * ks * ks * cin * cout * 2 + 127) & ~size_t(127);
     size_t plane = (((size_t)(cin / 8) * sy * sx * 16) + 127) & ~size_t(127);
-    return w + kPlanes * plane + 256;
+    return w + kPlanes * plane + 128 + 512;     // + barriers + bias
 }
 
 static bool umma_supported(const ConvParams &c) {
@@ -559,7 +771,22 @@ static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv throu
 
 int pack_weights_umma(fpl_net *net) {
     for (ConvParams &c : net->convs) {
-        if (c.cin % 16 || c.cout % 16) continue;         // first layer / final layer
+        if (c.cin == 1 && c.k == 3 && c.cout % 16 == 0) {   // first layer: K = 27 taps padded to 32
+            std::vector<__nv_bfloat16> pk((size_t)2 * 2 * c.cout * 8);
+            for (int s = 0; s < 2; ++s)
+                for (int h = 0; h < 2; ++h)
+                    for (int n = 0; n < c.cout; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int tp = 16 * s + 8 * h + e;
+                            const float v = tp < 27 ? c.kernel[(size_t)tp * c.cout + n] * c.scale[n] : 0.f;
+                            pk[(((size_t)s * 2 + h) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
+                        }
+            c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
+            FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
+            FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, pk.data(), c.packed_bytes, cudaMemcpyHostToDevice));
+            continue;
+        }
+        if (c.cin % 16 || c.cout % 16) continue;         // final layer
         const int taps = c.k * c.k * c.k, ksteps = c.cin / 16;
         std::vector<__nv_bfloat16> pk((size_t)taps * c.cin * c.cout);
         for (int t = 0; t < taps; ++t)
@@ -725,7 +952,23 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
                 FPL_REQUIRE(cp.k == 3 && blocks < 2147483647LL, "forward_umma: unsupported first layer");
                 ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
-                if (cp.cout == 48)
+                if (!g_force_direct && cp.d_packed && cp.cout % 16 == 0 && cp.cout <= 128) {
+                    FirstArgs fa;
+                    fa.in = d_tiles; fa.w_packed = (const __nv_bfloat16 *)cp.d_packed; fa.bias = cp.d_bias; fa.out = dst;
+                    fa.n_tiles = n_tiles; fa.din = d; fa.dout = dout; fa.cout = cp.cout;
+                    fa.n_xt = (dout + kTX - 1) / kTX; fa.n_yt = (dout + kTY - 1) / kTY;
+                    const long long base_items = (long long)n_tiles * fa.n_xt * fa.n_yt;
+                    int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
+                    if (n_zc < 1) n_zc = 1;
+                    int zc_len = (dout + n_zc - 1) / n_zc;
+                    if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
+                    fa.zc_len = zc_len; fa.n_zc = (dout + zc_len - 1) / zc_len;
+                    const int acc_cols = 2 * 2 * cp.cout;
+                    fa.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+                    const long long n_items = base_items * fa.n_zc;
+                    int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
+                    conv_first_umma_kernel<<<grid, kFirstThreads, 0, st>>>(fa);
+                } else if (cp.cout == 48)
                     conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
                 else if (cp.cout == 32)
                     conv_first_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
