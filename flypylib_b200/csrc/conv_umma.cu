@@ -192,11 +192,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
     }
 }
 
+// Accumulator placement ("kd fusion").  The three kd taps of a 3x3x3 kernel read the SAME shifted A
+// tile of input plane p and feed three DIFFERENT output planes z = p, p-1, p-2.  Their accumulators
+// are laid out in TMEM so that they sit in adjacent N-column blocks in kd order; one
+// tcgen05.mma with N = 3*Cout then updates all three at once and the A tile is read from shared
+// memory once instead of three times (the kernel is bound by that read, see profiles/).
+// Each M-tile owns a 256-column region of kBlocks = 256/Cout blocks; output number A (monotone
+// counter) lives in block kBlocks-1 - (A mod kBlocks), so consecutive outputs occupy descending
+// blocks and (p, p-1, p-2) are contiguous except where the ring wraps (then two MMAs are issued).
 template <int KS, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) {
     constexpr int SX = kTX + KS - 1, SY = kTY + KS - 1;
     constexpr int CIN_ATOMS = 2 * KSTEPS;
+    constexpr int kMaxBlocks = 8;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr uint32_t atom_stride = SY * SX * 16;                  // bytes between channel atoms of a plane
     constexpr uint32_t plane_bytes = CIN_ATOMS * atom_stride;
@@ -207,23 +216,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_planes + kPlanes * plane_pitch);
     uint64_t *plane_full = bars;                    // [kPlanes]
     uint64_t *plane_empty = bars + kPlanes;         // [kPlanes]
-    uint64_t *acc_full = bars + 2 * kPlanes;        // [kAccStages]
-    uint64_t *acc_empty = acc_full + kAccStages;    // [kAccStages]
-    uint64_t *w_full = acc_empty + kAccStages;      // [1]
+    uint64_t *acc_full = bars + 2 * kPlanes;        // [kMaxBlocks]
+    uint64_t *acc_empty = acc_full + kMaxBlocks;    // [kMaxBlocks]
+    uint64_t *w_full = acc_empty + kMaxBlocks;      // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
-    float *s_bias = reinterpret_cast<float *>(bars + 16);          // [cout]
+    float *s_bias = reinterpret_cast<float *>(bars + 32);          // [cout]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
+    const uint32_t N = (uint32_t)a.cout;
+    const uint32_t nblk = 256u / N > (uint32_t)kMaxBlocks ? (uint32_t)kMaxBlocks : 256u / N;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPlanes; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < kMaxBlocks; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < a.cout; i += blockDim.x) s_bias[i] = a.bias[i];
-    if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -265,62 +276,92 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_bf16(128, a.cout);
+        const uint32_t idesc_1 = make_idesc_bf16(128, (int)N);         // N field grows linearly with the run length
         // descriptor words in 16-byte units: lo = start | LBO << 16, hi = SBO | version 1 << 14
         const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
-        const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((uint32_t)a.cout << 16);     // LBO = Cout*16 bytes
-        const uint32_t b_step16 = (uint32_t)a.cout * 2u;                           // Cout*32 bytes per K step
+        const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((N * KS) << 16);   // LBO = KS*Cout*16 bytes
+        const uint32_t b_step16 = N * KS * 2u;                            // one (kh,kw,s) chunk = KS*Cout*32 bytes
         mbar_wait(w_full, 0);
-        uint32_t pc_base = 0, ac = 0;
+        uint32_t pc = 0, ac0 = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int zc = item % a.n_zc;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
-            for (int zo = 0; zo < nz; ++zo, ++ac) {
-                const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
-                mbar_wait(&acc_empty[as], aph ^ 1u);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + as * (2u * (uint32_t)a.cout);
-                const uint32_t d1 = d0 + (uint32_t)a.cout;
+            const int np = nz + KS - 1;
 #pragma unroll 1
-                for (int kd = 0; kd < KS; ++kd) {
-                    const uint32_t pi = pc_base + zo + kd;
-                    const uint32_t slot = pi % kPlanes, ph = (pi / kPlanes) & 1u;
-                    mbar_wait(&plane_full[slot], ph);
-                    tc_fence_after();
-                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
-                    uint32_t b_lo = b_lo0 + (uint32_t)(kd * KS * KS * KSTEPS) * b_step16;
-                    if (leader) {
-#pragma unroll
-                        for (int kh = 0; kh < KS; ++kh)
-#pragma unroll
-                            for (int kw = 0; kw < KS; ++kw)
-#pragma unroll
-                                for (int s = 0; s < KSTEPS; ++s) {
-                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
-                                    const uint32_t acc = (kd | kh | kw | s) ? 1u : 0u;
-                                    const uint64_t bdesc = desc64(b_lo, b_hi);
-                                    umma_bf16(d0, desc64(a_lo, a_hi), bdesc, idesc, acc);
-                                    umma_bf16(d1, desc64(a_lo + 8u, a_hi), bdesc, idesc, acc);
-                                    b_lo += b_step16;
-                                }
-                        // plane (zo+kd) is dead once output zo has consumed it as kd==0 (or at item end)
-                        if (kd == 0 || zo == nz - 1) umma_commit(&plane_empty[slot]);
-                    }
-                    __syncwarp();
+            for (int ip = 0; ip < np; ++ip, ++pc) {
+                const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
+                const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
+                const int kd_hi = ip < KS - 1 ? ip : KS - 1;
+                // accumulator blocks of the outputs fed by this plane: kd = kd_lo.. map to ascending
+                // blocks starting at blk0; the run breaks once where the block ring wraps to 0
+                const uint32_t L = (uint32_t)(kd_hi - kd_lo + 1);
+                const uint32_t r = (ac0 + (uint32_t)(ip - kd_lo)) % nblk;
+                const uint32_t len0 = L < r + 1u ? L : r + 1u, len1 = L - len0;
+                const uint32_t blk0 = nblk - 1u - r;
+                const uint32_t kd1 = (uint32_t)kd_lo + len0;
+                const uint32_t d_seg0 = tmem_base + blk0 * N, b_seg0 = (uint32_t)kd_lo * N;
+                const uint32_t d_seg1 = tmem_base, b_seg1 = kd1 * N;
+                const uint32_t i_seg0 = idesc_1 + ((((len0 - 1u) * N) >> 3) << 17);
+                const uint32_t i_seg1 = idesc_1 + (((((len1 ? len1 : 1u) - 1u) * N) >> 3) << 17);
+                if (kd_lo == 0) {               // a new output starts: its block must have been drained
+                    const uint32_t A = ac0 + (uint32_t)ip;
+                    mbar_wait(&acc_empty[blk0], ((A / nblk) & 1u) ^ 1u);
                 }
-                if (leader) umma_commit(&acc_full[as]);
+                mbar_wait(&plane_full[slot], ph);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+                    uint32_t b_lo = b_lo0;
+#pragma unroll 1
+                    for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < KS; ++kw)
+#pragma unroll
+                            for (int s = 0; s < KSTEPS; ++s) {
+                                const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
+                                const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
+                                if (kh == 0 && kw == 0 && s == 0) {
+                                    // first tap of the plane: the kd = 0 accumulator is overwritten, the
+                                    // others accumulate -> one MMA per kd
+#pragma unroll
+                                    for (int kd = 0; kd < KS; ++kd)
+                                        if (kd >= kd_lo && kd <= kd_hi) {
+                                            const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
+                                            const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
+                                            const uint32_t dcol = tmem_base + bl * N;
+                                            umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
+                                            umma_bf16(dcol + 256u, ad1, bd, idesc_1, kd ? 1u : 0u);
+                                        }
+                                } else {
+                                    const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
+                                    umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
+                                    umma_bf16(d_seg0 + 256u, ad1, bd0, i_seg0, 1u);
+                                    if (len1) {
+                                        const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
+                                        umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
+                                        umma_bf16(d_seg1 + 256u, ad1, bd1, i_seg1, 1u);
+                                    }
+                                }
+                                b_lo += b_step16;
+                            }
+                    umma_commit(&plane_empty[slot]);
+                    if (ip >= KS - 1) {         // output ip-(KS-1) has received its last plane
+                        const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
+                        umma_commit(&acc_full[nblk - 1u - (A % nblk)]);
+                    }
+                }
                 __syncwarp();
             }
-            pc_base += nz + KS - 1;
+            ac0 += (uint32_t)nz;
         }
     } else {
         // ===================================== epilogue =========================================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int m = (warp - 2) >> 2;                // which of the two M-tiles (x half) this warp drains
-        uint32_t ac = 0;
+        uint32_t A = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
             const int zc = t % a.n_zc; t /= a.n_zc;
@@ -329,21 +370,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int tile = t;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
-            for (int zo = 0; zo < nz; ++zo, ++ac) {
-                const uint32_t as = ac % kAccStages, aph = (ac / kAccStages) & 1u;
-                mbar_wait(&acc_full[as], aph);
+            for (int zo = 0; zo < nz; ++zo, ++A) {
+                const uint32_t bl = nblk - 1u - (A % nblk), ph = (A / nblk) & 1u;
+                mbar_wait(&acc_full[bl], ph);
                 tc_fence_after();
-                epilogue_tile(tmem_base + as * (2u * (uint32_t)a.cout) + (uint32_t)m * (uint32_t)a.cout, q, lane, a.cout,
-                              s_bias, a.relu, a.out, tile, a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
+                epilogue_tile(tmem_base + (uint32_t)m * 256u + bl * N, q, lane, a.cout, s_bias, a.relu, a.out, tile,
+                              a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                if (lane == 0) mbar_arrive(&acc_empty[bl]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,7 +796,7 @@ static size_t conv_smem_bytes(int ks, int cin, int cout) {
     const int sx = kTX + ks - 1, sy = kTY + ks - 1;
     size_t w = ((size_t)ks * ks * ks * cin * cout * 2 + 127) & ~size_t(127);
     size_t plane = (((size_t)(cin / 8) * sy * sx * 16) + 127) & ~size_t(127);
-    return w + kPlanes * plane + 128 + 512;     // + barriers + bias
+    return w + kPlanes * plane + 256 + 512;     // + barriers + bias
 }
 
 static bool umma_supported(const ConvParams &c) {
@@ -787,17 +828,23 @@ int pack_weights_umma(fpl_net *net) {
             continue;
         }
         if (c.cin % 16 || c.cout % 16) continue;         // final layer
-        const int taps = c.k * c.k * c.k, ksteps = c.cin / 16;
-        std::vector<__nv_bfloat16> pk((size_t)taps * c.cin * c.cout);
-        for (int t = 0; t < taps; ++t)
-            for (int s = 0; s < ksteps; ++s)
-                for (int h = 0; h < 2; ++h)
-                    for (int n = 0; n < c.cout; ++n)
-                        for (int e = 0; e < 8; ++e) {
-                            const int ci = 16 * s + 8 * h + e;
-                            const float v = c.kernel[((size_t)t * c.cin + ci) * c.cout + n] * c.scale[n];
-                            pk[((((size_t)t * ksteps + s) * 2 + h) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
-                        }
+        // operand-B image: chunk (kh,kw,s) = [2 K-halves][k*Cout rows, kd-major][8 bf16]; the k kd
+        // taps that share an A tile are adjacent row blocks so that one MMA with N = k*Cout covers them
+        const int ks = c.k, ksteps = c.cin / 16;
+        std::vector<__nv_bfloat16> pk((size_t)ks * ks * ks * c.cin * c.cout);
+        for (int kh = 0; kh < ks; ++kh)
+            for (int kw = 0; kw < ks; ++kw)
+                for (int s = 0; s < ksteps; ++s)
+                    for (int h = 0; h < 2; ++h)
+                        for (int kd = 0; kd < ks; ++kd)
+                            for (int n = 0; n < c.cout; ++n)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int ci = 16 * s + 8 * h + e;
+                                    const int tap = (kd * ks + kh) * ks + kw;
+                                    const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + n] * c.scale[n];
+                                    const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
+                                    pk[(((chunk * 2 + h) * ks + kd) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
+                                }
         c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
         FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
         FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, pk.data(), c.packed_bytes, cudaMemcpyHostToDevice));
