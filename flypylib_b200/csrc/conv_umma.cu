@@ -140,6 +140,7 @@ struct ConvArgs {
     int n_tiles, din, dout, cin_atoms, cout;
     int n_xt, n_yt, n_zc, zc_len;
     int relu;
+    int pool;                        // fuse MaxPooling3D(2): `out` is the pooled tensor (edge dout/2)
     uint32_t tmem_cols;
 };
 
@@ -188,6 +189,61 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
             tmem_ld_wait();
             if (c0 + 32 < cout) tmem_ld16(tcol + (uint32_t)(c0 + 32), ra);
             epilogue_store16(rb, c0 + 16, s_bias, relu, out, vox, cg_stride, ok);
+        }
+    }
+}
+
+// Epilogue with MaxPooling3D((2,2,2)) fused in (Keras floor semantics; the caller guarantees an even
+// conv output edge).  Max commutes with the per-channel bias add, ReLU and the bf16 rounding (all
+// monotone), so pooling is done on the raw fp32 accumulators: x pairs are adjacent lanes, y pairs are
+// lanes 8 apart, z pairs are consecutive output planes of the same warp (even plane parked in `hold`).
+// A "transpose-reduce" exchange leaves every lane of a 2x2 group with 4 of the 16 columns of a chunk:
+// column offset = 8*(x parity) + 4*(y parity); each lane then stores its 4 channels (8 bytes).
+template <int NCH>
+__device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int lane, const float *s_bias, int relu,
+                                                   __nv_bfloat16 *__restrict__ out, int tile, int dpool, int z,
+                                                   int y0, int x0, float (&hold)[NCH * 4]) {
+    const int row = q * 32 + lane;
+    const int y = y0 + (row >> 3), x = x0 + (row & 7);
+    const bool ok = (x < 2 * dpool) && (y < 2 * dpool);
+    const int xpar = lane & 1, ypar = (lane >> 3) & 1;
+    const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16);
+    uint32_t r[NCH][16];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld16(tcol + (uint32_t)(c * 16), r[c]);
+    tmem_ld_wait();
+    const size_t cg_stride = (size_t)dpool * dpool * dpool;
+    const size_t vox = (size_t)tile * (NCH * 2) * cg_stride + ((size_t)(z >> 1) * dpool + (y >> 1)) * dpool + (x >> 1);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        float v8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {       // x pair: keep columns [8*xpar, 8*xpar+8), trade the other half
+            const float keep = __uint_as_float(xpar ? r[c][8 + j] : r[c][j]);
+            const float give = __uint_as_float(xpar ? r[c][j] : r[c][8 + j]);
+            v8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, give, 1));
+        }
+        float v4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // y pair: keep [4*ypar, 4*ypar+4) of those
+            const float keep = ypar ? v8[4 + j] : v8[j];
+            const float give = ypar ? v8[j] : v8[4 + j];
+            v4[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+        }
+        if ((z & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hold[c * 4 + j] = v4[j];
+        } else if (ok) {
+            const int ch = c * 16 + xpar * 8 + ypar * 4;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o[j] = fmaxf(v4[j], hold[c * 4 + j]) + s_bias[ch + j];
+                if (relu) o[j] = fmaxf(o[j], 0.f);
+            }
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
+            *reinterpret_cast<uint2 *>(out + (vox + (size_t)(ch >> 3) * cg_stride) * 8 + (ch & 7)) = pk;
         }
     }
 }
@@ -362,6 +418,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int m = (warp - 2) >> 2;                // which of the two M-tiles (x half) this warp drains
         uint32_t A = 0;
+        float hold[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hold[j] = 0.f;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
             const int zc = t % a.n_zc; t /= a.n_zc;
@@ -374,7 +433,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                 const uint32_t bl = nblk - 1u - (A % nblk), ph = (A / nblk) & 1u;
                 mbar_wait(&acc_full[bl], ph);
                 tc_fence_after();
-                epilogue_tile(tmem_base + (uint32_t)m * 256u + bl * N, q, lane, a.cout, s_bias, a.relu, a.out, tile,
+                const uint32_t tacc = tmem_base + (uint32_t)m * 256u + bl * N;
+                if (a.pool) {
+                    if (a.cout == 48)
+                        epilogue_tile_pool<3>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
+                                              xt * kTX + m * 8, reinterpret_cast<float(&)[12]>(hold));
+                    else if (a.cout == 32)
+                        epilogue_tile_pool<2>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
+                                              xt * kTX + m * 8, reinterpret_cast<float(&)[8]>(hold));
+                    else
+                        epilogue_tile_pool<4>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
+                                              xt * kTX + m * 8, hold);
+                } else
+                epilogue_tile(tacc, q, lane, a.cout, s_bias, a.relu, a.out, tile,
                               a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
                 tc_fence_before();
                 __syncwarp();
@@ -809,6 +880,7 @@ static bool umma_supported(const ConvParams &c) {
 }
 
 static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv through the CUDA-core kernel
+static int g_no_pool_fusion = 0;  // test hook: keep MaxPooling3D as its own kernel
 
 int pack_weights_umma(fpl_net *net) {
     for (ConvParams &c : net->convs) {
@@ -860,7 +932,7 @@ void free_packed_umma(fpl_net *net) {
 }
 
 static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
-                            int n_tiles, int din, int relu, cudaStream_t st) {
+                            int n_tiles, int din, int relu, int pool, cudaStream_t st) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
     const int ks = c.k, dout = din - (ks - 1);
@@ -888,8 +960,10 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     if (n_zc < 1) n_zc = 1;
     int zc_len = (dout + n_zc - 1) / n_zc;
     if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
+    if (pool && (zc_len & 1)) ++zc_len;              // z pairs must not straddle work items
     a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
     a.relu = relu;
+    a.pool = pool;
     const int acc_cols = kAccStages * 2 * c.cout;
     a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const size_t smem = conv_smem_bytes(ks, c.cin, c.cout);
@@ -988,9 +1062,15 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
     bool cur_is_skip = false;
     int d = in_sz, c = 1;
     const int stream_blocks = ctx->sm_count * 8;
-    for (const Op &o : net->ops) {
+    bool skip_next_pool = false;
+    for (size_t oi = 0; oi < net->ops.size(); ++oi) {
+        const Op &o = net->ops[oi];
         if (o.kind == OP_CONV) {
             const ConvParams &cp = net->convs[o.conv_index];
+            // MaxPooling3D directly after this conv (and the conv output not kept as a skip): fuse it
+            const bool fuse_pool = !g_force_direct && !g_no_pool_fusion && cp.cin != 1 && umma_supported(cp) && cp.k == 3 &&
+                                   (cp.cout == 32 || cp.cout == 48 || cp.cout == 64) && oi + 1 < net->ops.size() &&
+                                   net->ops[oi + 1].kind == OP_POOL && ((d - (o.k - 1)) % 2 == 0);
             const int nb = take();
             if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
             __nv_bfloat16 *dst = (__nv_bfloat16 *)g_pool.buf[nb];
@@ -1023,13 +1103,16 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 FPL_LAUNCH_CHECK(ctx);
             } else {
                 const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_pool.buf[cur];
-                if (umma_supported(cp) && !g_force_direct) FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, 1, st));
+                if (umma_supported(cp) && !g_force_direct)
+                    FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, 1, fuse_pool ? 1 : 0, st));
                 else FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, 1, st));
             }
             if (cur >= 0 && !cur_is_skip) busy[cur] = false;
             cur = nb; cur_is_skip = false;
             d -= o.k - 1; c = o.cout;
+            if (fuse_pool) { d /= 2; skip_next_pool = true; }
         } else if (o.kind == OP_POOL) {
+            if (skip_next_pool) { skip_next_pool = false; continue; }
             const int nb = take();
             if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * c * 2.0 * d * d * d * 1.125);
@@ -1070,3 +1153,4 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
 }  // namespace fpl
 
 extern "C" int fpl_debug_force_direct_conv(int on) { fpl::net::g_force_direct = on; return FPL_OK; }
+extern "C" int fpl_debug_no_pool_fusion(int on) { fpl::net::g_no_pool_fusion = on; return FPL_OK; }

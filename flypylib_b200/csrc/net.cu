@@ -91,52 +91,53 @@ struct TileGrid {
 
 // tile t of the batch <- image[start : start+in_sz] (zero beyond the far edge), start = k*out_sz.
 // image either float32 or uint8 + (x-mean)/std in float32 (fplobjdetect.py:1106-1107).
+// One block per (tile, z, y) row, threads along x: no per-element integer division.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 gather_tiles_kernel(const T *__restrict__ img, float *__restrict__ tiles, TileGrid g, int tile0,
-                    int n_tiles, float mean, float stdv) {
-    const long long per_tile = (long long)g.in_sz * g.in_sz * g.in_sz;
-    const long long total = per_tile * n_tiles;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int t = (int)(i / per_tile);
-        long long rem = i - (long long)t * per_tile;
-        int x = (int)(rem % g.in_sz);
-        int y = (int)((rem / g.in_sz) % g.in_sz);
-        int z = (int)(rem / ((long long)g.in_sz * g.in_sz));
-        int tt = tile0 + t;
-        int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
-        long long gz = (long long)kz * g.out_sz + z, gy = (long long)ky * g.out_sz + y,
-                  gx = (long long)kx * g.out_sz + x;
-        float v = 0.f;
-        if (gz < g.Z && gy < g.Y && gx < g.X) {
-            T raw = img[(gz * g.Y + gy) * g.X + gx];
-            if (sizeof(T) == 1) v = __fdiv_rn(__fsub_rn((float)raw, mean), stdv);
-            else v = (float)raw;
+                    int n_tiles, float mean, float stdv, const int *__restrict__ tile_ids) {
+    const long long rows = (long long)n_tiles * g.in_sz * g.in_sz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int y = (int)(row % g.in_sz);
+        const int z = (int)((row / g.in_sz) % g.in_sz);
+        const int t = (int)(row / ((long long)g.in_sz * g.in_sz));
+        const int tt = tile_ids ? tile_ids[tile0 + t] : tile0 + t;
+        const int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
+        const long long gz = (long long)kz * g.out_sz + z, gy = (long long)ky * g.out_sz + y;
+        const long long gx0 = (long long)kx * g.out_sz;
+        float *dst = tiles + row * g.in_sz;
+        const bool row_ok = gz < g.Z && gy < g.Y;
+        const T *src = img + (gz * g.Y + gy) * g.X + gx0;
+        for (int x = threadIdx.x; x < g.in_sz; x += blockDim.x) {
+            float v = 0.f;
+            if (row_ok && gx0 + x < g.X) {
+                T raw = src[x];
+                if (sizeof(T) == 1) v = __fdiv_rn(__fsub_rn((float)raw, mean), stdv);
+                else v = (float)raw;
+            }
+            dst[x] = v;
         }
-        tiles[i] = v;
     }
 }
 
 // pred[off + k*out_sz + (0..ext)] <- tile output[0..ext), ext = min(out_sz, size - off - origin)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 scatter_tiles_kernel(const float *__restrict__ outs, float *__restrict__ pred, TileGrid g, int tile0,
-                     int n_tiles) {
-    const long long per_tile = (long long)g.out_sz * g.out_sz * g.out_sz;
-    const long long total = per_tile * n_tiles;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int t = (int)(i / per_tile);
-        long long rem = i - (long long)t * per_tile;
-        int x = (int)(rem % g.out_sz);
-        int y = (int)((rem / g.out_sz) % g.out_sz);
-        int z = (int)(rem / ((long long)g.out_sz * g.out_sz));
-        int tt = tile0 + t;
-        int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
-        long long gz = (long long)kz * g.out_sz + g.off + z, gy = (long long)ky * g.out_sz + g.off + y,
-                  gx = (long long)kx * g.out_sz + g.off + x;
-        if (gz < g.Z - g.off && gy < g.Y - g.off && gx < g.X - g.off)
-            pred[(gz * g.Y + gy) * g.X + gx] = outs[i];
+                     int n_tiles, const int *__restrict__ tile_ids) {
+    const long long rows = (long long)n_tiles * g.out_sz * g.out_sz;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int y = (int)(row % g.out_sz);
+        const int z = (int)((row / g.out_sz) % g.out_sz);
+        const int t = (int)(row / ((long long)g.out_sz * g.out_sz));
+        const int tt = tile_ids ? tile_ids[tile0 + t] : tile0 + t;
+        const int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
+        const long long gz = (long long)kz * g.out_sz + g.off + z, gy = (long long)ky * g.out_sz + g.off + y;
+        const long long gx0 = (long long)kx * g.out_sz + g.off;
+        if (gz >= g.Z - g.off || gy >= g.Y - g.off) continue;
+        const float *src = outs + row * g.out_sz;
+        float *dst = pred + (gz * g.Y + gy) * g.X + gx0;
+        for (int x = threadIdx.x; x < g.out_sz; x += blockDim.x)
+            if (gx0 + x < g.X - g.off) dst[x] = src[x];
     }
 }
 
@@ -171,6 +172,7 @@ int fpl_net_destroy(fpl_net *net) {
     free_device_weights(net);
     if (net->d_stage_in) cudaFree(net->d_stage_in);
     if (net->d_stage_out) cudaFree(net->d_stage_out);
+    if (net->d_tile_ids) cudaFree(net->d_tile_ids);
     delete net;
     return FPL_OK;
 }
@@ -300,7 +302,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     const int ref_out = net->info.infer_sz - 2 * off;
     TileGrid g;
     g.off = off;
-    g.out_sz = ref_out * net->tile_mult;
+    g.out_sz = ref_out;                     // reference grid; super-tiles are scheduled below
     g.in_sz = g.out_sz + 2 * off;
     g.Z = Z; g.Y = Y; g.X = X;
     g.nz = tiles_along(Z, off, g.out_sz);
@@ -317,45 +319,96 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         if (z1 > z0)
             FPL_CUDA_CHECK(cudaMemsetAsync(d_pred + z0 * Y * X, 0, sizeof(float) * (size_t)(z1 - z0) * Y * X, st));
     }
-    const long long n_tiles_total = (long long)(ze - zb) * g.ny * g.nx;
-    if (n_tiles_total <= 0) return FPL_OK;
-    // batch size: bounded by workspace (fp32 path works tile by tile anyway)
-    const size_t in_elems = (size_t)g.in_sz * g.in_sz * g.in_sz, out_elems = (size_t)g.out_sz * g.out_sz * g.out_sz;
-    int batch = net->precision == FPL_PREC_FP32 ? 4 : 8;
-    if (batch > n_tiles_total) batch = (int)n_tiles_total;
-    if (net->stage_in_cap < in_elems * batch || net->stage_out_cap < out_elems * batch) {
+    // ---- tile schedule -----------------------------------------------------------------------
+    // Phase 1 (VGG, tile_mult m > 1): super-tiles of m x m x m reference tiles.  Their origins stay
+    // on the reference grid (multiples of out_sz, itself a multiple of the net stride), the nets are
+    // shift-equivariant by rf_stride and the zero padding beyond the image is reproduced by the
+    // gather, so every voxel gets exactly the value the reference tile would give it -- with less
+    // halo recomputation.  Phase 2: the reference tiles not covered by super-tiles.
+    const int m = net->tile_mult;
+    const int nsz = m > 1 ? (ze - zb) / m : 0, nsy = m > 1 ? g.ny / m : 0, nsx = m > 1 ? g.nx / m : 0;
+    const bool have_super = nsz > 0 && nsy > 0 && nsx > 0;
+    std::vector<int> rest;
+    for (int kz = zb; kz < ze; ++kz)
+        for (int ky = 0; ky < g.ny; ++ky)
+            for (int kx = 0; kx < g.nx; ++kx) {
+                const bool in_super = have_super && (kz - zb) < nsz * m && ky < nsy * m && kx < nsx * m;
+                if (!in_super) rest.push_back((kz * g.ny + ky) * g.nx + kx);
+            }
+    struct Phase { TileGrid grid; long long n; int batch; const int *ids; int first; };
+    std::vector<Phase> phases;
+    int *d_ids = nullptr;
+    if (!rest.empty()) {
+        if (net->tile_ids_cap < rest.size()) {
+            FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (net->d_tile_ids) cudaFree(net->d_tile_ids);
+            net->d_tile_ids = nullptr; net->tile_ids_cap = 0;
+            FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_tile_ids, rest.size() * sizeof(int)));
+            net->tile_ids_cap = rest.size();
+        }
+        d_ids = net->d_tile_ids;
+    }
+    if (have_super) {
+        TileGrid gs = g;
+        gs.out_sz = g.out_sz * m; gs.in_sz = gs.out_sz + 2 * off;
+        gs.nz = nsz; gs.ny = nsy; gs.nx = nsx;
+        FPL_REQUIRE(zb == 0, "tile multiplier > 1 cannot be combined with a z tile range");
+        FPL_REQUIRE(out_size(net, gs.in_sz) == gs.out_sz, "internal: super-tile edge %d invalid", gs.in_sz);
+        const double per_tile_bytes = 96.0 * gs.in_sz * (double)gs.in_sz * gs.in_sz;
+        int bs = (int)(3.0e9 / per_tile_bytes); if (bs < 1) bs = 1; if (bs > 8) bs = 8;
+        phases.push_back({gs, (long long)nsz * nsy * nsx, bs, nullptr, 0});
+    }
+    if (!rest.empty()) {
+        // the previous call's list may still be in use by queued kernels of the same stream: ordered copy
+        FPL_CUDA_CHECK(cudaMemcpyAsync(d_ids, rest.data(), rest.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));     // `rest` is pageable host memory
+        phases.push_back({g, (long long)rest.size(), net->precision == FPL_PREC_FP32 ? 4 : 8, d_ids, 0});
+    }
+    size_t need_in = 0, need_out = 0;
+    for (Phase &ph : phases) {
+        if (ph.batch > ph.n) ph.batch = (int)ph.n;
+        size_t ie = (size_t)ph.grid.in_sz * ph.grid.in_sz * ph.grid.in_sz * ph.batch;
+        size_t oe = (size_t)ph.grid.out_sz * ph.grid.out_sz * ph.grid.out_sz * ph.batch;
+        if (ie > need_in) need_in = ie;
+        if (oe > need_out) need_out = oe;
+    }
+    if (net->stage_in_cap < need_in || net->stage_out_cap < need_out) {
         FPL_CUDA_CHECK(cudaStreamSynchronize(st));
         if (net->d_stage_in) cudaFree(net->d_stage_in);
         if (net->d_stage_out) cudaFree(net->d_stage_out);
         net->d_stage_in = net->d_stage_out = nullptr; net->stage_in_cap = net->stage_out_cap = 0;
-        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_in, sizeof(float) * in_elems * batch));
-        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_out, sizeof(float) * out_elems * batch));
-        net->stage_in_cap = in_elems * batch; net->stage_out_cap = out_elems * batch;
+        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_in, sizeof(float) * need_in));
+        FPL_CUDA_CHECK(cudaMalloc((void **)&net->d_stage_out, sizeof(float) * need_out));
+        net->stage_in_cap = need_in; net->stage_out_cap = need_out;
     }
     float *d_in = net->d_stage_in, *d_out = net->d_stage_out;
     int rc = FPL_OK;
-    const int tile_first = zb * g.ny * g.nx;
-    for (long long t0 = 0; t0 < n_tiles_total && rc == FPL_OK; t0 += batch) {
-        int nb = (int)((n_tiles_total - t0) < batch ? (n_tiles_total - t0) : batch);
-        int blocks = ctx->sm_count * 8;
-        {
-        fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * in_elems * (image_is_u8 ? 5.0 : 8.0));
-        if (image_is_u8)
-            gather_tiles_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)d_image, d_in, g,
-                                                                 tile_first + (int)t0, nb, norm_mean, norm_std);
-        else
-            gather_tiles_kernel<float><<<blocks, 256, 0, st>>>((const float *)d_image, d_in, g,
-                                                               tile_first + (int)t0, nb, 0.f, 1.f);
+    const int blocks = ctx->sm_count * 16;
+    for (const Phase &ph : phases) {
+        const TileGrid &tg = ph.grid;
+        const size_t in_elems = (size_t)tg.in_sz * tg.in_sz * tg.in_sz, out_elems = (size_t)tg.out_sz * tg.out_sz * tg.out_sz;
+        for (long long t0 = 0; t0 < ph.n && rc == FPL_OK; t0 += ph.batch) {
+            const int nb = (int)((ph.n - t0) < ph.batch ? (ph.n - t0) : ph.batch);
+            {
+                fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * in_elems * (image_is_u8 ? 5.0 : 8.0));
+                if (image_is_u8)
+                    gather_tiles_kernel<uint8_t><<<blocks, 128, 0, st>>>((const uint8_t *)d_image, d_in, tg, (int)t0, nb,
+                                                                         norm_mean, norm_std, ph.ids);
+                else
+                    gather_tiles_kernel<float><<<blocks, 128, 0, st>>>((const float *)d_image, d_in, tg, (int)t0, nb,
+                                                                       0.f, 1.f, ph.ids);
+            }
+            ctx->launches++;
+            if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, tg.in_sz, d_out, st);
+            else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st);
+            if (rc != FPL_OK) break;
+            {
+                fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);
+                scatter_tiles_kernel<<<blocks, 128, 0, st>>>(d_out, d_pred, tg, (int)t0, nb, ph.ids);
+            }
+            ctx->launches++;
         }
-        ctx->launches++;
-        if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, g.in_sz, d_out, st);
-        else rc = forward_umma(net, d_in, nb, g.in_sz, d_out, st);
         if (rc != FPL_OK) break;
-        {
-        fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);
-        scatter_tiles_kernel<<<blocks, 256, 0, st>>>(d_out, d_pred, g, tile_first + (int)t0, nb);
-        }
-        ctx->launches++;
     }
     if (rc != FPL_OK) return rc;
     FPL_CUDA_CHECK(cudaGetLastError());

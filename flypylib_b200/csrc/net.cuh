@@ -48,6 +48,7 @@ struct fpl_net {
     int tile_mult = 1;                         // VGG only: tile edge = tile_mult*out_sz + 2*off
     float *d_stage_in = nullptr, *d_stage_out = nullptr;   // tile staging of fpl_net_infer_volume (grow-only)
     size_t stage_in_cap = 0, stage_out_cap = 0;
+    int *d_tile_ids = nullptr; size_t tile_ids_cap = 0;    // reference-tile id list of the tiler
 };
 
 namespace fpl {

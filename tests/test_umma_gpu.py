@@ -39,3 +39,45 @@ def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
         want = M.forward(arch, w, x)
         e = np.abs(got.astype(np.float64) - want).max()
         assert e < 2e-2, "bf16 path vs float64 oracle: %g" % e
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_super_tiles_equal_reference_grid(precision):
+    """VGG: evaluating m x m x m reference tiles as one super-tile gives bit-identical maps
+    (origins stay on the reference grid; zero padding beyond the image is reproduced)."""
+    import torch
+    from flypylib_b200 import fplmodels, fplnetwork
+    from tests.golden import cases
+    net = fplnetwork.FplNetwork(fplmodels.vgg_like2)
+    net.train_single.set_weights(M.random_weights("vgg_like2", seed=5))
+    net.set_precision(precision)
+    net._set_infer()
+    shape = (270, 200, 185) if precision == "bf16" else (190, 185, 120)
+    u8 = torch.from_numpy(cases.em_volume(shape, seed=9)).cuda()
+    net.tile_multiplier = 1
+    ref = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+    net.tile_multiplier = 2
+    got = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+    assert np.array_equal(ref, got)
+    if precision == "bf16":
+        net.tile_multiplier = 3
+        got3 = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+        assert np.array_equal(ref, got3)
+
+
+def test_fused_pool_epilogue_is_bit_identical():
+    """MaxPooling3D fused into the conv epilogue == separate pooling kernel (same bf16 values)."""
+    import torch
+    from flypylib_b200 import fplmodels, _lib
+    lib = _lib.lib()
+    lib.fpl_debug_no_pool_fusion.argtypes = [ctypes.c_int]
+    w = M.random_weights("vgg_like2", seed=3)
+    x = np.random.default_rng(1).standard_normal((2, 68, 68, 68)).astype(np.float32)
+    outs = []
+    for off in (1, 0):
+        lib.fpl_debug_no_pool_fusion(off)
+        try:
+            outs.append(_predict("vgg_like2", 68, w, x, "bf16"))
+        finally:
+            lib.fpl_debug_no_pool_fusion(0)
+    assert np.array_equal(outs[0], outs[1])
