@@ -21,6 +21,7 @@
 #include "net.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace fpl {
 namespace net {
@@ -312,9 +313,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         uint32_t pc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
-            const int zc = t % a.n_zc; t /= a.n_zc;
+            // x patch fastest: CTAs running side by side sweep z in step and touch adjacent rows of HBM
             const int xt = t % a.n_xt; t /= a.n_xt;
             const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
@@ -342,7 +344,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         mbar_wait(w_full, 0);
         uint32_t pc = 0, ac0 = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int zc = item % a.n_zc;
+            const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
             const int np = nz + KS - 1;
@@ -423,9 +425,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         for (int j = 0; j < 16; ++j) hold[j] = 0.f;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
-            const int zc = t % a.n_zc; t /= a.n_zc;
+            // x patch fastest: CTAs running side by side sweep z in step and touch adjacent rows of HBM
             const int xt = t % a.n_xt; t /= a.n_xt;
             const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
@@ -468,31 +471,56 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
 constexpr int kFirstThreads = 416;           // warp 0 MMA, warps 1..8 epilogue, warps 9..12 builders
 struct FirstArgs {
     const float *in;                 // (tile, din, din, din) float32
-    const __nv_bfloat16 *w_packed;   // [2 ksteps][2][Cout][8], taps >= 27 zero, BN scale folded
-    const float *bias;
+    const __nv_bfloat16 *w_packed;   // [2 ksteps][2][Cout][8]; taps 0..26 = kernel*BN scale, 27/28 = bias hi/lo
+    const float *bias;               // unused by the kernel (bias rides in K slots 27/28)
     __nv_bfloat16 *out;
     int n_tiles, din, dout, cout;
     int n_xt, n_yt, n_zc, zc_len;
     uint32_t tmem_cols;
+    VolumeIO vio;                    // vio.img != nullptr: read the tile from the volume instead of `in`
+    int dbg;                         // experiments: 1 = skip global fetch, 2 = skip global store, 4 = skip build
 };
+
+// first-layer epilogue: the folded-BN bias is already inside the accumulator (two constant-one K
+// slots carry bias = hi + lo in bf16), so only ReLU (on packed bf16 pairs) and the store remain.
+__device__ __forceinline__ void first_store16(const uint32_t (&r)[16], int c0, __nv_bfloat16 *__restrict__ out,
+                                              size_t vox, size_t cg_stride, bool ok) {
+    if (!ok) return;
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 b2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(r[h * 8 + 2 * j]),
+                                                              __uint_as_float(r[h * 8 + 2 * j + 1])), zero);
+            pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+        }
+        *reinterpret_cast<uint4 *>(out + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
 
 __global__ void __launch_bounds__(kFirstThreads, 1)
 conv_first_umma_kernel(const FirstArgs a) {
     constexpr int SX = kTX + 2, SY = kTY + 2;
+    constexpr int PX = 20;                                     // ring row pitch (floats): 16-byte aligned rows
     constexpr int kRing = 4;
-    constexpr int kPer = (SY * SX + 127) / 128;                // input elements per builder thread and plane
+    constexpr int kBuilders = 128;                             // one thread per 2 x-adjacent accumulator rows
+    constexpr int kPer = (SY * SX + kBuilders - 1) / kBuilders; // input elements per builder thread and plane
     constexpr uint32_t kAStage = 2 * 4 * 128 * 16;            // 2 M-tiles x 4 atoms x 128 rows x 16 B
-    __shared__ __align__(128) uint8_t s_a[2 * kAStage];
-    __shared__ __align__(128) uint8_t s_w[2 * 2 * 128 * 16];   // up to Cout = 128
-    __shared__ float s_in[kRing][SY][SX];
-    __shared__ float s_bias[128];
-    __shared__ uint64_t bars[8];
+    constexpr int kSt = 4;                                     // pipeline depth (A stages and TMEM stages)
+    extern __shared__ __align__(128) uint8_t s_a[];            // kSt * kAStage bytes (dynamic)
+    __shared__ __align__(128) uint8_t s_w[2 * 2 * 64 * 16];    // Cout <= 64
+    __shared__ __align__(16) float s_in[kRing][SY][PX];
+    __shared__ float s_lut[256];          // uint8 -> (x-mean)/std, exact IEEE sub/div evaluated once per value
+    __shared__ uint64_t bars[4 * kSt];
     __shared__ uint32_t tmem_slot;
-    uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6;
+    uint64_t *a_full = bars, *a_empty = bars + kSt, *acc_full = bars + 2 * kSt, *acc_empty = bars + 3 * kSt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSt; ++i) {
             mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
         }
         fence_barrier_init();
@@ -500,7 +528,7 @@ conv_first_umma_kernel(const FirstArgs a) {
     // weights -> smem (generic proxy), made visible to the tensor core with a proxy fence
     for (int i = threadIdx.x; i < a.cout * 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(s_w)[i] = __ldg(reinterpret_cast<const uint4 *>(a.w_packed) + i);
-    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) s_bias[i] = a.bias[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = __fdiv_rn(__fsub_rn((float)i, a.vio.mean), a.vio.stdv);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) tmem_alloc(&tmem_slot, a.tmem_cols);
     tc_fence_before();
@@ -519,10 +547,10 @@ conv_first_umma_kernel(const FirstArgs a) {
         const uint32_t b_step16 = (uint32_t)a.cout * 2u;
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int zc = item % a.n_zc;
+            const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
             const int nz = min(a.zc_len, a.dout - zc * a.zc_len);
             for (int zo = 0; zo < nz; ++zo, ++ac) {
-                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+                const uint32_t st = ac % kSt, ph = (ac / kSt) & 1u;
                 mbar_wait(&acc_empty[st], ph ^ 1u);
                 mbar_wait(&a_full[st], ph);
                 tc_fence_after();
@@ -546,21 +574,42 @@ conv_first_umma_kernel(const FirstArgs a) {
         // ===================================== epilogue =========================================
         const int q = warp & 3;
         const int m = (warp - 1) >> 2;
+        const int row = q * 32 + lane;
+        const size_t cg_stride = (size_t)a.dout * a.dout * a.dout;
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
-            const int zc = t % a.n_zc; t /= a.n_zc;
+            // x patch fastest: CTAs running side by side sweep z in step and touch adjacent rows of HBM
             const int xt = t % a.n_xt; t /= a.n_xt;
             const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
+            const int y = yt * kTY + (row >> 3), x = xt * kTX + m * 8 + (row & 7);
+            const bool ok = (x < a.dout) && (y < a.dout) && !(a.dbg & 2);
+            const size_t vox0 = (size_t)tile * (a.cout >> 3) * cg_stride + ((size_t)z0 * a.dout + y) * a.dout + x;
             for (int zo = 0; zo < nz; ++zo, ++ac) {
-                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+                const uint32_t st = ac % kSt, ph = (ac / kSt) & 1u;
                 mbar_wait(&acc_full[st], ph);
                 tc_fence_after();
-                epilogue_tile(tmem_base + st * (2u * (uint32_t)a.cout) + (uint32_t)m * (uint32_t)a.cout, q, lane, a.cout,
-                              s_bias, 1, a.out, tile, a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
+                const uint32_t tcol = tmem_base + st * (2u * (uint32_t)a.cout) + (uint32_t)m * (uint32_t)a.cout +
+                                      ((uint32_t)(q * 32) << 16);
+                const size_t vox = vox0 + (size_t)zo * a.dout * a.dout;
+                uint32_t ra[16], rb[16];
+                tmem_ld16(tcol, ra);
+#pragma unroll 1
+                for (int c0 = 0; c0 < a.cout; c0 += 32) {
+                    tmem_ld_wait();
+                    const bool more = c0 + 16 < a.cout;
+                    if (more) tmem_ld16(tcol + (uint32_t)(c0 + 16), rb);
+                    first_store16(ra, c0, a.out, vox, cg_stride, ok);
+                    if (more) {
+                        tmem_ld_wait();
+                        if (c0 + 32 < a.cout) tmem_ld16(tcol + (uint32_t)(c0 + 32), ra);
+                        first_store16(rb, c0 + 16, a.out, vox, cg_stride, ok);
+                    }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[st]);
@@ -568,75 +617,117 @@ conv_first_umma_kernel(const FirstArgs a) {
         }
     } else {
         // ===================================== im2col builders ==================================
-        const int bt = threadIdx.x - 288;            // 0..127 = accumulator row
-        const int ly = bt >> 3, lx = bt & 7;
+        // thread -> M-tile bm, accumulator rows (ly, xq), (ly, xq+1): the 27 taps of 2 x-adjacent outputs
+        // need 3 planes x 3 rows x 4 floats, fetched as two 8-byte shared loads each.
+        const int bt = threadIdx.x - 288;            // 0..127
+        const int bm = bt >> 6, ly = (bt & 63) >> 2, xq = (bt & 3) * 2;
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
-            const int zc = t % a.n_zc; t /= a.n_zc;
+            // x patch fastest: CTAs running side by side sweep z in step and touch adjacent rows of HBM
             const int xt = t % a.n_xt; t /= a.n_xt;
             const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
-            const float *tin = a.in + (size_t)tile * a.din * a.din * a.din;
-            float pre[kPer];
-            auto fetch = [&](int zin) {            // this thread's share of input plane zin -> registers
+            // source of this thread's (up to kPer) elements of every input plane: either the float32
+            // tile batch or, with direct volume input, the volume itself at the tile origin of the
+            // reference grid (fplnetwork.py:149-157; zero beyond the far edge; (x-mean)/std for uint8)
+            long long plane_stride, z_lim, z_org = 0;
+            long long eoff[kPer];
+            bool eok[kPer];
+            int edst[kPer];
+            const uint8_t *src8 = nullptr;
+            const float *src32 = nullptr;
+            long long ox = 0, oy = 0, lim_y, lim_x, row_stride;
+            if (a.vio.img) {
+                const int tt = a.vio.ids ? a.vio.ids[a.vio.tile0 + tile] : a.vio.tile0 + tile;
+                ox = (long long)(tt % a.vio.g.nx) * a.vio.g.out_sz;
+                oy = (long long)((tt / a.vio.g.nx) % a.vio.g.ny) * a.vio.g.out_sz;
+                z_org = (long long)(tt / (a.vio.g.nx * a.vio.g.ny)) * a.vio.g.out_sz;
+                plane_stride = a.vio.g.Y * a.vio.g.X; row_stride = a.vio.g.X;
+                z_lim = a.vio.g.Z - z_org < a.din ? a.vio.g.Z - z_org : a.din;     // planes available
+                lim_y = a.vio.g.Y; lim_x = a.vio.g.X;
+                src8 = (const uint8_t *)a.vio.img; src32 = (const float *)a.vio.img;
+            } else {
+                plane_stride = (long long)a.din * a.din; row_stride = a.din;
+                z_lim = a.din; lim_y = a.din; lim_x = a.din;
+                src32 = a.in + (size_t)tile * a.din * a.din * a.din;
+            }
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = bt + k * kBuilders;
+                const int yy = i / SX, xx = i - yy * SX;
+                const int gy = yt * kTY + yy, gx = xt * kTX + xx;
+                eok[k] = i < SY * SX && gy < a.din && gx < a.din && oy + gy < lim_y && ox + gx < lim_x;
+                eoff[k] = (oy + gy) * row_stride + ox + gx;
+                edst[k] = yy * PX + xx;
+            }
+            const bool is_u8 = a.vio.img && a.vio.is_u8;
+            float preA[kPer], preB[kPer], preC[kPer];
+            auto fetch = [&](int zin, float (&pre)[kPer]) {   // this thread's share of input plane zin
 #pragma unroll
                 for (int k = 0; k < kPer; ++k) {
-                    const int i = bt + k * 128;
-                    const int yy = i / SX, xx = i - yy * SX;
-                    const int gy = yt * kTY + yy, gx = xt * kTX + xx;
                     float v = 0.f;
-                    if (i < SY * SX && zin < a.din && gy < a.din && gx < a.din)
-                        v = __ldg(tin + ((size_t)zin * a.din + gy) * a.din + gx);
+                    if (eok[k] && zin < z_lim && !(a.dbg & 1)) {
+                        const long long o = (z_org + zin) * plane_stride + eoff[k];
+                        if (is_u8) v = s_lut[__ldg(src8 + o)];
+                        else v = __ldg(src32 + o);
+                    }
                     pre[k] = v;
                 }
             };
-            auto stash = [&](int zin) {            // registers -> ring slot zin % kRing
+            auto stash = [&](int zin, const float (&pre)[kPer]) {   // registers -> ring slot zin % kRing
                 float *dst = &s_in[zin % kRing][0][0];
 #pragma unroll
-                for (int k = 0; k < kPer; ++k) {
-                    const int i = bt + k * 128;
-                    if (i < SY * SX) dst[i] = pre[k];
-                }
+                for (int k = 0; k < kPer; ++k)
+                    if (bt + k * kBuilders < SY * SX) dst[edst[k]] = pre[k];
             };
             // all builders are past their last read of the ring (barrier at the end of the previous plane)
-            fetch(z0); stash(z0);
-            fetch(z0 + 1); stash(z0 + 1);
-            fetch(z0 + 2);
+            fetch(z0, preA); stash(z0, preA);
+            fetch(z0 + 1, preA); stash(z0 + 1, preA);
+            fetch(z0 + 2, preA);
+            fetch(z0 + 3, preB);
+            fetch(z0 + 4, preC);
             for (int zo = 0; zo < nz; ++zo, ++ac) {
-                stash(z0 + zo + 2);
+                stash(z0 + zo + 2, preA);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (zo + 1 < nz) fetch(z0 + zo + 3);          // in flight while this plane is built
-                const uint32_t st = ac & 1u, ph = (ac >> 1) & 1u;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) { preA[k] = preB[k]; preB[k] = preC[k]; }
+                if (zo + 3 < nz) fetch(z0 + zo + 5, preC);    // three planes ahead: covers L2/DRAM latency
+                const uint32_t st = ac % kSt, ph = (ac / kSt) & 1u;
                 mbar_wait(&a_empty[st], ph ^ 1u);
-                uint8_t *abase = s_a + st * kAStage;
-                const float *p0 = &s_in[(z0 + zo) % kRing][ly][lx];
-                const float *p1 = &s_in[(z0 + zo + 1) % kRing][ly][lx];
-                const float *p2 = &s_in[(z0 + zo + 2) % kRing][ly][lx];
+                uint8_t *abase = s_a + st * kAStage + bm * 8192 + (ly * 8 + xq) * 16;
+                float f[3][3][4];
+                if (!(a.dbg & 4))
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    float v[32];
+                for (int kd = 0; kd < 3; ++kd) {
+                    const float *pl = &s_in[(z0 + zo + kd) % kRing][ly][bm * 8 + xq];
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh)
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const float2 va = *reinterpret_cast<const float2 *>(pl + kh * PX);
+                        const float2 vb = *reinterpret_cast<const float2 *>(pl + kh * PX + 2);
+                        f[kd][kh][0] = va.x; f[kd][kh][1] = va.y; f[kd][kh][2] = vb.x; f[kd][kh][3] = vb.y;
+                    }
+                }
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            v[kh * 3 + kw] = p0[kh * SX + m * 8 + kw];
-                            v[9 + kh * 3 + kw] = p1[kh * SX + m * 8 + kw];
-                            v[18 + kh * 3 + kw] = p2[kh * SX + m * 8 + kw];
-                        }
+                for (int j = 0; j < 2; ++j) {            // output row x = xq + j
 #pragma unroll
-                    for (int tp = 27; tp < 32; ++tp) v[tp] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k) {        // K atom = taps 8k .. 8k+7
                         uint32_t pk[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[k * 8 + 2 * j], v[k * 8 + 2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            float pv[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int tp = 8 * k + 2 * e2 + u;
+                                pv[u] = tp < 27 ? f[tp / 9][(tp / 3) % 3][j + tp % 3] : (tp < 29 ? 1.f : 0.f);
+                            }
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[0], pv[1]);
+                            pk[e2] = *reinterpret_cast<uint32_t *>(&b2);
                         }
-                        *reinterpret_cast<uint4 *>(abase + m * 8192 + k * 2048 + bt * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(abase + k * 2048 + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -762,7 +853,7 @@ upcat_blocked_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *
 // final Conv3D(1,(1,1,1)) + sigmoid (+ nearest up-sampling by `stride`, fplnetwork.py:99-105) -> float32 tile
 __global__ void __launch_bounds__(256)
 final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, float bias, float *__restrict__ out,
-                     int n_tiles, int d, int cg_in, int stride) {
+                     int n_tiles, int d, int cg_in, int stride, const VolumeIO vio) {
     const long long vox = (long long)d * d * d;
     const long long total = (long long)n_tiles * vox;
     const int dout = d * stride;
@@ -783,6 +874,20 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
         }
         const float pr = 1.f / (1.f + expf(-acc));
         const int x = (int)(v % d), y = (int)((v / d) % d), z = (int)(v / ((long long)d * d));
+        if (vio.pred) {
+            // scatter of fplnetwork.py:180-187: pred[off + origin + (0..ext)) <- tile output
+            const TileGrid &g = vio.g;
+            const int tt = vio.ids ? vio.ids[vio.tile0 + t] : vio.tile0 + t;
+            const long long bx = (long long)(tt % g.nx) * g.out_sz + g.off + (long long)x * stride;
+            const long long by = (long long)((tt / g.nx) % g.ny) * g.out_sz + g.off + (long long)y * stride;
+            const long long bz = (long long)(tt / (g.nx * g.ny)) * g.out_sz + g.off + (long long)z * stride;
+            for (int dz = 0; dz < stride; ++dz)
+                for (int dy = 0; dy < stride; ++dy)
+                    for (int dx = 0; dx < stride; ++dx)
+                        if (bz + dz < g.Z - g.off && by + dy < g.Y - g.off && bx + dx < g.X - g.off)
+                            vio.pred[((bz + dz) * g.Y + (by + dy)) * g.X + bx + dx] = pr;
+            continue;
+        }
         float *op = out + (size_t)t * dout * dout * dout;
         for (int dz = 0; dz < stride; ++dz)
             for (int dy = 0; dy < stride; ++dy)
@@ -891,7 +996,11 @@ int pack_weights_umma(fpl_net *net) {
                     for (int n = 0; n < c.cout; ++n)
                         for (int e = 0; e < 8; ++e) {
                             const int tp = 16 * s + 8 * h + e;
-                            const float v = tp < 27 ? c.kernel[(size_t)tp * c.cout + n] * c.scale[n] : 0.f;
+                            float v = tp < 27 ? c.kernel[(size_t)tp * c.cout + n] * c.scale[n] : 0.f;
+                            // folded-BN bias rides in two constant-one K slots as bf16 hi + lo parts
+                            const float b_hi = __bfloat162float(__float2bfloat16_rn(c.bias[n]));
+                            if (tp == 27) v = b_hi;
+                            if (tp == 28) v = c.bias[n] - b_hi;
                             pk[(((size_t)s * 2 + h) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
                         }
             c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
@@ -1032,7 +1141,8 @@ static int pool_reserve(size_t bytes) {
     return FPL_OK;
 }
 
-int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
+int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
+                 const VolumeIO *vio) {
     fpl_ctx *ctx = net->ctx;
     if (net->precision != FPL_PREC_BF16) {
         set_error("forward_umma: only the bf16 tcgen05 path is built (precision %d requested)", net->precision);
@@ -1079,7 +1189,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
                 FPL_REQUIRE(cp.k == 3 && blocks < 2147483647LL, "forward_umma: unsupported first layer");
                 ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
-                if (!g_force_direct && cp.d_packed && cp.cout % 16 == 0 && cp.cout <= 128) {
+                if (!g_force_direct && cp.d_packed && cp.cout % 16 == 0 && cp.cout <= 64) {
                     FirstArgs fa;
                     fa.in = d_tiles; fa.w_packed = (const __nv_bfloat16 *)cp.d_packed; fa.bias = cp.d_bias; fa.out = dst;
                     fa.n_tiles = n_tiles; fa.din = d; fa.dout = dout; fa.cout = cp.cout;
@@ -1090,11 +1200,19 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                     int zc_len = (dout + n_zc - 1) / n_zc;
                     if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
                     fa.zc_len = zc_len; fa.n_zc = (dout + zc_len - 1) / zc_len;
-                    const int acc_cols = 2 * 2 * cp.cout;
+                    const int acc_cols = 4 * 2 * cp.cout;       // kSt stages x 2 M-tiles
                     fa.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+                    if (vio) fa.vio = *vio;
+                    { const char *e = getenv("FPL_DBG_FIRST"); fa.dbg = e ? atoi(e) : 0; }
                     const long long n_items = base_items * fa.n_zc;
                     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
-                    conv_first_umma_kernel<<<grid, kFirstThreads, 0, st>>>(fa);
+                    const size_t first_smem = 4 * (2 * 4 * 128 * 16);
+                    FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_first_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)first_smem));
+                    conv_first_umma_kernel<<<grid, kFirstThreads, first_smem, st>>>(fa);
+                } else if (vio && vio->img) {
+                    set_error("forward_umma: direct volume input needs the tensor-core first layer");
+                    return FPL_ESTATE;
                 } else if (cp.cout == 48)
                     conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
                 else if (cp.cout == 32)
@@ -1142,7 +1260,8 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             const ConvParams &cp = net->convs[o.conv_index];
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * d * d * d * (c * 2.0 + 4.0 * net->info.rf_stride * net->info.rf_stride * net->info.rf_stride));
             final_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], cp.d_kernel, cp.bias[0],
-                                                               d_out, n_tiles, d, c / 8, net->info.rf_stride);
+                                                               d_out, n_tiles, d, c / 8, net->info.rf_stride,
+                                                               vio ? *vio : VolumeIO());
             FPL_LAUNCH_CHECK(ctx);
         }
     }

@@ -83,12 +83,6 @@ static void free_device_weights(fpl_net *n) {
 // ------------------------------------------------------------------------------------------------
 // tiler kernels
 // ------------------------------------------------------------------------------------------------
-struct TileGrid {
-    int nz, ny, nx;          // tiles per axis
-    int in_sz, out_sz, off;  // tile input edge, useful output edge (= stride of origins), rf_offset
-    long long Z, Y, X;
-};
-
 // tile t of the batch <- image[start : start+in_sz] (zero beyond the far edge), start = k*out_sz.
 // image either float32 or uint8 + (x-mean)/std in float32 (fplobjdetect.py:1106-1107).
 // One block per (tile, z, y) row, threads along x: no per-element integer division.
@@ -153,7 +147,12 @@ static int tiles_along(long long size, int off, int out_sz) {
 
 using namespace fpl::net;
 
+static int g_no_direct_io = 0;   // test hook: stage tiles through gather/scatter kernels on the tcgen05 path too
+
 extern "C" {
+
+int fpl_debug_no_direct_io(int on) { g_no_direct_io = on; return FPL_OK; }
+
 
 int fpl_net_create(fpl_ctx *ctx, int arch, fpl_net **out) {
     FPL_REQUIRE(ctx && out, "fpl_net_create: NULL argument");
@@ -372,7 +371,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         if (ie > need_in) need_in = ie;
         if (oe > need_out) need_out = oe;
     }
-    if (net->stage_in_cap < need_in || net->stage_out_cap < need_out) {
+    if ((net->stage_in_cap < need_in || net->stage_out_cap < need_out)) {
         FPL_CUDA_CHECK(cudaStreamSynchronize(st));
         if (net->d_stage_in) cudaFree(net->d_stage_in);
         if (net->d_stage_out) cudaFree(net->d_stage_out);
@@ -389,6 +388,10 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         const size_t in_elems = (size_t)tg.in_sz * tg.in_sz * tg.in_sz, out_elems = (size_t)tg.out_sz * tg.out_sz * tg.out_sz;
         for (long long t0 = 0; t0 < ph.n && rc == FPL_OK; t0 += ph.batch) {
             const int nb = (int)((ph.n - t0) < ph.batch ? (ph.n - t0) : ph.batch);
+            // tcgen05 path: the final layer scatters straight into the prediction volume; the input
+            // tile is still staged by the gather kernel (float32, L2 resident) -- reading the uint8
+            // volume directly from the first-layer builders measured slower (profiles/)
+            const bool fused_scatter = net->precision != FPL_PREC_FP32 && !g_no_direct_io;
             {
                 fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * in_elems * (image_is_u8 ? 5.0 : 8.0));
                 if (image_is_u8)
@@ -400,9 +403,13 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
             }
             ctx->launches++;
             if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, tg.in_sz, d_out, st);
-            else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st);
+            else if (fused_scatter) {
+                VolumeIO vio;
+                vio.g = tg; vio.tile0 = (int)t0; vio.ids = ph.ids; vio.pred = d_pred;
+                rc = forward_umma(net, d_in, nb, tg.in_sz, nullptr, st, &vio);
+            } else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st);
             if (rc != FPL_OK) break;
-            {
+            if (!fused_scatter) {
                 fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);
                 scatter_tiles_kernel<<<blocks, 128, 0, st>>>(d_out, d_pred, tg, (int)t0, nb, ph.ids);
             }

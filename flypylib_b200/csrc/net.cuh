@@ -30,6 +30,24 @@ struct ConvParams {                 // host copies (Keras order) + folded device
     size_t packed_bytes = 0;
 };
 
+// Tile grid of FplNetwork.infer (fplnetwork.py:146-160) and the optional direct volume I/O of a
+// forward pass: the first layer reads its input tile straight from the volume (zero beyond the far
+// edge, (x-mean)/std for uint8) and the final layer scatters straight into the prediction volume.
+struct TileGrid {
+    int nz, ny, nx;          // tiles per axis
+    int in_sz, out_sz, off;  // tile input edge, useful output edge (= stride of origins), rf_offset
+    long long Z, Y, X;
+};
+struct VolumeIO {
+    const void *img = nullptr;   // (Z,Y,X) uint8 or float32
+    int is_u8 = 0;
+    float mean = 0.f, stdv = 1.f;
+    TileGrid g{};
+    int tile0 = 0;               // first tile of the batch (index into ids, or linear tile id)
+    const int *ids = nullptr;    // optional linear tile ids
+    float *pred = nullptr;       // (Z,Y,X) float32
+};
+
 struct ArchInfo {
     int rf_size, rf_offset, rf_stride, infer_sz;
     bool final_bias;
@@ -58,7 +76,7 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                  cudaStream_t st);
 // tcgen05 path (conv_umma.cu)
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out,
-                 cudaStream_t st);
+                 cudaStream_t st, const VolumeIO *vio = nullptr);
 int pack_weights_umma(fpl_net *net);
 void free_packed_umma(fpl_net *net);
 // output edge of a tile for input edge in_sz (after the x rf_stride up-sampling); -1 if invalid

@@ -81,3 +81,19 @@ def test_fused_pool_epilogue_is_bit_identical():
         finally:
             lib.fpl_debug_no_pool_fusion(0)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("arch,shape", [("vgg_like2", (130, 190, 101)), ("unet_like2", (105, 100, 185))])
+def test_direct_volume_io_equals_reference_tiling_of_tile_api(arch, shape):
+    """bf16 infer (first layer gathers from the volume, final layer scatters into pred) == the
+    reference tiling (oracle infer_tiler, pinned to the reference) driven by our own tile-level predict."""
+    from flypylib_b200 import fplmodels, fplnetwork
+    from tests.golden import cases
+    net = fplnetwork.FplNetwork(getattr(fplmodels, arch))
+    net.train_single.set_weights(M.random_weights(arch, seed=8))
+    net.set_precision("bf16")
+    net._set_infer()
+    img = ((cases.em_volume(shape, seed=4).astype(np.float32) - 128.0) / 33.0).astype(np.float32)
+    got = net.infer(img)
+    want = M.infer_tiler(img, net.infer_network, net.infer_sz, net.rf_offset, n_gpu=1)
+    assert np.array_equal(got, want)
