@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--size", type=int, default=1024, help="volume edge (default: configs[1], 1024)")
     ap.add_argument("--model", default="vgg_like2", choices=["vgg_like", "vgg_like2", "unet_like2"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--tile-mult", type=int, default=1,
-                    help="VGG only: evaluate super-tiles of this many reference tiles per axis")
+    ap.add_argument("--tile-mult", type=int, default=None,
+                    help="VGG only: evaluate super-tiles of this many reference tiles per axis "
+                         "(bit-identical to the reference grid; default 4 for the VGGs, 1 for the U-Net)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -203,7 +204,7 @@ def main():
         return run_reference(args)
     import torch
     import torch.distributed as dist
-    from flypylib_b200 import fplmodels, fplnetwork, fplobjdetect, _lib
+    from flypylib_b200 import fplmodels, fplnetwork, fplobjdetect, multi_gpu, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +221,8 @@ def main():
     net.train_single.set_weights(seeded_weights(args.model))
     net.set_precision(args.precision)
     net._set_infer()
+    if args.tile_mult is None:
+        args.tile_mult = 1 if args.model == "unet_like2" else 4
     net.tile_multiplier = args.tile_mult
     ctx = _lib.context(local)
 
@@ -231,17 +234,10 @@ def main():
         net.infer_device(vol, normalize=NORM, out=pred)
         out = fplobjdetect.voxel2obj_device(pred, DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0),
                                             DET["buffer_sz"], DET["thd"])
-        if world > 1:
+        if world > 1:       # the only collective of the path: all-gather of the detection lists (NCCL)
             rows = torch.from_numpy(np.concatenate([out["locs"], out["conf"][:, None]], 1)).to(dev)
-            n = torch.tensor([rows.shape[0]], device=dev)
-            ns = [torch.zeros_like(n) for _ in range(world)]
-            dist.all_gather(ns, n)
-            m = int(max(int(v) for v in ns))
-            pad = torch.zeros((m, 4), dtype=torch.float64, device=dev)
-            pad[:rows.shape[0]] = rows
-            allr = [torch.zeros_like(pad) for _ in range(world)]
-            dist.all_gather(allr, pad)
-            return sum(int(v) for v in ns)
+            parts = multi_gpu.allgather_detections(rows)
+            return sum(int(p.shape[0]) for p in parts)
         return out["conf"].size
 
     def sync():
@@ -307,8 +303,12 @@ def main():
     pk = peaks()
     ms3, work3, cnt3 = prof["conv3"]
     achieved = (work3 / (ms3 * 1e-3) / 1e12) if ms3 > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv3_traffic.json")
+    if os.path.exists(tpath):       # dram bytes per launch of the dominant kernel from the committed ncu capture
+        traffic = json.load(open(tpath))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf"], "traffic": None,
+                "frac": achieved / pk["tf"], "traffic": traffic,
                 "kernel": "conv_umma_kernel<3> (tcgen05 implicit GEMM, 3x3x3 conv)",
                 "launches": int(cnt3 / max(1, args.steps)), "ms_per_step": ms3 / args.steps,
                 "peak_source": "%s bf16 sustained" % pk["src"]}
@@ -321,7 +321,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "%s (%s, tcgen05 implicit GEMM) inference + voxel2obj(r=27, sigma=5, buffer=15) on a "
-                                   "synthetic %d^3 uint8 EM volume per GPU, random-init weights, reference tile grid x%d"
+                                   "synthetic %d^3 uint8 EM volume per GPU, random-init weights, reference tile grid evaluated as %d^3-tile super-tiles"
                                    % (args.model, args.precision, size, args.tile_mult),
                        "l2": "inputs larger than L2 (1 GiB uint8 volume, 4 GiB probability map per step)",
                        "detections_per_step": int(n_det)},

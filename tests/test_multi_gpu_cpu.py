@@ -1,0 +1,74 @@
+"""CPU (gloo, world_size 2): host-side logic of the N>1 path -- layer partition, slab bounds,
+variable-length detection all-gather, merge order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from flypylib_b200 import multi_gpu
+
+
+def test_partition_and_slabs():
+    assert multi_gpu.partition_layers(25, 8) == [(0, 4), (4, 7), (7, 10), (10, 13), (13, 16), (16, 19), (19, 22), (22, 25)]
+    assert multi_gpu.partition_layers(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    # unet_like2 on 2048: 25 layers of 82
+    assert multi_gpu.tile_layers(2048, 9, 82) == 25
+    assert multi_gpu.tile_layers(1024, 10, 80) == 13
+    assert multi_gpu.tile_layers(15, 9, 82) == 0
+    (z0, z1), (p0, p1) = multi_gpu.slab_for_layers(4, 7, 2048, 9, 82)
+    assert (z0, z1) == (328, 592) and (p0, p1) == (337, 583)          # halo = 2*rf_offset = 18 planes
+    (z0, z1), (p0, p1) = multi_gpu.slab_for_layers(22, 25, 2048, 9, 82)
+    assert z1 == 2048 and p1 == 2039
+    # slabs of consecutive ranks tile the prediction rows exactly
+    rows = []
+    for b, e in multi_gpu.partition_layers(25, 8):
+        rows.append(multi_gpu.slab_for_layers(b, e, 2048, 9, 82)[1])
+    assert rows[0][0] == 9 and rows[-1][1] == 2039
+    assert all(rows[i][1] == rows[i + 1][0] for i in range(7))
+
+
+def test_merge_order():
+    a = np.array([[1, 2, 3, 0.5], [4, 5, 6, 0.9]])
+    b = np.array([[7, 8, 9, 0.9], [0, 0, 0, 0.1]])
+    m = multi_gpu.merge_detections([a, b, np.zeros((0, 4))])
+    assert np.array_equal(m['conf'], [0.9, 0.9, 0.5, 0.1])
+    assert np.array_equal(m['locs'][0], [4, 5, 6]) and np.array_equal(m['locs'][1], [7, 8, 9])
+    e = multi_gpu.merge_detections([])
+    assert e['locs'].shape == (0, 3) and e['conf'].shape == (0,)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(rank)
+        k = [3, 0][rank] if world == 2 else rank
+        rows = torch.from_numpy(np.concatenate([rng.integers(0, 100, (k, 3)).astype(np.float64),
+                                                rng.random((k, 1))], 1))
+        parts = multi_gpu.allgather_detections(rows)
+        assert len(parts) == world
+        assert parts[rank].shape == (k, 4) and torch.equal(parts[rank], rows)
+        merged = multi_gpu.merge_detections([p.numpy() for p in parts])
+        q.put((rank, [tuple(p.shape) for p in parts], merged['conf'].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_detections_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert res[0][1] == res[1][1] == [(3, 4), (0, 4)]      # one rank contributes an empty list
+    assert res[0][2] == res[1][2] and res[0][2] == sorted(res[0][2], reverse=True)
