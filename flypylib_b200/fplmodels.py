@@ -183,7 +183,51 @@ class Model(object):
             outs.append(ob.cpu().numpy()[..., None])
         return np.concatenate(outs, 0)
 
+    # ---- training (VGG builders, default binary_crossentropy + adam) ---------------------------
+    def configure_training(self, n_gpu, batch_size, input_shape):
+        """make_train_parallel bookkeeping: ranks, per-rank batch, patch edge."""
+        self._train_cfg = (int(n_gpu), int(batch_size), int(fplutils.to3d(input_shape)[0]))
+        self._trainer = None
+
+    def trainer(self):
+        from . import fpltrain
+        cfg = getattr(self, "_train_cfg", None)
+        if cfg is None:
+            raise RuntimeError("call FplNetwork.make_train_parallel(n_gpu, batch_size, input_shape) first")
+        if getattr(self, "_trainer", None) is None:
+            self._trainer = fpltrain.Trainer(self, cfg[2], cfg[1])
+        return self._trainer
+
+    def fit_generator(self, generator, steps_per_epoch, epochs, callbacks=None, verbose=1):
+        """Keras Model.fit_generator as FplNetwork.train uses it (fplnetwork.py:120-121): per epoch
+        steps_per_epoch batches from `generator`; callbacks receive on_epoch_end(epoch, logs)."""
+        if self.arch not in ("vgg_like", "vgg_like2"):
+            raise NotImplementedError("the B200 training step covers the VGG builders")
+        tr = self.trainer()
+        history = []
+        for epoch in range(int(epochs)):
+            loss_sum = acc_sum = 0.0
+            for _ in range(int(steps_per_epoch)):
+                data, labels = next(generator)
+                loss, acc = tr.train_on_batch(data, labels)
+                loss_sum += loss; acc_sum += acc
+            logs = {"acc": acc_sum / steps_per_epoch, "loss": loss_sum / steps_per_epoch}
+            history.append(logs)
+            tr.sync_to_model()
+            if verbose:
+                print("Epoch %d/%d - loss: %.4f - acc: %.4f" % (epoch + 1, epochs, logs["loss"], logs["acc"]))
+            for cb in (callbacks or []):
+                cb.on_epoch_end(epoch, logs)
+        return history
+
+    def save(self, path):
+        """Keras Model.save stand-in (h5py is unavailable): weights in get_weights() order as .npz."""
+        np.savez(path if str(path).endswith(".npz") else str(path) + ".npz", *self._weights)
+
     def close(self):
+        if getattr(self, "_trainer", None) is not None:
+            self._trainer.close()
+            self._trainer = None
         if self._net is not None:
             _lib.lib().fpl_net_destroy(self._net)
             self._net = None

@@ -15,6 +15,34 @@ from . import fplutils
 from . import fplmodels
 
 
+class CSVLogger(object):
+    """Keras CSVLogger stand-in: epoch,acc,loss rows (fplnetwork.py:115)."""
+
+    def __init__(self, filename):
+        self.filename = filename
+        self._started = False
+
+    def on_epoch_end(self, epoch, logs=None):
+        logs = logs or {}
+        keys = sorted(logs)
+        with open(self.filename, "a" if self._started else "w") as f:
+            if not self._started:
+                f.write(",".join(["epoch"] + keys) + "\n")
+            f.write(",".join([str(epoch)] + ["%r" % logs[k] for k in keys]) + "\n")
+        self._started = True
+
+
+class multi_gpu_callback(object):
+    """fplnetwork.py:9-17: save the single (un-replicated) model at the end of every epoch."""
+
+    def __init__(self, model, save_prefix):
+        self.model_to_save = model
+        self.save_prefix = save_prefix
+
+    def on_epoch_end(self, epoch, logs=None):
+        self.model_to_save.save('%s_%03d.h5' % (self.save_prefix, epoch))
+
+
 class FplNetwork:
     """deep learning/CNN class wrapping a B200 network (reference: wraps a keras model)
 
@@ -61,11 +89,25 @@ class FplNetwork:
         if self.infer_network is not None:
             self.infer_network.set_precision(precision)
 
-    def train(self, generator, steps_per_epoch, epochs, log_file, save_filepath):
-        raise NotImplementedError("training is not part of the B200 inference hot path (SURVEY 8a A8)")
+    def train(self, generator, steps_per_epoch, epochs,
+              log_file, save_filepath):
+        """fplnetwork.py:112-122: CSV log of the epoch metrics, per-epoch save of the single model,
+        fit over the generator, then rebuild the inference network with the trained weights."""
+        csv_logger = CSVLogger(log_file)
+        checkpoint = multi_gpu_callback(self.train_single, save_filepath)
+        callbacks = [csv_logger, checkpoint]
+        if not hasattr(self.train_network, "_train_cfg"):
+            self.make_train_parallel(1, 64, self.rf_size)
+        self.train_network.fit_generator(
+            generator, steps_per_epoch, epochs, callbacks=callbacks)
+        self._set_infer()
 
     def make_train_parallel(self, n_gpu, batch_size, input_shape):
-        raise NotImplementedError("training is not part of the B200 inference hot path (SURVEY 8a A8)")
+        """fplnetwork.py:124-128.  n_gpu towers of batch_size patches each = n_gpu ranks (one process per
+        GPU, torch.distributed/NCCL) that all-reduce their gradients; see fpltrain.Trainer."""
+        self.train_network = self.train_single
+        self.train_network.configure_training(n_gpu, batch_size, input_shape)
+        self.train_network.compile(**self.compile_args)
 
     def make_infer_parallel(self, n_gpu):
         """fplnetwork.py:130-134.  The reference replicates the graph on n_gpu towers inside one

@@ -169,6 +169,34 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
                          float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
                          int32_t z_tile_end, float *d_pred, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * data-parallel training step of the VGG builders (BASELINE config 5)
+ *   replaces one batch of Keras fit_generator (flypylib/fplnetwork.py:112-128) with the default
+ *   compile args loss='binary_crossentropy', optimizer='adam' (fplnetwork.py:74-77)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fpl_trainer fpl_trainer;
+
+/* patch_sz = rf_size of the builder (18 / 24: one output voxel per patch, fplobjdetect.py:77),
+ * batch = patches per GPU (64 in scripts/fpl_cx1_0_vgg_4ss.py:11-17) */
+int fpl_train_create(fpl_ctx *ctx, int arch, int patch_sz, int batch, fpl_trainer **out);
+int fpl_train_destroy(fpl_trainer *t);
+/* n_params: floats of the flat parameter vector (Keras get_weights() order, concatenated);
+ * n_bn: floats of the batch-statistics vector (per BN layer: mean[C], biased var[C]) */
+int fpl_train_sizes(const fpl_trainer *t, int64_t *n_params, int64_t *n_bn);
+/* forward (training mode: BN batch statistics per rank, Dropout(0.5) from a counter-based hash of
+ * dropout_seed) + loss + backward.  d_x: (batch, s,s,s) float32; d_labels: batch uint8 in {0,1};
+ * d_params / d_grads: n_params floats (grads of non-trainable slots are 0); loss_scale = 1/global_batch
+ * (Keras mean over the whole batch; gradients of all ranks are then SUMMED by the caller's all-reduce).
+ * h_loss_sum = sum of per-sample binary cross-entropies of this rank, h_correct = #(round(p) == y). */
+int fpl_train_forward_backward(fpl_trainer *t, const float *d_x, const uint8_t *d_labels, const float *d_params,
+                               float *d_grads, float *d_bn_batch, float loss_scale, uint64_t dropout_seed,
+                               double *h_loss_sum, int64_t *h_correct, void *stream);
+/* Adam step (Keras: lr_t = lr*sqrt(1-b2^t)/(1-b1^t), p -= lr_t*m/(sqrt(v)+eps)) on the trainable slots and
+ * moving-average update of the BN statistics (moving = moving*momentum + batch*(1-momentum)). */
+int fpl_train_apply(fpl_trainer *t, float *d_params, const float *d_grads, float *d_m, float *d_v,
+                    const float *d_bn_batch, int64_t step, float lr, float beta1, float beta2, float eps,
+                    float bn_momentum, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
