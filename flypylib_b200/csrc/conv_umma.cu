@@ -129,16 +129,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // the implicit-GEMM convolution kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kTX = 16, kTY = 16;            // output patch per CTA and z step (two M=128 tiles: x 0..7, 8..15)
-constexpr int kPlanes = 3;                   // input plane ring
 constexpr int kAccStages = 2;                // TMEM accumulator double buffering
 constexpr int kThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct ConvArgs {
-    const __nv_bfloat16 *w_packed;   // [tap][kstep][2][Cout][8] bf16, BN scale folded
-    const float *bias;               // [Cout] folded BN bias
-    __nv_bfloat16 *out;              // (tile, Cout/8, Dout, Dout, Dout, 8)
+    const __nv_bfloat16 *w_packed;   // operand-B image of this Cout split (see pack_weights_umma), BN scale folded
+    const float *bias;               // folded BN bias of this split [cout]
+    __nv_bfloat16 *out;              // (tile, cout_total/8, Dout, Dout, Dout, 8)  (pooled edge when pool)
     uint32_t w_bytes;
-    int n_tiles, din, dout, cin_atoms, cout;
+    int n_tiles, din, dout;
+    int cin_atoms_total;             // Cin / 8 of the input tensor
+    int nsub;                        // input channels are consumed in nsub sub-planes of 2*KSTEPS atoms each
+    int cout;                        // output channels of this launch (N of the MMA)
+    int cout_total, cout_off;        // position of this split inside the output tensor
+    int ring;                        // (sub-)plane ring depth, 2 or 3
     int n_xt, n_yt, n_zc, zc_len;
     int relu;
     int pool;                        // fuse MaxPooling3D(2): `out` is the pooled tensor (edge dout/2)
@@ -171,12 +175,12 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], int c0
 
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, int cout, const float *s_bias,
                                               int relu, __nv_bfloat16 *__restrict__ out, int tile, int dout, int z,
-                                              int y0, int x0) {
+                                              int y0, int x0, int cout_total, int cout_off) {
     const int row = q * 32 + lane;
     const int y = y0 + (row >> 3), x = x0 + (row & 7);
     const bool ok = (x < dout) && (y < dout);
     const size_t cg_stride = (size_t)dout * dout * dout;
-    const size_t vox = (size_t)tile * (cout >> 3) * cg_stride + ((size_t)z * dout + y) * dout + x;
+    const size_t vox = ((size_t)tile * (cout_total >> 3) + (cout_off >> 3)) * cg_stride + ((size_t)z * dout + y) * dout + x;
     const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16);
     uint32_t ra[16], rb[16];
     tmem_ld16(tcol, ra);
@@ -257,23 +261,25 @@ __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int
 // Each M-tile owns a 256-column region of kBlocks = 256/Cout blocks; output number A (monotone
 // counter) lives in block kBlocks-1 - (A mod kBlocks), so consecutive outputs occupy descending
 // blocks and (p, p-1, p-2) are contiguous except where the ring wraps (then two MMAs are issued).
-template <int KS, int KSTEPS>
+template <int KS, int KSTEPS, int TX>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) {
-    constexpr int SX = kTX + KS - 1, SY = kTY + KS - 1;
-    constexpr int CIN_ATOMS = 2 * KSTEPS;
-    constexpr int kMaxBlocks = 8;
+    constexpr int SX = TX + KS - 1, SY = kTY + KS - 1;
+    constexpr int MT = TX / 8;                      // M=128 tiles per plane patch (x halves)
+    constexpr int SUB_ATOMS = 2 * KSTEPS;           // channel atoms per (sub-)plane
+    constexpr int kMaxBlocks = 8, kMaxRing = 3;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr uint32_t atom_stride = SY * SX * 16;                  // bytes between channel atoms of a plane
-    constexpr uint32_t plane_bytes = CIN_ATOMS * atom_stride;
+    constexpr uint32_t plane_bytes = SUB_ATOMS * atom_stride;
     constexpr uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
     const uint32_t w_region = (a.w_bytes + 127u) & ~127u;
+    const uint32_t ring = (uint32_t)a.ring;
     uint8_t *s_w = smem_raw;
     uint8_t *s_planes = smem_raw + w_region;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_planes + kPlanes * plane_pitch);
-    uint64_t *plane_full = bars;                    // [kPlanes]
-    uint64_t *plane_empty = bars + kPlanes;         // [kPlanes]
-    uint64_t *acc_full = bars + 2 * kPlanes;        // [kMaxBlocks]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_planes + ring * plane_pitch);
+    uint64_t *plane_full = bars;                    // [kMaxRing]
+    uint64_t *plane_empty = bars + kMaxRing;        // [kMaxRing]
+    uint64_t *acc_full = bars + 2 * kMaxRing;       // [kMaxBlocks]
     uint64_t *acc_empty = acc_full + kMaxBlocks;    // [kMaxBlocks]
     uint64_t *w_full = acc_empty + kMaxBlocks;      // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
@@ -283,10 +289,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
     const uint32_t N = (uint32_t)a.cout;
     const uint32_t nblk = 256u / N > (uint32_t)kMaxBlocks ? (uint32_t)kMaxBlocks : 256u / N;
+    const int nsub = a.nsub;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kPlanes; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < kMaxBlocks; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < kMaxBlocks; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * MT); }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
@@ -321,15 +328,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int z0 = zc * a.zc_len;
             const int nz = min(a.zc_len, a.dout - z0);
             const int np = nz + KS - 1;
-            for (int p = 0; p < np; ++p, ++pc) {
-                const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
-                mbar_wait(&plane_empty[slot], ph ^ 1u);
-                if (leader) {
-                    mbar_expect_tx(&plane_full[slot], plane_bytes);
-                    tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * kTX * 8, yt * kTY,
-                                z0 + p, tile * CIN_ATOMS);
+            for (int p = 0; p < np; ++p)
+                for (int sub = 0; sub < nsub; ++sub, ++pc) {
+                    const uint32_t slot = pc % ring, ph = (pc / ring) & 1u;
+                    mbar_wait(&plane_empty[slot], ph ^ 1u);
+                    if (leader) {
+                        mbar_expect_tx(&plane_full[slot], plane_bytes);
+                        tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * TX * 8, yt * kTY,
+                                    z0 + p, tile * a.cin_atoms_total + sub * SUB_ATOMS);
+                    }
                 }
-            }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
@@ -340,7 +348,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         const uint32_t b_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
         const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((N * KS) << 16);   // LBO = KS*Cout*16 bytes
-        const uint32_t b_step16 = N * KS * 2u;                            // one (kh,kw,s) chunk = KS*Cout*32 bytes
+        const uint32_t b_step16 = N * KS * 2u;                            // one (kh,kw,kstep) chunk = KS*Cout*32 bytes
+        const uint32_t kt = (uint32_t)(nsub * KSTEPS);                    // K steps per tap over all sub-planes
         mbar_wait(w_full, 0);
         uint32_t pc = 0, ac0 = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -349,8 +358,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int nz = min(a.zc_len, a.dout - z0);
             const int np = nz + KS - 1;
 #pragma unroll 1
-            for (int ip = 0; ip < np; ++ip, ++pc) {
-                const uint32_t slot = pc % kPlanes, ph = (pc / kPlanes) & 1u;
+            for (int ip = 0; ip < np; ++ip) {
                 const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
                 const int kd_hi = ip < KS - 1 ? ip : KS - 1;
                 // accumulator blocks of the outputs fed by this plane: kd = kd_lo.. map to ascending
@@ -368,57 +376,62 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                     const uint32_t A = ac0 + (uint32_t)ip;
                     mbar_wait(&acc_empty[blk0], ((A / nblk) & 1u) ^ 1u);
                 }
-                mbar_wait(&plane_full[slot], ph);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
-                    uint32_t b_lo = b_lo0;
 #pragma unroll 1
-                    for (int kh = 0; kh < KS; ++kh)
+                for (int sub = 0; sub < nsub; ++sub, ++pc) {
+                    const uint32_t slot = pc % ring, ph = (pc / ring) & 1u;
+                    mbar_wait(&plane_full[slot], ph);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+#pragma unroll 1
+                        for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-                        for (int kw = 0; kw < KS; ++kw)
+                            for (int kw = 0; kw < KS; ++kw) {
+                                uint32_t b_lo = b_lo0 + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)(sub * KSTEPS)) * b_step16;
 #pragma unroll
-                            for (int s = 0; s < KSTEPS; ++s) {
-                                const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
-                                const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
-                                if (kh == 0 && kw == 0 && s == 0) {
-                                    // first tap of the plane: the kd = 0 accumulator is overwritten, the
-                                    // others accumulate -> one MMA per kd
+                                for (int s = 0; s < KSTEPS; ++s) {
+                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
+                                    const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
+                                    if (sub == 0 && kh == 0 && kw == 0 && s == 0) {
+                                        // first MMA of the plane: the kd = 0 accumulator is overwritten, the
+                                        // others accumulate -> one MMA per kd
 #pragma unroll
-                                    for (int kd = 0; kd < KS; ++kd)
-                                        if (kd >= kd_lo && kd <= kd_hi) {
-                                            const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
-                                            const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
-                                            const uint32_t dcol = tmem_base + bl * N;
-                                            umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
-                                            umma_bf16(dcol + 256u, ad1, bd, idesc_1, kd ? 1u : 0u);
+                                        for (int kd = 0; kd < KS; ++kd)
+                                            if (kd >= kd_lo && kd <= kd_hi) {
+                                                const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
+                                                const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
+                                                const uint32_t dcol = tmem_base + bl * N;
+                                                umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
+                                                if (MT == 2) umma_bf16(dcol + 256u, ad1, bd, idesc_1, kd ? 1u : 0u);
+                                            }
+                                    } else {
+                                        const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
+                                        umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
+                                        if (MT == 2) umma_bf16(d_seg0 + 256u, ad1, bd0, i_seg0, 1u);
+                                        if (len1) {
+                                            const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
+                                            umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
+                                            if (MT == 2) umma_bf16(d_seg1 + 256u, ad1, bd1, i_seg1, 1u);
                                         }
-                                } else {
-                                    const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
-                                    umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
-                                    umma_bf16(d_seg0 + 256u, ad1, bd0, i_seg0, 1u);
-                                    if (len1) {
-                                        const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
-                                        umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
-                                        umma_bf16(d_seg1 + 256u, ad1, bd1, i_seg1, 1u);
                                     }
+                                    b_lo += b_step16;
                                 }
-                                b_lo += b_step16;
                             }
-                    umma_commit(&plane_empty[slot]);
-                    if (ip >= KS - 1) {         // output ip-(KS-1) has received its last plane
-                        const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
-                        umma_commit(&acc_full[nblk - 1u - (A % nblk)]);
+                        umma_commit(&plane_empty[slot]);
+                        if (sub == nsub - 1 && ip >= KS - 1) {   // output ip-(KS-1) has received its last plane
+                            const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
+                            umma_commit(&acc_full[nblk - 1u - (A % nblk)]);
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             ac0 += (uint32_t)nz;
         }
-    } else {
+    } else if ((warp - 2) >> 2 < MT) {
         // ===================================== epilogue =========================================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int m = (warp - 2) >> 2;                // which of the two M-tiles (x half) this warp drains
+        const int m = (warp - 2) >> 2;                // which of the M-tiles (x half) this warp drains
         uint32_t A = 0;
         float hold[16];
 #pragma unroll
@@ -440,16 +453,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                 if (a.pool) {
                     if (a.cout == 48)
                         epilogue_tile_pool<3>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * kTX + m * 8, reinterpret_cast<float(&)[12]>(hold));
+                                              xt * TX + m * 8, reinterpret_cast<float(&)[12]>(hold));
                     else if (a.cout == 32)
                         epilogue_tile_pool<2>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * kTX + m * 8, reinterpret_cast<float(&)[8]>(hold));
+                                              xt * TX + m * 8, reinterpret_cast<float(&)[8]>(hold));
                     else
                         epilogue_tile_pool<4>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * kTX + m * 8, hold);
+                                              xt * TX + m * 8, hold);
                 } else
                 epilogue_tile(tacc, q, lane, a.cout, s_bias, a.relu, a.out, tile,
-                              a.dout, z0 + zo, yt * kTY, xt * kTX + m * 8);
+                              a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.cout_total, a.cout_off);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[bl]);
@@ -968,21 +981,53 @@ static EncodeTiledFn get_encode_fn() {
 
 static constexpr size_t kMaxDynSmem = 232448;   // 227 KB
 
-static size_t conv_smem_bytes(int ks, int cin, int cout) {
-    const int sx = kTX + ks - 1, sy = kTY + ks - 1;
-    size_t w = ((size_t)ks * ks * ks * cin * cout * 2 + 127) & ~size_t(127);
-    size_t plane = (((size_t)(cin / 8) * sy * sx * 16) + 127) & ~size_t(127);
-    return w + kPlanes * plane + 256 + 512;     // + barriers + bias
+// How one GEMM-shaped convolution is mapped onto conv_umma_kernel so that the packed weights of a
+// launch stay resident in shared memory beside the input ring:
+//   n_split  : the output channels are computed in n_split launches of n = cout/n_split columns
+//   nsub     : the input channels are streamed as nsub sub-planes of 16*ksteps channels
+//   tx       : patch width (16: two M-tiles per plane, 8: one)        ring: (sub-)plane ring depth
+struct ConvPlan { int n_split, n, nsub, ksteps, tx, ring; size_t smem; bool ok; };
+
+static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring) {
+    const int sx = tx + ks - 1, sy = kTY + ks - 1;
+    size_t w = ((size_t)ks * ks * ks * cin * n * 2 + 127) & ~size_t(127);
+    size_t plane = (((size_t)(cin / nsub / 8) * sy * sx * 16) + 127) & ~size_t(127);
+    return w + ring * plane + 384 + 512;        // + barriers + bias
 }
 
-static bool umma_supported(const ConvParams &c) {
-    if (c.cin % 16 || c.cout % 16 || c.cout > 128) return false;
-    if (c.k != 1 && c.k != 3) return false;
-    const int ksteps = c.cin / 16;
-    if (c.k == 3 && !(ksteps == 2 || ksteps == 3 || ksteps == 4)) return false;
-    if (c.k == 1 && !(ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6)) return false;
-    return conv_smem_bytes(c.k, c.cin, c.cout) <= kMaxDynSmem;
+static bool have_instance(int ks, int ksteps, int tx) {
+    if (ks == 3 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
+    if (ks == 3 && tx == 8) return ksteps == 4;
+    if (ks == 1 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
+    return false;
 }
+
+static ConvPlan plan_conv(const ConvParams &c) {
+    ConvPlan best{0, 0, 0, 0, 0, 0, 0, false};
+    if (c.cin % 16 || c.cout % 16 || c.cout > 128 || (c.k != 1 && c.k != 3)) return best;
+    const int txs[2] = {16, 8};
+    for (int ti = 0; ti < 2; ++ti)
+        for (int nsub = 1; nsub <= 4; ++nsub) {
+            if (c.cin % (16 * nsub)) continue;
+            const int ksteps = c.cin / 16 / nsub;
+            if (!have_instance(c.k, ksteps, txs[ti])) continue;
+            for (int split = 1; split <= 8; split *= 2) {
+                if (c.cout % (16 * split)) continue;
+                const int n = c.cout / split;
+                for (int ring = 3; ring >= 2; --ring) {
+                    if (nsub > 1 && ring > 2) continue;
+                    const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring);
+                    if (sm <= kMaxDynSmem) {
+                        // prefer: no split, single plane, wide patch, deep ring (loop order) -- first hit wins
+                        return ConvPlan{split, n, nsub, ksteps, txs[ti], ring, sm, true};
+                    }
+                }
+            }
+        }
+    return best;
+}
+
+static bool umma_supported(const ConvParams &c) { return plan_conv(c).ok; }
 
 static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv through the CUDA-core kernel
 static int g_no_pool_fusion = 0;  // test hook: keep MaxPooling3D as its own kernel
@@ -1009,23 +1054,27 @@ int pack_weights_umma(fpl_net *net) {
             continue;
         }
         if (c.cin % 16 || c.cout % 16) continue;         // final layer
-        // operand-B image: chunk (kh,kw,s) = [2 K-halves][k*Cout rows, kd-major][8 bf16]; the k kd
-        // taps that share an A tile are adjacent row blocks so that one MMA with N = k*Cout covers them
-        const int ks = c.k, ksteps = c.cin / 16;
+        // operand-B image per Cout split g: chunk (kh,kw,kstep) = [2 K-halves][k*n rows, kd-major][8 bf16];
+        // the k kd taps that share an A tile are adjacent row blocks so that one MMA with N = k*n covers them
+        const ConvPlan plan = plan_conv(c);
+        if (!plan.ok) continue;
+        const int ks = c.k, ksteps = c.cin / 16, n = plan.n;
         std::vector<__nv_bfloat16> pk((size_t)ks * ks * ks * c.cin * c.cout);
-        for (int kh = 0; kh < ks; ++kh)
-            for (int kw = 0; kw < ks; ++kw)
-                for (int s = 0; s < ksteps; ++s)
-                    for (int h = 0; h < 2; ++h)
-                        for (int kd = 0; kd < ks; ++kd)
-                            for (int n = 0; n < c.cout; ++n)
-                                for (int e = 0; e < 8; ++e) {
-                                    const int ci = 16 * s + 8 * h + e;
-                                    const int tap = (kd * ks + kh) * ks + kw;
-                                    const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + n] * c.scale[n];
-                                    const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
-                                    pk[(((chunk * 2 + h) * ks + kd) * c.cout + n) * 8 + e] = __float2bfloat16_rn(v);
-                                }
+        const size_t split_elems = (size_t)ks * ks * ks * c.cin * n;
+        for (int g = 0; g < plan.n_split; ++g)
+            for (int kh = 0; kh < ks; ++kh)
+                for (int kw = 0; kw < ks; ++kw)
+                    for (int s = 0; s < ksteps; ++s)
+                        for (int h = 0; h < 2; ++h)
+                            for (int kd = 0; kd < ks; ++kd)
+                                for (int nn = 0; nn < n; ++nn)
+                                    for (int e = 0; e < 8; ++e) {
+                                        const int ci = 16 * s + 8 * h + e, co = g * n + nn;
+                                        const int tap = (kd * ks + kh) * ks + kw;
+                                        const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + co] * c.scale[co];
+                                        const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
+                                        pk[g * split_elems + (((chunk * 2 + h) * ks + kd) * n + nn) * 8 + e] = __float2bfloat16_rn(v);
+                                    }
         c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
         FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
         FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, pk.data(), c.packed_bytes, cudaMemcpyHostToDevice));
@@ -1044,25 +1093,27 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
                             int n_tiles, int din, int relu, int pool, cudaStream_t st) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
+    const ConvPlan plan = plan_conv(c);
+    FPL_REQUIRE(plan.ok, "conv_umma: no plan for k=%d Cin=%d Cout=%d", c.k, c.cin, c.cout);
+    FPL_REQUIRE(!pool || (plan.n_split == 1 && plan.tx == 16), "conv_umma: pooled epilogue needs an unsplit 16-wide plan");
     const int ks = c.k, dout = din - (ks - 1);
-    const int sx = kTX + ks - 1, sy = kTY + ks - 1;
+    const int sx = plan.tx + ks - 1, sy = kTY + ks - 1;
     const int cin_atoms = c.cin / 8;
     CUtensorMap tmap;
     cuuint64_t gdim[4] = {(cuuint64_t)din * 8, (cuuint64_t)din, (cuuint64_t)din, (cuuint64_t)n_tiles * cin_atoms};
     cuuint64_t gstride[3] = {(cuuint64_t)din * 16, (cuuint64_t)din * din * 16, (cuuint64_t)din * din * din * 16};
-    cuuint32_t box[4] = {(cuuint32_t)sx * 8, (cuuint32_t)sy, 1, (cuuint32_t)cin_atoms};
+    cuuint32_t box[4] = {(cuuint32_t)sx * 8, (cuuint32_t)sy, 1, (cuuint32_t)(2 * plan.ksteps)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FPL_ECUDA; }
     ConvArgs a;
-    a.w_packed = (const __nv_bfloat16 *)c.d_packed;
-    a.bias = c.d_bias;
     a.out = out;
-    a.w_bytes = (uint32_t)c.packed_bytes;
-    a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.cin_atoms = cin_atoms; a.cout = c.cout;
-    a.n_xt = (dout + kTX - 1) / kTX; a.n_yt = (dout + kTY - 1) / kTY;
+    a.w_bytes = (uint32_t)(c.packed_bytes / plan.n_split);
+    a.n_tiles = n_tiles; a.din = din; a.dout = dout;
+    a.cin_atoms_total = cin_atoms; a.nsub = plan.nsub; a.cout = plan.n; a.cout_total = c.cout; a.ring = plan.ring;
+    a.n_xt = (dout + plan.tx - 1) / plan.tx; a.n_yt = (dout + kTY - 1) / kTY;
     // z chunking: aim for >= 4 work items per SM so the persistent CTAs stay balanced
     const long long base_items = (long long)n_tiles * a.n_xt * a.n_yt;
     int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
@@ -1073,30 +1124,36 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
     a.relu = relu;
     a.pool = pool;
-    const int acc_cols = kAccStages * 2 * c.cout;
-    a.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
-    const size_t smem = conv_smem_bytes(ks, c.cin, c.cout);
+    a.tmem_cols = 512;
+    const size_t smem = plan.smem;
     const long long n_items = base_items * a.n_zc;
     ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
                    2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
-    const int ksteps = c.cin / 16;
-#define FPL_LAUNCH_UMMA(KS_, KST_)                                                                               \
-    do {                                                                                                          \
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_>,                                          \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-        conv_umma_kernel<KS_, KST_><<<grid, kThreads, smem, st>>>(tmap, a);                                       \
-    } while (0)
-    if (ks == 3 && ksteps == 3) FPL_LAUNCH_UMMA(3, 3);
-    else if (ks == 3 && ksteps == 2) FPL_LAUNCH_UMMA(3, 2);
-    else if (ks == 3 && ksteps == 4) FPL_LAUNCH_UMMA(3, 4);
-    else if (ks == 1 && ksteps == 2) FPL_LAUNCH_UMMA(1, 2);
-    else if (ks == 1 && ksteps == 3) FPL_LAUNCH_UMMA(1, 3);
-    else if (ks == 1 && ksteps == 4) FPL_LAUNCH_UMMA(1, 4);
-    else if (ks == 1 && ksteps == 6) FPL_LAUNCH_UMMA(1, 6);
-    else { set_error("conv_umma: no instantiation for k=%d Cin=%d", ks, c.cin); return FPL_EINVAL; }
+    for (int g = 0; g < plan.n_split; ++g) {
+        a.w_packed = (const __nv_bfloat16 *)((const uint8_t *)c.d_packed + (size_t)g * a.w_bytes);
+        a.bias = c.d_bias + g * plan.n;
+        a.cout_off = g * plan.n;
+#define FPL_LAUNCH_UMMA(KS_, KST_, TX_)                                                                          \
+        do {                                                                                                      \
+            FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_>,                                 \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            conv_umma_kernel<KS_, KST_, TX_><<<grid, kThreads, smem, st>>>(tmap, a);                              \
+        } while (0)
+        const int kst = plan.ksteps;
+        if (ks == 3 && plan.tx == 16 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16);
+        else if (ks == 3 && plan.tx == 16 && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16);
+        else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16);
+        else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16);
+        else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8);
+        else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16);
+        else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16);
+        else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16);
+        else if (ks == 1 && kst == 6) FPL_LAUNCH_UMMA(1, 6, 16);
+        else { set_error("conv_umma: no instantiation for k=%d ksteps=%d tx=%d", ks, kst, plan.tx); return FPL_EINVAL; }
 #undef FPL_LAUNCH_UMMA
-    FPL_LAUNCH_CHECK(ctx);
+        FPL_LAUNCH_CHECK(ctx);
+    }
     return FPL_OK;
 }
 
@@ -1180,7 +1237,8 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             // MaxPooling3D directly after this conv (and the conv output not kept as a skip): fuse it
             const bool fuse_pool = !g_force_direct && !g_no_pool_fusion && cp.cin != 1 && umma_supported(cp) && cp.k == 3 &&
                                    (cp.cout == 32 || cp.cout == 48 || cp.cout == 64) && oi + 1 < net->ops.size() &&
-                                   net->ops[oi + 1].kind == OP_POOL && ((d - (o.k - 1)) % 2 == 0);
+                                   net->ops[oi + 1].kind == OP_POOL && ((d - (o.k - 1)) % 2 == 0) &&
+                                   plan_conv(cp).n_split == 1 && plan_conv(cp).tx == 16;
             const int nb = take();
             if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
             __nv_bfloat16 *dst = (__nv_bfloat16 *)g_pool.buf[nb];
