@@ -297,23 +297,47 @@ select_hist_kernel(const float *__restrict__ v, long long n, SelectState *s, int
     if (threadIdx.x == 0 && nan_local) atomicAdd(&s->nan_count, (unsigned long long)nan_local);
 }
 
-// single thread: add the implicit zeros, locate the bin holding `rank`, extend the prefix, clear hist
-__global__ void select_scan_kernel(SelectState *s, int shift, int bins) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block: add the implicit zeros, locate the bin holding `rank` (parallel prefix over <= 2048 bins),
+// extend the prefix, clear the histogram
+__global__ void __launch_bounds__(1024)
+select_scan_kernel(SelectState *s, int shift, int bins) {
+    __shared__ unsigned long long cum[2048];
+    __shared__ int sel_bin;
+    const int t = threadIdx.x;
     const unsigned zkey = 0x80000000u;     // key of +0.0f
-    if ((zkey & s->prefix_mask) == s->prefix)
-        s->hist[(zkey >> shift) & (unsigned)(bins - 1)] += s->extra_zeros;
-    unsigned long long rank = s->rank, cum = 0;
-    int sel = bins - 1;
-    for (int b = 0; b < bins; ++b) {
-        unsigned long long c = s->hist[b];
-        if (rank < cum + c) { sel = b; break; }
-        cum += c;
+    const bool zero_here = (zkey & s->prefix_mask) == s->prefix;
+    const int zbin = (int)((zkey >> shift) & (unsigned)(bins - 1));
+    for (int b = t; b < 2048; b += 1024) {
+        unsigned long long c = b < bins ? s->hist[b] : 0ULL;
+        if (zero_here && b == zbin) c += s->extra_zeros;
+        cum[b] = c;
     }
-    s->rank = rank - cum;
-    s->prefix |= ((unsigned)sel) << shift;
-    s->prefix_mask |= ((unsigned)(bins - 1)) << shift;
-    for (int b = 0; b < bins; ++b) s->hist[b] = 0;
+    if (t == 0) sel_bin = bins - 1;
+    __syncthreads();
+    for (int off = 1; off < 2048; off <<= 1) {          // Hillis-Steele inclusive scan, two entries per thread
+        unsigned long long v0 = 0, v1 = 0;
+        const int b0 = t, b1 = t + 1024;
+        if (b0 >= off) v0 = cum[b0 - off];
+        if (b1 >= off) v1 = cum[b1 - off];
+        __syncthreads();
+        cum[b0] += v0; cum[b1] += v1;
+        __syncthreads();
+    }
+    const unsigned long long rank = s->rank;
+    for (int b = t; b < bins; b += 1024) {
+        const unsigned long long before = b ? cum[b - 1] : 0ULL;
+        if (rank >= before && rank < cum[b]) sel_bin = b;     // exactly one bin satisfies this
+    }
+    __syncthreads();
+    const int sel = sel_bin;
+    const unsigned long long before = sel ? cum[sel - 1] : 0ULL;
+    __syncthreads();
+    for (int b = t; b < bins; b += 1024) s->hist[b] = 0;
+    if (t == 0) {
+        s->rank = rank - before;
+        s->prefix |= ((unsigned)sel) << shift;
+        s->prefix_mask |= ((unsigned)(bins - 1)) << shift;
+    }
 }
 
 struct ThreshOut {            // device
@@ -465,15 +489,26 @@ __device__ __forceinline__ int isqrt_floor(int v) {
 }
 
 // one block per worklist entry: is there a better valid voxel inside the ball (d2 <= r^2)?
+// Rows (dz,dy) of the ball are x-runs of half width hw(dz,dy) (table in shared memory); every warp
+// takes kRowsPerStep rows at a time and issues all their loads before testing any (the scan is a
+// pure latency problem: ~82 k coalesced 4-byte reads per entry, almost all of them "not better").
+constexpr int kRowsPerStep = 4;
 __global__ void __launch_bounds__(256)
 nms_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d, int r,
                      const unsigned long long *__restrict__ w_idx, const float *__restrict__ w_val,
                      unsigned long long *det_idx, float *det_val, unsigned long long *sel_idx,
                      long long det_capacity, Counters *cnt) {
+    extern __shared__ short s_hw[];                 // (2r+1)^2 half widths, -1 outside the ball
     __shared__ int found;
     const unsigned long long nW = cnt->n_work;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int side = 2 * r + 1;
+    const int side = 2 * r + 1, nrows = side * side;
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+        const int dz = i / side - r, dy = i % side - r;
+        const int rem = r * r - dz * dz - dy * dy;
+        s_hw[i] = rem < 0 ? (short)-1 : (short)isqrt_floor(rem);
+    }
+    __syncthreads();
     for (unsigned long long w = blockIdx.x; w < nW; w += gridDim.x) {
         if (threadIdx.x == 0) found = 0;
         __syncthreads();
@@ -482,23 +517,40 @@ nms_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ s
         const long long x = (long long)(idx % (unsigned long long)d.X);
         const long long y = (long long)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
         const long long z = (long long)(idx / ((unsigned long long)d.X * d.Y));
-        for (int row = warp; row < side * side; row += nwarps) {
+        for (int row0 = warp * kRowsPerStep; row0 < nrows; row0 += nwarps * kRowsPerStep) {
             if (*(volatile int *)&found) break;
-            int dz = row / side - r, dy = row % side - r;
-            int rem = r * r - dz * dz - dy * dy;
-            if (rem < 0) continue;
-            long long zz = z + dz, yy = y + dy;
-            if (zz < 0 || zz >= d.Z || yy < 0 || yy >= d.Y) continue;
-            int hw = isqrt_floor(rem);
-            long long x0 = x - hw < 0 ? 0 : x - hw;
-            long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
-            unsigned long long rowbase = ((unsigned long long)zz * d.Y + yy) * d.X;
-            bool hit = false;
-            for (long long xx = x0 + lane; xx <= x1; xx += 32) {
-                unsigned long long q = rowbase + xx;
-                float vq = __ldg(v + q);
-                if ((vq > val || (vq == val && q < idx)) && !is_suppressed(sup, q)) hit = true;
+            float f[kRowsPerStep][2];
+            unsigned long long q0[kRowsPerStep];
+            int n_valid[kRowsPerStep];
+#pragma unroll
+            for (int u = 0; u < kRowsPerStep; ++u) {
+                const int row = row0 + u;
+                n_valid[u] = 0; q0[u] = 0;
+                f[u][0] = f[u][1] = -INFINITY;
+                if (row < nrows) {
+                    const int hw = s_hw[row];
+                    const long long zz = z + row / side - r, yy = y + row % side - r;
+                    if (hw >= 0 && zz >= 0 && zz < d.Z && yy >= 0 && yy < d.Y) {
+                        const long long x0 = x - hw < 0 ? 0 : x - hw;
+                        const long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
+                        n_valid[u] = (int)(x1 - x0 + 1);
+                        q0[u] = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
+                        if (lane < n_valid[u]) f[u][0] = __ldg(v + q0[u] + lane);
+                        if (lane + 32 < n_valid[u]) f[u][1] = __ldg(v + q0[u] + lane + 32);
+                    }
+                }
             }
+            bool hit = false;
+#pragma unroll
+            for (int u = 0; u < kRowsPerStep; ++u)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float vq = f[u][h];
+                    if (vq >= val && lane + 32 * h < n_valid[u]) {
+                        const unsigned long long q = q0[u] + lane + 32 * h;
+                        if ((vq > val || q < idx) && !is_suppressed(sup, q)) hit = true;
+                    }
+                }
             if (__any_sync(0xffffffffu, hit)) { if (lane == 0) found = 1; }
         }
         __syncthreads();
@@ -636,7 +688,7 @@ static int check_params(const fpl_v2o_params *p, int64_t Z, int64_t Y, int64_t X
     FPL_REQUIRE(p != nullptr, "voxel2obj: params is NULL");
     FPL_REQUIRE(Z > 0 && Y > 0 && X > 0, "voxel2obj: empty volume (%lld,%lld,%lld)", (long long)Z,
                 (long long)Y, (long long)X);
-    FPL_REQUIRE(p->obj_min_dist >= 0, "voxel2obj: obj_min_dist must be >= 0");
+    FPL_REQUIRE(p->obj_min_dist >= 0 && p->obj_min_dist <= 64, "voxel2obj: obj_min_dist must be in 0..64");
     FPL_REQUIRE(p->lw >= -1 && p->lw <= kMaxLw, "voxel2obj: Gaussian half width %d unsupported (max %d)",
                 p->lw, kMaxLw);
     FPL_REQUIRE(p->lw < 0 || p->h_weights != nullptr, "voxel2obj: weights missing");
@@ -679,7 +731,7 @@ static int select_rank(fpl_ctx *ctx, const float *d_v, long long n, unsigned lon
     for (int pass = 0; pass < 3; ++pass) {
         select_hist_kernel<<<blocks, 512, 0, st>>>(d_v, n, d_state, shifts[pass], bins[pass], pass == 0);
         FPL_LAUNCH_CHECK(ctx);
-        select_scan_kernel<<<1, 32, 0, st>>>(d_state, shifts[pass], bins[pass]);
+        select_scan_kernel<<<1, 1024, 0, st>>>(d_state, shifts[pass], bins[pass]);
         FPL_LAUNCH_CHECK(ctx);
     }
     return FPL_OK;
@@ -791,7 +843,7 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
         nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_smooth, B.sup, d, a_idx, a_val, b_idx,
                                                             b_val, B.w_idx, B.w_val, cand_cap, B.cnt);
         FPL_LAUNCH_CHECK(ctx);
-        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.w_idx, B.w_val,
+        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, (size_t)(2 * r + 1) * (2 * r + 1) * sizeof(short), st>>>(d_smooth, B.sup, d, r, B.w_idx, B.w_val,
                                                                B.det_idx, B.det_val, B.sel_idx, det_cap,
                                                                B.cnt);
         FPL_LAUNCH_CHECK(ctx);
