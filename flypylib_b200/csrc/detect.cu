@@ -83,10 +83,10 @@ __global__ void gauss_generic_kernel(const float *__restrict__ in, float *__rest
 // (every source value is converted to double once per run).
 // ------------------------------------------------------------------------------------------------
 constexpr int kLines = 64;
-constexpr int kGroups = 4;
+constexpr int kGroups = 2;          // 128-thread blocks: more, finer-grained blocks per SM overlap load and FP64 phases
 constexpr int kRun = 8;
 constexpr int kRunsPerThread = 4;
-constexpr int kTN = kGroups * kRunsPerThread * kRun;   // 128 outputs along the axis per block
+constexpr int kTN = kGroups * kRunsPerThread * kRun;   // 64 outputs along the axis per block
 
 template <int LW>
 __device__ __forceinline__ void run_from_window(const double (&x)[kRun + 2 * LW], const Taps &taps,

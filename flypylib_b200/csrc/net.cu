@@ -361,7 +361,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         // the previous call's list may still be in use by queued kernels of the same stream: ordered copy
         FPL_CUDA_CHECK(cudaMemcpyAsync(d_ids, rest.data(), rest.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         FPL_CUDA_CHECK(cudaStreamSynchronize(st));     // `rest` is pageable host memory
-        phases.push_back({g, (long long)rest.size(), net->precision == FPL_PREC_FP32 ? 4 : 8, d_ids, 0});
+        phases.push_back({g, (long long)rest.size(), net->precision == FPL_PREC_FP32 ? 4 : 32, d_ids, 0});
     }
     size_t need_in = 0, need_out = 0;
     for (Phase &ph : phases) {
