@@ -142,7 +142,7 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(arch, n_tiles=3, v2o_edge=224):
+def cpu_baseline(arch, n_tiles=24, v2o_edge=320):
     """Oracle (CPU port of the reference path) on a bounded sample of the same workload:
     n_tiles reference tiles through the torch-CPU restatement of the Keras graph (all host threads) +
     voxel2obj (C restatement, OpenMP Gaussian + sorted greedy) on a v2o_edge^3 crop."""
@@ -182,7 +182,7 @@ def run_reference(args):
     for i in range(args.warmup + args.steps):
         if i < args.warmup and i > 0:
             continue                        # one warm-up pass is enough for a CPU library path
-        last = cpu_baseline(args.model, n_tiles=2, v2o_edge=192)
+        last = cpu_baseline(args.model, n_tiles=16, v2o_edge=288)
         if i >= args.warmup:
             vals.append(last["value"])
     v = float(np.mean(vals)) if vals else last["value"]

@@ -116,9 +116,33 @@ gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long
     const float *src = in + o * n * inner;
     float *dst = out + o * n * inner;
     const bool live = i < inner;
-    for (int row = ty; row < kTN + 2 * LW; row += kGroups) {
-        long long q = line_src(n0 - LW + row, n, r);
-        tile[row][tx] = (live && q >= 0) ? __ldg(src + q * inner + i) : 0.f;
+    {
+        // stage the (kTN + 2 LW) x 64 source tile: loads are issued in batches of kBatch rows before any is
+        // stored, so that kBatch global loads per thread are in flight (the pass is latency bound otherwise)
+        constexpr int kRowsT = (kTN + 2 * LW + kGroups - 1) / kGroups;
+        constexpr int kBatch = 14;
+        // no reflection can occur when the tile (with halo) stays inside the zero-padded line
+        const bool simple = (n0 - LW + r >= 0) && (n0 + kTN + LW - 1 < n + r);
+#pragma unroll 1
+        for (int b0 = 0; b0 < kRowsT; b0 += kBatch) {
+            float tmp[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int row = ty + (b0 + b) * kGroups;
+                float vv = 0.f;
+                if (b0 + b < kRowsT && row < kTN + 2 * LW && live) {
+                    const long long p = n0 - LW + row;
+                    const long long q = simple ? ((p >= 0 && p < n) ? p : -1) : line_src(p, n, r);
+                    if (q >= 0) vv = __ldg(src + q * inner + i);
+                }
+                tmp[b] = vv;
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int row = ty + (b0 + b) * kGroups;
+                if (b0 + b < kRowsT && row < kTN + 2 * LW) tile[row][tx] = tmp[b];
+            }
+        }
     }
     __syncthreads();
 #pragma unroll 1
@@ -153,12 +177,37 @@ gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long 
     const long long n0 = (long long)(blockIdx.x % nchunks) * kTN;
     const long long row0 = (long long)(blockIdx.x / nchunks) * kLines;
     constexpr int kW = kTN + 2 * LW;
-    for (int idx = tid; idx < kLines * kW; idx += kLines * kGroups) {
-        int rr = idx / kW, xx = idx - rr * kW;
-        long long q = line_src(n0 - LW + xx, n, r);
-        float v = 0.f;
-        if (row0 + rr < rows && q >= 0) v = __ldg(in + (row0 + rr) * n + q);
-        tile[xx * kPitch + rr] = v;
+    {
+        // thread -> (row group, x lane): each warp reads 32 consecutive x of one row (coalesced); loads are
+        // batched (kBatch in flight per thread) before the transposed stores
+        constexpr int kThreadsB = kLines * kGroups;
+        constexpr int kXL = 32;                              // x lanes
+        constexpr int kRG = kThreadsB / kXL;                 // rows handled concurrently
+        constexpr int kXSteps = (kW + kXL - 1) / kXL;
+        constexpr int kBatch = 8;
+        const int xl = tid % kXL, rg = tid / kXL;
+        const bool simple = (n0 - LW + r >= 0) && (n0 + kTN + LW - 1 < n + r);
+#pragma unroll 1
+        for (int rr0 = rg; rr0 < kLines; rr0 += kRG * kBatch) {
+#pragma unroll 1
+            for (int xs = 0; xs < kXSteps; ++xs) {
+                const int xx = xs * kXL + xl;
+                const long long p = n0 - LW + xx;
+                long long q = -1;
+                if (xx < kW) q = simple ? ((p >= 0 && p < n) ? p : -1) : line_src(p, n, r);
+                float tmp[kBatch];
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const int rr = rr0 + b * kRG;
+                    tmp[b] = (rr < kLines && row0 + rr < rows && q >= 0) ? __ldg(in + (row0 + rr) * n + q) : 0.f;
+                }
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) {
+                    const int rr = rr0 + b * kRG;
+                    if (rr < kLines && xx < kW) tile[xx * kPitch + rr] = tmp[b];
+                }
+            }
+        }
     }
     __syncthreads();
     float res[kRunsPerThread][kRun];

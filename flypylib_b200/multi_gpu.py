@@ -68,28 +68,38 @@ def merge_detections(parts):
     return {'locs': rows[:, :3].copy(), 'conf': rows[:, 3].copy()}
 
 
+def slab_detections(pred_slab_fn, Z, rank, world, obj_min_dist, smoothing_sigma, buffer_sz, thd=0):
+    """Detections rank `rank` of `world` owns under the substack semantics of full_roi_inference
+    (flypylib/fplobjdetect.py:841-986, :1031-1034): slab [z0,z1) of the volume, extended by buffer_sz planes on
+    each side, is an independent voxel2obj (own percentile, own greedy NMS); detections outside [z0,z1) are
+    dropped (the reference drops the buffer zone, fplobjdetect.py:239-250).  pred_slab_fn(lo, hi) returns the
+    CUDA float32 probability map of planes [lo,hi).  Returns (K,4) float64 rows (x,y,z,conf), z global."""
+    from . import fplobjdetect
+    z0, z1 = partition_layers(Z, world)[rank]
+    if z1 <= z0:
+        return np.zeros((0, 4))
+    lo, hi = max(0, z0 - buffer_sz), min(Z, z1 + buffer_sz)
+    out = fplobjdetect.voxel2obj_device(pred_slab_fn(lo, hi), obj_min_dist, smoothing_sigma, (0, 0, lo), 0, thd)
+    rows = np.concatenate([out['locs'], out['conf'][:, None]], 1)
+    return rows[(rows[:, 2] >= z0) & (rows[:, 2] < z1)]
+
+
 def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigma, buffer_sz, thd=0,
                      group=None):
-    """Reference substack semantics (full_roi_inference, fplobjdetect.py:841-986) over z-slabs: the volume
-    is cut into world_size slabs along z, each extended by buffer_sz (>= obj_min_dist) planes; every rank
-    runs infer + voxel2obj on its slab independently (own percentile, own NMS) and drops detections in the
-    buffer zone; the lists are all-gathered.  Returns the merged dict on every rank."""
+    """z-slab sharded T-bar detection on the ranks of `group` (one process per GPU): every rank runs
+    infer + voxel2obj on its slab (+ buffer) with no communication, then the per-slab detection lists are
+    all-gathered (NCCL) -- the only collective of the path.  Returns the merged dict on every rank."""
     import torch
     import torch.distributed as dist
-    from . import fplobjdetect
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     Z = int(image_dev.shape[0])
-    cuts = partition_layers(Z, world)
-    z0, z1 = cuts[rank]
-    lo, hi = max(0, z0 - buffer_sz), min(Z, z1 + buffer_sz)
-    sub = image_dev[lo:hi].contiguous()
-    pred = network.infer_device(sub, normalize=normalize)
-    out = fplobjdetect.voxel2obj_device(pred, obj_min_dist, smoothing_sigma, (0, 0, lo), 0, thd)
-    rows = np.concatenate([out['locs'], out['conf'][:, None]], 1)
-    keep = (rows[:, 2] >= z0) & (rows[:, 2] < z1)          # own slab only: the buffer belongs to neighbours
-    rows = rows[keep]
+
+    def pred_slab(lo, hi):
+        return network.infer_device(image_dev[lo:hi].contiguous(), normalize=normalize)
+
+    rows = slab_detections(pred_slab, Z, rank, world, obj_min_dist, smoothing_sigma, buffer_sz, thd)
     if world == 1:
         return merge_detections([rows])
-    parts = allgather_detections(torch.from_numpy(rows).to(image_dev.device), group)
+    parts = allgather_detections(torch.from_numpy(np.ascontiguousarray(rows)).to(image_dev.device), group)
     return merge_detections([p.cpu().numpy() for p in parts])

@@ -119,3 +119,26 @@ def test_large_volume_properties():
     assert len(pairs) == 0
     lo = out["locs"].min(0); hi = out["locs"].max(0)
     assert np.all(lo >= 30) and np.all(hi < 512 - 30)
+
+
+def test_slab_sharded_detection_matches_reference_substack_semantics():
+    """N>1 detection path (emulated ranks on one GPU): per-slab voxel2obj with a buffer, detections in the
+    buffer dropped, lists merged == the same procedure carried out with the oracle (reference function
+    restated) on every slab.  This is full_roi_inference's substack semantics (fplobjdetect.py:841-986)."""
+    import torch
+    from flypylib_b200 import multi_gpu
+    pm = cases.prob_map((200, 120, 110), 31, "uniform")
+    d = torch.from_numpy(pm).cuda()
+    world, r, sigma, buf = 3, 12, 2.0, 16
+    parts, want_parts = [], []
+    for rank in range(world):
+        parts.append(multi_gpu.slab_detections(lambda lo, hi: d[lo:hi].contiguous(), 200, rank, world, r, sigma, buf))
+        z0, z1 = multi_gpu.partition_layers(200, world)[rank]
+        lo, hi = max(0, z0 - buf), min(200, z1 + buf)
+        o = O.voxel2obj(pm[lo:hi], r, sigma, (0, 0, lo), 0, 0, impl="c")
+        rows = np.concatenate([o["locs"], o["conf"][:, None]], 1)
+        want_parts.append(rows[(rows[:, 2] >= z0) & (rows[:, 2] < z1)])
+    got = multi_gpu.merge_detections(parts)
+    want = multi_gpu.merge_detections(want_parts)
+    assert got["conf"].size > 20
+    assert np.array_equal(got["locs"], want["locs"]) and np.array_equal(got["conf"], want["conf"])
