@@ -329,10 +329,21 @@ select_hist_kernel(const float *__restrict__ v, long long n, SelectState *s, int
             else { if (run) atomicAdd(&h[last_bin], run); last_bin = b; run = 1; }
         }
     };
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-         i += (long long)gridDim.x * blockDim.x) {
-        float4 q = __ldg(v4 + i);
-        feed(q.x); feed(q.y); feed(q.z); feed(q.w);
+    {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n4; i += 4 * stride) {      // four 16-byte loads in flight per thread
+            const float4 q0 = __ldg(v4 + i), q1 = __ldg(v4 + i + stride), q2 = __ldg(v4 + i + 2 * stride),
+                         q3 = __ldg(v4 + i + 3 * stride);
+            feed(q0.x); feed(q0.y); feed(q0.z); feed(q0.w);
+            feed(q1.x); feed(q1.y); feed(q1.z); feed(q1.w);
+            feed(q2.x); feed(q2.y); feed(q2.z); feed(q2.w);
+            feed(q3.x); feed(q3.y); feed(q3.z); feed(q3.w);
+        }
+        for (; i < n4; i += stride) {
+            const float4 q = __ldg(v4 + i);
+            feed(q.x); feed(q.y); feed(q.z); feed(q.w);
+        }
     }
     // tail
     for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -427,36 +438,65 @@ struct Counters {                       // device
     unsigned long long pad;
 };
 
+// every thread takes 8 consecutive voxels (two 16-byte loads in flight), a warp reserves its output
+// range with one atomic; candidate order in the list is irrelevant to the result
 __global__ void __launch_bounds__(256)
 compact_candidates_kernel(const float *__restrict__ v, long long n, double thresh,
                           unsigned long long *cand_idx, float *cand_val, long long capacity,
                           Counters *cnt) {
-    __shared__ unsigned block_count;
-    __shared__ unsigned long long block_base;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += stride) {
-        long long i = i0 + threadIdx.x;
-        if (threadIdx.x == 0) block_count = 0;
+    const unsigned lane = threadIdx.x & 31;
+    const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    const long long n8 = (n + 7) / 8;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c - threadIdx.x < n8;
+         c += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = c * 8;
+        float f[8];
+        if (c < n8 && aligned && i0 + 8 <= n) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4 *>(v + i0));
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(v + i0) + 1);
+            f[0] = a4.x; f[1] = a4.y; f[2] = a4.z; f[3] = a4.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (c < n8 && i0 + j < n) ? __ldg(v + i0 + j) : 0.f;
+        }
+        unsigned mask = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (((double)f[j] > thresh) && (f[j] > 0.f)) mask |= 1u << j;
+        const unsigned cnt_me = __popc(mask);
+        // exclusive prefix over the warp
+        unsigned pre = cnt_me;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= (unsigned)o) pre += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
+        // one global atomic per block iteration (2048 voxels): warp totals -> shared -> block base
+        __shared__ unsigned s_wtot[8];
+        __shared__ unsigned long long s_base;
+        const unsigned wid = threadIdx.x >> 5;
+        if (lane == 31) s_wtot[wid] = total;
         __syncthreads();
-        float f = 0.f; bool is_c = false;
-        if (i < n) { f = __ldg(v + i); is_c = ((double)f > thresh) && (f > 0.f); }
-        unsigned ballot = __ballot_sync(0xffffffffu, is_c);
-        unsigned lane = threadIdx.x & 31;
-        unsigned warp_off = 0;
-        if (ballot) {
-            if (lane == 0) warp_off = atomicAdd(&block_count, __popc(ballot));
-            warp_off = __shfl_sync(0xffffffffu, warp_off, 0);
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += s_wtot[k];
+            s_base = t ? atomicAdd(&cnt->n_cand, (unsigned long long)t) : 0ULL;
         }
         __syncthreads();
-        if (threadIdx.x == 0 && block_count)
-            block_base = atomicAdd(&cnt->n_cand, (unsigned long long)block_count);
+        unsigned wbefore = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if ((unsigned)k < wid) wbefore += s_wtot[k];
+        unsigned long long pos = s_base + wbefore + (pre - cnt_me);
         __syncthreads();
-        if (is_c) {
-            unsigned long long pos = block_base + warp_off + __popc(ballot & ((1u << lane) - 1u));
-            if ((long long)pos < capacity) { cand_idx[pos] = (unsigned long long)i; cand_val[pos] = f; }
-            else atomicAdd(&cnt->overflow, 1ULL);
-        }
-        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (mask & (1u << j)) {
+                if ((long long)pos < capacity) { cand_idx[pos] = (unsigned long long)(i0 + j); cand_val[pos] = f[j]; }
+                else atomicAdd(&cnt->overflow, 1ULL);
+                ++pos;
+            }
     }
 }
 
@@ -464,6 +504,19 @@ compact_candidates_kernel(const float *__restrict__ v, long long n, double thres
 // NMS rounds
 // ------------------------------------------------------------------------------------------------
 struct Dims { long long Z, Y, X; };
+
+// flat index -> (z,y,x); 32-bit arithmetic whenever the volume has fewer than 2^32 voxels
+__device__ __forceinline__ void decode_idx(unsigned long long idx, const Dims &d, long long &z, long long &y, long long &x) {
+    if ((unsigned long long)d.Z * d.Y * d.X <= 0xffffffffULL) {
+        const unsigned i = (unsigned)idx, X = (unsigned)d.X, Y = (unsigned)d.Y;
+        const unsigned row = i / X;
+        x = i - row * X; z = row / Y; y = row - (unsigned)z * Y;
+    } else {
+        x = (long long)(idx % (unsigned long long)d.X);
+        y = (long long)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        z = (long long)(idx / ((unsigned long long)d.X * d.Y));
+    }
+}
 
 __device__ __forceinline__ bool is_suppressed(const unsigned *sup, unsigned long long idx) {
     return (sup[idx >> 5] >> (idx & 31)) & 1u;
@@ -487,9 +540,8 @@ nms_filter_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup,
             alive = !is_suppressed(sup, idx);
         }
         if (alive) {
-            long long x = (long long)(idx % (unsigned long long)d.X);
-            long long y = (long long)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
-            long long z = (long long)(idx / ((unsigned long long)d.X * d.Y));
+            long long x, y, z;
+            decode_idx(idx, d, z, y, x);
             bool better = false;
             for (int dz = -1; dz <= 1 && !better; ++dz) {
                 long long zz = z + dz; if (zz < 0 || zz >= d.Z) continue;
@@ -537,69 +589,113 @@ __device__ __forceinline__ int isqrt_floor(int v) {
     return s;
 }
 
+// ---- brick maxima: G[bz][by][bx] = max of the smoothed map over an 8^3 brick (validity-agnostic) -----
+constexpr int kBrick = 8;
+__global__ void __launch_bounds__(256)
+brick_max_kernel(const float *__restrict__ v, Dims d, int gy, int gx, float *__restrict__ g) {
+    // one block per (bz, by) brick row.  Warp w owns 8 of the 64 (z,y) rows; a lane owns one brick
+    // (8 consecutive x) per 256-wide chunk and keeps all its 8 rows' loads in flight.
+    extern __shared__ float s_max[];                 // [gx]
+    const int bz = blockIdx.x / gy, by = blockIdx.x % gy;
+    for (int i = threadIdx.x; i < gx; i += blockDim.x) s_max[i] = -INFINITY;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec_ok = (d.X % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    for (long long xc = 0; xc < d.X; xc += 256) {
+        const long long x = xc + 8 * lane;
+        float m = -INFINITY;
+        if (x < d.X) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = warp + 8 * k;
+                const long long z = (long long)bz * kBrick + row / kBrick, y = (long long)by * kBrick + row % kBrick;
+                if (z >= d.Z || y >= d.Y) continue;
+                const float *rp = v + (z * d.Y + y) * d.X + x;
+                if (vec_ok && x + 8 <= d.X) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(rp));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+                    m = fmaxf(m, fmaxf(fmaxf(fmaxf(a4.x, a4.y), fmaxf(a4.z, a4.w)), fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w))));
+                } else {
+                    for (int e = 0; e < 8 && x + e < d.X; ++e) m = fmaxf(m, __ldg(rp + e));
+                }
+            }
+            // float max via integer atomics on the monotone key of non-negative values
+            atomicMax(reinterpret_cast<int *>(&s_max[x / kBrick]), m >= 0.f ? __float_as_int(m) : (int)0x80000000);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < gx; i += blockDim.x) g[((size_t)bz * gy + by) * gx + i] = s_max[i];
+}
+
 // one block per worklist entry: is there a better valid voxel inside the ball (d2 <= r^2)?
-// Rows (dz,dy) of the ball are x-runs of half width hw(dz,dy) (table in shared memory); every warp
-// takes kRowsPerStep rows at a time and issues all their loads before testing any (the scan is a
-// pure latency problem: ~82 k coalesced 4-byte reads per entry, almost all of them "not better").
-constexpr int kRowsPerStep = 4;
+// A voxel better than p has value >= S(p), so it can only sit in a brick whose maximum is >= S(p).
+// Phase 1 lists those bricks (of the <= 8^3 bricks touching the ball; the brick grid is a few MB and
+// stays in L2); phase 2 scans only the listed bricks densely, testing distance, order and validity.
+// For an isolated peak the list is empty apart from its own blob.  Exactness does not depend on the
+// grid ignoring validity: it only over-approximates the set of bricks to scan.
 __global__ void __launch_bounds__(256)
 nms_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d, int r,
+                     const float *__restrict__ g, int gz, int gy, int gx,
                      const unsigned long long *__restrict__ w_idx, const float *__restrict__ w_val,
                      unsigned long long *det_idx, float *det_val, unsigned long long *sel_idx,
                      long long det_capacity, Counters *cnt) {
-    extern __shared__ short s_hw[];                 // (2r+1)^2 half widths, -1 outside the ball
-    __shared__ int found;
+    __shared__ int s_list[1024];
+    __shared__ int s_n, found;
     const unsigned long long nW = cnt->n_work;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int side = 2 * r + 1, nrows = side * side;
-    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
-        const int dz = i / side - r, dy = i % side - r;
-        const int rem = r * r - dz * dz - dy * dy;
-        s_hw[i] = rem < 0 ? (short)-1 : (short)isqrt_floor(rem);
-    }
-    __syncthreads();
+    const int r2 = r * r;
     for (unsigned long long w = blockIdx.x; w < nW; w += gridDim.x) {
-        if (threadIdx.x == 0) found = 0;
+        if (threadIdx.x == 0) { found = 0; s_n = 0; }
         __syncthreads();
         const unsigned long long idx = w_idx[w];
         const float val = w_val[w];
-        const long long x = (long long)(idx % (unsigned long long)d.X);
-        const long long y = (long long)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
-        const long long z = (long long)(idx / ((unsigned long long)d.X * d.Y));
-        for (int row0 = warp * kRowsPerStep; row0 < nrows; row0 += nwarps * kRowsPerStep) {
+        const int x = (int)(idx % (unsigned long long)d.X);
+        const int y = (int)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        const int z = (int)(idx / ((unsigned long long)d.X * d.Y));
+        const int bz0 = max(z - r, 0) / kBrick, bz1 = min((long long)z + r, d.Z - 1) / kBrick;
+        const int by0 = max(y - r, 0) / kBrick, by1 = min((long long)y + r, d.Y - 1) / kBrick;
+        const int bx0 = max(x - r, 0) / kBrick, bx1 = min((long long)x + r, d.X - 1) / kBrick;
+        const int nbz = bz1 - bz0 + 1, nby = by1 - by0 + 1, nbx = bx1 - bx0 + 1;
+        for (int i = threadIdx.x; i < nbz * nby * nbx; i += blockDim.x) {
+            const int bx = bx0 + i % nbx, by = by0 + (i / nbx) % nby, bz = bz0 + i / (nbx * nby);
+            const float gm = __ldg(g + ((size_t)bz * gy + by) * gx + bx);
+            if (!(gm >= val)) continue;
+            // closest point of the brick to p
+            const int cz = min(max(z, bz * kBrick), bz * kBrick + kBrick - 1);
+            const int cy = min(max(y, by * kBrick), by * kBrick + kBrick - 1);
+            const int cx = min(max(x, bx * kBrick), bx * kBrick + kBrick - 1);
+            const int dd = (cz - z) * (cz - z) + (cy - y) * (cy - y) + (cx - x) * (cx - x);
+            if (dd > r2) continue;
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < 1024) s_list[slot] = (bz << 20) | (by << 10) | bx;
+        }
+        __syncthreads();
+        const int nlist = min(s_n, 1024);           // <= 8^3 bricks can touch a ball of radius <= 27
+        for (int li = warp; li < nlist; li += nwarps) {
             if (*(volatile int *)&found) break;
-            float f[kRowsPerStep][2];
-            unsigned long long q0[kRowsPerStep];
-            int n_valid[kRowsPerStep];
+            const int code = s_list[li];
+            const int bz = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
+            bool hit = false;
+            // 64 rows of 8 voxels: lane -> rows (lane, lane + 32), 8 voxels each as two float4
 #pragma unroll
-            for (int u = 0; u < kRowsPerStep; ++u) {
-                const int row = row0 + u;
-                n_valid[u] = 0; q0[u] = 0;
-                f[u][0] = f[u][1] = -INFINITY;
-                if (row < nrows) {
-                    const int hw = s_hw[row];
-                    const long long zz = z + row / side - r, yy = y + row % side - r;
-                    if (hw >= 0 && zz >= 0 && zz < d.Z && yy >= 0 && yy < d.Y) {
-                        const long long x0 = x - hw < 0 ? 0 : x - hw;
-                        const long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
-                        n_valid[u] = (int)(x1 - x0 + 1);
-                        q0[u] = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
-                        if (lane < n_valid[u]) f[u][0] = __ldg(v + q0[u] + lane);
-                        if (lane + 32 < n_valid[u]) f[u][1] = __ldg(v + q0[u] + lane + 32);
-                    }
+            for (int h = 0; h < 2; ++h) {
+                const int row = lane + 32 * h;
+                const long long zz = (long long)bz * kBrick + row / kBrick, yy = (long long)by * kBrick + row % kBrick;
+                if (zz >= d.Z || yy >= d.Y) continue;
+                const int dzy = (int)((zz - z) * (zz - z) + (yy - y) * (yy - y));
+                if (dzy > r2) continue;
+                const unsigned long long rowbase = ((unsigned long long)zz * d.Y + yy) * d.X;
+#pragma unroll
+                for (int e = 0; e < kBrick; ++e) {
+                    const long long xx = (long long)bx * kBrick + e;
+                    if (xx >= d.X) break;
+                    const int ddx = (int)(xx - x);
+                    if (dzy + ddx * ddx > r2) continue;
+                    const unsigned long long q = rowbase + xx;
+                    const float vq = __ldg(v + q);
+                    if ((vq > val || (vq == val && q < idx)) && !is_suppressed(sup, q)) hit = true;
                 }
             }
-            bool hit = false;
-#pragma unroll
-            for (int u = 0; u < kRowsPerStep; ++u)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float vq = f[u][h];
-                    if (vq >= val && lane + 32 * h < n_valid[u]) {
-                        const unsigned long long q = q0[u] + lane + 32 * h;
-                        if ((vq > val || q < idx) && !is_suppressed(sup, q)) hit = true;
-                    }
-                }
             if (__any_sync(0xffffffffu, hit)) { if (lane == 0) found = 1; }
         }
         __syncthreads();
@@ -814,6 +910,7 @@ struct DetectBuffers {
     unsigned *skey;
     Counters *cnt;
     unsigned long long *n_out;
+    float *grid;                    // brick maxima
     long long cand_cap, work_cap, det_cap, sort_cap;
 };
 
@@ -829,6 +926,7 @@ static size_t detect_workspace_bytes(long long n, long long cand_cap, long long 
     long long sp = next_pow2(det_cap);
     add(sp * 4); add(sp * 8);
     add(sizeof(Counters)); add(64);
+    add(((size_t)n / 64 + 4 * (size_t)cbrt((double)n) * (size_t)cbrt((double)n) + 4096) * 4);   // brick grid (generous)
     return b + 4096;
 }
 
@@ -858,6 +956,9 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
     B.sidx = (unsigned long long *)A.take(sp * 8);
     B.cnt = (Counters *)A.take(sizeof(Counters));
     B.n_out = (unsigned long long *)A.take(64);
+    const int gz = (int)((Z + kBrick - 1) / kBrick), gy = (int)((Y + kBrick - 1) / kBrick), gx = (int)((X + kBrick - 1) / kBrick);
+    B.grid = (float *)A.take((size_t)gz * gy * gx * 4);
+    if (!B.grid) { fpl::set_error("voxel2obj: workspace too small for the brick grid"); return FPL_ENOMEM; }
     if (!B.sup || !B.a_idx || !B.b_idx || !B.a_val || !B.b_val || !B.w_idx || !B.w_val || !B.det_idx ||
         !B.det_val || !B.sel_idx || !B.skey || !B.sidx || !B.cnt || !B.n_out) {
         fpl::set_error("voxel2obj: internal workspace sizing error");
@@ -873,6 +974,9 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
                                                           cand_cap, B.cnt);
     FPL_LAUNCH_CHECK(ctx);
 
+    FPL_REQUIRE(gz < 2048 && gy < 1024 && gx < 1024 && r <= 27 + 4, "voxel2obj: volume / radius outside the brick-grid limits");
+    brick_max_kernel<<<gz * gy, 256, gx * sizeof(float), st>>>(d_smooth, d, gy, gx, B.grid);
+    FPL_LAUNCH_CHECK(ctx);
     Counters *h_cnt = (Counters *)ctx->h_pinned;
     FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     FPL_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -892,7 +996,7 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
         nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_smooth, B.sup, d, a_idx, a_val, b_idx,
                                                             b_val, B.w_idx, B.w_val, cand_cap, B.cnt);
         FPL_LAUNCH_CHECK(ctx);
-        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, (size_t)(2 * r + 1) * (2 * r + 1) * sizeof(short), st>>>(d_smooth, B.sup, d, r, B.w_idx, B.w_val,
+        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.grid, gz, gy, gx, B.w_idx, B.w_val,
                                                                B.det_idx, B.det_val, B.sel_idx, det_cap,
                                                                B.cnt);
         FPL_LAUNCH_CHECK(ctx);
