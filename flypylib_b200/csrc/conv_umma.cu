@@ -137,7 +137,8 @@ struct ConvArgs {
     const float *bias;               // folded BN bias of this split [cout]
     __nv_bfloat16 *out;              // (tile, cout_total/8, Dout, Dout, Dout, 8)  (pooled edge when pool)
     uint32_t w_bytes;
-    int n_tiles, din, dout;
+    int n_tiles, din, dout;          // x/y extent of the input / output tensors
+    int din_z, dout_z;               // z extent (tiles may be z-slabs: full xy extent, limited z)
     int cin_atoms_total;             // Cin / 8 of the input tensor
     int nsub;                        // input channels are consumed in nsub sub-planes of 2*KSTEPS atoms each
     int cout;                        // output channels of this launch (N of the MMA)
@@ -175,11 +176,11 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t (&r)[16], int c0
 
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane, int cout, const float *s_bias,
                                               int relu, __nv_bfloat16 *__restrict__ out, int tile, int dout, int z,
-                                              int y0, int x0, int cout_total, int cout_off) {
+                                              int y0, int x0, int cout_total, int cout_off, int dout_z) {
     const int row = q * 32 + lane;
     const int y = y0 + (row >> 3), x = x0 + (row & 7);
     const bool ok = (x < dout) && (y < dout);
-    const size_t cg_stride = (size_t)dout * dout * dout;
+    const size_t cg_stride = (size_t)dout_z * dout * dout;
     const size_t vox = ((size_t)tile * (cout_total >> 3) + (cout_off >> 3)) * cg_stride + ((size_t)z * dout + y) * dout + x;
     const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16);
     uint32_t ra[16], rb[16];
@@ -207,7 +208,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, int q, int lane
 template <int NCH>
 __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int lane, const float *s_bias, int relu,
                                                    __nv_bfloat16 *__restrict__ out, int tile, int dpool, int z,
-                                                   int y0, int x0, float (&hold)[NCH * 4]) {
+                                                   int y0, int x0, float (&hold)[NCH * 4], int dpool_z) {
     const int row = q * 32 + lane;
     const int y = y0 + (row >> 3), x = x0 + (row & 7);
     const bool ok = (x < 2 * dpool) && (y < 2 * dpool);
@@ -217,7 +218,7 @@ __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int
 #pragma unroll
     for (int c = 0; c < NCH; ++c) tmem_ld16(tcol + (uint32_t)(c * 16), r[c]);
     tmem_ld_wait();
-    const size_t cg_stride = (size_t)dpool * dpool * dpool;
+    const size_t cg_stride = (size_t)dpool_z * dpool * dpool;
     const size_t vox = (size_t)tile * (NCH * 2) * cg_stride + ((size_t)(z >> 1) * dpool + (y >> 1)) * dpool + (x >> 1);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -326,7 +327,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
-            const int nz = min(a.zc_len, a.dout - z0);
+            const int nz = min(a.zc_len, a.dout_z - z0);
             const int np = nz + KS - 1;
             for (int p = 0; p < np; ++p)
                 for (int sub = 0; sub < nsub; ++sub, ++pc) {
@@ -355,7 +356,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
             const int z0 = zc * a.zc_len;
-            const int nz = min(a.zc_len, a.dout - z0);
+            const int nz = min(a.zc_len, a.dout_z - z0);
             const int np = nz + KS - 1;
 #pragma unroll 1
             for (int ip = 0; ip < np; ++ip) {
@@ -444,7 +445,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
-            const int nz = min(a.zc_len, a.dout - z0);
+            const int nz = min(a.zc_len, a.dout_z - z0);
             for (int zo = 0; zo < nz; ++zo, ++A) {
                 const uint32_t bl = nblk - 1u - (A % nblk), ph = (A / nblk) & 1u;
                 mbar_wait(&acc_full[bl], ph);
@@ -453,16 +454,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                 if (a.pool) {
                     if (a.cout == 48)
                         epilogue_tile_pool<3>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * TX + m * 8, reinterpret_cast<float(&)[12]>(hold));
+                                              xt * TX + m * 8, reinterpret_cast<float(&)[12]>(hold), a.dout_z >> 1);
                     else if (a.cout == 32)
                         epilogue_tile_pool<2>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * TX + m * 8, reinterpret_cast<float(&)[8]>(hold));
+                                              xt * TX + m * 8, reinterpret_cast<float(&)[8]>(hold), a.dout_z >> 1);
                     else
                         epilogue_tile_pool<4>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
-                                              xt * TX + m * 8, hold);
+                                              xt * TX + m * 8, hold, a.dout_z >> 1);
                 } else
                 epilogue_tile(tacc, q, lane, a.cout, s_bias, a.relu, a.out, tile,
-                              a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.cout_total, a.cout_off);
+                              a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.cout_total, a.cout_off, a.dout_z);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[bl]);
@@ -487,7 +488,8 @@ struct FirstArgs {
     const __nv_bfloat16 *w_packed;   // [2 ksteps][2][Cout][8]; taps 0..26 = kernel*BN scale, 27/28 = bias hi/lo
     const float *bias;               // unused by the kernel (bias rides in K slots 27/28)
     __nv_bfloat16 *out;
-    int n_tiles, din, dout, cout;
+    int n_tiles, din, dout, cout;    // din/dout: x/y extent
+    int din_z, dout_z;               // z extent
     int n_xt, n_yt, n_zc, zc_len;
     uint32_t tmem_cols;
     VolumeIO vio;                    // vio.img != nullptr: read the tile from the volume instead of `in`
@@ -561,7 +563,7 @@ conv_first_umma_kernel(const FirstArgs a) {
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
-            const int nz = min(a.zc_len, a.dout - zc * a.zc_len);
+            const int nz = min(a.zc_len, a.dout_z - zc * a.zc_len);
             for (int zo = 0; zo < nz; ++zo, ++ac) {
                 const uint32_t st = ac % kSt, ph = (ac / kSt) & 1u;
                 mbar_wait(&acc_empty[st], ph ^ 1u);
@@ -588,7 +590,7 @@ conv_first_umma_kernel(const FirstArgs a) {
         const int q = warp & 3;
         const int m = (warp - 1) >> 2;
         const int row = q * 32 + lane;
-        const size_t cg_stride = (size_t)a.dout * a.dout * a.dout;
+        const size_t cg_stride = (size_t)a.dout_z * a.dout * a.dout;
         uint32_t ac = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
@@ -598,7 +600,7 @@ conv_first_umma_kernel(const FirstArgs a) {
             const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
-            const int nz = min(a.zc_len, a.dout - z0);
+            const int nz = min(a.zc_len, a.dout_z - z0);
             const int y = yt * kTY + (row >> 3), x = xt * kTX + m * 8 + (row & 7);
             const bool ok = (x < a.dout) && (y < a.dout) && !(a.dbg & 2);
             const size_t vox0 = (size_t)tile * (a.cout >> 3) * cg_stride + ((size_t)z0 * a.dout + y) * a.dout + x;
@@ -643,7 +645,7 @@ conv_first_umma_kernel(const FirstArgs a) {
             const int zc = t % a.n_zc; t /= a.n_zc;
             const int tile = t;
             const int z0 = zc * a.zc_len;
-            const int nz = min(a.zc_len, a.dout - z0);
+            const int nz = min(a.zc_len, a.dout_z - z0);
             // source of this thread's (up to kPer) elements of every input plane: either the float32
             // tile batch or, with direct volume input, the volume itself at the tile origin of the
             // reference grid (fplnetwork.py:149-157; zero beyond the far edge; (x-mean)/std for uint8)
@@ -658,15 +660,15 @@ conv_first_umma_kernel(const FirstArgs a) {
                 const int tt = a.vio.ids ? a.vio.ids[a.vio.tile0 + tile] : a.vio.tile0 + tile;
                 ox = (long long)(tt % a.vio.g.nx) * a.vio.g.out_sz;
                 oy = (long long)((tt / a.vio.g.nx) % a.vio.g.ny) * a.vio.g.out_sz;
-                z_org = (long long)(tt / (a.vio.g.nx * a.vio.g.ny)) * a.vio.g.out_sz;
+                z_org = a.vio.g.z_base + (long long)(tt / (a.vio.g.nx * a.vio.g.ny)) * a.vio.g.out_z;
                 plane_stride = a.vio.g.Y * a.vio.g.X; row_stride = a.vio.g.X;
-                z_lim = a.vio.g.Z - z_org < a.din ? a.vio.g.Z - z_org : a.din;     // planes available
+                z_lim = a.vio.g.Z - z_org < a.din_z ? a.vio.g.Z - z_org : a.din_z;     // planes available
                 lim_y = a.vio.g.Y; lim_x = a.vio.g.X;
                 src8 = (const uint8_t *)a.vio.img; src32 = (const float *)a.vio.img;
             } else {
                 plane_stride = (long long)a.din * a.din; row_stride = a.din;
-                z_lim = a.din; lim_y = a.din; lim_x = a.din;
-                src32 = a.in + (size_t)tile * a.din * a.din * a.din;
+                z_lim = a.din_z; lim_y = a.din; lim_x = a.din;
+                src32 = a.in + (size_t)tile * a.din_z * a.din * a.din;
             }
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
@@ -817,16 +819,16 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 
 // MaxPooling3D((2,2,2)); one thread = one output atom (8 channels of one voxel)
 __global__ void __launch_bounds__(256)
-pool_blocked_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_cg_total, int din) {
-    const int dout = din / 2;
-    const long long total = n_cg_total * dout * dout * dout;
+pool_blocked_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_cg_total, int din, int din_z) {
+    const int dout = din / 2, dout_z = din_z / 2;
+    const long long total = n_cg_total * dout_z * dout * dout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long v = i;
         const int x = (int)(v % dout); v /= dout;
         const int y = (int)(v % dout); v /= dout;
-        const int z = (int)(v % dout); v /= dout;       // v = tile*CG + cg
-        const uint4 *ip = in + ((size_t)v * din + 2 * z) * din * din;
+        const int z = (int)(v % dout_z); v /= dout_z;   // v = tile*CG + cg
+        const uint4 *ip = in + ((size_t)v * din_z + 2 * z) * din * din;
         uint4 m = __ldg(ip + (size_t)(2 * y) * din + 2 * x);
         m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x + 1));
         m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x));
@@ -866,8 +868,8 @@ upcat_blocked_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *
 // final Conv3D(1,(1,1,1)) + sigmoid (+ nearest up-sampling by `stride`, fplnetwork.py:99-105) -> float32 tile
 __global__ void __launch_bounds__(256)
 final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, float bias, float *__restrict__ out,
-                     int n_tiles, int d, int cg_in, int stride, const VolumeIO vio) {
-    const long long vox = (long long)d * d * d;
+                     int n_tiles, int d, int cg_in, int stride, const VolumeIO vio, int d_z) {
+    const long long vox = (long long)d_z * d * d;
     const long long total = (long long)n_tiles * vox;
     const int dout = d * stride;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -893,19 +895,19 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
             const int tt = vio.ids ? vio.ids[vio.tile0 + t] : vio.tile0 + t;
             const long long bx = (long long)(tt % g.nx) * g.out_sz + g.off + (long long)x * stride;
             const long long by = (long long)((tt / g.nx) % g.ny) * g.out_sz + g.off + (long long)y * stride;
-            const long long bz = (long long)(tt / (g.nx * g.ny)) * g.out_sz + g.off + (long long)z * stride;
-            for (int dz = 0; dz < stride; ++dz)
-                for (int dy = 0; dy < stride; ++dy)
-                    for (int dx = 0; dx < stride; ++dx)
-                        if (bz + dz < g.Z - g.off && by + dy < g.Y - g.off && bx + dx < g.X - g.off)
-                            vio.pred[((bz + dz) * g.Y + (by + dy)) * g.X + bx + dx] = pr;
+            const long long bz = g.z_base + (long long)(tt / (g.nx * g.ny)) * g.out_z + g.off + (long long)z * stride;
+            for (int ez = 0; ez < stride; ++ez)
+                for (int ey = 0; ey < stride; ++ey)
+                    for (int ex = 0; ex < stride; ++ex)
+                        if (bz + ez < g.Z - g.off && by + ey < g.Y - g.off && bx + ex < g.X - g.off)
+                            vio.pred[((bz + ez) * g.Y + (by + ey)) * g.X + bx + ex] = pr;
             continue;
         }
-        float *op = out + (size_t)t * dout * dout * dout;
-        for (int dz = 0; dz < stride; ++dz)
-            for (int dy = 0; dy < stride; ++dy)
-                for (int dx = 0; dx < stride; ++dx)
-                    op[((size_t)(z * stride + dz) * dout + (y * stride + dy)) * dout + (x * stride + dx)] = pr;
+        float *op = out + (size_t)t * ((size_t)d_z * stride) * dout * dout;
+        for (int ez = 0; ez < stride; ++ez)
+            for (int ey = 0; ey < stride; ++ey)
+                for (int ex = 0; ex < stride; ++ex)
+                    op[((size_t)(z * stride + ez) * dout + (y * stride + ey)) * dout + (x * stride + ex)] = pr;
     }
 }
 
@@ -1090,18 +1092,18 @@ void free_packed_umma(fpl_net *net) {
 }
 
 static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
-                            int n_tiles, int din, int relu, int pool, cudaStream_t st) {
+                            int n_tiles, int din, int din_z, int relu, int pool, cudaStream_t st) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
     const ConvPlan plan = plan_conv(c);
     FPL_REQUIRE(plan.ok, "conv_umma: no plan for k=%d Cin=%d Cout=%d", c.k, c.cin, c.cout);
     FPL_REQUIRE(!pool || (plan.n_split == 1 && plan.tx == 16), "conv_umma: pooled epilogue needs an unsplit 16-wide plan");
-    const int ks = c.k, dout = din - (ks - 1);
+    const int ks = c.k, dout = din - (ks - 1), dout_z = din_z - (ks - 1);
     const int sx = plan.tx + ks - 1, sy = kTY + ks - 1;
     const int cin_atoms = c.cin / 8;
     CUtensorMap tmap;
-    cuuint64_t gdim[4] = {(cuuint64_t)din * 8, (cuuint64_t)din, (cuuint64_t)din, (cuuint64_t)n_tiles * cin_atoms};
-    cuuint64_t gstride[3] = {(cuuint64_t)din * 16, (cuuint64_t)din * din * 16, (cuuint64_t)din * din * din * 16};
+    cuuint64_t gdim[4] = {(cuuint64_t)din * 8, (cuuint64_t)din, (cuuint64_t)din_z, (cuuint64_t)n_tiles * cin_atoms};
+    cuuint64_t gstride[3] = {(cuuint64_t)din * 16, (cuuint64_t)din * din * 16, (cuuint64_t)din * din * din_z * 16};
     cuuint32_t box[4] = {(cuuint32_t)sx * 8, (cuuint32_t)sy, 1, (cuuint32_t)(2 * plan.ksteps)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, gdim, gstride, box, estr,
@@ -1111,24 +1113,24 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     ConvArgs a;
     a.out = out;
     a.w_bytes = (uint32_t)(c.packed_bytes / plan.n_split);
-    a.n_tiles = n_tiles; a.din = din; a.dout = dout;
+    a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.din_z = din_z; a.dout_z = dout_z;
     a.cin_atoms_total = cin_atoms; a.nsub = plan.nsub; a.cout = plan.n; a.cout_total = c.cout; a.ring = plan.ring;
     a.n_xt = (dout + plan.tx - 1) / plan.tx; a.n_yt = (dout + kTY - 1) / kTY;
     // z chunking: aim for >= 4 work items per SM so the persistent CTAs stay balanced
     const long long base_items = (long long)n_tiles * a.n_xt * a.n_yt;
     int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
     if (n_zc < 1) n_zc = 1;
-    int zc_len = (dout + n_zc - 1) / n_zc;
-    if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
+    int zc_len = (dout_z + n_zc - 1) / n_zc;
+    if (zc_len < 8) zc_len = dout_z < 8 ? dout_z : 8;
     if (pool && (zc_len & 1)) ++zc_len;              // z pairs must not straddle work items
-    a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
+    a.zc_len = zc_len; a.n_zc = (dout_z + zc_len - 1) / zc_len;
     a.relu = relu;
     a.pool = pool;
     a.tmem_cols = 512;
     const size_t smem = plan.smem;
     const long long n_items = base_items * a.n_zc;
     ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
-                   2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
+                   2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout_z * dout * dout);
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
     for (int g = 0; g < plan.n_split; ++g) {
         a.w_packed = (const __nv_bfloat16 *)((const uint8_t *)c.d_packed + (size_t)g * a.w_bytes);
@@ -1174,90 +1176,83 @@ static int launch_conv_direct(fpl_ctx *ctx, const ConvParams &c, const __nv_bflo
     return FPL_OK;
 }
 
-// activation buffer pool (device), grow-only, owned by the net
-struct ActPool {
-    static constexpr int kBufs = 4;
-    void *buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-    size_t cap = 0;
-};
-static ActPool g_pool;       // one process = one GPU (one rank per device)
+// activation buffer pool (device): exact-size buffers, best fit, grow-only; one process = one GPU
+struct PoolBuf { void *p; size_t cap; bool busy; };
+static std::vector<PoolBuf> g_bufs;
 
-static int pool_reserve(size_t bytes) {
-    if (bytes <= g_pool.cap) return FPL_OK;
-    for (int i = 0; i < ActPool::kBufs; ++i) { if (g_pool.buf[i]) cudaFree(g_pool.buf[i]); g_pool.buf[i] = nullptr; }
-    g_pool.cap = 0;
-    for (int i = 0; i < ActPool::kBufs; ++i) {
-        cudaError_t e = cudaMalloc(&g_pool.buf[i], bytes);
+static int pool_take(size_t bytes, cudaStream_t st) {
+    int best = -1;
+    for (size_t i = 0; i < g_bufs.size(); ++i)
+        if (!g_bufs[i].busy && g_bufs[i].cap >= bytes && (best < 0 || g_bufs[i].cap < g_bufs[best].cap)) best = (int)i;
+    if (best < 0) {
+        cudaStreamSynchronize(st);
+        // drop idle buffers that are too small to be useful again before growing
+        void *p = nullptr;
+        const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            set_error("forward_umma: activation pool allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-            return FPL_ENOMEM;
+            for (size_t i = 0; i < g_bufs.size();)       // release every idle buffer and retry once
+                if (!g_bufs[i].busy) { cudaFree(g_bufs[i].p); g_bufs.erase(g_bufs.begin() + i); } else ++i;
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("forward_umma: activation buffer of %zu bytes: %s", want, cudaGetErrorString(e));
+                return -1;
+            }
         }
+        g_bufs.push_back(PoolBuf{p, want, false});
+        best = (int)g_bufs.size() - 1;
     }
-    g_pool.cap = bytes;
-    return FPL_OK;
+    g_bufs[best].busy = true;
+    return best;
 }
 
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
-                 const VolumeIO *vio) {
+                 const VolumeIO *vio, int in_z) {
     fpl_ctx *ctx = net->ctx;
     if (net->precision != FPL_PREC_BF16) {
         set_error("forward_umma: only the bf16 tcgen05 path is built (precision %d requested)", net->precision);
         return FPL_ESTATE;
     }
-    // size the pool: largest activation tensor of the batch
-    size_t max_bytes = 0;
-    {
-        int d = in_sz, c = 1, sc[4] = {0, 0, 0, 0};
-        for (const Op &o : net->ops) {
-            if (o.kind == OP_CONV) { d -= o.k - 1; c = o.cout; }
-            else if (o.kind == OP_POOL) d /= 2;
-            else if (o.kind == OP_SAVE) sc[o.slot] = c;
-            else if (o.kind == OP_UPCAT) { d *= 2; c += sc[o.slot]; }
-            size_t b = (size_t)n_tiles * d * d * d * c * 2;
-            if (b > max_bytes) max_bytes = b;
-        }
-    }
-    if (max_bytes > g_pool.cap) {
-        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-        FPL_TRY(pool_reserve(max_bytes + 4096));
-    }
-    bool busy[ActPool::kBufs] = {false, false, false, false};
-    auto take = [&]() { for (int i = 0; i < ActPool::kBufs; ++i) if (!busy[i]) { busy[i] = true; return i; } return -1; };
-    int cur = -1;                 // buffer index holding the current activation (-1: the fp32 input tiles)
+    if (in_z <= 0) in_z = in_sz;
+    for (PoolBuf &b : g_bufs) b.busy = false;
+    auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
+    int cur = -1;                 // pool buffer holding the current activation (-1: the fp32 input tiles)
     int skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
     bool cur_is_skip = false;
-    int d = in_sz, c = 1;
+    int d = in_sz, dzv = in_z, c = 1;          // x/y extent, z extent, channels of the current activation
     const int stream_blocks = ctx->sm_count * 8;
     bool skip_next_pool = false;
     for (size_t oi = 0; oi < net->ops.size(); ++oi) {
         const Op &o = net->ops[oi];
         if (o.kind == OP_CONV) {
             const ConvParams &cp = net->convs[o.conv_index];
+            const int dout = d - (o.k - 1), dout_z = dzv - (o.k - 1);
             // MaxPooling3D directly after this conv (and the conv output not kept as a skip): fuse it
             const bool fuse_pool = !g_force_direct && !g_no_pool_fusion && cp.cin != 1 && umma_supported(cp) && cp.k == 3 &&
                                    (cp.cout == 32 || cp.cout == 48 || cp.cout == 64) && oi + 1 < net->ops.size() &&
-                                   net->ops[oi + 1].kind == OP_POOL && ((d - (o.k - 1)) % 2 == 0) &&
+                                   net->ops[oi + 1].kind == OP_POOL && (dout % 2 == 0) && (dout_z % 2 == 0) &&
                                    plan_conv(cp).n_split == 1 && plan_conv(cp).tx == 16;
-            const int nb = take();
-            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
-            __nv_bfloat16 *dst = (__nv_bfloat16 *)g_pool.buf[nb];
+            const size_t out_bytes = fuse_pool ? (size_t)n_tiles * (dout_z / 2) * (dout / 2) * (dout / 2) * cp.cout * 2
+                                               : (size_t)n_tiles * dout_z * dout * dout * cp.cout * 2;
+            const int nb = pool_take(out_bytes, st);
+            if (nb < 0) return FPL_ENOMEM;
+            __nv_bfloat16 *dst = (__nv_bfloat16 *)g_bufs[nb].p;
             if (cp.cin == 1) {
-                const int dout = d - 2;
-                const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
-                FPL_REQUIRE(cp.k == 3 && blocks < 2147483647LL, "forward_umma: unsupported first layer");
-                ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
+                FPL_REQUIRE(cp.k == 3, "forward_umma: unsupported first layer");
+                ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout_z * dout * dout);
                 if (!g_force_direct && cp.d_packed && cp.cout % 16 == 0 && cp.cout <= 64) {
                     FirstArgs fa;
                     fa.in = d_tiles; fa.w_packed = (const __nv_bfloat16 *)cp.d_packed; fa.bias = cp.d_bias; fa.out = dst;
-                    fa.n_tiles = n_tiles; fa.din = d; fa.dout = dout; fa.cout = cp.cout;
+                    fa.n_tiles = n_tiles; fa.din = d; fa.dout = dout; fa.din_z = dzv; fa.dout_z = dout_z; fa.cout = cp.cout;
                     fa.n_xt = (dout + kTX - 1) / kTX; fa.n_yt = (dout + kTY - 1) / kTY;
                     const long long base_items = (long long)n_tiles * fa.n_xt * fa.n_yt;
                     int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
                     if (n_zc < 1) n_zc = 1;
-                    int zc_len = (dout + n_zc - 1) / n_zc;
-                    if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
-                    fa.zc_len = zc_len; fa.n_zc = (dout + zc_len - 1) / zc_len;
+                    int zc_len = (dout_z + n_zc - 1) / n_zc;
+                    if (zc_len < 8) zc_len = dout_z < 8 ? dout_z : 8;
+                    fa.zc_len = zc_len; fa.n_zc = (dout_z + zc_len - 1) / zc_len;
                     const int acc_cols = 4 * 2 * cp.cout;       // kSt stages x 2 M-tiles
                     fa.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
                     if (vio) fa.vio = *vio;
@@ -1268,58 +1263,64 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                     FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_first_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                         (int)first_smem));
                     conv_first_umma_kernel<<<grid, kFirstThreads, first_smem, st>>>(fa);
-                } else if (vio && vio->img) {
-                    set_error("forward_umma: direct volume input needs the tensor-core first layer");
-                    return FPL_ESTATE;
-                } else if (cp.cout == 48)
-                    conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
-                else if (cp.cout == 32)
-                    conv_first_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
-                else { set_error("forward_umma: first layer Cout %d unsupported", cp.cout); return FPL_EINVAL; }
+                } else {
+                    const long long blocks = (long long)n_tiles * dout * dout * ((dout + 127) / 128);
+                    FPL_REQUIRE(!(vio && vio->img), "forward_umma: direct volume input needs the tensor-core first layer");
+                    FPL_REQUIRE(dzv == d && blocks < 2147483647LL, "forward_umma: CUDA-core first layer handles cubic tiles only");
+                    if (cp.cout == 48)
+                        conv_first_kernel<48><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
+                    else if (cp.cout == 32)
+                        conv_first_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
+                    else { set_error("forward_umma: first layer Cout %d unsupported", cp.cout); return FPL_EINVAL; }
+                }
                 FPL_LAUNCH_CHECK(ctx);
             } else {
-                const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_pool.buf[cur];
+                const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_bufs[cur].p;
                 if (umma_supported(cp) && !g_force_direct)
-                    FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, 1, fuse_pool ? 1 : 0, st));
-                else FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, 1, st));
+                    FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, dzv, 1, fuse_pool ? 1 : 0, st));
+                else {
+                    FPL_REQUIRE(dzv == d, "forward_umma: CUDA-core convolution handles cubic tiles only");
+                    FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, 1, st));
+                }
             }
-            if (cur >= 0 && !cur_is_skip) busy[cur] = false;
+            if (!cur_is_skip) release(cur);
             cur = nb; cur_is_skip = false;
-            d -= o.k - 1; c = o.cout;
-            if (fuse_pool) { d /= 2; skip_next_pool = true; }
+            d = dout; dzv = dout_z; c = o.cout;
+            if (fuse_pool) { d /= 2; dzv /= 2; skip_next_pool = true; }
         } else if (o.kind == OP_POOL) {
             if (skip_next_pool) { skip_next_pool = false; continue; }
-            const int nb = take();
-            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
-            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * c * 2.0 * d * d * d * 1.125);
-            pool_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], (uint4 *)g_pool.buf[nb],
-                                                              (long long)n_tiles * (c / 8), d);
+            const int nb = pool_take((size_t)n_tiles * (dzv / 2) * (d / 2) * (d / 2) * c * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * c * 2.0 * dzv * d * d * 1.125);
+            pool_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, (uint4 *)g_bufs[nb].p,
+                                                              (long long)n_tiles * (c / 8), d, dzv);
             FPL_LAUNCH_CHECK(ctx);
-            if (!cur_is_skip) busy[cur] = false;
+            if (!cur_is_skip) release(cur);
             cur = nb; cur_is_skip = false;
-            d /= 2;
+            d /= 2; dzv /= 2;
         } else if (o.kind == OP_SAVE) {
             skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_c[o.slot] = c;
             cur_is_skip = true;
         } else if (o.kind == OP_UPCAT) {
-            const int nb = take();
-            if (nb < 0) { set_error("forward_umma: activation pool exhausted"); return FPL_ESTATE; }
+            FPL_REQUIRE(dzv == d, "forward_umma: the U-Net runs on cubic tiles");
+            const int nb = pool_take((size_t)n_tiles * 8 * d * d * d * (c + skip_c[o.slot]) * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * (c + skip_c[o.slot]) * 2.0 * 8.0 * d * d * d * 2);
-            upcat_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], d, c / 8,
-                                                               (const uint4 *)g_pool.buf[skip_buf[o.slot]],
+            upcat_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, d, c / 8,
+                                                               (const uint4 *)g_bufs[skip_buf[o.slot]].p,
                                                                skip_d[o.slot], skip_c[o.slot] / 8, o.crop,
-                                                               (uint4 *)g_pool.buf[nb], n_tiles);
+                                                               (uint4 *)g_bufs[nb].p, n_tiles);
             FPL_LAUNCH_CHECK(ctx);
-            if (!cur_is_skip) busy[cur] = false;
-            busy[skip_buf[o.slot]] = false;
+            if (!cur_is_skip) release(cur);
+            release(skip_buf[o.slot]);
             cur = nb; cur_is_skip = false;
-            d *= 2; c += skip_c[o.slot];
+            d *= 2; dzv *= 2; c += skip_c[o.slot];
         } else if (o.kind == OP_FINAL) {
             const ConvParams &cp = net->convs[o.conv_index];
-            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * d * d * d * (c * 2.0 + 4.0 * net->info.rf_stride * net->info.rf_stride * net->info.rf_stride));
-            final_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_pool.buf[cur], cp.d_kernel, cp.bias[0],
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * dzv * d * d * (c * 2.0 + 4.0 * net->info.rf_stride * net->info.rf_stride * net->info.rf_stride));
+            final_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, cp.d_kernel, cp.bias[0],
                                                                d_out, n_tiles, d, c / 8, net->info.rf_stride,
-                                                               vio ? *vio : VolumeIO());
+                                                               vio ? *vio : VolumeIO(), dzv);
             FPL_LAUNCH_CHECK(ctx);
         }
     }

@@ -90,14 +90,14 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 gather_tiles_kernel(const T *__restrict__ img, float *__restrict__ tiles, TileGrid g, int tile0,
                     int n_tiles, float mean, float stdv, const int *__restrict__ tile_ids) {
-    const long long rows = (long long)n_tiles * g.in_sz * g.in_sz;
+    const long long rows = (long long)n_tiles * g.in_z * g.in_sz;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int y = (int)(row % g.in_sz);
-        const int z = (int)((row / g.in_sz) % g.in_sz);
-        const int t = (int)(row / ((long long)g.in_sz * g.in_sz));
+        const int z = (int)((row / g.in_sz) % g.in_z);
+        const int t = (int)(row / ((long long)g.in_sz * g.in_z));
         const int tt = tile_ids ? tile_ids[tile0 + t] : tile0 + t;
         const int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
-        const long long gz = (long long)kz * g.out_sz + z, gy = (long long)ky * g.out_sz + y;
+        const long long gz = g.z_base + (long long)kz * g.out_z + z, gy = (long long)ky * g.out_sz + y;
         const long long gx0 = (long long)kx * g.out_sz;
         float *dst = tiles + row * g.in_sz;
         const bool row_ok = gz < g.Z && gy < g.Y;
@@ -118,14 +118,14 @@ gather_tiles_kernel(const T *__restrict__ img, float *__restrict__ tiles, TileGr
 __global__ void __launch_bounds__(128)
 scatter_tiles_kernel(const float *__restrict__ outs, float *__restrict__ pred, TileGrid g, int tile0,
                      int n_tiles, const int *__restrict__ tile_ids) {
-    const long long rows = (long long)n_tiles * g.out_sz * g.out_sz;
+    const long long rows = (long long)n_tiles * g.out_z * g.out_sz;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int y = (int)(row % g.out_sz);
-        const int z = (int)((row / g.out_sz) % g.out_sz);
-        const int t = (int)(row / ((long long)g.out_sz * g.out_sz));
+        const int z = (int)((row / g.out_sz) % g.out_z);
+        const int t = (int)(row / ((long long)g.out_sz * g.out_z));
         const int tt = tile_ids ? tile_ids[tile0 + t] : tile0 + t;
         const int kx = tt % g.nx, ky = (tt / g.nx) % g.ny, kz = tt / (g.nx * g.ny);
-        const long long gz = (long long)kz * g.out_sz + g.off + z, gy = (long long)ky * g.out_sz + g.off + y;
+        const long long gz = g.z_base + (long long)kz * g.out_z + g.off + z, gy = (long long)ky * g.out_sz + g.off + y;
         const long long gx0 = (long long)kx * g.out_sz + g.off;
         if (gz >= g.Z - g.off || gy >= g.Y - g.off) continue;
         const float *src = outs + row * g.out_sz;
@@ -147,11 +147,13 @@ static int tiles_along(long long size, int off, int out_sz) {
 
 using namespace fpl::net;
 
+static int g_no_slab_mode = 0;   // test hook: keep cubic super-tiles on the tcgen05 path
 static int g_no_direct_io = 0;   // test hook: stage tiles through gather/scatter kernels on the tcgen05 path too
 
 extern "C" {
 
 int fpl_debug_no_direct_io(int on) { g_no_direct_io = on; return FPL_OK; }
+int fpl_debug_no_slab_mode(int on) { g_no_slab_mode = on; return FPL_OK; }
 
 
 int fpl_net_create(fpl_ctx *ctx, int arch, fpl_net **out) {
@@ -303,6 +305,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     g.off = off;
     g.out_sz = ref_out;                     // reference grid; super-tiles are scheduled below
     g.in_sz = g.out_sz + 2 * off;
+    g.in_z = g.in_sz; g.out_z = g.out_sz; g.z_base = 0;
     g.Z = Z; g.Y = Y; g.X = X;
     g.nz = tiles_along(Z, off, g.out_sz);
     g.ny = tiles_along(Y, off, g.out_sz);
@@ -325,17 +328,46 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     // gather, so every voxel gets exactly the value the reference tile would give it -- with less
     // halo recomputation.  Phase 2: the reference tiles not covered by super-tiles.
     const int m = net->tile_mult;
-    const int nsz = m > 1 ? (ze - zb) / m : 0, nsy = m > 1 ? g.ny / m : 0, nsx = m > 1 ? g.nx / m : 0;
+    struct Phase { TileGrid grid; long long n; int batch; const int *ids; int first; };
+    std::vector<Phase> phases;
+    // z-slab mode (tcgen05 path, VGG, m > 1): one tile spans the full x/y extent of the volume (no
+    // halo recomputation in x and y at all) and m reference tile layers in z; the remaining layers form
+    // one thinner slab.  Used when the x/y tile counts are similar and the largest activation of a slab
+    // (first conv output, 96 B per voxel) fits comfortably in HBM.
+    bool slab_mode = false;
+    if (m > 1 && net->precision != FPL_PREC_FP32 && zb == 0 && ze == g.nz && !g_no_slab_mode) {
+        const int nxy = g.ny > g.nx ? g.ny : g.nx, nmin = g.ny < g.nx ? g.ny : g.nx;
+        int mz = m < g.nz ? m : g.nz;
+        const double xy_bytes = 96.0 * ((double)nxy * g.out_sz + 2 * off) * ((double)nxy * g.out_sz + 2 * off);
+        while (mz > 1 && xy_bytes * (mz * g.out_sz + 2 * off) > 48e9) --mz;
+        if (nxy > 0 && nmin * 5 >= nxy * 4 && xy_bytes * (mz * g.out_sz + 2 * off) <= 48e9) {
+            slab_mode = true;
+            TileGrid gs = g;
+            gs.out_sz = nxy * g.out_sz; gs.in_sz = gs.out_sz + 2 * off;
+            gs.ny = gs.nx = 1;
+            const int n_full = g.nz / mz, rem = g.nz % mz;
+            if (n_full > 0) {
+                gs.out_z = mz * g.out_sz; gs.in_z = gs.out_z + 2 * off; gs.nz = n_full; gs.z_base = 0;
+                phases.push_back({gs, (long long)n_full, 1, nullptr, 0});
+            }
+            if (rem > 0) {
+                gs.out_z = rem * g.out_sz; gs.in_z = gs.out_z + 2 * off; gs.nz = 1;
+                gs.z_base = (long long)n_full * mz * g.out_sz;
+                phases.push_back({gs, 1, 1, nullptr, 0});
+            }
+        }
+    }
+    const int nsz = (m > 1 && !slab_mode) ? (ze - zb) / m : 0, nsy = (m > 1 && !slab_mode) ? g.ny / m : 0,
+              nsx = (m > 1 && !slab_mode) ? g.nx / m : 0;
     const bool have_super = nsz > 0 && nsy > 0 && nsx > 0;
     std::vector<int> rest;
+    if (!slab_mode)
     for (int kz = zb; kz < ze; ++kz)
         for (int ky = 0; ky < g.ny; ++ky)
             for (int kx = 0; kx < g.nx; ++kx) {
                 const bool in_super = have_super && (kz - zb) < nsz * m && ky < nsy * m && kx < nsx * m;
                 if (!in_super) rest.push_back((kz * g.ny + ky) * g.nx + kx);
             }
-    struct Phase { TileGrid grid; long long n; int batch; const int *ids; int first; };
-    std::vector<Phase> phases;
     int *d_ids = nullptr;
     if (!rest.empty()) {
         if (net->tile_ids_cap < rest.size()) {
@@ -350,6 +382,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     if (have_super) {
         TileGrid gs = g;
         gs.out_sz = g.out_sz * m; gs.in_sz = gs.out_sz + 2 * off;
+        gs.out_z = gs.out_sz; gs.in_z = gs.in_sz;
         gs.nz = nsz; gs.ny = nsy; gs.nx = nsx;
         FPL_REQUIRE(zb == 0, "tile multiplier > 1 cannot be combined with a z tile range");
         FPL_REQUIRE(out_size(net, gs.in_sz) == gs.out_sz, "internal: super-tile edge %d invalid", gs.in_sz);
@@ -366,8 +399,9 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     size_t need_in = 0, need_out = 0;
     for (Phase &ph : phases) {
         if (ph.batch > ph.n) ph.batch = (int)ph.n;
-        size_t ie = (size_t)ph.grid.in_sz * ph.grid.in_sz * ph.grid.in_sz * ph.batch;
-        size_t oe = (size_t)ph.grid.out_sz * ph.grid.out_sz * ph.grid.out_sz * ph.batch;
+        size_t ie = (size_t)ph.grid.in_z * ph.grid.in_sz * ph.grid.in_sz * ph.batch;
+        size_t oe = (size_t)ph.grid.out_z * ph.grid.out_sz * ph.grid.out_sz * ph.batch;
+        if (net->precision != FPL_PREC_FP32 && !g_no_direct_io) oe = 1;      // the final layer scatters directly
         if (ie > need_in) need_in = ie;
         if (oe > need_out) need_out = oe;
     }
@@ -385,7 +419,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     const int blocks = ctx->sm_count * 16;
     for (const Phase &ph : phases) {
         const TileGrid &tg = ph.grid;
-        const size_t in_elems = (size_t)tg.in_sz * tg.in_sz * tg.in_sz, out_elems = (size_t)tg.out_sz * tg.out_sz * tg.out_sz;
+        const size_t in_elems = (size_t)tg.in_z * tg.in_sz * tg.in_sz, out_elems = (size_t)tg.out_z * tg.out_sz * tg.out_sz;
         for (long long t0 = 0; t0 < ph.n && rc == FPL_OK; t0 += ph.batch) {
             const int nb = (int)((ph.n - t0) < ph.batch ? (ph.n - t0) : ph.batch);
             // tcgen05 path: the final layer scatters straight into the prediction volume; the input
@@ -406,8 +440,8 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
             else if (fused_scatter) {
                 VolumeIO vio;
                 vio.g = tg; vio.tile0 = (int)t0; vio.ids = ph.ids; vio.pred = d_pred;
-                rc = forward_umma(net, d_in, nb, tg.in_sz, nullptr, st, &vio);
-            } else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st);
+                rc = forward_umma(net, d_in, nb, tg.in_sz, nullptr, st, &vio, tg.in_z);
+            } else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st, nullptr, tg.in_z);
             if (rc != FPL_OK) break;
             if (!fused_scatter) {
                 fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);

@@ -35,7 +35,9 @@ struct ConvParams {                 // host copies (Keras order) + folded device
 // edge, (x-mean)/std for uint8) and the final layer scatters straight into the prediction volume.
 struct TileGrid {
     int nz, ny, nx;          // tiles per axis
-    int in_sz, out_sz, off;  // tile input edge, useful output edge (= stride of origins), rf_offset
+    int in_sz, out_sz, off;  // x/y: tile input edge, useful output edge (= stride of origins), rf_offset
+    int in_z, out_z;         // z: the same for the z axis (z-slab tiles have a different z extent)
+    long long z_base;        // z origin of tile layer 0 of this grid
     long long Z, Y, X;
 };
 struct VolumeIO {
@@ -76,7 +78,7 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                  cudaStream_t st);
 // tcgen05 path (conv_umma.cu)
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out,
-                 cudaStream_t st, const VolumeIO *vio = nullptr);
+                 cudaStream_t st, const VolumeIO *vio = nullptr, int in_z = 0);   // in_z = 0: cubic tiles
 int pack_weights_umma(fpl_net *net);
 void free_packed_umma(fpl_net *net);
 // output edge of a tile for input edge in_sz (after the x rf_stride up-sampling); -1 if invalid

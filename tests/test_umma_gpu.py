@@ -60,9 +60,20 @@ def test_super_tiles_equal_reference_grid(precision):
     got = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
     assert np.array_equal(ref, got)
     if precision == "bf16":
+        # m = 2, 3 above/below run as z-slab tiles (full x/y extent); also keep the cubic super-tile schedule
         net.tile_multiplier = 3
         got3 = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
         assert np.array_equal(ref, got3)
+        from flypylib_b200 import _lib
+        lib = _lib.lib()
+        lib.fpl_debug_no_slab_mode.argtypes = [ctypes.c_int]
+        lib.fpl_debug_no_slab_mode(1)
+        try:
+            net.tile_multiplier = 2
+            got2c = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+        finally:
+            lib.fpl_debug_no_slab_mode(0)
+        assert np.array_equal(ref, got2c)
 
 
 def test_fused_pool_epilogue_is_bit_identical():
