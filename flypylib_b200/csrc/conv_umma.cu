@@ -147,6 +147,7 @@ struct ConvArgs {
     int n_xt, n_yt, n_zc, zc_len;
     int relu;
     int pool;                        // fuse MaxPooling3D(2): `out` is the pooled tensor (edge dout/2)
+    int max_blk;                     // cap on accumulator blocks per M-tile region (0: 256/cout)
     uint32_t tmem_cols;
 };
 
@@ -289,7 +290,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
     const uint32_t N = (uint32_t)a.cout;
-    const uint32_t nblk = 256u / N > (uint32_t)kMaxBlocks ? (uint32_t)kMaxBlocks : 256u / N;
+    uint32_t nblk_ = 256u / N > (uint32_t)kMaxBlocks ? (uint32_t)kMaxBlocks : 256u / N;
+    if (a.max_blk > 0 && (uint32_t)a.max_blk < nblk_) nblk_ = (uint32_t)a.max_blk;
+    const uint32_t nblk = nblk_;
     const int nsub = a.nsub;
 
     if (threadIdx.x == 0) {
@@ -911,6 +914,424 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused first + second convolution (VGG: Conv3D(1->C1,3^3)+BN+ReLU -> Conv3D(C1->C2,3^3)+BN+ReLU
+// [+ MaxPooling3D]).  The first layer's output (96 B per voxel) is the largest tensor of the network;
+// here it never leaves the SM: for every z step the CTA computes the halo'd 18x18xC1 plane the second
+// convolution needs straight into the shared-memory plane ring (in the UMMA layout TMA would have
+// produced), on the tensor pipe, in the shadow of the second convolution's MMAs.
+//   warp 0        loads the packed second-layer weights (cp.async.bulk), resident for the CTA's lifetime
+//   warp 1        MMA issuer: first-layer MMAs (3 M-tiles x 2 K-steps per plane, K = 27 taps + bias slots)
+//                 two planes ahead of the kd-fused second-layer MMAs (as in conv_umma_kernel)
+//   warps 2..9    second-layer epilogue (bias, ReLU, optional fused max-pool, bf16 store)
+//   warps 10..13  builders: raw input planes -> ring; im2col rows of the 324 plane voxels -> A1 tiles
+//   warps 14..17  first-layer epilogue: TMEM -> ReLU -> bf16 -> plane ring slot, then signal plane_full
+// Arithmetic is identical to the two separate kernels (same MMA shapes, same K order, same rounding),
+// so the result is bit-identical to the unfused path.
+// TMEM: second-layer accumulators 2 M-tile regions x 3 blocks x C2 columns; first-layer tiles at 288 + 48 t.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 576;
+struct FusedArgs {
+    const float *in;                 // (tile, din_z, din, din) float32 raw tiles
+    const __nv_bfloat16 *w1_packed;  // first layer  [2][2][C1][8] (bias in K slots 27/28)
+    const __nv_bfloat16 *w2_packed;  // second layer operand-B image (kd-major chunks)
+    const float *bias2;
+    __nv_bfloat16 *out;              // second layer output (pooled when pool)
+    uint32_t w2_bytes;
+    int n_tiles, din, din_z;         // raw tile x/y and z extent
+    int dout, dout_z;                // second-layer output extents (din - 4)
+    int n_xt, n_yt, n_zc, zc_len;
+    int pool;
+    VolumeIO vio;
+};
+
+template <int C1, int C2>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+conv_fused12_kernel(const FusedArgs a) {
+    constexpr int KS = 3, KSTEPS = C1 / 16, TX = 16;
+    constexpr int SX = TX + 2, SY = kTY + 2;                       // first-layer plane the second conv reads
+    constexpr int NV = SY * SX;                                    // 324 plane voxels
+    constexpr int NT1 = (NV + 127) / 128;                          // 3 first-layer M-tiles
+    constexpr int RX = SX + 2, RY = SY + 2, RP = 20;               // raw plane 20 x 20, pitch 20 floats
+    constexpr int kRing = 4;
+    constexpr uint32_t atom_stride = NV * 16;
+    constexpr uint32_t plane_bytes = (C1 / 8) * atom_stride;
+    constexpr uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
+    constexpr uint32_t kA1Bytes = NT1 * 4 * 128 * 16;
+    constexpr uint32_t N = C2, NBLK = 3, kRegion = NBLK * N, kL1Col = 2 * kRegion;
+    static_assert(kL1Col + NT1 * C1 <= 512, "TMEM budget");
+    static_assert(RX <= RP && C1 % 16 == 0 && C2 % 16 == 0, "shape");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t w_region = (a.w2_bytes + 127u) & ~127u;
+    uint8_t *s_w2 = smem_raw;
+    uint8_t *s_planes = s_w2 + w_region;
+    uint8_t *s_a1 = s_planes + 2 * plane_pitch;
+    uint8_t *s_w1 = s_a1 + kA1Bytes;
+    float *s_rawp = reinterpret_cast<float *>(s_w1 + 2 * 2 * C1 * 16);
+    float *s_lut = s_rawp + kRing * RY * RP;
+    float *s_bias = s_lut + 256;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + 128);
+    uint64_t *w_full = bars;                 // [1]
+    uint64_t *plane_full = bars + 1;         // [2]  first-layer epilogue -> second-layer MMAs
+    uint64_t *plane_empty = bars + 3;        // [2]  second-layer MMAs done with the slot
+    uint64_t *a1_full = bars + 5;            // [1]  builders -> first-layer MMAs
+    uint64_t *a1_empty = bars + 6;           // [1]
+    uint64_t *l1_full = bars + 7;            // [3]  first-layer accumulator tiles
+    uint64_t *l1_empty = bars + 10;          // [3]
+    uint64_t *acc_full = bars + 13;          // [3]  second-layer accumulator blocks
+    uint64_t *acc_empty = bars + 16;         // [3]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&plane_full[i], 4); mbar_init(&plane_empty[i], 1); }
+        mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_w1)[i] = __ldg(reinterpret_cast<const uint4 *>(a.w1_packed) + i);
+    for (int i = threadIdx.x; i < (int)(kA1Bytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_a1)[i] = make_uint4(0, 0, 0, 0);          // rows >= 324 stay zero
+    for (int i = threadIdx.x; i < C2; i += blockDim.x) s_bias[i] = a.bias2[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = __fdiv_rn(__fsub_rn((float)i, a.vio.mean), a.vio.stdv);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== weight loader =====================================
+        if (elect_one()) {
+            mbar_expect_tx(w_full, a.w2_bytes);
+            for (uint32_t off = 0; off < a.w2_bytes; off += 32768u) {
+                uint32_t n = a.w2_bytes - off < 32768u ? a.w2_bytes - off : 32768u;
+                bulk_load_1d(s_w2 + off, reinterpret_cast<const uint8_t *>(a.w2_packed) + off, n, w_full);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        const bool leader = elect_one();
+        const uint32_t idesc_1 = make_idesc_bf16(128, (int)N);
+        const uint32_t idesc_l1 = make_idesc_bf16(128, C1);
+        const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
+        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * KS) << 16);
+        const uint32_t b_step16 = N * KS * 2u;
+        const uint32_t a1_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a1_lo0 = (smem_u32(s_a1) >> 4) | ((2048u >> 4) << 16);
+        const uint32_t b1_lo0 = (smem_u32(s_w1) >> 4) | ((uint32_t)C1 << 16);
+        mbar_wait(w_full, 0);
+        uint32_t pc1 = 0;          // first-layer planes issued
+        uint32_t pc2 = 0;          // second-layer planes issued
+        uint32_t ac0 = 0;
+        auto issue_l1 = [&]() {    // first-layer MMAs of plane pc1 (all three M-tiles)
+            mbar_wait(a1_full, pc1 & 1u);
+#pragma unroll 1
+            for (int t = 0; t < NT1; ++t) {
+                mbar_wait(&l1_empty[t], (pc1 & 1u) ^ 1u);
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+                        umma_bf16(tmem_base + kL1Col + (uint32_t)t * C1,
+                                  desc64(a1_lo0 + (uint32_t)t * (8192u >> 4) + s * (4096u >> 4), a1_hi),
+                                  desc64(b1_lo0 + s * (uint32_t)(C1 * 2), b_hi), idesc_l1, s ? 1u : 0u);
+                    umma_commit(&l1_full[t]);
+                }
+                __syncwarp();
+            }
+            if (leader) umma_commit(a1_empty);
+            __syncwarp();
+            ++pc1;
+        };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout_z - z0);
+            const int np = nz + KS - 1;
+            issue_l1();
+            issue_l1();                              // np >= 3 always
+#pragma unroll 1
+            for (int ip = 0; ip < np; ++ip, ++pc2) {
+                const uint32_t slot = pc2 & 1u, ph = (pc2 >> 1) & 1u;
+                const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
+                const int kd_hi = ip < KS - 1 ? ip : KS - 1;
+                const uint32_t L = (uint32_t)(kd_hi - kd_lo + 1);
+                const uint32_t r = (ac0 + (uint32_t)(ip - kd_lo)) % NBLK;
+                const uint32_t len0 = L < r + 1u ? L : r + 1u, len1 = L - len0;
+                const uint32_t blk0 = NBLK - 1u - r;
+                const uint32_t kd1 = (uint32_t)kd_lo + len0;
+                const uint32_t d_seg0 = tmem_base + blk0 * N, b_seg0 = (uint32_t)kd_lo * N;
+                const uint32_t d_seg1 = tmem_base, b_seg1 = kd1 * N;
+                const uint32_t i_seg0 = idesc_1 + ((((len0 - 1u) * N) >> 3) << 17);
+                const uint32_t i_seg1 = idesc_1 + (((((len1 ? len1 : 1u) - 1u) * N) >> 3) << 17);
+                if (kd_lo == 0) {
+                    const uint32_t A = ac0 + (uint32_t)ip;
+                    mbar_wait(&acc_empty[blk0], ((A / NBLK) & 1u) ^ 1u);
+                }
+                mbar_wait(&plane_full[slot], ph);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+#pragma unroll 1
+                    for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < KS; ++kw) {
+                            uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
+#pragma unroll
+                            for (int s = 0; s < KSTEPS; ++s) {
+                                const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
+                                const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
+                                if (kh == 0 && kw == 0 && s == 0) {
+#pragma unroll
+                                    for (int kd = 0; kd < KS; ++kd)
+                                        if (kd >= kd_lo && kd <= kd_hi) {
+                                            const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
+                                            const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
+                                            const uint32_t dcol = tmem_base + bl * N;
+                                            umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
+                                            umma_bf16(dcol + kRegion, ad1, bd, idesc_1, kd ? 1u : 0u);
+                                        }
+                                } else {
+                                    const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
+                                    umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
+                                    umma_bf16(d_seg0 + kRegion, ad1, bd0, i_seg0, 1u);
+                                    if (len1) {
+                                        const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
+                                        umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
+                                        umma_bf16(d_seg1 + kRegion, ad1, bd1, i_seg1, 1u);
+                                    }
+                                }
+                                b_lo += b_step16;
+                            }
+                        }
+                    umma_commit(&plane_empty[slot]);
+                    if (ip >= KS - 1) {
+                        const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
+                        umma_commit(&acc_full[NBLK - 1u - (A % NBLK)]);
+                    }
+                }
+                __syncwarp();
+                if (ip + 2 < np) issue_l1();          // first-layer plane ip+2 behind this plane's MMAs
+            }
+            ac0 += (uint32_t)nz;
+        }
+    } else if (warp < 10) {
+        // ===================================== second-layer epilogue =============================
+        const int q = warp & 3;
+        const int m = (warp - 2) >> 2;
+        uint32_t A = 0;
+        float hold[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hold[j] = 0.f;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout_z - z0);
+            for (int zo = 0; zo < nz; ++zo, ++A) {
+                const uint32_t bl = NBLK - 1u - (A % NBLK), ph = (A / NBLK) & 1u;
+                mbar_wait(&acc_full[bl], ph);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)m * kRegion + bl * N;
+                if (a.pool)
+                    epilogue_tile_pool<C2 / 16>(tacc, q, lane, s_bias, 1, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
+                                                xt * TX + m * 8, reinterpret_cast<float(&)[C2 / 4]>(hold), a.dout_z >> 1);
+                else
+                    epilogue_tile(tacc, q, lane, C2, s_bias, 1, a.out, tile, a.dout, z0 + zo, yt * kTY, xt * TX + m * 8,
+                                  C2, 0, a.dout_z);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[bl]);
+            }
+        }
+    } else if (warp < 14) {
+        // ===================================== builders ==========================================
+        // raw planes: (20 x 20) floats per z, ring of 4; per first-layer plane p the 27 taps of the 324 voxels
+        // (flat v = y1*18 + x1) are written as im2col rows of A1; a task = two x-adjacent voxels.
+        const int bt = threadIdx.x - 320;             // 0..127
+        constexpr int kPer = (RY * RX + 127) / 128;   // raw elements per thread and plane (4)
+        constexpr int kTasks = SY * (SX / 2);         // 162
+        uint32_t pc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int t = item;
+            const int xt = t % a.n_xt; t /= a.n_xt;
+            const int yt = t % a.n_yt; t /= a.n_yt;
+            const int zc = t % a.n_zc; t /= a.n_zc;
+            const int tile = t;
+            const int z0 = zc * a.zc_len;
+            const int nz = min(a.zc_len, a.dout_z - z0);
+            const int np = nz + KS - 1;                // first-layer planes of this item
+            const int nraw = np + 2;                   // raw planes z0 .. z0+np+1
+            long long plane_stride, z_lim, z_org = 0, ox = 0, oy = 0, lim_y, lim_x, row_stride;
+            const uint8_t *src8 = nullptr; const float *src32 = nullptr;
+            if (a.vio.img) {
+                const int tt = a.vio.ids ? a.vio.ids[a.vio.tile0 + tile] : a.vio.tile0 + tile;
+                ox = (long long)(tt % a.vio.g.nx) * a.vio.g.out_sz;
+                oy = (long long)((tt / a.vio.g.nx) % a.vio.g.ny) * a.vio.g.out_sz;
+                z_org = a.vio.g.z_base + (long long)(tt / (a.vio.g.nx * a.vio.g.ny)) * a.vio.g.out_z;
+                plane_stride = a.vio.g.Y * a.vio.g.X; row_stride = a.vio.g.X;
+                z_lim = a.vio.g.Z - z_org < a.din_z ? a.vio.g.Z - z_org : a.din_z;
+                lim_y = a.vio.g.Y; lim_x = a.vio.g.X;
+                src8 = (const uint8_t *)a.vio.img; src32 = (const float *)a.vio.img;
+            } else {
+                plane_stride = (long long)a.din * a.din; row_stride = a.din;
+                z_lim = a.din_z; lim_y = a.din; lim_x = a.din;
+                src32 = a.in + (size_t)tile * a.din_z * a.din * a.din;
+            }
+            long long eoff[kPer]; bool eok[kPer]; int edst[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int i = bt + k * 128;
+                const int yy = i / RX, xx = i - yy * RX;
+                const int gy = yt * kTY + yy, gx = xt * TX + xx;
+                eok[k] = i < RY * RX && gy < a.din && gx < a.din && oy + gy < lim_y && ox + gx < lim_x;
+                eoff[k] = (oy + gy) * row_stride + ox + gx;
+                edst[k] = yy * RP + xx;
+            }
+            const bool is_u8 = a.vio.img && a.vio.is_u8;
+            float preA[kPer], preB[kPer], preC[kPer];
+            auto fetch = [&](int zin, float (&pre)[kPer]) {
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    float v = 0.f;
+                    if (eok[k] && zin < z_lim && zin < z0 + nraw) {
+                        const long long o = (z_org + zin) * plane_stride + eoff[k];
+                        if (is_u8) v = s_lut[__ldg(src8 + o)];
+                        else v = __ldg(src32 + o);
+                    }
+                    pre[k] = v;
+                }
+            };
+            auto stash = [&](int zin, const float (&pre)[kPer]) {
+                float *dst = s_rawp + (zin % kRing) * RY * RP;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k)
+                    if (bt + k * 128 < RY * RX) dst[edst[k]] = pre[k];
+            };
+            fetch(z0, preA); stash(z0, preA);
+            fetch(z0 + 1, preA); stash(z0 + 1, preA);
+            fetch(z0 + 2, preA);
+            fetch(z0 + 3, preB);
+            fetch(z0 + 4, preC);
+            for (int p = 0; p < np; ++p, ++pc) {
+                stash(z0 + p + 2, preA);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) { preA[k] = preB[k]; preB[k] = preC[k]; }
+                fetch(z0 + p + 5, preC);
+                mbar_wait(a1_empty, (pc & 1u) ^ 1u);
+#pragma unroll 1
+                for (int task = bt; task < kTasks; task += 128) {
+                    const int y1 = task / (SX / 2), x1 = (task - y1 * (SX / 2)) * 2;
+                    float f[3][3][4];
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const float *pl = s_rawp + ((z0 + p + kd) % kRing) * RY * RP + y1 * RP + x1;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const float2 va = *reinterpret_cast<const float2 *>(pl + kh * RP);
+                            const float2 vb = *reinterpret_cast<const float2 *>(pl + kh * RP + 2);
+                            f[kd][kh][0] = va.x; f[kd][kh][1] = va.y; f[kd][kh][2] = vb.x; f[kd][kh][3] = vb.y;
+                        }
+                    }
+                    const int v0 = y1 * SX + x1;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int v = v0 + j;
+                        uint8_t *arow = s_a1 + (v >> 7) * 8192 + (v & 127) * 16;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                float pv[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int tp = 8 * k + 2 * e2 + u;
+                                    pv[u] = tp < 27 ? f[tp / 9][(tp / 3) % 3][j + tp % 3] : (tp < 29 ? 1.f : 0.f);
+                                }
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[0], pv[1]);
+                                pk[e2] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                            *reinterpret_cast<uint4 *>(arow + k * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a1_full);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // raw ring is free for the next item
+        }
+    } else {
+        // ===================================== first-layer epilogue ==============================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t pc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
+            const int nz = min(a.zc_len, a.dout_z - zc * a.zc_len);
+            const int np = nz + KS - 1;
+            for (int p = 0; p < np; ++p, ++pc) {
+                const uint32_t slot = pc & 1u, ph = (pc >> 1) & 1u;
+                mbar_wait(&plane_empty[slot], ph ^ 1u);          // second-layer MMAs are done with this slot
+                uint8_t *pl = s_planes + slot * plane_pitch;
+#pragma unroll 1
+                for (int t = 0; t < NT1; ++t) {
+                    mbar_wait(&l1_full[t], pc & 1u);
+                    tc_fence_after();
+                    const int v = t * 128 + row;
+                    const uint32_t tcol = tmem_base + kL1Col + (uint32_t)t * C1 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C1; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tcol + (uint32_t)c0, r);
+                        tmem_ld_wait();
+                        if (v < NV) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __nv_bfloat162 b2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(r[h * 8 + 2 * j]),
+                                                                                      __uint_as_float(r[h * 8 + 2 * j + 1])), zero);
+                                    pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+                                }
+                                *reinterpret_cast<uint4 *>(pl + (size_t)((c0 >> 3) + h) * atom_stride + (size_t)v * 16) =
+                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&l1_empty[t]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&plane_full[slot]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // Generic CUDA-core convolution on the blocked layout.  Used (a) for layers whose packed weights do
 // not fit next to the input ring in shared memory (until their streaming variant lands) and (b) by
 // the tests as an independent check of the tcgen05 kernel on identical bf16 inputs.
@@ -999,7 +1420,7 @@ static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring) {
 
 static bool have_instance(int ks, int ksteps, int tx) {
     if (ks == 3 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
-    if (ks == 3 && tx == 8) return ksteps == 4;
+    if (ks == 3 && tx == 8) return ksteps == 4 || ksteps == 3;
     if (ks == 1 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
     return false;
 }
@@ -1007,7 +1428,8 @@ static bool have_instance(int ks, int ksteps, int tx) {
 static ConvPlan plan_conv(const ConvParams &c) {
     ConvPlan best{0, 0, 0, 0, 0, 0, 0, false};
     if (c.cin % 16 || c.cout % 16 || c.cout > 128 || (c.k != 1 && c.k != 3)) return best;
-    const int txs[2] = {16, 8};
+    int txs[2] = {16, 8};
+    if (getenv("FPL_DBG_TX8")) { txs[0] = 8; txs[1] = 16; }
     for (int ti = 0; ti < 2; ++ti)
         for (int nsub = 1; nsub <= 4; ++nsub) {
             if (c.cin % (16 * nsub)) continue;
@@ -1033,6 +1455,7 @@ static bool umma_supported(const ConvParams &c) { return plan_conv(c).ok; }
 
 static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv through the CUDA-core kernel
 static int g_no_pool_fusion = 0;  // test hook: keep MaxPooling3D as its own kernel
+static int g_no_conv12_fusion = 0; // test hook: run the first two convolutions as separate kernels
 
 int pack_weights_umma(fpl_net *net) {
     for (ConvParams &c : net->convs) {
@@ -1097,7 +1520,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
     const ConvPlan plan = plan_conv(c);
     FPL_REQUIRE(plan.ok, "conv_umma: no plan for k=%d Cin=%d Cout=%d", c.k, c.cin, c.cout);
-    FPL_REQUIRE(!pool || (plan.n_split == 1 && plan.tx == 16), "conv_umma: pooled epilogue needs an unsplit 16-wide plan");
+    FPL_REQUIRE(!pool || plan.n_split == 1, "conv_umma: pooled epilogue needs an unsplit plan");
     const int ks = c.k, dout = din - (ks - 1), dout_z = din_z - (ks - 1);
     const int sx = plan.tx + ks - 1, sy = kTY + ks - 1;
     const int cin_atoms = c.cin / 8;
@@ -1126,6 +1549,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     a.zc_len = zc_len; a.n_zc = (dout_z + zc_len - 1) / zc_len;
     a.relu = relu;
     a.pool = pool;
+    { const char *e = getenv("FPL_DBG_MAXBLK"); a.max_blk = e ? atoi(e) : 0; }
     a.tmem_cols = 512;
     const size_t smem = plan.smem;
     const long long n_items = base_items * a.n_zc;
@@ -1148,6 +1572,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
         else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16);
         else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16);
         else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8);
+        else if (ks == 3 && plan.tx == 8 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 8);
         else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16);
         else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16);
         else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16);
@@ -1226,6 +1651,55 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
     bool skip_next_pool = false;
     for (size_t oi = 0; oi < net->ops.size(); ++oi) {
         const Op &o = net->ops[oi];
+        if (o.kind == OP_CONV && oi == 0 && !g_force_direct && !g_no_conv12_fusion && oi + 1 < net->ops.size() &&
+            net->ops[1].kind == OP_CONV) {
+            // first + second convolution fused (conv_fused12_kernel): the first layer's output stays on chip
+            const ConvParams &c1 = net->convs[o.conv_index], &c2 = net->convs[net->ops[1].conv_index];
+            const ConvPlan p2 = plan_conv(c2);
+            const bool shape_ok = c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 &&
+                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && d >= 8 && dzv >= 8;
+            if (shape_ok) {
+                const int dout = d - 4, dout_z = dzv - 4;
+                const bool pool = !g_no_pool_fusion && net->ops.size() > 2 && net->ops[2].kind == OP_POOL &&
+                                  dout % 2 == 0 && dout_z % 2 == 0;
+                const size_t out_bytes = pool ? (size_t)n_tiles * (dout_z / 2) * (dout / 2) * (dout / 2) * c2.cout * 2
+                                              : (size_t)n_tiles * dout_z * dout * dout * c2.cout * 2;
+                const int nb = pool_take(out_bytes, st);
+                if (nb < 0) return FPL_ENOMEM;
+                FusedArgs fa;
+                fa.in = d_tiles; fa.w1_packed = (const __nv_bfloat16 *)c1.d_packed;
+                fa.w2_packed = (const __nv_bfloat16 *)c2.d_packed; fa.bias2 = c2.d_bias;
+                fa.out = (__nv_bfloat16 *)g_bufs[nb].p; fa.w2_bytes = (uint32_t)c2.packed_bytes;
+                fa.n_tiles = n_tiles; fa.din = d; fa.din_z = dzv; fa.dout = dout; fa.dout_z = dout_z;
+                fa.n_xt = (dout + kTX - 1) / kTX; fa.n_yt = (dout + kTY - 1) / kTY;
+                const long long base_items = (long long)n_tiles * fa.n_xt * fa.n_yt;
+                int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
+                if (n_zc < 1) n_zc = 1;
+                int zc_len = (dout_z + n_zc - 1) / n_zc;
+                if (zc_len < 8) zc_len = dout_z < 8 ? dout_z : 8;
+                if (pool && (zc_len & 1)) ++zc_len;
+                fa.zc_len = zc_len; fa.n_zc = (dout_z + zc_len - 1) / zc_len;
+                fa.pool = pool ? 1 : 0;
+                if (vio) fa.vio = *vio;
+                const long long n_items = base_items * fa.n_zc;
+                int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
+                const size_t smem = ((c2.packed_bytes + 127) & ~size_t(127)) + 2 * 31104 + 3 * 8192 + 2 * 2 * 48 * 16 +
+                                    4 * 20 * 20 * 4 + 1024 + 512 + 256;
+                {
+                    ProfScope prof(ctx, st, PROF_CONV3,
+                                   2.0 * 27 * 48 * 48 * (double)n_tiles * dout_z * dout * dout +
+                                   2.0 * 27 * 48 * (double)n_tiles * (dout_z + 2) * (dout + 2) * (dout + 2));
+                    FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    conv_fused12_kernel<48, 48><<<grid, kFusedThreads, smem, st>>>(fa);
+                    FPL_LAUNCH_CHECK(ctx);
+                }
+                cur = nb; cur_is_skip = false;
+                d = dout; dzv = dout_z; c = c2.cout;
+                if (pool) { d /= 2; dzv /= 2; }
+                oi += pool ? 2 : 1;          // the second convolution (and the pooling) are done
+                continue;
+            }
+        }
         if (o.kind == OP_CONV) {
             const ConvParams &cp = net->convs[o.conv_index];
             const int dout = d - (o.k - 1), dout_z = dzv - (o.k - 1);
@@ -1233,7 +1707,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             const bool fuse_pool = !g_force_direct && !g_no_pool_fusion && cp.cin != 1 && umma_supported(cp) && cp.k == 3 &&
                                    (cp.cout == 32 || cp.cout == 48 || cp.cout == 64) && oi + 1 < net->ops.size() &&
                                    net->ops[oi + 1].kind == OP_POOL && (dout % 2 == 0) && (dout_z % 2 == 0) &&
-                                   plan_conv(cp).n_split == 1 && plan_conv(cp).tx == 16;
+                                   plan_conv(cp).n_split == 1;
             const size_t out_bytes = fuse_pool ? (size_t)n_tiles * (dout_z / 2) * (dout / 2) * (dout / 2) * cp.cout * 2
                                                : (size_t)n_tiles * dout_z * dout * dout * cp.cout * 2;
             const int nb = pool_take(out_bytes, st);
@@ -1332,3 +1806,4 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
 
 extern "C" int fpl_debug_force_direct_conv(int on) { fpl::net::g_force_direct = on; return FPL_OK; }
 extern "C" int fpl_debug_no_pool_fusion(int on) { fpl::net::g_no_pool_fusion = on; return FPL_OK; }
+extern "C" int fpl_debug_no_conv12_fusion(int on) { fpl::net::g_no_conv12_fusion = on; return FPL_OK; }

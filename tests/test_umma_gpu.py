@@ -108,3 +108,26 @@ def test_direct_volume_io_equals_reference_tiling_of_tile_api(arch, shape):
     got = net.infer(img)
     want = M.infer_tiler(img, net.infer_network, net.infer_sz, net.rf_offset, n_gpu=1)
     assert np.array_equal(got, want)
+
+
+def test_fused_first_two_convs_are_bit_identical():
+    """conv_fused12_kernel (first layer computed on chip into the second conv's plane ring) == the two
+    separate kernels, with and without the fused max-pool, on tiles with ragged patch edges."""
+    from flypylib_b200 import _lib
+    lib = _lib.lib()
+    lib.fpl_debug_no_conv12_fusion.argtypes = [ctypes.c_int]
+    lib.fpl_debug_no_pool_fusion.argtypes = [ctypes.c_int]
+    w = M.random_weights("vgg_like2", seed=21)
+    for s, n in [(36, 2), (60, 1), (100, 2)]:
+        x = np.random.default_rng(s).standard_normal((n, s, s, s)).astype(np.float32)
+        for nopool in (0, 1):
+            outs = []
+            for nofuse in (1, 0):
+                lib.fpl_debug_no_conv12_fusion(nofuse)
+                lib.fpl_debug_no_pool_fusion(nopool)
+                try:
+                    outs.append(_predict("vgg_like2", s, w, x, "bf16"))
+                finally:
+                    lib.fpl_debug_no_conv12_fusion(0)
+                    lib.fpl_debug_no_pool_fusion(0)
+            assert np.array_equal(outs[0], outs[1]), (s, n, nopool)
