@@ -1633,6 +1633,17 @@ static int pool_take(size_t bytes, cudaStream_t st) {
     return best;
 }
 
+// true when forward_umma will take the fused first+second convolution path, whose builders can read the
+// input tile straight from the (uint8 / float32) volume -- no float32 tile staging needed
+bool umma_reads_volume(const fpl_net *net) {
+    if (g_force_direct || g_no_conv12_fusion || net->precision != FPL_PREC_BF16) return false;
+    if (net->ops.size() < 2 || net->ops[0].kind != OP_CONV || net->ops[1].kind != OP_CONV) return false;
+    const ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
+    const ConvPlan p2 = plan_conv(c2);
+    return c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 && c2.cout == 48 &&
+           p2.ok && p2.n_split == 1 && p2.nsub == 1;
+}
+
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
                  const VolumeIO *vio, int in_z) {
     fpl_ctx *ctx = net->ctx;

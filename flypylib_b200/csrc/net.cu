@@ -402,6 +402,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         size_t ie = (size_t)ph.grid.in_z * ph.grid.in_sz * ph.grid.in_sz * ph.batch;
         size_t oe = (size_t)ph.grid.out_z * ph.grid.out_sz * ph.grid.out_sz * ph.batch;
         if (net->precision != FPL_PREC_FP32 && !g_no_direct_io) oe = 1;      // the final layer scatters directly
+        if (net->precision != FPL_PREC_FP32 && !g_no_direct_io && umma_reads_volume(net)) ie = 1;
         if (ie > need_in) need_in = ie;
         if (oe > need_out) need_out = oe;
     }
@@ -422,11 +423,13 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         const size_t in_elems = (size_t)tg.in_z * tg.in_sz * tg.in_sz, out_elems = (size_t)tg.out_z * tg.out_sz * tg.out_sz;
         for (long long t0 = 0; t0 < ph.n && rc == FPL_OK; t0 += ph.batch) {
             const int nb = (int)((ph.n - t0) < ph.batch ? (ph.n - t0) : ph.batch);
-            // tcgen05 path: the final layer scatters straight into the prediction volume; the input
-            // tile is still staged by the gather kernel (float32, L2 resident) -- reading the uint8
-            // volume directly from the first-layer builders measured slower (profiles/)
+            // tcgen05 path: the final layer scatters straight into the prediction volume; the input tile is
+            // staged by the gather kernel (float32, L2 resident) unless the fused first+second convolution
+            // kernel runs, whose builders read the volume directly in the shadow of the MMAs
             const bool fused_scatter = net->precision != FPL_PREC_FP32 && !g_no_direct_io;
-            {
+            // ... and when the first two convolutions run fused, its builders gather straight from the volume
+            const bool direct_in = fused_scatter && umma_reads_volume(net);
+            if (!direct_in) {
                 fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * in_elems * (image_is_u8 ? 5.0 : 8.0));
                 if (image_is_u8)
                     gather_tiles_kernel<uint8_t><<<blocks, 128, 0, st>>>((const uint8_t *)d_image, d_in, tg, (int)t0, nb,
@@ -434,20 +437,21 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
                 else
                     gather_tiles_kernel<float><<<blocks, 128, 0, st>>>((const float *)d_image, d_in, tg, (int)t0, nb,
                                                                        0.f, 1.f, ph.ids);
+                ctx->launches++;
             }
-            ctx->launches++;
             if (net->precision == FPL_PREC_FP32) rc = forward_fp32(net, d_in, nb, tg.in_sz, d_out, st);
             else if (fused_scatter) {
                 VolumeIO vio;
                 vio.g = tg; vio.tile0 = (int)t0; vio.ids = ph.ids; vio.pred = d_pred;
+                if (direct_in) { vio.img = d_image; vio.is_u8 = image_is_u8; vio.mean = norm_mean; vio.stdv = norm_std; }
                 rc = forward_umma(net, d_in, nb, tg.in_sz, nullptr, st, &vio, tg.in_z);
             } else rc = forward_umma(net, d_in, nb, tg.in_sz, d_out, st, nullptr, tg.in_z);
             if (rc != FPL_OK) break;
             if (!fused_scatter) {
                 fpl::ProfScope prof(ctx, st, fpl::PROF_TILER, (double)nb * out_elems * 8.0);
                 scatter_tiles_kernel<<<blocks, 128, 0, st>>>(d_out, d_pred, tg, (int)t0, nb, ph.ids);
+                ctx->launches++;
             }
-            ctx->launches++;
         }
         if (rc != FPL_OK) break;
     }

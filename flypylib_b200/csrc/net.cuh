@@ -80,6 +80,7 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out,
                  cudaStream_t st, const VolumeIO *vio = nullptr, int in_z = 0);   // in_z = 0: cubic tiles
 int pack_weights_umma(fpl_net *net);
+bool umma_reads_volume(const fpl_net *net);
 void free_packed_umma(fpl_net *net);
 // output edge of a tile for input edge in_sz (after the x rf_stride up-sampling); -1 if invalid
 int out_size(const fpl_net *net, int in_sz);
