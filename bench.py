@@ -217,7 +217,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    net = fplnetwork.FplNetwork(getattr(fplmodels, args.model))
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):    # model.summary() (fplnetwork.py:58) must not precede the JSON line
+        net = fplnetwork.FplNetwork(getattr(fplmodels, args.model))
     net.train_single.set_weights(seeded_weights(args.model))
     net.set_precision(args.precision)
     net._set_infer()

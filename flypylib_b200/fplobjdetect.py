@@ -160,3 +160,128 @@ def voxel2obj(pred, obj_min_dist, smoothing_sigma,
         _lib.context()          # raises when there is no GPU: no CPU fallback
         dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
     return voxel2obj_device(dev, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+
+
+# ---------------------------------------------------------------------------------------------
+# Detection scoring: obj_match / obj_pr / obj_pr_curve / aggregate_pr.
+# Host-side evaluation, not part of the GPU hot path; it exists so that the "bf16 keeps detection
+# F1 within 0.5 %" criterion can be measured with the reference's own definition of a match.
+# The reference solves the matching as an integer program through PuLP (fplobjdetect.py:259-318);
+# PuLP is absent here, and the program is a bipartite minimum-cost partial matching, solved exactly
+# per connected component of the admissible-pair graph with the Hungarian method.
+# ---------------------------------------------------------------------------------------------
+import collections
+
+PR_Result = collections.namedtuple('PR_Result', 'num_tp tot_pred tot_gt pp rr match')
+
+
+def obj_match(dists, allow_mult=False):
+    """Optimal prediction/ground-truth matching (flypylib/fplobjdetect.py:259-318).
+
+    ``dists`` is the (N,M) distance matrix minus the distance threshold: negative entries are the
+    admissible pairs.  Minimises the summed entry over the chosen pairs subject to "each ground
+    truth at most once" and, unless ``allow_mult``, "each prediction at most once".  Returns the
+    (N,M) boolean match matrix.  Every admissible cost is negative, so with ``allow_mult`` the
+    optimum is simply: each ground-truth column takes its best admissible prediction.
+    """
+    from scipy.optimize import linear_sum_assignment
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    d = np.asarray(dists, dtype=np.float64)
+    n_pred, n_gt = d.shape
+    out = np.zeros((n_pred, n_gt), dtype=bool)
+    ok = d < 0
+    if not ok.any():
+        return out
+    if allow_mult:
+        masked = np.where(ok, d, np.inf)
+        best = masked.argmin(axis=0)
+        cols = np.nonzero(ok.any(axis=0))[0]
+        out[best[cols], cols] = True
+        return out
+    ii, jj = np.nonzero(ok)
+    graph = coo_matrix((np.ones(ii.size, np.int8), (ii, jj + n_pred)), shape=(n_pred + n_gt,) * 2)
+    _, comp = connected_components(graph, directed=False)
+    order = np.argsort(comp[ii], kind='stable')
+    ii, jj = ii[order], jj[order]
+    bounds = np.flatnonzero(np.diff(comp[ii])) + 1
+    for ri, ci in zip(np.split(ii, bounds), np.split(jj, bounds)):
+        rows, cols = np.unique(ri), np.unique(ci)
+        if rows.size == 1 or cols.size == 1:                 # star: the single best pair wins
+            k = d[ri, ci].argmin()
+            out[ri[k], ci[k]] = True
+            continue
+        sub = d[np.ix_(rows, cols)]
+        cost = np.where(sub < 0, sub, 0.0)                   # 0 == "leave unmatched"
+        a, b = linear_sum_assignment(cost)
+        keep = cost[a, b] < 0
+        out[rows[a[keep]], cols[b[keep]]] = True
+    return out
+
+
+def obj_pr(predict_locs, groundtruth_locs, dist_thresh, predict_lbls=None, groundtruth_lbls=None,
+           allow_mult=False):
+    """Precision / recall of predicted against ground-truth locations (fplobjdetect.py:320-374).
+
+    Returns ``PR_Result(num_tp, tot_pred, tot_gt, pp, rr, match)`` with the reference's conventions:
+    an empty side gives ``pp = 1`` when there are no predictions and ``rr = 1`` when there is no
+    ground truth, ``match = None``; otherwise ``pp = num_tp / N`` and ``rr = num_tp / M`` while
+    ``tot_pred`` additionally counts the surplus matches of multiply-matched predictions.
+    """
+    predict_locs = np.asarray(predict_locs)
+    groundtruth_locs = np.asarray(groundtruth_locs)
+    n_pred, n_gt = predict_locs.shape[0], groundtruth_locs.shape[0]
+    if n_pred == 0 or n_gt == 0:
+        return PR_Result(num_tp=0, tot_pred=n_pred, tot_gt=n_gt, pp=1 if n_pred == 0 else 0,
+                         rr=1 if n_gt == 0 else 0, match=None)
+    diff = predict_locs.reshape((-1, 1, 3)) - groundtruth_locs.reshape((1, -1, 3))
+    dists = np.sqrt((diff ** 2).sum(axis=2))
+    dists -= dist_thresh
+    if predict_lbls is not None:
+        differ = (np.reshape(predict_lbls, (-1, 1)) != np.reshape(groundtruth_lbls, (1, -1)))
+        dists += (dist_thresh + 1.) * differ.astype('float32')
+    match = obj_match(dists, allow_mult=allow_mult)
+    num_tp = match.sum()
+    surplus = np.maximum(match.sum(axis=1) - 1, 0).sum()
+    return PR_Result(num_tp=num_tp, tot_pred=n_pred + surplus, tot_gt=n_gt, pp=num_tp / n_pred,
+                     rr=num_tp / n_gt, match=match)
+
+
+def obj_pr_curve(predict, groundtruth, dist_thresh, thresholds, predict_lbls=None,
+                 groundtruth_lbls=None, allow_mult=False):
+    """Precision / recall at each confidence threshold (fplobjdetect.py:376-434): predictions with
+    ``conf >= thresholds[t]`` are scored by :func:`obj_pr`; ``match`` is the first threshold's matrix.
+    ``predict`` / ``groundtruth`` are ``{'locs','conf'}`` dicts or paths of json files written by
+    ``fplsynapses.tbars_to_json_format``."""
+    from . import fplsynapses
+    if isinstance(predict, str):
+        predict = fplsynapses.load_from_json(predict)
+    if isinstance(groundtruth, str):
+        groundtruth = fplsynapses.load_from_json(groundtruth)
+    thresholds = np.asarray(thresholds)
+    cols = {k: np.zeros((thresholds.size,)) for k in ('num_tp', 'tot_pred', 'tot_gt', 'pp', 'rr')}
+    match = None
+    for t in range(thresholds.size):
+        sel = predict['conf'] >= thresholds[t]
+        lbls = predict_lbls[sel] if predict_lbls is not None else None
+        res = obj_pr(predict['locs'][sel, :], groundtruth['locs'], dist_thresh, lbls, groundtruth_lbls,
+                     allow_mult=allow_mult)
+        for k in cols:
+            cols[k][t] = getattr(res, k)
+        if match is None:
+            match = res.match
+    return PR_Result(match=match, **cols)
+
+
+def aggregate_pr(results):
+    """Pool per-substack PR curves (fplobjdetect.py:437-453): counts add, precision and recall are
+    recomputed from the pooled counts with the reference's 10e-8 guard."""
+    num_tp = np.zeros(results[0].num_tp.shape)
+    tot_pred = np.zeros_like(num_tp)
+    tot_gt = np.zeros_like(num_tp)
+    for res in results:
+        num_tp += res.num_tp
+        tot_pred += res.tot_pred
+        tot_gt += res.tot_gt
+    return PR_Result(num_tp=num_tp, tot_pred=tot_pred, tot_gt=tot_gt, pp=num_tp / (tot_pred + 10e-8),
+                     rr=num_tp / (tot_gt + 10e-8), match=None)

@@ -9,6 +9,10 @@ Outputs (committed):
                                       makes (fplobjdetect.py:159-183) on SciPy/NumPy of this image
   tests/golden/infer_tiler_golden.npz reference ``FplNetwork.infer`` tiling/scatter run unmodified
                                       with a deterministic fake ``infer_network`` (fplnetwork.py:136-189)
+  tests/golden/eval_golden.json       reference ``obj_pr`` / ``obj_pr_curve`` / ``aggregate_pr``
+                                      (fplobjdetect.py:320-453) run unmodified with the exhaustive
+                                      ``oracle/match_oracle.py`` standing in for the PuLP solver, and the
+                                      reference json writers/reader (fplsynapses.py:11-111) run unmodified
 """
 import hashlib
 import os
@@ -76,7 +80,78 @@ def golden_infer_tiler(ref):
     np.savez_compressed(os.path.join(HERE, "infer_tiler_golden.npz"), **out)
 
 
+def eval_cases():
+    """Seeded (pred, gt) detection sets for the scoring goldens: jittered ground truth + spurious
+    predictions + misses, continuous coordinates (no exact cost ties)."""
+    out = []
+    for seed, n_gt, n_extra, n_miss, box in [(1, 12, 4, 2, 120.0), (2, 9, 0, 0, 60.0), (3, 14, 6, 5, 80.0),
+                                             (4, 6, 10, 1, 50.0)]:
+        rng = np.random.default_rng(seed)
+        gt = rng.uniform(0, box, (n_gt, 3))
+        keep = np.ones(n_gt, bool); keep[rng.choice(n_gt, n_miss, replace=False)] = False
+        pred = np.concatenate([gt[keep] + rng.normal(0, 6.0, (keep.sum(), 3)), rng.uniform(0, box, (n_extra, 3))])
+        conf = rng.uniform(0.2, 1.0, pred.shape[0])
+        out.append((pred, conf, gt))
+    return out
+
+
+def golden_eval(ref):
+    import json
+    import tempfile
+    from oracle import match_oracle
+    import flypylib.fplsynapses as ref_syn          # unmodified reference module (stubs for dvid/h5py)
+    F = ref.fplobjdetect
+    F.obj_match = match_oracle.obj_match            # PuLP stand-in: exact exhaustive solver
+    thresholds = np.array([0.0, 0.3, 0.5, 0.7, 0.9, 2.0])
+    doc = {"thresholds": thresholds.tolist(), "pr": [], "formats": []}
+    curves = []
+    for pred, conf, gt in eval_cases():
+        for allow_mult in (False, True):
+            r = F.obj_pr(pred, gt, 27.0, allow_mult=allow_mult)
+            c = F.obj_pr_curve({"locs": pred, "conf": conf}, {"locs": gt}, 27.0, thresholds, allow_mult=allow_mult)
+            if not allow_mult:
+                curves.append(c)
+            doc["pr"].append({"pred": pred.tolist(), "conf": conf.tolist(), "gt": gt.tolist(), "allow_mult": allow_mult,
+                              "num_tp": int(r.num_tp), "tot_pred": int(r.tot_pred), "tot_gt": int(r.tot_gt),
+                              "pp": float(r.pp), "rr": float(r.rr),
+                              "match_cost": float((np.sqrt(((pred[:, None] - gt[None]) ** 2).sum(2)) - 27.0)[r.match].sum()),
+                              "curve": {k: np.asarray(getattr(c, k)).tolist() for k in ("num_tp", "tot_pred", "tot_gt", "pp", "rr")}})
+    agg = F.aggregate_pr(curves)
+    doc["aggregate"] = {k: np.asarray(getattr(agg, k)).tolist() for k in ("num_tp", "tot_pred", "tot_gt", "pp", "rr")}
+    e = F.obj_pr(np.zeros((0, 3)), np.zeros((4, 3)), 27.0)
+    doc["empty_pred"] = [int(e.num_tp), int(e.tot_pred), int(e.tot_gt), e.pp, e.rr, e.match]
+    e = F.obj_pr(np.zeros((3, 3)), np.zeros((0, 3)), 27.0)
+    doc["empty_gt"] = [int(e.num_tp), int(e.tot_pred), int(e.tot_gt), e.pp, e.rr, e.match]
+    # wire formats
+    rng = np.random.default_rng(7)
+    tb = {"locs": rng.uniform(0, 500, (9, 3)), "conf": rng.uniform(0, 1, 9)}
+    tb["conf"][0] = 0.0005; tb["conf"][1] = 0.9995
+    dvid = ref_syn.tbars_to_json_format(tb, labels=np.arange(9) * 7)
+    dvid_nolab = ref_syn.tbars_to_json_format(tb, user_name="someone")
+    rav = ref_syn.tbars_to_json_format_raveler(tb)
+    mixed = dvid_nolab + [{"Kind": "PostSyn", "Pos": [1, 2, 3], "Prop": {}},
+                          {"Kind": "PreSyn", "Pos": [4, 5, 6], "Prop": {"err": "0.25"}}]
+    back_dvid = ref_syn.load_from_json(json.dumps(mixed))
+    back_nested = ref_syn.load_from_json(json.dumps([dvid_nolab]))
+    back_rav = ref_syn.load_from_json(json.dumps(rav))
+    back_buf = ref_syn.load_from_json(json.dumps(dvid_nolab), vol_sz=500, buffer=(60, 40, 80))
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        path = f.name
+    ref_syn.tbars_to_json_format(tb, json_file=path)
+    file_text = open(path).read(); os.unlink(path)
+
+    def pack(t):
+        return {k: [None if (isinstance(x, float) and x != x) else x for x in np.asarray(v).tolist()] if np.asarray(v).ndim == 1
+                else np.asarray(v).tolist() for k, v in t.items()}
+    doc["formats"] = {"locs": tb["locs"].tolist(), "conf": tb["conf"].tolist(), "dvid_labels": dvid, "dvid_user": dvid_nolab,
+                      "raveler": rav, "mixed": mixed, "back_dvid": pack(back_dvid), "back_nested": pack(back_nested),
+                      "back_raveler": pack(back_rav), "back_buffer": pack(back_buf), "file_text": file_text}
+    json.dump(doc, open(os.path.join(HERE, "eval_golden.json"), "w"))
+    print("eval goldens: %d pr cases" % len(doc["pr"]))
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
     golden_voxel2obj(ref)
     golden_infer_tiler(ref)
+    golden_eval(ref)

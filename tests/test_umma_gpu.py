@@ -131,3 +131,28 @@ def test_fused_first_two_convs_are_bit_identical():
                     lib.fpl_debug_no_conv12_fusion(0)
                     lib.fpl_debug_no_pool_fusion(0)
             assert np.array_equal(outs[0], outs[1]), (s, n, nopool)
+
+
+@pytest.mark.parametrize("arch,shape", [("vgg_like2", (260, 250, 270)), ("unet_like2", (190, 200, 210))])
+def test_bf16_preserves_detection_f1(arch, shape):
+    """north_star: the bf16 path must preserve detection F1 within 0.5 %.  The fp32 path's detections
+    (same volume, same weights, same voxel2obj parameters) are the ground truth; bf16 detections are
+    scored against them with the reference's own matching rule (obj_pr, distance threshold =
+    obj_min_dist as in fplobjdetect.py:478)."""
+    import torch
+    from flypylib_b200 import fplmodels, fplnetwork, fplobjdetect
+    import bench
+    vol = torch.from_numpy(cases.em_volume(shape, seed=21)).cuda()
+    dets = {}
+    for prec in ("fp32", "bf16"):
+        net = fplnetwork.FplNetwork(getattr(fplmodels, arch))
+        net.train_single.set_weights(bench.seeded_weights(arch))
+        net.set_precision(prec)
+        net._set_infer()
+        pred = net.infer_device(vol, normalize=(128.0, 33.0))
+        dets[prec] = fplobjdetect.voxel2obj_device(pred, 27, 5, (0, 0, 0), 15, 0)
+    gt, pd = dets["fp32"], dets["bf16"]
+    assert gt["conf"].size > 20
+    r = fplobjdetect.obj_pr(pd["locs"], gt["locs"], 27.0)
+    f1 = 2.0 * r.pp * r.rr / (r.pp + r.rr)
+    assert f1 >= 0.995, (f1, r.num_tp, r.tot_pred, r.tot_gt)
