@@ -263,11 +263,21 @@ __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int
 // Each M-tile owns a 256-column region of kBlocks = 256/Cout blocks; output number A (monotone
 // counter) lives in block kBlocks-1 - (A mod kBlocks), so consecutive outputs occupy descending
 // blocks and (p, p-1, p-2) are contiguous except where the ring wraps (then two MMAs are issued).
-template <int KS, int KSTEPS, int TX>
+//
+// ROT variant ("rotating window", KS = 3, two M-tiles): three accumulator blocks per M-tile form a ring
+// (output A in block 2 - A mod 3), so the blocks fed by one input plane are ALWAYS the three adjacent
+// N-column blocks 0,1,2 -- only the assignment kd -> block rotates with A mod 3.  The packed weights
+// carry the kd row blocks as [kd0 kd1 kd2 kd0 kd1]; the three cyclic orders are the three windows of
+// that sequence, selected by the start address of the B descriptor.  Every (tap, K-step) is then ONE
+// tcgen05.mma with N = 3*Cout on every plane (no split where a ring wraps), i.e. the A tile is read from
+// shared memory once.  The two M-tiles are issued one after the other (own full/empty barriers), so the
+// epilogue of an M-tile drains its finished block while the other M-tile's MMAs run.
+template <int KS, int KSTEPS, int TX, bool ROT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) {
     constexpr int SX = TX + KS - 1, SY = kTY + KS - 1;
     constexpr int MT = TX / 8;                      // M=128 tiles per plane patch (x halves)
+    static_assert(!ROT || (KS == 3 && MT == 2), "ROT needs a 3x3x3 kernel and two M-tiles");
     constexpr int SUB_ATOMS = 2 * KSTEPS;           // channel atoms per (sub-)plane
     constexpr int kMaxBlocks = 8, kMaxRing = 3;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -292,12 +302,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
     const uint32_t N = (uint32_t)a.cout;
     uint32_t nblk_ = 256u / N > (uint32_t)kMaxBlocks ? (uint32_t)kMaxBlocks : 256u / N;
     if (a.max_blk > 0 && (uint32_t)a.max_blk < nblk_) nblk_ = (uint32_t)a.max_blk;
-    const uint32_t nblk = nblk_;
+    const uint32_t nblk = ROT ? 3u : nblk_;
     const int nsub = a.nsub;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMaxRing; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < kMaxBlocks; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * MT); }
+        for (int i = 0; i < kMaxBlocks; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], ROT ? 4 : 4 * MT); }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
@@ -356,6 +366,77 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         const uint32_t kt = (uint32_t)(nsub * KSTEPS);                    // K steps per tap over all sub-planes
         mbar_wait(w_full, 0);
         uint32_t pc = 0, ac0 = 0;
+        if constexpr (ROT) {
+            const uint32_t idesc_3 = make_idesc_bf16(128, (int)(3u * N));
+            const uint32_t b_lo0r = (smem_u32(s_w) >> 4) | ((N * 5u) << 16);   // LBO = 5*Cout*16 bytes
+            const uint32_t b_step16r = N * 5u * 2u;                            // chunk = 5*Cout*32 bytes
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
+                const int z0 = zc * a.zc_len;
+                const int nz = min(a.zc_len, a.dout_z - z0);
+                const int np = nz + KS - 1;
+#pragma unroll 1
+                for (int ip = 0; ip < np; ++ip) {
+                    const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
+                    const int kd_hi = ip < KS - 1 ? ip : KS - 1;
+                    const bool full = kd_lo == 0 && kd_hi == KS - 1;
+                    const uint32_t A0 = ac0 + (uint32_t)ip;            // output fed through kd = 0
+                    const uint32_t r = A0 % 3u;
+                    const uint32_t win = ((r + 1u) % 3u) * N;          // window start (rows) inside [kd0 kd1 kd2 kd0 kd1]
+#pragma unroll 1
+                    for (int sub = 0; sub < nsub; ++sub, ++pc) {
+                        const uint32_t slot = pc % ring, ph = (pc / ring) & 1u;
+                        mbar_wait(&plane_full[slot], ph);
+                        tc_fence_after();
+                        const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+#pragma unroll 1
+                        for (int m = 0; m < 2; ++m) {
+                            if (sub == 0 && kd_lo == 0)             // the block of the new output must have been drained
+                                mbar_wait(&acc_empty[m * 3 + (2u - r)], ((A0 / 3u) & 1u) ^ 1u);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t d_reg = tmem_base + (uint32_t)m * 256u;
+#pragma unroll 1
+                                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                                    for (int kw = 0; kw < KS; ++kw) {
+                                        uint32_t b_lo = b_lo0r + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)(sub * KSTEPS)) * b_step16r;
+#pragma unroll
+                                        for (int s = 0; s < KSTEPS; ++s) {
+                                            const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4) +
+                                                                  (uint32_t)m * 8u;
+                                            const uint64_t ad = desc64(a_lo, a_hi);
+                                            const bool first = sub == 0 && kh == 0 && kw == 0 && s == 0;
+                                            if (full && !first) {
+                                                umma_bf16(d_reg, ad, desc64(b_lo + win, b_hi), idesc_3, 1u);
+                                            } else {
+                                                // plane at a z-chunk edge, or the first MMA of a plane (the kd = 0
+                                                // accumulator is overwritten, the others accumulate): one MMA per kd
+#pragma unroll
+                                                for (int kd = 0; kd < KS; ++kd)
+                                                    if (kd >= kd_lo && kd <= kd_hi) {
+                                                        const uint32_t bl = 2u - (r + 3u - (uint32_t)kd) % 3u;
+                                                        umma_bf16(d_reg + bl * N, ad, desc64(b_lo + (uint32_t)kd * N, b_hi), idesc_1,
+                                                                  (first && kd == 0) ? 0u : 1u);
+                                                    }
+                                            }
+                                            b_lo += b_step16r;
+                                        }
+                                    }
+                                if (sub == nsub - 1 && ip >= KS - 1) {   // output ip-(KS-1) has received its last plane
+                                    const uint32_t Ad = ac0 + (uint32_t)(ip - (KS - 1));
+                                    umma_commit(&acc_full[m * 3 + (2u - Ad % 3u)]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (leader) umma_commit(&plane_empty[slot]);
+                        __syncwarp();
+                    }
+                }
+                ac0 += (uint32_t)nz;
+            }
+        } else
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int zc = (item / (a.n_xt * a.n_yt)) % a.n_zc;
             const int z0 = zc * a.zc_len;
@@ -451,7 +532,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
             const int nz = min(a.zc_len, a.dout_z - z0);
             for (int zo = 0; zo < nz; ++zo, ++A) {
                 const uint32_t bl = nblk - 1u - (A % nblk), ph = (A / nblk) & 1u;
-                mbar_wait(&acc_full[bl], ph);
+                const uint32_t bar_i = ROT ? (uint32_t)m * 3u + bl : bl;       // ROT: barriers per M-tile
+                mbar_wait(&acc_full[bar_i], ph);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)m * 256u + bl * N;
                 if (a.pool) {
@@ -469,7 +551,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                               a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.cout_total, a.cout_off, a.dout_z);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[bl]);
+                if (lane == 0) mbar_arrive(&acc_empty[bar_i]);
             }
         }
     }
@@ -851,21 +933,24 @@ upcat_blocked_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *
                      int crop, uint4 *__restrict__ out, int n_tiles) {
     const int dout = 2 * da, cg_out = cga + cgs;
     const long long total = (long long)n_tiles * cg_out * dout * dout * dout;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto src = [&](long long i) -> const uint4 * {
         long long v = i;
         const int x = (int)(v % dout); v /= dout;
         const int y = (int)(v % dout); v /= dout;
         const int z = (int)(v % dout); v /= dout;
         const int cg = (int)(v % cg_out);
         const int t = (int)(v / cg_out);
-        uint4 r;
-        if (cg < cga)
-            r = __ldg(a + ((((size_t)t * cga + cg) * da + z / 2) * da + y / 2) * da + x / 2);
-        else
-            r = __ldg(skip + ((((size_t)t * cgs + (cg - cga)) * ds + z + crop) * ds + y + crop) * ds + x + crop);
-        out[i] = r;
+        if (cg < cga) return a + ((((size_t)t * cga + cg) * da + z / 2) * da + y / 2) * da + x / 2;
+        return skip + ((((size_t)t * cgs + (cg - cga)) * ds + z + crop) * ds + y + crop) * ds + x + crop;
+    };
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {           // four 16-byte loads in flight per thread
+        const uint4 r0 = __ldg(src(i)), r1 = __ldg(src(i + stride)), r2 = __ldg(src(i + 2 * stride)),
+                    r3 = __ldg(src(i + 3 * stride));
+        out[i] = r0; out[i + stride] = r1; out[i + 2 * stride] = r2; out[i + 3 * stride] = r3;
     }
+    for (; i < total; i += stride) out[i] = __ldg(src(i));
 }
 
 // final Conv3D(1,(1,1,1)) + sigmoid (+ nearest up-sampling by `stride`, fplnetwork.py:99-105) -> float32 tile
@@ -978,9 +1063,9 @@ conv_fused12_kernel(const FusedArgs a) {
     uint64_t *a1_empty = bars + 6;           // [1]
     uint64_t *l1_full = bars + 7;            // [3]  first-layer accumulator tiles
     uint64_t *l1_empty = bars + 10;          // [3]
-    uint64_t *acc_full = bars + 13;          // [3]  second-layer accumulator blocks
-    uint64_t *acc_empty = bars + 16;         // [3]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+    uint64_t *acc_full = bars + 13;          // [2][3]  second-layer accumulator blocks, per M-tile
+    uint64_t *acc_empty = bars + 19;         // [2][3]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
@@ -989,10 +1074,8 @@ conv_fused12_kernel(const FusedArgs a) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&plane_full[i], 4); mbar_init(&plane_empty[i], 1); }
         mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
-        }
+        for (int i = 0; i < 3; ++i) { mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4); }
+        for (int i = 0; i < 6; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x)
@@ -1025,8 +1108,9 @@ conv_fused12_kernel(const FusedArgs a) {
         const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
-        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * KS) << 16);
-        const uint32_t b_step16 = N * KS * 2u;
+        const uint32_t idesc_3 = make_idesc_bf16(128, (int)(3u * N));
+        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * 5u) << 16);       // [kd0 kd1 kd2 kd0 kd1] row blocks (ROT)
+        const uint32_t b_step16 = N * 5u * 2u;
         const uint32_t a1_hi = (128u >> 4) | (1u << 14);
         const uint32_t a1_lo0 = (smem_u32(s_a1) >> 4) | ((2048u >> 4) << 16);
         const uint32_t b1_lo0 = (smem_u32(s_w1) >> 4) | ((uint32_t)C1 << 16);
@@ -1066,61 +1150,52 @@ conv_fused12_kernel(const FusedArgs a) {
                 const uint32_t slot = pc2 & 1u, ph = (pc2 >> 1) & 1u;
                 const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
                 const int kd_hi = ip < KS - 1 ? ip : KS - 1;
-                const uint32_t L = (uint32_t)(kd_hi - kd_lo + 1);
-                const uint32_t r = (ac0 + (uint32_t)(ip - kd_lo)) % NBLK;
-                const uint32_t len0 = L < r + 1u ? L : r + 1u, len1 = L - len0;
-                const uint32_t blk0 = NBLK - 1u - r;
-                const uint32_t kd1 = (uint32_t)kd_lo + len0;
-                const uint32_t d_seg0 = tmem_base + blk0 * N, b_seg0 = (uint32_t)kd_lo * N;
-                const uint32_t d_seg1 = tmem_base, b_seg1 = kd1 * N;
-                const uint32_t i_seg0 = idesc_1 + ((((len0 - 1u) * N) >> 3) << 17);
-                const uint32_t i_seg1 = idesc_1 + (((((len1 ? len1 : 1u) - 1u) * N) >> 3) << 17);
-                if (kd_lo == 0) {
-                    const uint32_t A = ac0 + (uint32_t)ip;
-                    mbar_wait(&acc_empty[blk0], ((A / NBLK) & 1u) ^ 1u);
-                }
+                const bool full = kd_lo == 0 && kd_hi == KS - 1;
+                const uint32_t A0 = ac0 + (uint32_t)ip;            // output fed through kd = 0
+                const uint32_t r = A0 % NBLK;
+                const uint32_t win = ((r + 1u) % 3u) * N;          // rotating window, see conv_umma_kernel<.., ROT>
                 mbar_wait(&plane_full[slot], ph);
                 tc_fence_after();
-                if (leader) {
-                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+                const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
 #pragma unroll 1
-                    for (int kh = 0; kh < KS; ++kh)
+                for (int m = 0; m < 2; ++m) {
+                    if (kd_lo == 0) mbar_wait(&acc_empty[m * 3 + (2u - r)], ((A0 / NBLK) & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t d_reg = tmem_base + (uint32_t)m * kRegion;
+#pragma unroll 1
+                        for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-                        for (int kw = 0; kw < KS; ++kw) {
-                            uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
+                            for (int kw = 0; kw < KS; ++kw) {
+                                uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
 #pragma unroll
-                            for (int s = 0; s < KSTEPS; ++s) {
-                                const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
-                                const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
-                                if (kh == 0 && kw == 0 && s == 0) {
+                                for (int s = 0; s < KSTEPS; ++s) {
+                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4) +
+                                                          (uint32_t)m * 8u;
+                                    const uint64_t ad = desc64(a_lo, a_hi);
+                                    const bool first = kh == 0 && kw == 0 && s == 0;
+                                    if (full && !first) {
+                                        umma_bf16(d_reg, ad, desc64(b_lo + win, b_hi), idesc_3, 1u);
+                                    } else {
 #pragma unroll
-                                    for (int kd = 0; kd < KS; ++kd)
-                                        if (kd >= kd_lo && kd <= kd_hi) {
-                                            const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
-                                            const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
-                                            const uint32_t dcol = tmem_base + bl * N;
-                                            umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
-                                            umma_bf16(dcol + kRegion, ad1, bd, idesc_1, kd ? 1u : 0u);
-                                        }
-                                } else {
-                                    const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
-                                    umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
-                                    umma_bf16(d_seg0 + kRegion, ad1, bd0, i_seg0, 1u);
-                                    if (len1) {
-                                        const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
-                                        umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
-                                        umma_bf16(d_seg1 + kRegion, ad1, bd1, i_seg1, 1u);
+                                        for (int kd = 0; kd < KS; ++kd)
+                                            if (kd >= kd_lo && kd <= kd_hi) {
+                                                const uint32_t bl = 2u - (r + 3u - (uint32_t)kd) % 3u;
+                                                umma_bf16(d_reg + bl * N, ad, desc64(b_lo + (uint32_t)kd * N, b_hi), idesc_1,
+                                                          (first && kd == 0) ? 0u : 1u);
+                                            }
                                     }
+                                    b_lo += b_step16;
                                 }
-                                b_lo += b_step16;
                             }
+                        if (ip >= KS - 1) {
+                            const uint32_t Ad = ac0 + (uint32_t)(ip - (KS - 1));
+                            umma_commit(&acc_full[m * 3 + (2u - Ad % NBLK)]);
                         }
-                    umma_commit(&plane_empty[slot]);
-                    if (ip >= KS - 1) {
-                        const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
-                        umma_commit(&acc_full[NBLK - 1u - (A % NBLK)]);
                     }
+                    __syncwarp();
                 }
+                if (leader) umma_commit(&plane_empty[slot]);
                 __syncwarp();
                 if (ip + 2 < np) issue_l1();          // first-layer plane ip+2 behind this plane's MMAs
             }
@@ -1144,7 +1219,7 @@ conv_fused12_kernel(const FusedArgs a) {
             const int nz = min(a.zc_len, a.dout_z - z0);
             for (int zo = 0; zo < nz; ++zo, ++A) {
                 const uint32_t bl = NBLK - 1u - (A % NBLK), ph = (A / NBLK) & 1u;
-                mbar_wait(&acc_full[bl], ph);
+                mbar_wait(&acc_full[m * 3 + bl], ph);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)m * kRegion + bl * N;
                 if (a.pool)
@@ -1155,7 +1230,7 @@ conv_fused12_kernel(const FusedArgs a) {
                                   C2, 0, a.dout_z);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[bl]);
+                if (lane == 0) mbar_arrive(&acc_empty[m * 3 + bl]);
             }
         }
     } else if (warp < 14) {
@@ -1409,11 +1484,13 @@ static constexpr size_t kMaxDynSmem = 232448;   // 227 KB
 //   n_split  : the output channels are computed in n_split launches of n = cout/n_split columns
 //   nsub     : the input channels are streamed as nsub sub-planes of 16*ksteps channels
 //   tx       : patch width (16: two M-tiles per plane, 8: one)        ring: (sub-)plane ring depth
-struct ConvPlan { int n_split, n, nsub, ksteps, tx, ring; size_t smem; bool ok; };
+struct ConvPlan { int n_split, n, nsub, ksteps, tx, ring; size_t smem; bool ok; bool rot; };
 
-static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring) {
+// rot: the packed weights hold 5 instead of 3 kd row blocks (see the ROT variant of conv_umma_kernel)
+static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring, bool rot) {
     const int sx = tx + ks - 1, sy = kTY + ks - 1;
-    size_t w = ((size_t)ks * ks * ks * cin * n * 2 + 127) & ~size_t(127);
+    const size_t kd_blocks = rot ? 5 : ks;
+    size_t w = ((size_t)ks * ks * kd_blocks * cin * n * 2 + 127) & ~size_t(127);
     size_t plane = (((size_t)(cin / nsub / 8) * sy * sx * 16) + 127) & ~size_t(127);
     return w + ring * plane + 384 + 512;        // + barriers + bias
 }
@@ -1425,11 +1502,34 @@ static bool have_instance(int ks, int ksteps, int tx) {
     return false;
 }
 
+// Modelled cycles per (tap, K-step, M-tile) unit, times the number of Cout launches.  The kernel is
+// bound by the tensor core's operand reads from shared memory (128 B / cycle): per unit the A tile
+// (128 rows x 32 B) is read once per MMA the unit is issued as, the B tile (kd-fused N rows x 32 B) once;
+// the MMA itself takes N/2 cycles.  Without ROT a unit splits in two MMAs where the accumulator ring
+// wraps (2 of nblk planes).
+static double plan_cost(const ConvParams &c, const ConvPlan &p) {
+    const double N = (c.k == 3 ? 3.0 : 1.0) * p.n;
+    const double units = (double)c.k * c.k * (c.cin / 16);
+    double a_reads = 1.0;
+    if (c.k == 3) {
+        int nblk = 256 / p.n; if (nblk > 8) nblk = 8;
+        a_reads = p.rot ? 1.0 + 2.0 / units : 1.0 + 2.0 / nblk + 2.0 / units;
+    }
+    const double smem_cyc = (a_reads * 4096.0 + N * 32.0) / 128.0, mma_cyc = N / 2.0;
+    double cost = (smem_cyc > mma_cyc ? smem_cyc : mma_cyc) * p.n_split;
+    if (p.tx == 8) cost *= 1.15;          // wider relative halo per plane load
+    if (p.ring == 2) cost *= 1.03;        // shallower prefetch
+    if (p.nsub > 1) cost *= 1.02;
+    return cost;
+}
+
 static ConvPlan plan_conv(const ConvParams &c) {
-    ConvPlan best{0, 0, 0, 0, 0, 0, 0, false};
+    ConvPlan best{0, 0, 0, 0, 0, 0, 0, false, false};
     if (c.cin % 16 || c.cout % 16 || c.cout > 128 || (c.k != 1 && c.k != 3)) return best;
+    static const int legacy = getenv("FPL_PLAN_LEGACY") ? atoi(getenv("FPL_PLAN_LEGACY")) : 0;
     int txs[2] = {16, 8};
     if (getenv("FPL_DBG_TX8")) { txs[0] = 8; txs[1] = 16; }
+    double best_cost = 0.0;
     for (int ti = 0; ti < 2; ++ti)
         for (int nsub = 1; nsub <= 4; ++nsub) {
             if (c.cin % (16 * nsub)) continue;
@@ -1438,12 +1538,17 @@ static ConvPlan plan_conv(const ConvParams &c) {
             for (int split = 1; split <= 8; split *= 2) {
                 if (c.cout % (16 * split)) continue;
                 const int n = c.cout / split;
-                for (int ring = 3; ring >= 2; --ring) {
-                    if (nsub > 1 && ring > 2) continue;
-                    const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring);
-                    if (sm <= kMaxDynSmem) {
-                        // prefer: no split, single plane, wide patch, deep ring (loop order) -- first hit wins
-                        return ConvPlan{split, n, nsub, ksteps, txs[ti], ring, sm, true};
+                for (int rot = 1; rot >= 0; --rot) {
+                    if (rot && (c.k != 3 || txs[ti] != 16 || legacy || 3 * n > 256)) continue;
+                    for (int ring = 3; ring >= 2; --ring) {
+                        if (nsub > 1 && ring > 2) continue;
+                        const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring, rot != 0);
+                        if (sm > kMaxDynSmem) continue;
+                        const ConvPlan cand{split, n, nsub, ksteps, txs[ti], ring, sm, true, rot != 0};
+                        // legacy: no split, single plane, wide patch, deep ring (loop order) -- first hit wins
+                        if (legacy) return cand;
+                        const double cost = plan_cost(c, cand);
+                        if (!best.ok || cost < best_cost - 1e-9) { best = cand; best_cost = cost; }
                     }
                 }
             }
@@ -1483,22 +1588,24 @@ int pack_weights_umma(fpl_net *net) {
         // the k kd taps that share an A tile are adjacent row blocks so that one MMA with N = k*n covers them
         const ConvPlan plan = plan_conv(c);
         if (!plan.ok) continue;
-        const int ks = c.k, ksteps = c.cin / 16, n = plan.n;
-        std::vector<__nv_bfloat16> pk((size_t)ks * ks * ks * c.cin * c.cout);
-        const size_t split_elems = (size_t)ks * ks * ks * c.cin * n;
+        // ROT plans store the kd row blocks as [kd0 kd1 kd2 kd0 kd1] (all three cyclic orders are windows)
+        const int ks = c.k, ksteps = c.cin / 16, n = plan.n, nkb = plan.rot ? 5 : ks;
+        std::vector<__nv_bfloat16> pk((size_t)ks * ks * nkb * c.cin * c.cout);
+        const size_t split_elems = (size_t)ks * ks * nkb * c.cin * n;
         for (int g = 0; g < plan.n_split; ++g)
             for (int kh = 0; kh < ks; ++kh)
                 for (int kw = 0; kw < ks; ++kw)
                     for (int s = 0; s < ksteps; ++s)
                         for (int h = 0; h < 2; ++h)
-                            for (int kd = 0; kd < ks; ++kd)
+                            for (int kb = 0; kb < nkb; ++kb)
                                 for (int nn = 0; nn < n; ++nn)
                                     for (int e = 0; e < 8; ++e) {
+                                        const int kd = kb % ks;
                                         const int ci = 16 * s + 8 * h + e, co = g * n + nn;
                                         const int tap = (kd * ks + kh) * ks + kw;
                                         const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + co] * c.scale[co];
                                         const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
-                                        pk[g * split_elems + (((chunk * 2 + h) * ks + kd) * n + nn) * 8 + e] = __float2bfloat16_rn(v);
+                                        pk[g * split_elems + (((chunk * 2 + h) * nkb + kb) * n + nn) * 8 + e] = __float2bfloat16_rn(v);
                                     }
         c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
         FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
@@ -1560,23 +1667,27 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
         a.w_packed = (const __nv_bfloat16 *)((const uint8_t *)c.d_packed + (size_t)g * a.w_bytes);
         a.bias = c.d_bias + g * plan.n;
         a.cout_off = g * plan.n;
-#define FPL_LAUNCH_UMMA(KS_, KST_, TX_)                                                                          \
+#define FPL_LAUNCH_UMMA(KS_, KST_, TX_, ROT_)                                                                    \
         do {                                                                                                      \
-            FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_>,                                 \
+            FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_, ROT_>,                           \
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-            conv_umma_kernel<KS_, KST_, TX_><<<grid, kThreads, smem, st>>>(tmap, a);                              \
+            conv_umma_kernel<KS_, KST_, TX_, ROT_><<<grid, kThreads, smem, st>>>(tmap, a);                        \
         } while (0)
         const int kst = plan.ksteps;
-        if (ks == 3 && plan.tx == 16 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16);
-        else if (ks == 3 && plan.tx == 16 && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16);
-        else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16);
-        else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16);
-        else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8);
-        else if (ks == 3 && plan.tx == 8 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 8);
-        else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16);
-        else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16);
-        else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16);
-        else if (ks == 1 && kst == 6) FPL_LAUNCH_UMMA(1, 6, 16);
+        if (plan.rot && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, true);
+        else if (plan.rot && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, true);
+        else if (plan.rot && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, true);
+        else if (plan.rot && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, true);
+        else if (ks == 3 && plan.tx == 16 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, false);
+        else if (ks == 3 && plan.tx == 16 && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, false);
+        else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, false);
+        else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, false);
+        else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8, false);
+        else if (ks == 3 && plan.tx == 8 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 8, false);
+        else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16, false);
+        else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16, false);
+        else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16, false);
+        else if (ks == 1 && kst == 6) FPL_LAUNCH_UMMA(1, 6, 16, false);
         else { set_error("conv_umma: no instantiation for k=%d ksteps=%d tx=%d", ks, kst, plan.tx); return FPL_EINVAL; }
 #undef FPL_LAUNCH_UMMA
         FPL_LAUNCH_CHECK(ctx);
@@ -1641,7 +1752,7 @@ bool umma_reads_volume(const fpl_net *net) {
     const ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
     const ConvPlan p2 = plan_conv(c2);
     return c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 && c2.cout == 48 &&
-           p2.ok && p2.n_split == 1 && p2.nsub == 1;
+           p2.ok && p2.n_split == 1 && p2.nsub == 1 && p2.rot;
 }
 
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
@@ -1668,7 +1779,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             const ConvParams &c1 = net->convs[o.conv_index], &c2 = net->convs[net->ops[1].conv_index];
             const ConvPlan p2 = plan_conv(c2);
             const bool shape_ok = c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 &&
-                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && d >= 8 && dzv >= 8;
+                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && p2.rot && d >= 8 && dzv >= 8;
             if (shape_ok) {
                 const int dout = d - 4, dout_z = dzv - 4;
                 const bool pool = !g_no_pool_fusion && net->ops.size() > 2 && net->ops[2].kind == OP_POOL &&

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import models_oracle as M
+from tests.golden import cases
 
 pytestmark = pytest.mark.gpu
 
