@@ -1063,9 +1063,9 @@ conv_fused12_kernel(const FusedArgs a) {
     uint64_t *a1_empty = bars + 6;           // [1]
     uint64_t *l1_full = bars + 7;            // [3]  first-layer accumulator tiles
     uint64_t *l1_empty = bars + 10;          // [3]
-    uint64_t *acc_full = bars + 13;          // [2][3]  second-layer accumulator blocks, per M-tile
-    uint64_t *acc_empty = bars + 19;         // [2][3]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+    uint64_t *acc_full = bars + 13;          // [3]  second-layer accumulator blocks
+    uint64_t *acc_empty = bars + 16;         // [3]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
@@ -1074,8 +1074,10 @@ conv_fused12_kernel(const FusedArgs a) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&plane_full[i], 4); mbar_init(&plane_empty[i], 1); }
         mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4); }
-        for (int i = 0; i < 6; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x)
@@ -1108,9 +1110,8 @@ conv_fused12_kernel(const FusedArgs a) {
         const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
-        const uint32_t idesc_3 = make_idesc_bf16(128, (int)(3u * N));
-        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * 5u) << 16);       // [kd0 kd1 kd2 kd0 kd1] row blocks (ROT)
-        const uint32_t b_step16 = N * 5u * 2u;
+        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * KS) << 16);
+        const uint32_t b_step16 = N * KS * 2u;
         const uint32_t a1_hi = (128u >> 4) | (1u << 14);
         const uint32_t a1_lo0 = (smem_u32(s_a1) >> 4) | ((2048u >> 4) << 16);
         const uint32_t b1_lo0 = (smem_u32(s_w1) >> 4) | ((uint32_t)C1 << 16);
@@ -1150,52 +1151,61 @@ conv_fused12_kernel(const FusedArgs a) {
                 const uint32_t slot = pc2 & 1u, ph = (pc2 >> 1) & 1u;
                 const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
                 const int kd_hi = ip < KS - 1 ? ip : KS - 1;
-                const bool full = kd_lo == 0 && kd_hi == KS - 1;
-                const uint32_t A0 = ac0 + (uint32_t)ip;            // output fed through kd = 0
-                const uint32_t r = A0 % NBLK;
-                const uint32_t win = ((r + 1u) % 3u) * N;          // rotating window, see conv_umma_kernel<.., ROT>
+                const uint32_t L = (uint32_t)(kd_hi - kd_lo + 1);
+                const uint32_t r = (ac0 + (uint32_t)(ip - kd_lo)) % NBLK;
+                const uint32_t len0 = L < r + 1u ? L : r + 1u, len1 = L - len0;
+                const uint32_t blk0 = NBLK - 1u - r;
+                const uint32_t kd1 = (uint32_t)kd_lo + len0;
+                const uint32_t d_seg0 = tmem_base + blk0 * N, b_seg0 = (uint32_t)kd_lo * N;
+                const uint32_t d_seg1 = tmem_base, b_seg1 = kd1 * N;
+                const uint32_t i_seg0 = idesc_1 + ((((len0 - 1u) * N) >> 3) << 17);
+                const uint32_t i_seg1 = idesc_1 + (((((len1 ? len1 : 1u) - 1u) * N) >> 3) << 17);
+                if (kd_lo == 0) {
+                    const uint32_t A = ac0 + (uint32_t)ip;
+                    mbar_wait(&acc_empty[blk0], ((A / NBLK) & 1u) ^ 1u);
+                }
                 mbar_wait(&plane_full[slot], ph);
                 tc_fence_after();
-                const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+                if (leader) {
+                    const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
 #pragma unroll 1
-                for (int m = 0; m < 2; ++m) {
-                    if (kd_lo == 0) mbar_wait(&acc_empty[m * 3 + (2u - r)], ((A0 / NBLK) & 1u) ^ 1u);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t d_reg = tmem_base + (uint32_t)m * kRegion;
-#pragma unroll 1
-                        for (int kh = 0; kh < KS; ++kh)
+                    for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-                            for (int kw = 0; kw < KS; ++kw) {
-                                uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
+                        for (int kw = 0; kw < KS; ++kw) {
+                            uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
 #pragma unroll
-                                for (int s = 0; s < KSTEPS; ++s) {
-                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4) +
-                                                          (uint32_t)m * 8u;
-                                    const uint64_t ad = desc64(a_lo, a_hi);
-                                    const bool first = kh == 0 && kw == 0 && s == 0;
-                                    if (full && !first) {
-                                        umma_bf16(d_reg, ad, desc64(b_lo + win, b_hi), idesc_3, 1u);
-                                    } else {
+                            for (int s = 0; s < KSTEPS; ++s) {
+                                const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
+                                const uint64_t ad0 = desc64(a_lo, a_hi), ad1 = desc64(a_lo + 8u, a_hi);
+                                if (kh == 0 && kw == 0 && s == 0) {
 #pragma unroll
-                                        for (int kd = 0; kd < KS; ++kd)
-                                            if (kd >= kd_lo && kd <= kd_hi) {
-                                                const uint32_t bl = 2u - (r + 3u - (uint32_t)kd) % 3u;
-                                                umma_bf16(d_reg + bl * N, ad, desc64(b_lo + (uint32_t)kd * N, b_hi), idesc_1,
-                                                          (first && kd == 0) ? 0u : 1u);
-                                            }
+                                    for (int kd = 0; kd < KS; ++kd)
+                                        if (kd >= kd_lo && kd <= kd_hi) {
+                                            const uint32_t bl = (uint32_t)kd < kd1 ? blk0 + (uint32_t)(kd - kd_lo) : (uint32_t)kd - kd1;
+                                            const uint64_t bd = desc64(b_lo + (uint32_t)kd * N, b_hi);
+                                            const uint32_t dcol = tmem_base + bl * N;
+                                            umma_bf16(dcol, ad0, bd, idesc_1, kd ? 1u : 0u);
+                                            umma_bf16(dcol + kRegion, ad1, bd, idesc_1, kd ? 1u : 0u);
+                                        }
+                                } else {
+                                    const uint64_t bd0 = desc64(b_lo + b_seg0, b_hi);
+                                    umma_bf16(d_seg0, ad0, bd0, i_seg0, 1u);
+                                    umma_bf16(d_seg0 + kRegion, ad1, bd0, i_seg0, 1u);
+                                    if (len1) {
+                                        const uint64_t bd1 = desc64(b_lo + b_seg1, b_hi);
+                                        umma_bf16(d_seg1, ad0, bd1, i_seg1, 1u);
+                                        umma_bf16(d_seg1 + kRegion, ad1, bd1, i_seg1, 1u);
                                     }
-                                    b_lo += b_step16;
                                 }
+                                b_lo += b_step16;
                             }
-                        if (ip >= KS - 1) {
-                            const uint32_t Ad = ac0 + (uint32_t)(ip - (KS - 1));
-                            umma_commit(&acc_full[m * 3 + (2u - Ad % NBLK)]);
                         }
+                    umma_commit(&plane_empty[slot]);
+                    if (ip >= KS - 1) {
+                        const uint32_t A = ac0 + (uint32_t)(ip - (KS - 1));
+                        umma_commit(&acc_full[NBLK - 1u - (A % NBLK)]);
                     }
-                    __syncwarp();
                 }
-                if (leader) umma_commit(&plane_empty[slot]);
                 __syncwarp();
                 if (ip + 2 < np) issue_l1();          // first-layer plane ip+2 behind this plane's MMAs
             }
@@ -1219,7 +1229,7 @@ conv_fused12_kernel(const FusedArgs a) {
             const int nz = min(a.zc_len, a.dout_z - z0);
             for (int zo = 0; zo < nz; ++zo, ++A) {
                 const uint32_t bl = NBLK - 1u - (A % NBLK), ph = (A / NBLK) & 1u;
-                mbar_wait(&acc_full[m * 3 + bl], ph);
+                mbar_wait(&acc_full[bl], ph);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)m * kRegion + bl * N;
                 if (a.pool)
@@ -1230,7 +1240,7 @@ conv_fused12_kernel(const FusedArgs a) {
                                   C2, 0, a.dout_z);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[m * 3 + bl]);
+                if (lane == 0) mbar_arrive(&acc_empty[bl]);
             }
         }
     } else if (warp < 14) {
@@ -1752,7 +1762,7 @@ bool umma_reads_volume(const fpl_net *net) {
     const ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
     const ConvPlan p2 = plan_conv(c2);
     return c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 && c2.cout == 48 &&
-           p2.ok && p2.n_split == 1 && p2.nsub == 1 && p2.rot;
+           p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot;
 }
 
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
@@ -1779,7 +1789,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             const ConvParams &c1 = net->convs[o.conv_index], &c2 = net->convs[net->ops[1].conv_index];
             const ConvPlan p2 = plan_conv(c2);
             const bool shape_ok = c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 &&
-                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && p2.rot && d >= 8 && dzv >= 8;
+                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot && d >= 8 && dzv >= 8;
             if (shape_ok) {
                 const int dout = d - 4, dout_z = dzv - 4;
                 const bool pool = !g_no_pool_fusion && net->ops.size() > 2 && net->ops[2].kind == OP_POOL &&
