@@ -33,6 +33,38 @@ namespace v2o {
 constexpr int kMaxLw = 32;                 // sigma <= 16 (truncate 2.0)
 struct Taps { double w[2 * kMaxLw + 1]; }; // correlate-order taps, centre at w[lw]
 
+// monotone uint32 key of a float32 (radix select, cut-offs): a < b  <=>  key(a) < key(b)
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+struct SelectState {                 // lives in device memory
+    unsigned long long rank;         // rank still to locate inside the current prefix class
+    unsigned prefix;                 // key bits fixed so far (high bits)
+    unsigned prefix_mask;            // which bits are fixed
+    unsigned long long extra_zeros;  // implicit +0.0 values of the never-materialised border
+    unsigned long long nan_count;
+    unsigned long long n_above;      // interior values whose key lies above the current prefix class
+    unsigned long long n_bin;        // interior values inside the current prefix class
+    unsigned long long hist[16][2048];   // kHistSlots partial histograms: blocks spread their flushes over the slots
+};
+constexpr int kHistSlots = 16;
+
+// run-length compressed feed of a block-level shared-memory histogram
+struct HistFeed {
+    unsigned last_bin = 0xffffffffu, run = 0;
+    __device__ __forceinline__ void add(unsigned *h, unsigned b) {
+        if (b == last_bin) { ++run; }
+        else { if (run) atomicAdd(&h[last_bin], run); last_bin = b; run = 1; }
+    }
+    __device__ __forceinline__ void flush(unsigned *h) { if (run) atomicAdd(&h[last_bin], run); run = 0; last_bin = 0xffffffffu; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // index map of one filtered line: interior coordinate p (may lie outside [0,n)) -> interior source
 // index, or -1 when the padded-and-reflected line holds a pad zero there.
@@ -88,26 +120,75 @@ constexpr int kRun = 8;
 constexpr int kRunsPerThread = 4;
 constexpr int kTN = kGroups * kRunsPerThread * kRun;   // 64 outputs along the axis per block
 
+// Exact SciPy chain of one output: tmp = x0*w0; tmp += (x[-j] + x[+j]) * w[j], every operation rounded.
+template <int LW>
+__device__ __forceinline__ float exact_output(const double (&x)[kRun + 2 * LW], const Taps &taps, int c) {
+    double tmp = __dmul_rn(x[c], taps.w[LW]);
+#pragma unroll
+    for (int j = -LW; j < 0; ++j)
+        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(x[c + j], x[c - j]), taps.w[LW + j]));
+    return (float)tmp;
+}
+
+// kRun outputs from a register window.
+//
+// Certified fast chain (cert > 0, all window inputs and all taps non-negative): the FP64 pipe is the
+// bound of this kernel (31 non-fused DP operations per output), so the chain is first evaluated with
+// the product and the accumulate FUSED (t' = fma(x[-j]+x[+j], w[j], t'): 21 DP operations).  With
+// non-negative terms every partial sum is bounded by the result, and the two chains differ by at most
+// (1 + 2*LW) * 2^-53 relative, i.e. < 22 ulp(t') for LW <= 10.  float32(t') therefore equals the
+// reference's float32(t) unless t' lies within that distance of a float32 rounding boundary (the low
+// 29 mantissa bits of t' within `cert` >= 64 of 2^28), or outside the float32 normal range.  Those
+// outputs (about 2.4e-7 of them at cert = 64) are recomputed with the exact chain; all others are proven
+// to round identically.  Exactness never rests on the fast chain.
 template <int LW>
 __device__ __forceinline__ void run_from_window(const double (&x)[kRun + 2 * LW], const Taps &taps,
-                                                float (&res)[kRun]) {
+                                                float (&res)[kRun], bool nonneg, unsigned cert,
+                                                const float *win, int wstride) {
+    if (cert && nonneg) {
+        unsigned bad = 0;
 #pragma unroll
-    for (int q = 0; q < kRun; ++q) {
-        const int c = q + LW;
-        double tmp = __dmul_rn(x[c], taps.w[LW]);
+        for (int q = 0; q < kRun; ++q) {
+            const int c = q + LW;
+            double t = __dmul_rn(x[c], taps.w[LW]);
 #pragma unroll
-        for (int j = -LW; j < 0; ++j)
-            tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(x[c + j], x[c - j]), taps.w[LW + j]));
-        res[q] = (float)tmp;
+            for (int j = -LW; j < 0; ++j) t = __fma_rn(__dadd_rn(x[c + j], x[c - j]), taps.w[LW + j], t);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+            const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32);
+            const unsigned dist = (lo & 0x1fffffffu) - (0x10000000u - cert);      // <= 2*cert near a boundary
+            const unsigned e = (hi >> 20) & 0x7ffu;                                // sign bit is clear
+            // safe exponent range: 2^-125 <= t < 2^127 (float32 normal, no overflow); exact zero is safe
+            const bool unsafe = (dist <= 2u * cert) || ((e - 898u) >= 252u && bits != 0ULL);
+            res[q] = (float)t;
+            bad |= (unsafe ? 1u : 0u) << q;
+        }
+        // rare: recompute the flagged outputs with the exact chain, re-reading the window from shared
+        // memory (kept out of the unrolled register code on purpose)
+#pragma unroll 1
+        for (int q = 0; bad >> q; ++q)
+            if ((bad >> q) & 1u) {
+                const float *wp = win + (q + LW) * wstride;
+                double tmp = __dmul_rn((double)wp[0], taps.w[LW]);
+#pragma unroll
+                for (int j = -LW; j < 0; ++j)
+                    tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)wp[j * wstride], (double)wp[-j * wstride]), taps.w[LW + j]));
+                const float rv = (float)tmp;
+#pragma unroll
+                for (int qq = 0; qq < kRun; ++qq)
+                    if (qq == q) res[qq] = rv;            // predicated moves: res stays in registers
+            }
+        return;
     }
+#pragma unroll
+    for (int q = 0; q < kRun; ++q) res[q] = exact_output<LW>(x, taps, q + LW);
 }
 
 // filtered axis has stride `inner` (> 1 in practice: z and y passes); lines are contiguous in memory
 template <int LW>
 __global__ void __launch_bounds__(kLines * kGroups)
 gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long long n,
-                     long long inner, int r, Taps taps) {
-    __shared__ float tile[kTN + 2 * LW][kLines];
+                     long long inner, int r, Taps taps, unsigned cert) {
+    __shared__ __align__(16) float tile[kTN + 2 * LW][kLines];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const unsigned nchunks = (unsigned)((n + kTN - 1) / kTN);
     const long long n0 = (long long)(blockIdx.x % nchunks) * kTN;      // n-chunk fastest: blocks that
@@ -116,13 +197,32 @@ gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long
     const float *src = in + o * n * inner;
     float *dst = out + o * n * inner;
     const bool live = i < inner;
-    {
+    // no reflection can occur when the tile (with halo) stays inside the zero-padded line
+    const bool simple = (n0 - LW + r >= 0) && (n0 + kTN + LW - 1 < n + r);
+    const long long i0 = i - tx;
+    if (simple && (inner & 3) == 0 && i0 + kLines <= inner && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // vector staging (the passes are instruction-issue bound, profiles/): the 64 lines of a tile row are
+        // contiguous in memory -> 16 float4 per row, 8 rows per step, every load of the thread in flight at once
+        constexpr int kW = kTN + 2 * LW, kSteps = (kW + 7) / 8;
+        const int tid = ty * kLines + tx, c4 = tid & 15, r0 = tid >> 4;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + i0) + c4;
+        float4 tmp[kSteps];
+#pragma unroll
+        for (int sidx = 0; sidx < kSteps; ++sidx) {
+            const int row = r0 + 8 * sidx;
+            const long long p = n0 - LW + row;
+            tmp[sidx] = (row < kW && p >= 0 && p < n) ? __ldg(s4 + p * (inner >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < kSteps; ++sidx) {
+            const int row = r0 + 8 * sidx;
+            if (row < kW) *reinterpret_cast<float4 *>(&tile[row][4 * c4]) = tmp[sidx];
+        }
+    } else {
         // stage the (kTN + 2 LW) x 64 source tile: loads are issued in batches of kBatch rows before any is
         // stored, so that kBatch global loads per thread are in flight (the pass is latency bound otherwise)
         constexpr int kRowsT = (kTN + 2 * LW + kGroups - 1) / kGroups;
         constexpr int kBatch = 14;
-        // no reflection can occur when the tile (with halo) stays inside the zero-padded line
-        const bool simple = (n0 - LW + r >= 0) && (n0 + kTN + LW - 1 < n + r);
 #pragma unroll 1
         for (int b0 = 0; b0 < kRowsT; b0 += kBatch) {
             float tmp[kBatch];
@@ -150,10 +250,15 @@ gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long
         const int base = (ty * kRunsPerThread + run) * kRun;
         if (n0 + base >= n) break;
         double x[kRun + 2 * LW];
+        unsigned sgn = 0;
 #pragma unroll
-        for (int k = 0; k < kRun + 2 * LW; ++k) x[k] = (double)tile[base + k][tx];
+        for (int k = 0; k < kRun + 2 * LW; ++k) {
+            const float tv = tile[base + k][tx];
+            sgn |= __float_as_uint(tv);
+            x[k] = (double)tv;
+        }
         float res[kRun];
-        run_from_window<LW>(x, taps, res);
+        run_from_window<LW>(x, taps, res, (sgn >> 31) == 0u, cert, &tile[base][tx], kLines);
         if (live) {
 #pragma unroll
             for (int q = 0; q < kRun; ++q)
@@ -168,7 +273,7 @@ gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long
 template <int LW>
 __global__ void __launch_bounds__(kLines * kGroups)
 gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long long rows,
-                    long long n, int r, Taps taps) {
+                    long long n, int r, Taps taps, unsigned cert) {
     constexpr int kPitch = kLines + 1;
     __shared__ float tile[(kTN + 2 * LW) * kPitch];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -177,7 +282,36 @@ gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long 
     const long long n0 = (long long)(blockIdx.x % nchunks) * kTN;
     const long long row0 = (long long)(blockIdx.x / nchunks) * kLines;
     constexpr int kW = kTN + 2 * LW;
-    {
+    const bool simple_t = (n0 - LW + r >= 0) && (n0 + kTN + LW - 1 < n + r);
+    const bool vec_rows = (n & 3) == 0 && row0 + kLines <= rows;
+    if (simple_t && vec_rows && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        // vector staging: a warp covers 4 rows x 8 float4 (128 contiguous bytes per row); with the 65-word
+        // pitch the transposed scalar stores of such a group hit 32 different banks
+        constexpr int kLWa = (LW + 3) & ~3, kShift = kLWa - LW;       // tile origin rounded down to 4 floats
+        constexpr int kCG = (kTN + 2 * kLWa + 31) / 32;                // column groups of 32 floats
+        constexpr int kIters = (16 * kCG + 3) / 4;                     // per warp (4 warps)
+        const int w = tid >> 5, lane = tid & 31, c4l = lane & 7, rl = lane >> 3;
+        float4 tmp[kIters];
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+            const int it = w + 4 * j, rg = it / kCG, cg = it - rg * kCG;
+            const long long xg = n0 - kLWa + 4 * (cg * 8 + c4l);
+            tmp[j] = (it < 16 * kCG && xg >= 0 && xg < n)
+                         ? __ldg(reinterpret_cast<const float4 *>(in + (row0 + rg * 4 + rl) * n + xg))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < kIters; ++j) {
+            const int it = w + 4 * j, rg = it / kCG, cg = it - rg * kCG;
+            if (it < 16 * kCG) {
+                const int xx0 = 4 * (cg * 8 + c4l) - kShift, rr = rg * 4 + rl;
+                const float e4[4] = {tmp[j].x, tmp[j].y, tmp[j].z, tmp[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (xx0 + e >= 0 && xx0 + e < kW) tile[(xx0 + e) * kPitch + rr] = e4[e];
+            }
+        }
+    } else {
         // thread -> (row group, x lane): each warp reads 32 consecutive x of one row (coalesced); loads are
         // batched (kBatch in flight per thread) before the transposed stores
         constexpr int kThreadsB = kLines * kGroups;
@@ -215,9 +349,14 @@ gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long 
     for (int run = 0; run < kRunsPerThread; ++run) {
         const int base = (ty * kRunsPerThread + run) * kRun;
         double x[kRun + 2 * LW];
+        unsigned sgn = 0;
 #pragma unroll
-        for (int k = 0; k < kRun + 2 * LW; ++k) x[k] = (double)tile[(base + k) * kPitch + tx];
-        run_from_window<LW>(x, taps, res[run]);
+        for (int k = 0; k < kRun + 2 * LW; ++k) {
+            const float tv = tile[(base + k) * kPitch + tx];
+            sgn |= __float_as_uint(tv);
+            x[k] = (double)tv;
+        }
+        run_from_window<LW>(x, taps, res[run], (sgn >> 31) == 0u, cert, &tile[base * kPitch + tx], kPitch);
     }
     __syncthreads();
 #pragma unroll
@@ -226,29 +365,50 @@ gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long 
 #pragma unroll
         for (int q = 0; q < kRun; ++q) tile[(base + q) * kPitch + tx] = res[run][q];
     }
+
     __syncthreads();
+    if (vec_rows && n0 + kTN <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int w = tid >> 5, lane = tid & 31, c4l = lane & 7, rl = lane >> 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                       // 16 row groups x 2 column groups over 4 warps
+            const int it = w + 4 * j, rg = it >> 1, cg = it & 1;
+            const int xx0 = 4 * (cg * 8 + c4l), rr = rg * 4 + rl;
+            const float4 o4 = make_float4(tile[xx0 * kPitch + rr], tile[(xx0 + 1) * kPitch + rr],
+                                          tile[(xx0 + 2) * kPitch + rr], tile[(xx0 + 3) * kPitch + rr]);
+            *reinterpret_cast<float4 *>(out + (row0 + rr) * n + n0 + xx0) = o4;
+        }
+        return;
+    }
     for (int idx = tid; idx < kLines * kTN; idx += kLines * kGroups) {
         int rr = idx / kTN, xx = idx - rr * kTN;
         if (row0 + rr < rows && n0 + xx < n) out[(row0 + rr) * n + n0 + xx] = tile[xx * kPitch + rr];
     }
 }
 
+// certified-FMA margin (double ulps); 0 = exact chain only.  Off by default: the passes turned out to be
+// instruction-issue bound, not FP64-pipe bound (ncu: issue slots 78 % busy, FP64 pipe 32 %), and the
+// certificate's integer work costs more issue slots than the 10 fused operations save (profiles/).
+static unsigned g_gauss_cert = 0;
+
 template <int LW>
 static int launch_pass_fast(fpl_ctx *ctx, const float *in, float *out, long long outer, long long n,
                             long long inner, int r, const Taps &taps, cudaStream_t st) {
     dim3 block(kLines, kGroups);
     const long long nchunks = (n + kTN - 1) / kTN;
+    // the certificate needs non-negative taps (Gaussian taps always are) and its error bound covers LW <= 10
+    unsigned cert = LW <= 10 ? g_gauss_cert : 0u;
+    for (int i = 0; i < 2 * LW + 1; ++i) if (!(taps.w[i] >= 0.0)) cert = 0u;
     if (inner == 1) {
         const long long rows = outer;
         const long long gx = nchunks * ((rows + kLines - 1) / kLines);
         FPL_REQUIRE(gx < 2147483647LL, "gauss pass: volume too large for one launch");
-        gauss_contig_kernel<LW><<<dim3((unsigned)gx), block, 0, st>>>(in, out, rows, n, r, taps);
+        gauss_contig_kernel<LW><<<dim3((unsigned)gx), block, 0, st>>>(in, out, rows, n, r, taps, cert);
         FPL_LAUNCH_CHECK(ctx);
         return FPL_OK;
     }
     const long long gx = nchunks * ((inner + kLines - 1) / kLines);
     FPL_REQUIRE(gx < 2147483647LL && outer <= 65535, "gauss pass: volume too large for one launch");
-    gauss_strided_kernel<LW><<<dim3((unsigned)gx, (unsigned)outer), block, 0, st>>>(in, out, n, inner, r, taps);
+    gauss_strided_kernel<LW><<<dim3((unsigned)gx, (unsigned)outer), block, 0, st>>>(in, out, n, inner, r, taps, cert);
     FPL_LAUNCH_CHECK(ctx);
     return FPL_OK;
 }
@@ -279,31 +439,13 @@ static int launch_pass(fpl_ctx *ctx, const float *in, float *out, long long oute
 // ------------------------------------------------------------------------------------------------
 // radix select
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned f2key(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key2f(unsigned k) {
-    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(u);
-}
-
-struct SelectState {                 // lives in device memory
-    unsigned long long rank;         // rank still to locate inside the current prefix class
-    unsigned prefix;                 // key bits fixed so far (high bits)
-    unsigned prefix_mask;            // which bits are fixed
-    unsigned long long extra_zeros;  // implicit +0.0 values of the never-materialised border
-    unsigned long long nan_count;
-    unsigned long long hist[2048];
-};
-
 constexpr int kHistBits0 = 11, kHistBits1 = 11, kHistBits2 = 10;
 
 __global__ void select_init_kernel(SelectState *s, unsigned long long rank,
                                    unsigned long long extra_zeros) {
     int t = threadIdx.x;
-    for (int b = t; b < 2048; b += blockDim.x) s->hist[b] = 0;
-    if (t == 0) { s->rank = rank; s->prefix = 0; s->prefix_mask = 0; s->extra_zeros = extra_zeros; s->nan_count = 0; }
+    for (int b = t; b < kHistSlots * 2048; b += blockDim.x) (&s->hist[0][0])[b] = 0;
+    if (t == 0) { s->rank = rank; s->prefix = 0; s->prefix_mask = 0; s->extra_zeros = extra_zeros; s->nan_count = 0; s->n_above = 0; s->n_bin = 0; }
 }
 
 // histogram of ((key >> shift) & (bins-1)) over values whose key matches the current prefix
@@ -353,7 +495,7 @@ select_hist_kernel(const float *__restrict__ v, long long n, SelectState *s, int
     if (my_nan) atomicAdd(&nan_local, my_nan);
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
-        if (h[b]) atomicAdd(&s->hist[b], (unsigned long long)h[b]);
+        if (h[b]) atomicAdd(&s->hist[blockIdx.x % kHistSlots][b], (unsigned long long)h[b]);
     if (threadIdx.x == 0 && nan_local) atomicAdd(&s->nan_count, (unsigned long long)nan_local);
 }
 
@@ -368,7 +510,9 @@ select_scan_kernel(SelectState *s, int shift, int bins) {
     const bool zero_here = (zkey & s->prefix_mask) == s->prefix;
     const int zbin = (int)((zkey >> shift) & (unsigned)(bins - 1));
     for (int b = t; b < 2048; b += 1024) {
-        unsigned long long c = b < bins ? s->hist[b] : 0ULL;
+        unsigned long long c = 0ULL;
+        if (b < bins)
+            for (int sl = 0; sl < kHistSlots; ++sl) c += s->hist[sl][b];
         if (zero_here && b == zbin) c += s->extra_zeros;
         cum[b] = c;
     }
@@ -391,9 +535,13 @@ select_scan_kernel(SelectState *s, int shift, int bins) {
     __syncthreads();
     const int sel = sel_bin;
     const unsigned long long before = sel ? cum[sel - 1] : 0ULL;
+    const unsigned long long upto = cum[sel], total = cum[bins - 1];
     __syncthreads();
-    for (int b = t; b < bins; b += 1024) s->hist[b] = 0;
+    for (int b = t; b < kHistSlots * 2048; b += 1024) (&s->hist[0][0])[b] = 0;
     if (t == 0) {
+        // interior (materialised) values above / inside the selected bin: the implicit zeros are not interior
+        s->n_above += (total - upto) - ((zero_here && zbin > sel) ? s->extra_zeros : 0ULL);
+        s->n_bin = (upto - before) - ((zero_here && zbin == sel) ? s->extra_zeros : 0ULL);
         s->rank = rank - before;
         s->prefix |= ((unsigned)sel) << shift;
         s->prefix_mask |= ((unsigned)(bins - 1)) << shift;
@@ -638,17 +786,21 @@ nms_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ s
                      const float *__restrict__ g, int gz, int gy, int gx,
                      const unsigned long long *__restrict__ w_idx, const float *__restrict__ w_val,
                      unsigned long long *det_idx, float *det_val, unsigned long long *sel_idx,
-                     long long det_capacity, Counters *cnt) {
+                     long long det_capacity, Counters *cnt, const SelectState *cut) {
     __shared__ int s_list[1024];
     __shared__ int s_n, found;
     const unsigned long long nW = cnt->n_work;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int r2 = r * r;
+    // fast path, first round: the worklist holds every local maximum above the level-1 cut-off; entries
+    // below the (meanwhile known) level-2 cut-off are not part of the candidate superset
+    const unsigned cutoff = cut ? (cut->prefix > 0x80000001u ? cut->prefix : 0x80000001u) : 0u;
     for (unsigned long long w = blockIdx.x; w < nW; w += gridDim.x) {
-        if (threadIdx.x == 0) { found = 0; s_n = 0; }
-        __syncthreads();
         const unsigned long long idx = w_idx[w];
         const float val = w_val[w];
+        if (cut && f2key(val) < cutoff) continue;          // block-uniform
+        if (threadIdx.x == 0) { found = 0; s_n = 0; }
+        __syncthreads();
         const int x = (int)(idx % (unsigned long long)d.X);
         const int y = (int)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
         const int z = (int)(idx / ((unsigned long long)d.X * d.Y));
@@ -791,7 +943,8 @@ __global__ void bitonic_step_kernel(unsigned *skey, unsigned long long *sidx, lo
 __global__ void __launch_bounds__(1024)
 finish_rows_kernel(const unsigned *skey, const unsigned long long *sidx, long long n, Dims d,
                    int bx, int by, int bz, double ox, double oy, double oz, double *rows,
-                   long long capacity, unsigned long long *n_out, unsigned long long *overflow) {
+                   long long capacity, unsigned long long *n_out, unsigned long long *overflow,
+                   const ThreshOut *tout) {
     __shared__ unsigned warp_tot[32];
     __shared__ unsigned long long base;
     if (threadIdx.x == 0) base = 0;
@@ -807,7 +960,11 @@ finish_rows_kernel(const unsigned *skey, const unsigned long long *sidx, long lo
             long long zi = (long long)(idx / ((unsigned long long)d.X * d.Y));
             keep = xi >= bx && yi >= by && zi >= bz && xi < d.X - bx && yi < d.Y - by && zi < d.Z - bz;
             x = (double)xi + ox; y = (double)yi + oy; z = (double)zi + oz;
-            c = (double)key2f(~skey[i]);
+            const float cf = key2f(~skey[i]);
+            c = (double)cf;
+            // fast path: NMS ran on a superset (cut-off below the threshold); selected points that are not
+            // candidates of the reference (pred > thresh, and the loop stops at max_val <= 0) are dropped here
+            if (tout) keep = keep && (c > tout->thresh) && (cf > 0.f);
         }
         unsigned m = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_tot[warp] = __popc(m);
@@ -903,6 +1060,263 @@ static int threshold_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
     return FPL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused ("fast") detection path: two dense passes over the smoothed map instead of five
+//   level-1 select histogram  : taken by the Gaussian x pass (gauss_contig_kernel) on its way out
+//   dense pass 1              : level-2 histogram + 8^3 brick maxima + every 26-neighbourhood local
+//                               maximum above the level-1 cut-off (= worklist of the first NMS round:
+//                               with nothing suppressed yet, "no better valid neighbour" is exactly
+//                               "local maximum", decided once from data that is being streamed anyway)
+//   [round 1: ball check + suppression of the local maxima above the level-2 cut-off]
+//   dense pass 2              : level-3 histogram + compaction of the not yet suppressed voxels
+//                               above the level-2 cut-off (the survivors that later rounds work on)
+// The NMS runs on a SUPERSET of the reference's candidates: cut-off c <= threshold (the lower edge of
+// the 22-bit radix class that holds the percentile).  Greedy selection in descending (value, -index)
+// order reaches every true candidate before any extra element, and an extra element is only selected
+// when its ball holds no better valid voxel, so it can only suppress voxels that are not candidates
+// either: the selection among true candidates is unchanged, and selected extras (value <= threshold)
+// are dropped when the rows are written (finish_rows_kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void select_copy_kernel(const SelectState *src, SelectState *dst) {
+    for (int b = threadIdx.x; b < 2048; b += blockDim.x) {       // dst was cleared by select_init_kernel
+        unsigned long long c = 0ULL;
+        for (int sl = 0; sl < kHistSlots; ++sl) c += src->hist[sl][b];
+        dst->hist[0][b] = c;
+    }
+    if (threadIdx.x == 0) dst->nan_count = src->nan_count;
+}
+
+__device__ __forceinline__ unsigned cutoff_key(const SelectState *s) {
+    // lower edge of the current prefix class, but never below the smallest positive value
+    return s->prefix > 0x80000001u ? s->prefix : 0x80000001u;
+}
+
+// (z,y,x) has no better voxel in the rows (z+dz, y+dy), (dz,dy) != (0,0), at x-1..x+1.  "Better" is the
+// order of the greedy loop: larger value, or equal value and lower flat index.  All 24 loads are issued
+// before the first comparison (one memory latency instead of a chain of dependent ones).
+__device__ __forceinline__ bool no_better_in_other_rows(const float *__restrict__ v, Dims d, long long z, long long y,
+                                                        long long x, float val) {
+    float q[8][3];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        const int o = nb < 4 ? nb : nb + 1;                      // (dz,dy) in row-major order, skipping (0,0)
+        const long long zz = z + (o / 3 - 1), yy = y + (o % 3 - 1);
+        const bool rok = zz >= 0 && zz < d.Z && yy >= 0 && yy < d.Y;
+        const float *rp = v + ((unsigned long long)(rok ? zz : z) * d.Y + (rok ? yy : y)) * d.X;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const long long xx = x + dx - 1;
+            q[nb][dx] = (rok && xx >= 0 && xx < d.X) ? __ldg(rp + xx) : -INFINITY;
+        }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+            ok = ok && !(nb < 4 ? (q[nb][dx] >= val) : (q[nb][dx] > val));   // rows before (z,y) hold lower flat indices
+    return ok;
+}
+
+// Persistent blocks over (bz, by) brick rows (8 z x 8 y rows x all x); warp w owns y offset w, a lane owns 8
+// consecutive x per 256-wide chunk for all 8 z (32-byte vector loads, 8 rows in flight).  Stage 1 (unrolled,
+// registers only): brick maximum, level-2 histogram, candidates that survive the x-neighbour test.  Stage 2
+// (rare, rolled, out of line): the remaining 24 neighbours of those few voxels, re-read through L1/L2.
+__global__ void __launch_bounds__(256)
+dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, float *__restrict__ g,
+                   SelectState *st, int ns, unsigned long long *w_idx, float *w_val, long long w_cap,
+                   Counters *cnt) {
+    extern __shared__ unsigned dsm[];
+    float *s_max = reinterpret_cast<float *>(dsm);          // [gx]
+    unsigned *h2 = dsm + ((gx + 31) & ~31);                 // [ns][2048]
+    for (int i = threadIdx.x; i < ns * 2048; i += blockDim.x) h2[i] = 0;
+    const unsigned pre0 = st[0].prefix, msk0 = st[0].prefix_mask;
+    const unsigned pre1 = ns > 1 ? st[1].prefix : pre0, msk1 = ns > 1 ? st[1].prefix_mask : 0xffffffffu;
+    const bool two = ns > 1;
+    const unsigned cutoff = cutoff_key(&st[0]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec_ok = (d.X % 4 == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    for (int br = blockIdx.x; br < gz * gy; br += gridDim.x) {
+        const int bz = br / gy, by = br % gy;
+        for (int i = threadIdx.x; i < gx; i += blockDim.x) s_max[i] = -INFINITY;
+        __syncthreads();
+        const long long y = (long long)by * kBrick + warp;
+        for (long long xc = 0; xc < d.X; xc += 256) {
+            const long long x = xc + 8 * lane;
+            float f[8][8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long z = (long long)bz * kBrick + k;
+                const bool rok = z < d.Z && y < d.Y && x < d.X;
+                const float *rp = v + (z * d.Y + y) * d.X + x;
+                if (rok && vec_ok && x + 8 <= d.X) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(rp));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+                    f[k][0] = a4.x; f[k][1] = a4.y; f[k][2] = a4.z; f[k][3] = a4.w;
+                    f[k][4] = b4.x; f[k][5] = b4.y; f[k][6] = b4.z; f[k][7] = b4.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[k][e] = (rok && x + e < d.X) ? __ldg(rp + e) : -INFINITY;
+                }
+            }
+            float m = -INFINITY;
+            unsigned long long cmask = 0ULL;
+            // x neighbours across the lane boundary (all lanes take part in the shuffles)
+            float lf[8], rt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long z = (long long)bz * kBrick + k;
+                lf[k] = __shfl_up_sync(0xffffffffu, f[k][7], 1); rt[k] = __shfl_down_sync(0xffffffffu, f[k][0], 1);
+                if (lane == 0 || lane == 31) {
+                    const bool rok = z < d.Z && y < d.Y;
+                    const float *rp = v + (z * d.Y + y) * d.X;
+                    if (lane == 0) lf[k] = (rok && x > 0 && x - 1 < d.X) ? __ldg(rp + x - 1) : -INFINITY;
+                    else rt[k] = (rok && x + 8 < d.X) ? __ldg(rp + x + 8) : -INFINITY;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float fe = f[k][e];                      // -inf outside the volume
+                    m = fmaxf(m, fe);
+                    const unsigned key = f2key(fe);
+                    if ((key & msk0) == pre0) atomicAdd(&h2[(key >> 10) & 2047u], 1u);
+                    if (two && (key & msk1) == pre1) atomicAdd(&h2[2048 + ((key >> 10) & 2047u)], 1u);
+                    const float le = e ? f[k][e - 1] : lf[k], re = e < 7 ? f[k][e + 1] : rt[k];
+                    // lower flat index wins ties: the left neighbour beats an equal value, the right one does not
+                    bool c = key >= cutoff && !(le >= fe) && !(re > fe);
+                    // the z neighbours inside the brick are in this thread's registers: plane below first (lower index)
+                    if (c && k > 0) {
+                        const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
+                        c = !(a0 >= fe) && !(a1 >= fe) && !(a2 >= fe);
+                    }
+                    if (c && k < 7) {
+                        const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
+                        c = !(a0 > fe) && !(a1 > fe) && !(a2 > fe);
+                    }
+                    if (c) cmask |= 1ULL << (k * 8 + e);
+                }
+            }
+            if (x < d.X)
+                atomicMax(reinterpret_cast<int *>(&s_max[x / kBrick]), m >= 0.f ? __float_as_int(m) : (int)0x80000000);
+#pragma unroll 1
+            while (cmask) {
+                const int b = __ffsll((long long)cmask) - 1;
+                cmask &= cmask - 1ULL;
+                const long long z = (long long)bz * kBrick + (b >> 3), xx = x + (b & 7);
+                const unsigned long long idx = ((unsigned long long)z * d.Y + y) * d.X + xx;
+                const float val = __ldg(v + idx);
+                if (no_better_in_other_rows(v, d, z, y, xx, val)) {
+                    const unsigned long long pos = atomicAdd(&cnt->n_work, 1ULL);
+                    if ((long long)pos < w_cap) { w_idx[pos] = idx; w_val[pos] = val; }
+                    else atomicAdd(&cnt->overflow, 1ULL);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < gx; i += blockDim.x) g[((size_t)bz * gy + by) * gx + i] = s_max[i];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < ns * 2048; i += blockDim.x)
+        if (h2[i]) atomicAdd(&st[i >> 11].hist[blockIdx.x % kHistSlots][i & 2047], (unsigned long long)h2[i]);
+}
+
+// level-3 histogram + compaction of the still valid voxels above the level-2 cut-off (list A).
+// A thread takes kCh chunks of 8 consecutive voxels per iteration (8 x 16-byte loads in flight); the block
+// reserves its output range with one global atomic per iteration (list order is irrelevant to the result).
+__global__ void __launch_bounds__(256)
+dense_pass2_kernel(const float *__restrict__ v, long long n, const unsigned *__restrict__ sup, SelectState *st,
+                   int ns, unsigned long long *cand_idx, float *cand_val, long long capacity, Counters *cnt) {
+    constexpr int kCh = 4;
+    __shared__ unsigned h3[2 * 1024];
+    for (int i = threadIdx.x; i < ns * 1024; i += blockDim.x) h3[i] = 0;
+    __syncthreads();
+    const unsigned pre0 = st[0].prefix, msk0 = st[0].prefix_mask;
+    const unsigned pre1 = ns > 1 ? st[1].prefix : pre0, msk1 = ns > 1 ? st[1].prefix_mask : msk0;
+    const unsigned cutoff = cutoff_key(&st[0]);
+    const unsigned lane = threadIdx.x & 31;
+    const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    const long long n8 = (n + 7) / 8;
+    HistFeed feed0, feed1;
+    for (long long c0 = (long long)blockIdx.x * (kCh * 256); c0 < n8; c0 += (long long)gridDim.x * (kCh * 256)) {
+        float f[kCh][8];
+        unsigned valid[kCh];
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+            const long long c = c0 + k * 256 + threadIdx.x, i0 = c * 8;
+            valid[k] = 0;
+            if (c < n8 && aligned && i0 + 8 <= n) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(v + i0));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(v + i0) + 1);
+                f[k][0] = a4.x; f[k][1] = a4.y; f[k][2] = a4.z; f[k][3] = a4.w;
+                f[k][4] = b4.x; f[k][5] = b4.y; f[k][6] = b4.z; f[k][7] = b4.w;
+                valid[k] = 0xffu;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = c < n8 && i0 + j < n;
+                    f[k][j] = ok ? __ldg(v + i0 + j) : 0.f;
+                    if (ok) valid[k] |= 1u << j;
+                }
+            }
+        }
+        unsigned mask[kCh], cnt_me = 0;
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+            const long long i0 = (c0 + k * 256 + threadIdx.x) * 8;
+            unsigned m = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (valid[k] & (1u << j)) {
+                    const unsigned key = f2key(f[k][j]);
+                    if ((key & msk0) == pre0) feed0.add(h3, key & 1023u);
+                    if (ns > 1 && (key & msk1) == pre1) feed1.add(h3 + 1024, key & 1023u);
+                    if (key >= cutoff) m |= 1u << j;
+                }
+            if (m) m &= ~((sup[i0 >> 5] >> (i0 & 31)) & 0xffu);     // i0 is a multiple of 8: one byte of one word
+            mask[k] = m;
+            cnt_me += __popc(m);
+        }
+        unsigned pre = cnt_me;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= (unsigned)o) pre += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
+        // one global atomic per warp and iteration, and only where there is something to append (list order
+        // is irrelevant to the result); no block-level barrier in the streaming loop
+        unsigned long long wbase = 0;
+        if (total) {
+            if (lane == 0) wbase = atomicAdd(&cnt->n_cand, (unsigned long long)total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        }
+        unsigned long long pos = wbase + (pre - cnt_me);
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+            const long long i0 = (c0 + k * 256 + threadIdx.x) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (mask[k] & (1u << j)) {
+                    if ((long long)pos < capacity) { cand_idx[pos] = (unsigned long long)(i0 + j); cand_val[pos] = f[k][j]; }
+                    else atomicAdd(&cnt->overflow, 1ULL);
+                    ++pos;
+                }
+        }
+    }
+    feed0.flush(h3);
+    if (ns > 1) feed1.flush(h3 + 1024);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns * 1024; i += blockDim.x)
+        if (h3[i]) atomicAdd(&st[i >> 10].hist[blockIdx.x % kHistSlots][i & 1023], (unsigned long long)h3[i]);
+}
+
+// between round 1 and dense pass 2: the worklist of round 1 is spent, list A starts empty
+__global__ void fast_reset_kernel(Counters *cnt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cnt->n_cand = 0; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0; }
+}
+
 struct DetectBuffers {
     unsigned *sup; size_t sup_words;
     unsigned long long *a_idx, *b_idx, *w_idx, *det_idx, *sel_idx, *sidx;
@@ -911,43 +1325,44 @@ struct DetectBuffers {
     Counters *cnt;
     unsigned long long *n_out;
     float *grid;                    // brick maxima
-    long long cand_cap, work_cap, det_cap, sort_cap;
+    int gz, gy, gx;
+    long long list_cap, det_cap;
 };
 
 static long long next_pow2(long long v) { long long p = 1; while (p < v) p <<= 1; return p; }
 
-static size_t detect_workspace_bytes(long long n, long long cand_cap, long long det_cap) {
+static size_t brick_grid_bytes(int64_t Z, int64_t Y, int64_t X) {
+    return (size_t)((Z + kBrick - 1) / kBrick) * ((Y + kBrick - 1) / kBrick) * ((X + kBrick - 1) / kBrick) * 4;
+}
+
+static size_t detect_workspace_bytes(int64_t Z, int64_t Y, int64_t X, long long list_cap, long long det_cap) {
+    const long long n = Z * Y * X;
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 255) & ~size_t(255); };
     add(((size_t)n + 31) / 32 * 4);
-    add(cand_cap * 8); add(cand_cap * 8); add(cand_cap * 4); add(cand_cap * 4);   // A, B
-    add(cand_cap * 8); add(cand_cap * 4);                                          // worklist
+    add(list_cap * 8); add(list_cap * 8); add(list_cap * 4); add(list_cap * 4);   // A, B
+    add(list_cap * 8); add(list_cap * 4);                                          // worklist
     add(det_cap * 8); add(det_cap * 4); add(det_cap * 8);                          // det, sel
     long long sp = next_pow2(det_cap);
     add(sp * 4); add(sp * 8);
     add(sizeof(Counters)); add(64);
-    add(((size_t)n / 64 + 4 * (size_t)cbrt((double)n) * (size_t)cbrt((double)n) + 4096) * 4);   // brick grid (generous)
+    add(brick_grid_bytes(Z, Y, X));
     return b + 4096;
 }
 
-static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, int64_t X,
-                       const fpl_v2o_params *p, double threshold, long long cand_cap, double *d_dets,
-                       int64_t capacity, int64_t *h_count, int64_t *h_stats, cudaStream_t st) {
+static int take_detect_buffers(fpl_ctx *ctx, int64_t Z, int64_t Y, int64_t X, long long list_cap, long long det_cap,
+                               DetectBuffers &B, cudaStream_t st) {
     const long long n = Z * Y * X;
-    const int r = p->obj_min_dist;
-    Dims d{Z, Y, X};
-    long long det_cap = capacity > 0 ? capacity : 1;
-    // worklist capacity: every candidate could in principle be a local maximum
-    DetectBuffers B;
     fpl::Arena &A = ctx->arena;
+    B.list_cap = list_cap; B.det_cap = det_cap;
     B.sup_words = ((size_t)n + 31) / 32;
     B.sup = (unsigned *)A.take(B.sup_words * 4);
-    B.a_idx = (unsigned long long *)A.take(cand_cap * 8);
-    B.b_idx = (unsigned long long *)A.take(cand_cap * 8);
-    B.a_val = (float *)A.take(cand_cap * 4);
-    B.b_val = (float *)A.take(cand_cap * 4);
-    B.w_idx = (unsigned long long *)A.take(cand_cap * 8);
-    B.w_val = (float *)A.take(cand_cap * 4);
+    B.a_idx = (unsigned long long *)A.take(list_cap * 8);
+    B.b_idx = (unsigned long long *)A.take(list_cap * 8);
+    B.a_val = (float *)A.take(list_cap * 4);
+    B.b_val = (float *)A.take(list_cap * 4);
+    B.w_idx = (unsigned long long *)A.take(list_cap * 8);
+    B.w_val = (float *)A.take(list_cap * 4);
     B.det_idx = (unsigned long long *)A.take(det_cap * 8);
     B.det_val = (float *)A.take(det_cap * 4);
     B.sel_idx = (unsigned long long *)A.take(det_cap * 8);
@@ -956,49 +1371,38 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
     B.sidx = (unsigned long long *)A.take(sp * 8);
     B.cnt = (Counters *)A.take(sizeof(Counters));
     B.n_out = (unsigned long long *)A.take(64);
-    const int gz = (int)((Z + kBrick - 1) / kBrick), gy = (int)((Y + kBrick - 1) / kBrick), gx = (int)((X + kBrick - 1) / kBrick);
-    B.grid = (float *)A.take((size_t)gz * gy * gx * 4);
-    if (!B.grid) { fpl::set_error("voxel2obj: workspace too small for the brick grid"); return FPL_ENOMEM; }
+    B.gz = (int)((Z + kBrick - 1) / kBrick); B.gy = (int)((Y + kBrick - 1) / kBrick); B.gx = (int)((X + kBrick - 1) / kBrick);
+    B.grid = (float *)A.take(brick_grid_bytes(Z, Y, X));
     if (!B.sup || !B.a_idx || !B.b_idx || !B.a_val || !B.b_val || !B.w_idx || !B.w_val || !B.det_idx ||
-        !B.det_val || !B.sel_idx || !B.skey || !B.sidx || !B.cnt || !B.n_out) {
+        !B.det_val || !B.sel_idx || !B.skey || !B.sidx || !B.cnt || !B.n_out || !B.grid) {
         fpl::set_error("voxel2obj: internal workspace sizing error");
         return FPL_ENOMEM;
     }
+    FPL_REQUIRE(B.gz < 2048 && B.gy < 1024 && B.gx < 1024 && B.gx * sizeof(float) <= 16384,
+                "voxel2obj: volume outside the brick-grid limits");
     FPL_CUDA_CHECK(cudaMemsetAsync(B.sup, 0, B.sup_words * 4, st));
     FPL_CUDA_CHECK(cudaMemsetAsync(B.cnt, 0, sizeof(Counters), st));
     FPL_CUDA_CHECK(cudaMemsetAsync(B.n_out, 0, 64, st));
+    return FPL_OK;
+}
 
+// NMS rounds on candidate list A (count `remaining`, also in cnt->n_cand) until no valid candidate is left.
+// *h_cnt (pinned) holds the counters of the last completed round on return.
+static int run_rounds(fpl_ctx *ctx, DetectBuffers &B, const float *d_smooth, Dims d, int r, unsigned long long remaining,
+                      long long *rounds, Counters *h_cnt, int64_t capacity, cudaStream_t st) {
     const int grid_stream = ctx->sm_count * 8;
-    fpl::ProfScope prof(ctx, st, fpl::PROF_NMS, 4.0 * (double)n);
-    compact_candidates_kernel<<<grid_stream, 256, 0, st>>>(d_smooth, n, threshold, B.a_idx, B.a_val,
-                                                          cand_cap, B.cnt);
-    FPL_LAUNCH_CHECK(ctx);
-
-    FPL_REQUIRE(gz < 2048 && gy < 1024 && gx < 1024 && r <= 27 + 4, "voxel2obj: volume / radius outside the brick-grid limits");
-    brick_max_kernel<<<gz * gy, 256, gx * sizeof(float), st>>>(d_smooth, d, gy, gx, B.grid);
-    FPL_LAUNCH_CHECK(ctx);
-    Counters *h_cnt = (Counters *)ctx->h_pinned;
-    FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (h_cnt->overflow) {
-        fpl::set_error("voxel2obj: candidate list overflow (%llu > %lld)", h_cnt->n_cand, cand_cap);
-        return FPL_EOVERFLOW;
-    }
-    const unsigned long long n_candidates = h_cnt->n_cand;
-    long long rounds = 0;
-    unsigned long long remaining = n_candidates;
     unsigned long long *a_idx = B.a_idx, *b_idx = B.b_idx;
     float *a_val = B.a_val, *b_val = B.b_val;
     while (remaining > 0) {
-        ++rounds;
+        ++*rounds;
         long long fblocks = (long long)((remaining + 255) / 256);
         if (fblocks > grid_stream) fblocks = grid_stream;
         nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_smooth, B.sup, d, a_idx, a_val, b_idx,
-                                                            b_val, B.w_idx, B.w_val, cand_cap, B.cnt);
+                                                            b_val, B.w_idx, B.w_val, B.list_cap, B.cnt);
         FPL_LAUNCH_CHECK(ctx);
-        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.grid, gz, gy, gx, B.w_idx, B.w_val,
-                                                               B.det_idx, B.det_val, B.sel_idx, det_cap,
-                                                               B.cnt);
+        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.grid, B.gz, B.gy, B.gx, B.w_idx, B.w_val,
+                                                               B.det_idx, B.det_val, B.sel_idx, B.det_cap,
+                                                               B.cnt, nullptr);
         FPL_LAUNCH_CHECK(ctx);
         nms_suppress_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(B.sup, d, r, B.sel_idx, B.cnt);
         FPL_LAUNCH_CHECK(ctx);
@@ -1020,33 +1424,72 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
         remaining = h_cnt->n_next;
         unsigned long long *ti = a_idx; a_idx = b_idx; b_idx = ti;
         float *tv = a_val; a_val = b_val; b_val = tv;
-        if (h_cnt->n_next == h_cnt->n_sel_round) {
-            // everything left was selected this round
-            remaining = 0;
-        }
+        if (h_cnt->n_next == h_cnt->n_sel_round) remaining = 0;     // everything left was selected this round
     }
+    return FPL_OK;
+}
+
+// order (conf desc, flat index asc), un-pad, buffer crop, offset -> d_dets; d_tout != nullptr additionally
+// drops selected points that are not above the threshold (fast path)
+static int finish_detections(fpl_ctx *ctx, DetectBuffers &B, unsigned long long n_det, Dims d, const fpl_v2o_params *p,
+                             double *d_dets, int64_t capacity, const ThreshOut *d_tout, unsigned long long *n_rows,
+                             cudaStream_t st) {
+    *n_rows = 0;
+    if (n_det == 0) return FPL_OK;
+    const int grid_stream = ctx->sm_count * 8;
+    long long np2 = next_pow2((long long)n_det);
+    int sblocks = (int)((np2 + 255) / 256); if (sblocks > grid_stream) sblocks = grid_stream;
+    sort_prepare_kernel<<<sblocks, 256, 0, st>>>(B.det_idx, B.det_val, (long long)n_det, np2, B.skey, B.sidx);
+    FPL_LAUNCH_CHECK(ctx);
+    for (long long k = 2; k <= np2; k <<= 1)
+        for (long long j = k >> 1; j > 0; j >>= 1) {
+            bitonic_step_kernel<<<sblocks, 256, 0, st>>>(B.skey, B.sidx, np2, j, k);
+            FPL_LAUNCH_CHECK(ctx);
+        }
+    finish_rows_kernel<<<1, 1024, 0, st>>>(B.skey, B.sidx, (long long)n_det, d, p->buffer_xyz[0],
+                                           p->buffer_xyz[1], p->buffer_xyz[2], p->offset_xyz[0],
+                                           p->offset_xyz[1], p->offset_xyz[2], d_dets, capacity,
+                                           B.n_out, &B.cnt->overflow, d_tout);
+    FPL_LAUNCH_CHECK(ctx);
+    unsigned long long *h_n = (unsigned long long *)((char *)ctx->h_pinned + 1024);
+    FPL_CUDA_CHECK(cudaMemcpyAsync(h_n, B.n_out, 8, cudaMemcpyDeviceToHost, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_rows = *h_n;
+    return FPL_OK;
+}
+
+// classic path: threshold known; candidates = smooth > threshold, compacted by a dense pass
+static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, int64_t X,
+                       const fpl_v2o_params *p, double threshold, long long cand_cap, double *d_dets,
+                       int64_t capacity, int64_t *h_count, int64_t *h_stats, cudaStream_t st) {
+    const long long n = Z * Y * X;
+    const int r = p->obj_min_dist;
+    Dims d{Z, Y, X};
+    long long det_cap = capacity > 0 ? capacity : 1;
+    DetectBuffers B;
+    FPL_TRY(take_detect_buffers(ctx, Z, Y, X, cand_cap, det_cap, B, st));
+
+    const int grid_stream = ctx->sm_count * 8;
+    fpl::ProfScope prof(ctx, st, fpl::PROF_NMS, 4.0 * (double)n);
+    compact_candidates_kernel<<<grid_stream, 256, 0, st>>>(d_smooth, n, threshold, B.a_idx, B.a_val,
+                                                          cand_cap, B.cnt);
+    FPL_LAUNCH_CHECK(ctx);
+    FPL_REQUIRE(r <= 27 + 4, "voxel2obj: radius outside the brick-grid limits");
+    brick_max_kernel<<<B.gz * B.gy, 256, B.gx * sizeof(float), st>>>(d_smooth, d, B.gy, B.gx, B.grid);
+    FPL_LAUNCH_CHECK(ctx);
+    Counters *h_cnt = (Counters *)ctx->h_pinned;
+    FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_cnt->overflow) {
+        fpl::set_error("voxel2obj: candidate list overflow (%llu > %lld)", h_cnt->n_cand, cand_cap);
+        return FPL_EOVERFLOW;
+    }
+    const unsigned long long n_candidates = h_cnt->n_cand;
+    long long rounds = 0;
+    FPL_TRY(run_rounds(ctx, B, d_smooth, d, r, n_candidates, &rounds, h_cnt, capacity, st));
     const unsigned long long n_det = h_cnt->n_det * (rounds > 0 ? 1 : 0);
     unsigned long long n_rows = 0;
-    if (n_det > 0) {
-        long long np2 = next_pow2((long long)n_det);
-        int sblocks = (int)((np2 + 255) / 256); if (sblocks > grid_stream) sblocks = grid_stream;
-        sort_prepare_kernel<<<sblocks, 256, 0, st>>>(B.det_idx, B.det_val, (long long)n_det, np2, B.skey, B.sidx);
-        FPL_LAUNCH_CHECK(ctx);
-        for (long long k = 2; k <= np2; k <<= 1)
-            for (long long j = k >> 1; j > 0; j >>= 1) {
-                bitonic_step_kernel<<<sblocks, 256, 0, st>>>(B.skey, B.sidx, np2, j, k);
-                FPL_LAUNCH_CHECK(ctx);
-            }
-        finish_rows_kernel<<<1, 1024, 0, st>>>(B.skey, B.sidx, (long long)n_det, d, p->buffer_xyz[0],
-                                               p->buffer_xyz[1], p->buffer_xyz[2], p->offset_xyz[0],
-                                               p->offset_xyz[1], p->offset_xyz[2], d_dets, capacity,
-                                               B.n_out, &B.cnt->overflow);
-        FPL_LAUNCH_CHECK(ctx);
-        unsigned long long *h_n = (unsigned long long *)((char *)ctx->h_pinned + 1024);
-        FPL_CUDA_CHECK(cudaMemcpyAsync(h_n, B.n_out, 8, cudaMemcpyDeviceToHost, st));
-        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-        n_rows = *h_n;
-    }
+    FPL_TRY(finish_detections(ctx, B, n_det, d, p, d_dets, capacity, nullptr, &n_rows, st));
     if (h_count) *h_count = (int64_t)n_rows;
     if (h_stats) {
         h_stats[0] = (int64_t)n_candidates;
@@ -1055,6 +1498,124 @@ static int detect_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y
         h_stats[3] = (int64_t)n_det;
         h_stats[4] = h_stats[5] = h_stats[6] = h_stats[7] = 0;
     }
+    return FPL_OK;
+}
+
+// fused path of fpl_voxel2obj (see the comment above select_copy_kernel).  Returns FPL_OK with *done = false
+// when the map does not suit it (candidate superset too large: massive ties / saturated maps); the caller
+// then runs the classic path on the smoothed map.
+struct FastHost {                  // pinned scratch layout
+    Counters cnt;
+    unsigned long long n_above[2], n_bin[2], nan_count;
+    ThreshOut tout;
+};
+
+__global__ void fast_collect_kernel(const SelectState *st, int ns, const Counters *cnt, FastHost *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    out->cnt = *cnt;
+    for (int i = 0; i < 2; ++i) { out->n_above[i] = st[i < ns ? i : 0].n_above; out->n_bin[i] = st[i < ns ? i : 0].n_bin; }
+    out->nan_count = st[0].nan_count;
+}
+
+static int voxel2obj_fast(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, int64_t X,
+                          const fpl_v2o_params *p, SelectState *d_states, bool level1_done, ThreshOut *d_tout,
+                          long long list_cap, double *d_dets, int64_t capacity, int64_t *h_count,
+                          double *h_threshold, int64_t *h_stats, cudaStream_t st, bool *done) {
+    *done = false;
+    const long long n = Z * Y * X;
+    const int r = p->obj_min_dist;
+    Dims d{Z, Y, X};
+    const int ns = p->rank_hi != p->rank_lo ? 2 : 1;
+    const int grid_stream = ctx->sm_count * 8;
+    long long det_cap = capacity > 0 ? capacity : 1;
+    DetectBuffers B;
+    FPL_TRY(take_detect_buffers(ctx, Z, Y, X, list_cap, det_cap, B, st));
+    FPL_REQUIRE(r <= 27 + 4, "voxel2obj: radius outside the brick-grid limits");
+    FastHost *h = (FastHost *)ctx->h_pinned;
+    FastHost *d_host = (FastHost *)ctx->arena.take(sizeof(FastHost));
+    FPL_REQUIRE(d_host != nullptr && sizeof(FastHost) <= 1024, "voxel2obj: workspace sizing error");
+    long long rounds = 0;
+    {
+        fpl::ProfScope prof(ctx, st, fpl::PROF_SELECT, 4.0 * (double)n);
+        if (!level1_done) {                       // Gaussian ran through the generic kernel / sigma == 0
+            select_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_smooth, n, &d_states[0], 21, 2048, 1);
+            FPL_LAUNCH_CHECK(ctx);
+        }
+        if (ns > 1) { select_copy_kernel<<<1, 256, 0, st>>>(&d_states[0], &d_states[1]); FPL_LAUNCH_CHECK(ctx); }
+        for (int i = 0; i < ns; ++i) { select_scan_kernel<<<1, 1024, 0, st>>>(&d_states[i], 21, 2048); FPL_LAUNCH_CHECK(ctx); }
+        const size_t sm1 = (size_t)(((B.gx + 31) & ~31) + ns * 2048) * 4;
+        int g1 = ctx->sm_count * 2; if (g1 > B.gz * B.gy) g1 = B.gz * B.gy;
+        dense_pass1_kernel<<<g1, 256, sm1, st>>>(d_smooth, d, B.gz, B.gy, B.gx, B.grid, d_states, ns, B.w_idx, B.w_val,
+                                                B.list_cap, B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        for (int i = 0; i < ns; ++i) { select_scan_kernel<<<1, 1024, 0, st>>>(&d_states[i], 10, 2048); FPL_LAUNCH_CHECK(ctx); }
+        fast_collect_kernel<<<1, 32, 0, st>>>(d_states, ns, B.cnt, d_host);
+        FPL_LAUNCH_CHECK(ctx);
+        FPL_CUDA_CHECK(cudaMemcpyAsync(h, d_host, sizeof(FastHost), cudaMemcpyDeviceToHost, st));
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    // every voxel at or above the level-2 cut-off (class of rank_lo) is a potential list entry
+    const unsigned long long superset = h->n_above[0] + h->n_bin[0];
+    if (h->nan_count == 0 && (h->cnt.overflow || superset > (unsigned long long)list_cap)) return FPL_OK;   // -> classic path
+    if (h->nan_count) {
+        // np.percentile of a map with NaNs is NaN and `pred > nan` selects nothing (fplobjdetect.py:183-185)
+        if (h_count) *h_count = 0;
+        if (h_threshold) *h_threshold = nan("");
+        if (h_stats) for (int i = 0; i < 8; ++i) h_stats[i] = 0;
+        *done = true;
+        return FPL_OK;
+    }
+    unsigned long long n_first = 0;
+    {
+        fpl::ProfScope prof(ctx, st, fpl::PROF_NMS, 4.0 * (double)n);
+        // round 1: the local maxima are the worklist
+        ++rounds;
+        nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.grid, B.gz, B.gy, B.gx, B.w_idx, B.w_val,
+                                                               B.det_idx, B.det_val, B.sel_idx, B.det_cap, B.cnt, &d_states[0]);
+        FPL_LAUNCH_CHECK(ctx);
+        nms_suppress_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(B.sup, d, r, B.sel_idx, B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        fast_reset_kernel<<<1, 32, 0, st>>>(B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        dense_pass2_kernel<<<grid_stream, 256, 0, st>>>(d_smooth, n, B.sup, d_states, ns, B.a_idx, B.a_val, B.list_cap, B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        for (int i = 0; i < ns; ++i) { select_scan_kernel<<<1, 1024, 0, st>>>(&d_states[i], 0, 1024); FPL_LAUNCH_CHECK(ctx); }
+        threshold_kernel<<<1, 32, 0, st>>>(&d_states[0], &d_states[ns - 1], p->gamma, p->thd, d_tout);
+        FPL_LAUNCH_CHECK(ctx);
+        fast_collect_kernel<<<1, 32, 0, st>>>(d_states, ns, B.cnt, d_host);
+        FPL_LAUNCH_CHECK(ctx);
+        FPL_CUDA_CHECK(cudaMemcpyAsync(h, d_host, sizeof(FastHost), cudaMemcpyDeviceToHost, st));
+        FPL_CUDA_CHECK(cudaMemcpyAsync(&h->tout, d_tout, sizeof(ThreshOut), cudaMemcpyDeviceToHost, st));
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h->cnt.overflow) {
+            fpl::set_error("voxel2obj: detection / candidate capacity too small (detections %llu, capacity %lld)",
+                           h->cnt.n_det, (long long)capacity);
+            return FPL_EOVERFLOW;
+        }
+        n_first = h->cnt.n_det;
+        const double threshold = h->tout.thresh;
+        const unsigned long long n_gt = h->n_above[ns - 1];       // values above the order statistic (stats only)
+        const unsigned long long ball_first = h->cnt.ball_checks;
+        if (h_threshold) *h_threshold = threshold;
+        Counters *h_cnt = &h->cnt;
+        Counters last = *h_cnt;
+        if (h_cnt->n_cand > 0) {
+            FPL_TRY(run_rounds(ctx, B, d_smooth, d, r, h_cnt->n_cand, &rounds, h_cnt, capacity, st));
+            last = *h_cnt;
+        }
+        const unsigned long long n_det = last.n_det;
+        unsigned long long n_rows = 0;
+        FPL_TRY(finish_detections(ctx, B, n_det, d, p, d_dets, capacity, d_tout, &n_rows, st));
+        if (h_count) *h_count = (int64_t)n_rows;
+        if (h_stats) {
+            h_stats[0] = (int64_t)n_gt;
+            h_stats[1] = rounds;
+            h_stats[2] = (int64_t)(last.ball_checks > ball_first ? last.ball_checks : ball_first);
+            h_stats[3] = (int64_t)n_det;
+            h_stats[4] = (int64_t)superset; h_stats[5] = (int64_t)n_first; h_stats[6] = 1; h_stats[7] = 0;
+        }
+    }
+    *done = true;
     return FPL_OK;
 }
 
@@ -1069,6 +1630,9 @@ extern "C" {
 
 // test hook: route every Gaussian pass through the generic one-thread-per-output kernel
 int fpl_debug_force_generic_gauss(int on) { g_force_generic_gauss = on; return FPL_OK; }
+// test hook: margin of the certified-FMA Gaussian chain in double ulps (default 64; 0 = exact chain only;
+// 1 << 28 = every output fails the certificate and is recomputed exactly)
+int fpl_debug_gauss_cert(int margin) { fpl::v2o::g_gauss_cert = (unsigned)margin; return FPL_OK; }
 
 int fpl_v2o_smooth(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,
                    const fpl_v2o_params *p, float *d_smooth, void *stream) {
@@ -1126,11 +1690,15 @@ int fpl_v2o_detect(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, in
     FPL_CUDA_CHECK(cudaStreamSynchronize(st));
     // without a percentile rank the only safe bound is every voxel
     long long cand_cap = (p->rank_lo > 0) ? candidate_capacity(p, Z, Y, X) : (long long)(Z * Y * X);
-    FPL_TRY(ctx->arena.reserve(detect_workspace_bytes(Z * Y * X, cand_cap, capacity > 0 ? capacity : 1)));
+    FPL_TRY(ctx->arena.reserve(detect_workspace_bytes(Z, Y, X, cand_cap, capacity > 0 ? capacity : 1)));
     ctx->arena.reset();
     return detect_impl(ctx, d_smooth, Z, Y, X, p, threshold, cand_cap, d_dets, capacity, h_count,
                        h_stats, st);
 }
+
+static int g_v2o_classic = 0;
+// test hook: run fpl_voxel2obj through the classic (five dense passes) path
+int fpl_debug_v2o_classic(int on) { g_v2o_classic = on; return FPL_OK; }
 
 int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,
                   const fpl_v2o_params *p, double *d_dets, int64_t capacity, int64_t *h_count,
@@ -1141,16 +1709,39 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
     cudaStream_t st = (cudaStream_t)stream;
     FPL_CUDA_CHECK(cudaStreamSynchronize(st));
     const size_t n = (size_t)Z * Y * X;
+    const int r = p->obj_min_dist;
     const long long cand_cap = candidate_capacity(p, Z, Y, X);
-    size_t need = 2 * (n * sizeof(float) + 512) + 2 * sizeof(SelectState) + sizeof(ThreshOut) + 4096 +
-                  detect_workspace_bytes((long long)n, cand_cap, capacity > 0 ? capacity : 1);
+    // fused path: lists hold a superset of the candidates (everything from the lower edge of the percentile's
+    // 22-bit radix class upwards) -> some slack on top of the exact candidate bound
+    long long list_cap = cand_cap + cand_cap / 8 + 65536;
+    if (list_cap > (long long)n) list_cap = (long long)n;
+    const bool try_fast = !g_v2o_classic && r > 0;
+    size_t need = 2 * (n * sizeof(float) + 512) + 2 * sizeof(SelectState) + sizeof(ThreshOut) + 4096 + 2048 +
+                  detect_workspace_bytes(Z, Y, X, try_fast ? list_cap : cand_cap, capacity > 0 ? capacity : 1);
     FPL_TRY(ctx->arena.reserve(need));
     ctx->arena.reset();
     float *smooth = (float *)ctx->arena.take(n * sizeof(float));
     float *tmp = (float *)ctx->arena.take(n * sizeof(float));
     SelectState *states = (SelectState *)ctx->arena.take(2 * sizeof(SelectState));
     ThreshOut *tout = (ThreshOut *)ctx->arena.take(sizeof(ThreshOut));
-    FPL_TRY(smooth_impl(ctx, d_pred, Z, Y, X, p, smooth, tmp, st, g_force_generic_gauss != 0));
+    if (try_fast) {
+        const unsigned long long n_pad = (unsigned long long)(Z + 2 * r) * (Y + 2 * r) * (X + 2 * r);
+        FPL_REQUIRE(p->rank_lo >= 0 && (unsigned long long)p->rank_lo < n_pad && p->rank_hi >= 0 &&
+                    (unsigned long long)p->rank_hi < n_pad, "voxel2obj: percentile ranks out of range");
+        select_init_kernel<<<1, 256, 0, st>>>(&states[0], (unsigned long long)p->rank_lo, n_pad - n);
+        FPL_LAUNCH_CHECK(ctx);
+        select_init_kernel<<<1, 256, 0, st>>>(&states[1], (unsigned long long)p->rank_hi, n_pad - n);
+        FPL_LAUNCH_CHECK(ctx);
+        FPL_TRY(smooth_impl(ctx, d_pred, Z, Y, X, p, smooth, tmp, st, g_force_generic_gauss != 0));
+        const size_t mark = ctx->arena.used;
+        bool done = false;
+        FPL_TRY(voxel2obj_fast(ctx, smooth, Z, Y, X, p, states, false, tout, list_cap, d_dets, capacity, h_count,
+                               h_threshold, h_stats, st, &done));
+        if (done) return FPL_OK;
+        ctx->arena.used = mark;             // superset too large for the lists: classic path on the smoothed map
+    } else {
+        FPL_TRY(smooth_impl(ctx, d_pred, Z, Y, X, p, smooth, tmp, st, g_force_generic_gauss != 0));
+    }
     FPL_TRY(threshold_impl(ctx, smooth, Z, Y, X, p, tout, states, st));
     ThreshOut *h = (ThreshOut *)((char *)ctx->h_pinned + 2048);
     FPL_CUDA_CHECK(cudaMemcpyAsync(h, tout, sizeof(ThreshOut), cudaMemcpyDeviceToHost, st));

@@ -173,3 +173,50 @@ def infer_tiler(image, infer_network, infer_sz, rf_offset, n_gpu=1):
     for i, (lo, hi, ext) in enumerate(spans):
         pred[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = pb[i, :ext[0], :ext[1], :ext[2], 0]
     return pred
+
+
+def detector_weights(arch, sample, seed=7, final_logit=(-3.0, 6.0)):
+    """Weights that make `arch` a (crude but genuine) bright-blob detector, for the detection-F1 test.
+
+    Every kernel is |glorot_uniform| (non-negative) and every BatchNormalization is *calibrated* on
+    `sample` ((N,D,H,W) float32, already normalised): moving_mean / moving_variance are the measured
+    per-channel statistics of the convolution output, gamma = 1, beta = 0 -- what a trained network's
+    moving statistics look like.  Non-negative kernels, positive BN scale, ReLU, max-pool, up-sampling
+    and concatenation are all monotone, so the output probability is a monotone function of local
+    brightness: planted bright blobs become peaks of the probability map.  The final bias (VGGs) shifts
+    the median logit to final_logit[0]; the final kernel is scaled so that the sample's logit spread
+    (99.9th percentile - median) is final_logit[1]."""
+    rng = np.random.default_rng(seed)
+    ops, _, _, final_bias = ARCHS[arch]
+    t = torch.as_tensor(np.asarray(sample, dtype=np.float32))[:, None]
+    ws, skips = [], {}
+    for op in ops:
+        if op[0] == "C":
+            _, k, cin, cout = op
+            lim = np.sqrt(6.0 / (k ** 3 * cin + k ** 3 * cout))
+            kern = rng.uniform(0, lim, (k, k, k, cin, cout)).astype(np.float32)
+            t = F.conv3d(t, torch.as_tensor(kern).permute(4, 3, 0, 1, 2))
+            mean = t.mean(dim=(0, 2, 3, 4)); var = t.var(dim=(0, 2, 3, 4), unbiased=False)
+            ws += [kern, np.ones(cout, np.float32), np.zeros(cout, np.float32), mean.numpy().astype(np.float32),
+                   var.numpy().astype(np.float32)]
+            t = torch.relu((t - mean.view(1, -1, 1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1, 1) + BN_EPS))
+        elif op[0] == "P":
+            t = F.max_pool3d(t, 2)
+        elif op[0] == "S":
+            skips[op[1]] = t
+        elif op[0] == "U":
+            up = t.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+            sk = skips[op[1]]
+            if op[2]:
+                sk = sk[:, :, op[2]:-op[2], op[2]:-op[2], op[2]:-op[2]]
+            t = torch.cat([up, sk], 1)
+        elif op[0] == "F":
+            cin = op[1]
+            kern = rng.uniform(0, np.sqrt(6.0 / (cin + 1)), (1, 1, 1, cin, 1)).astype(np.float32)
+            logit = F.conv3d(t, torch.as_tensor(kern).permute(4, 3, 0, 1, 2)).flatten()
+            med = float(logit.median()); hi = float(torch.quantile(logit[:: max(1, logit.numel() // 1000000)], 0.999))
+            scale = final_logit[1] / max(hi - med, 1e-6)
+            ws.append((kern * np.float32(scale)).astype(np.float32))
+            if final_bias:
+                ws.append(np.asarray([final_logit[0] - med * scale], np.float32))
+    return ws

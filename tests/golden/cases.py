@@ -94,3 +94,29 @@ class FakeNet:
         return (core * 0.5 + ramp).astype(np.float32)
 
 
+
+
+def blob_volume(shape, n_side, seed=5, amp=100.0, sigma=4.0, margin=34, noise=0.3):
+    """EM-like uint8 volume with planted bright blobs (synthetic "T-bars") on a jittered n_side^3 grid;
+    returns (volume, centres as (K,3) float64 in (x,y,z) order)."""
+    rng = np.random.default_rng(seed)
+    vol = 128.0 + noise * (em_volume(shape, seed=seed + 1).astype(np.float32) - 128.0)
+    Z, Y, X = shape
+    w = int(3 * sigma)
+    ax = np.arange(-w, w + 1, dtype=np.float64)
+    g = np.exp(-0.5 * (ax / sigma) ** 2)
+    bump = (g[:, None, None] * g[None, :, None] * g[None, None, :]).astype(np.float32)
+    centres = []
+    for iz in range(n_side):
+        for iy in range(n_side):
+            for ix in range(n_side):
+                if rng.random() < 0.25:
+                    continue
+                c = []
+                for i, n in zip((iz, iy, ix), (Z, Y, X)):
+                    cell = (n - 2 * margin) / n_side
+                    c.append(int(margin + (i + 0.5) * cell + rng.uniform(-0.15, 0.15) * cell))
+                z, y, x = c
+                vol[z - w:z + w + 1, y - w:y + w + 1, x - w:x + w + 1] += amp * bump
+                centres.append((x, y, z))
+    return np.clip(vol, 0, 255).astype(np.uint8), np.asarray(centres, dtype=np.float64)

@@ -64,8 +64,21 @@ def test_stages_bit_exact_vs_oracle_and_golden(case, generic):
     assert np.array_equal(rows[:, 3], GOLD[name + "/conf"])
 
 
-@pytest.mark.parametrize("case", cases.VOXEL2OBJ_CASES[:8], ids=[c[0] for c in cases.VOXEL2OBJ_CASES[:8]])
-def test_dropin_voxel2obj_matches_golden(case):
+@pytest.fixture(params=["fused", "classic"])
+def v2o_path(request):
+    """fpl_voxel2obj has two detection paths: the fused one (level-1 select histogram inside the Gaussian
+    x pass, two dense passes, NMS on a candidate superset) and the classic one it falls back to when the
+    superset does not fit its lists.  Every drop-in parity test runs through both."""
+    from flypylib_b200 import _lib
+    lib = _lib.lib()
+    lib.fpl_debug_v2o_classic.argtypes = [ctypes.c_int]
+    lib.fpl_debug_v2o_classic(1 if request.param == "classic" else 0)
+    yield request.param
+    lib.fpl_debug_v2o_classic(0)
+
+
+@pytest.mark.parametrize("case", cases.VOXEL2OBJ_CASES, ids=[c[0] for c in cases.VOXEL2OBJ_CASES])
+def test_dropin_voxel2obj_matches_golden(case, v2o_path):
     from flypylib_b200 import fplobjdetect
     name, shape, seed, kind, r, sigma, thd, buf, off = case
     pred = cases.prob_map(shape, seed, kind)
@@ -78,7 +91,7 @@ def test_dropin_voxel2obj_matches_golden(case):
 
 @pytest.mark.parametrize("shape,kind,seed", [((200, 190, 210), "blobs", 21), ((192, 192, 192), "uniform", 22),
                                              ((256, 256, 256), "blobs", 23), ((180, 200, 170), "ties", 24)])
-def test_medium_volumes_vs_c_oracle(shape, kind, seed):
+def test_medium_volumes_vs_c_oracle(shape, kind, seed, v2o_path):
     """Reference parameters (r=27, sigma=5) at sizes the C oracle finishes in seconds."""
     from flypylib_b200 import fplobjdetect
     pred = cases.prob_map(shape, seed, kind)
@@ -90,7 +103,7 @@ def test_medium_volumes_vs_c_oracle(shape, kind, seed):
     assert np.array_equal(got["conf"], want["conf"])
 
 
-def test_nan_and_saturation_edge_cases():
+def test_nan_and_saturation_edge_cases(v2o_path):
     from flypylib_b200 import fplobjdetect
     a = cases.prob_map((40, 40, 40), 3, "blobs")
     a[5, 6, 7] = np.nan
@@ -105,11 +118,22 @@ def test_large_volume_properties():
     pairwise distance > r, confidences sorted, every detection above the threshold, idempotent."""
     import torch
     from flypylib_b200 import fplobjdetect
+    from flypylib_b200 import _lib
     pred = cases.prob_map((512, 512, 512), 77, "blobs")
     d = torch.from_numpy(pred).cuda()
     out, st = fplobjdetect.voxel2obj_device(d, 27, 5, (0, 0, 0), 30, 0, return_stats=True)
     out2 = fplobjdetect.voxel2obj_device(d, 27, 5, (0, 0, 0), 30, 0)
     assert np.array_equal(out["locs"], out2["locs"]) and np.array_equal(out["conf"], out2["conf"])
+    # fused path == classic path (exact threshold first, then candidates = smooth > threshold)
+    lib = _lib.lib()
+    lib.fpl_debug_v2o_classic.argtypes = [ctypes.c_int]
+    lib.fpl_debug_v2o_classic(1)
+    try:
+        out3, st3 = fplobjdetect.voxel2obj_device(d, 27, 5, (0, 0, 0), 30, 0, return_stats=True)
+    finally:
+        lib.fpl_debug_v2o_classic(0)
+    assert st3["threshold"] == st["threshold"]
+    assert np.array_equal(out["locs"], out3["locs"]) and np.array_equal(out["conf"], out3["conf"])
     conf = out["conf"]
     assert conf.size > 100
     assert np.all(np.diff(conf) <= 0)
@@ -144,7 +168,7 @@ def test_slab_sharded_detection_matches_reference_substack_semantics():
     assert np.array_equal(got["locs"], want["locs"]) and np.array_equal(got["conf"], want["conf"])
 
 
-def test_randomised_parameters_vs_oracle():
+def test_randomised_parameters_vs_oracle(v2o_path):
     """Seeded sweep over shapes / radii / sigmas / thd / buffers / offsets / map kinds (the reference has no
     tests of its own): CUDA result must equal the C oracle bit-for-bit every time."""
     from flypylib_b200 import fplobjdetect
@@ -163,3 +187,29 @@ def test_randomised_parameters_vs_oracle():
         ctx = "case %d shape %s r %d sigma %g thd %g buf %s off %s" % (it, shape, r, sigma, thd, buf, off)
         assert np.array_equal(got["locs"], want["locs"]), ctx
         assert np.array_equal(got["conf"], want["conf"]), ctx
+
+
+@pytest.mark.parametrize("margin", [0, 64, 4096, 1 << 28], ids=["exact-only", "default", "wide", "all-recomputed"])
+def test_gaussian_certified_chain_is_bit_exact(margin):
+    """The Gaussian passes evaluate a fused (FMA) chain first and prove per output that it rounds to the same
+    float32 as SciPy's separately rounded chain; outputs that fail the certificate are recomputed exactly.
+    Whatever the margin (0 = fast chain off, 2^28 = every output recomputed), the smoothed map must be
+    bit-identical to the oracle -- including negative inputs (certificate not applicable) and huge/tiny values."""
+    from flypylib_b200 import _lib
+    lib = _lib.lib()
+    lib.fpl_debug_gauss_cert.argtypes = [ctypes.c_int]
+    rng = np.random.default_rng(5)
+    maps = [cases.prob_map((70, 66, 90), 11, "blobs"), cases.prob_map((64, 64, 64), 12, "ties"),
+            (rng.standard_normal((48, 50, 52)) * 3).astype(np.float32),                  # negative inputs
+            (rng.random((40, 40, 70), dtype=np.float32) * np.float32(1e-38)),             # float32 subnormal results
+            (rng.random((40, 40, 70), dtype=np.float32) * np.float32(3e38))]              # near overflow
+    lib.fpl_debug_gauss_cert(margin)
+    try:
+        for i, pm in enumerate(maps):
+            for r, sigma in ((6, 5.0), (5, 1.5)):
+                s_gpu, _, _, _ = _stages(pm, r, sigma, (0, 0, 0), 0, 0)
+                _, s_ref, _ = O.voxel2obj(pm, r, sigma, (0, 0, 0), 0, 0, impl="c", return_intermediates=True)
+                interior = np.ascontiguousarray(s_ref[r:r + pm.shape[0], r:r + pm.shape[1], r:r + pm.shape[2]])
+                assert np.array_equal(s_gpu.view(np.uint32), interior.view(np.uint32)), (i, r, sigma)
+    finally:
+        lib.fpl_debug_gauss_cert(0)
