@@ -285,3 +285,169 @@ def aggregate_pr(results):
         tot_gt += res.tot_gt
     return PR_Result(num_tp=num_tp, tot_pred=tot_pred, tot_gt=tot_gt, pp=num_tp / (tot_pred + 10e-8),
                      rr=num_tp / (tot_gt + 10e-8), match=None)
+
+
+# ---------------------------------------------------------------------------------------------
+# Substack driver: full_roi_inference and its fri_* helpers
+# (flypylib/fplobjdetect.py:841-1059) -- the production caller on both sides of the hot path.
+# Kept: ROI text file -> szyx substacks, size + 2*buffer cubes zero-padded at the volume faces,
+# the uint8 normalisation with `global_frac`, the per-substack norm .txt and result pickles (resume),
+# voxel2obj per substack with the substack offset and buffer, all.p.  Changed, B200-first: no worker
+# processes (voxel2obj cannot run in forked children of a CUDA process -- it runs inline, on the
+# probability map that is still resident in HBM); with torch.distributed initialised the substacks are
+# dealt round-robin to the ranks (one process per GPU) and the detection lists are all-gathered.
+# Out of scope: DVID / DICED / N5 volume services (libdvid, diced, z5py are storage/network control
+# plane) -- `data_source` is any (Z,Y,X) uint8 array-like that supports slicing (numpy array,
+# numpy.memmap, or an object with .shape and __getitem__), which is what the reference's
+# "n5://" branch reduces the store to (fplobjdetect.py:1040-1068).
+# ---------------------------------------------------------------------------------------------
+import os
+import pickle
+import sys
+
+from .fplutils import szyx, roi_from_txt  # noqa: E402,F401
+
+
+def fri_filename(working_dir, substack):
+    """Result pickle of a substack (fplobjdetect.py:1153-1155)."""
+    return '%s/%d_%d_%d_%d.p' % (working_dir, substack.size, substack.z, substack.y, substack.x)
+
+
+def fri_get_image(substack_info, volume):
+    """Cut the (size + 2*buffer)^3 cube of a substack out of `volume` (zeros beyond its faces) and
+    normalise it as the reference does (fplobjdetect.py:1021-1112): mean of the voxels in (1, 200)
+    blended with the global mean by ``global_frac`` = image_normalize[2] (1 when absent), divided by
+    image_normalize[1]; the statistics go to ``<norm_dir>/<size>_<z>_<y>_<x>.txt``.
+    Returns ``(float32 image or None, substack)``; None when the cube lies outside the volume."""
+    substack, image_normalize, buffer_sz, norm_dir = substack_info
+    image_sz = substack.size + 2 * buffer_sz
+    image_offset = [substack.z - buffer_sz, substack.y - buffer_sz, substack.x - buffer_sz]
+    full_size = volume.shape
+    image = np.zeros((image_sz, image_sz, image_sz), 'uint8')
+    lo = np.maximum(image_offset, 0)
+    hi = np.minimum(np.asarray(image_offset) + image_sz, full_size)
+    if lo[0] > hi[0] or lo[1] > hi[1] or lo[2] > hi[2]:
+        return (None, substack)
+    image[(lo[0] - image_offset[0]):(hi[0] - image_offset[0]),
+          (lo[1] - image_offset[1]):(hi[1] - image_offset[1]),
+          (lo[2] - image_offset[2]):(hi[2] - image_offset[2])] = volume[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+    im_raw_mn, im_raw_std = np.mean(image), np.std(image)
+    idx = ((image < 200) & (image > 1))
+    if np.sum(idx) > 0:
+        im_flt_mn, im_flt_std = np.mean(image[idx]), np.std(image[idx])
+    else:
+        im_flt_mn, im_flt_std = image_normalize[0], image_normalize[1]
+    global_frac = 1. if len(image_normalize) < 3 else image_normalize[2]
+    mn_use = global_frac * image_normalize[0] + (1 - global_frac) * im_flt_mn
+    image = (image.astype('float32') - mn_use) / image_normalize[1]
+    norm_fn = '%s/%d_%d_%d_%d.txt' % (norm_dir, substack.size, substack.z, substack.y, substack.x)
+    with open(norm_fn, 'w') as f_out:
+        f_out.write('%d,%d,%d,%d,%d,%g,%g,%g,%g,%g,%g,%g,%g\n' %
+                    (substack.size, buffer_sz, substack.z, substack.y, substack.x,
+                     image_normalize[0], image_normalize[1], global_frac, mn_use,
+                     im_flt_mn, im_flt_std, im_raw_mn, im_raw_std))
+    return (image, substack)
+
+
+def fri_postprocess(pred, working_dir, obj_min_dist, smoothing_sigma, substack, buffer_sz, thd):
+    """voxel2obj of one substack's prediction with the substack's (x,y,z) offset and buffer; the result is
+    pickled to fri_filename (fplobjdetect.py:1114-1151).  `pred` may be a numpy array or a CUDA tensor
+    (the map FplNetwork.infer_device left in HBM).  Returns the pickle's file name."""
+    ff = fri_filename(working_dir, substack)
+    if pred is None:
+        out = {'locs': np.zeros((0, 3)), 'conf': np.zeros(0)}
+    else:
+        out = voxel2obj(pred, obj_min_dist, smoothing_sigma,
+                        (substack.x - buffer_sz, substack.y - buffer_sz, substack.z - buffer_sz),
+                        buffer_sz, thd)
+    with open(ff, 'wb') as f_out:
+        pickle.dump(out, f_out)
+    return ff
+
+
+def full_roi_inference(data_source, dvid_uuid, dvid_roi, network, thd, working_dir, image_normalize,
+                       obj_min_dist=27, smoothing_sigma=5, buffer_sz=35, partition_size=16,
+                       local_cache_dir=None, roi_force_file=False, instance_name='grayscale',
+                       dvid_seg_info=None):
+    """Predictions of a trained network inside an ROI, substack by substack, cached on disk so that a
+    second call resumes (flypylib/fplobjdetect.py:841-986; parameters as there).
+
+    ``data_source``: (Z,Y,X) uint8 array-like (see the section comment); ``dvid_roi``: ROI text file
+    (``size,z,y,x`` per line); ``dvid_uuid``, ``partition_size``, ``local_cache_dir``, ``roi_force_file``,
+    ``instance_name`` are accepted for signature compatibility and unused; ``dvid_seg_info`` must be None
+    (segmentation-aware suppression is out of scope).  Returns ``{'locs','conf'}`` over all substacks in
+    ROI-file order and writes it to ``<working_dir>/all.p``.
+
+    With ``torch.distributed`` initialised (one process per GPU) rank r processes the pending substacks
+    r, r+world, ...; per-substack pickles are written by the rank that computed them and every rank
+    returns the complete result (all-gather of the detection lists)."""
+    if dvid_seg_info is not None:
+        raise NotImplementedError("segmentation-aware suppression is not part of the B200 hot path")
+    if isinstance(data_source, str):
+        raise NotImplementedError("DVID / DICED / N5 volume services are out of scope; pass the volume as an "
+                                  "array-like (numpy.memmap works for volumes larger than host memory)")
+    os.makedirs(working_dir, exist_ok=True)
+    norm_dir = '%s/norm' % working_dir
+    os.makedirs(norm_dir, exist_ok=True)
+    roi = roi_from_txt(dvid_roi)
+
+    world, rank = 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        dist = None
+
+    results = {}                    # substack index -> (locs, conf)
+    pending = []
+    for si, rr in enumerate(roi[0]):
+        ff = fri_filename(working_dir, rr)
+        if os.path.isfile(ff):
+            with open(ff, 'rb') as f_in:
+                obj = pickle.load(f_in)
+            results[si] = (obj['locs'], obj['conf'])
+            continue
+        pending.append((si, szyx(rr.size, rr.z, rr.y, rr.x)))
+    if rank == 0:
+        print('already processed: %d' % len(results))
+        print('to process: %d' % len(pending))
+
+    n_done = 0
+    for pi, (si, ss) in enumerate(pending):
+        if pi % world != rank:
+            continue
+        image, _ = fri_get_image([ss, image_normalize, buffer_sz, norm_dir], data_source)
+        pred = None
+        if image is not None:
+            # keep the map on the device when the network offers it (no 4 B/voxel round trip over PCIe)
+            if hasattr(network, 'infer_device'):
+                import torch
+                pred = network.infer_device(torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).cuda())
+            else:
+                pred = network.infer(image)
+        ff = fri_postprocess(pred, working_dir, obj_min_dist, smoothing_sigma, ss, buffer_sz, thd)
+        with open(ff, 'rb') as f_in:
+            obj = pickle.load(f_in)
+        results[si] = (obj['locs'], obj['conf'])
+        n_done += 1
+        if rank == 0:
+            sys.stdout.write('\r%d' % n_done)
+            sys.stdout.flush()
+
+    if world > 1:
+        mine = [(si,) + results[si] for pi, (si, _) in enumerate(pending) if pi % world == rank]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        for part in gathered:
+            for si, l, c in part:
+                results[si] = (l, c)
+
+    order = sorted(results)
+    locs = np.concatenate([np.asarray(results[si][0]).reshape(-1, 3) for si in order]) if order else np.zeros((0, 3))
+    conf = np.concatenate([np.asarray(results[si][1]).reshape(-1) for si in order]) if order else np.zeros(0)
+    obj = {'locs': locs, 'conf': conf}
+    if rank == 0:
+        with open('%s/all.p' % working_dir, 'wb') as f_out:
+            pickle.dump(obj, f_out)
+    return obj

@@ -23,3 +23,11 @@ def set_filter(radius, return_dist=False):
     if return_dist:
         return dd <= radius, dd
     return dd <= radius
+
+
+def roi_from_txt(filename):
+    """Substack list of an ROI text file, one ``size,z,y,x`` line per substack, wrapped in a one-element
+    list like DVID's ``get_roi_partition`` result (flypylib/fplutils.py:24-30, fplobjdetect.py:1210-1216)."""
+    with open(filename, 'r') as f_in:
+        lines = f_in.read().splitlines()
+    return [[szyx(*[int(nn) for nn in ss.split(',')]) for ss in lines if ss.strip()], ]

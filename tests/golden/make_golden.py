@@ -9,6 +9,8 @@ Outputs (committed):
                                       makes (fplobjdetect.py:159-183) on SciPy/NumPy of this image
   tests/golden/infer_tiler_golden.npz reference ``FplNetwork.infer`` tiling/scatter run unmodified
                                       with a deterministic fake ``infer_network`` (fplnetwork.py:136-189)
+  tests/golden/substack_golden.npz    reference ``fri_get_image`` (fplobjdetect.py:1021-1112) run unmodified on an
+                                      in-memory store: substack cubes, normalisation, norm .txt lines
   tests/golden/eval_golden.json       reference ``obj_pr`` / ``obj_pr_curve`` / ``aggregate_pr``
                                       (fplobjdetect.py:320-453) run unmodified with the exhaustive
                                       ``oracle/match_oracle.py`` standing in for the PuLP solver, and the
@@ -150,8 +152,44 @@ def golden_eval(ref):
     print("eval goldens: %d pr cases" % len(doc["pr"]))
 
 
+class FakeStore(object):
+    """Array-like volume store for the reference's "n5" branch of fri_get_image (shape + slicing)."""
+
+    def __init__(self, a):
+        self.a, self.shape = a, a.shape
+
+    def __getitem__(self, k):
+        return self.a[k]
+
+
+def golden_substack_images(ref):
+    """Reference fri_get_image (fplobjdetect.py:1021-1112) run unmodified on an in-memory volume store:
+    cube extraction with zero padding at the faces, the global_frac normalisation and the norm .txt line."""
+    import tempfile
+    sys.modules["z5py"].dataset.Dataset = FakeStore         # the reference isinstance()-checks its store type
+    F = ref.fplobjdetect
+    vol = cases.em_volume((70, 64, 80), seed=9)
+    vol[:, :5] = 0; vol[:, -4:] = 255                        # values outside (1,200) for the filtered mean
+    out = {"volume": vol}
+    specs = [("inside", F.szyx(24, 20, 20, 24), 6, (128., 33.)), ("corner", F.szyx(24, 0, 0, 0), 8, (120., 30., 0.25)),
+             ("far", F.szyx(32, 48, 40, 56), 10, (128., 33., 0.0)), ("outside", F.szyx(16, 200, 10, 10), 4, (128., 33.))]
+    with tempfile.TemporaryDirectory() as nd:
+        for name, ss, buf, norm in specs:
+            img, _ = F.fri_get_image([ss, None, None, list(norm), buf, None, nd, "grayscale"], FakeStore(vol), True)
+            out[name + "/spec"] = np.asarray([ss.size, ss.z, ss.y, ss.x, buf], dtype=np.int64)
+            out[name + "/norm"] = np.asarray(norm, dtype=np.float64)
+            out[name + "/none"] = np.asarray(img is None)
+            if img is not None:
+                out[name + "/image"] = img
+                txt = open("%s/%d_%d_%d_%d.txt" % (nd, ss.size, ss.z, ss.y, ss.x)).read()
+                out[name + "/txt"] = np.frombuffer(txt.encode(), dtype=np.uint8)
+            print("%-8s %s" % (name, None if img is None else (img.shape, img.dtype, float(img.mean()))))
+    np.savez_compressed(os.path.join(HERE, "substack_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
     golden_voxel2obj(ref)
     golden_infer_tiler(ref)
     golden_eval(ref)
+    golden_substack_images(ref)
