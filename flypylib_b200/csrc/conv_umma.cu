@@ -1013,7 +1013,8 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
 //   warps 14..17  first-layer epilogue: TMEM -> ReLU -> bf16 -> plane ring slot, then signal plane_full
 // Arithmetic is identical to the two separate kernels (same MMA shapes, same K order, same rounding),
 // so the result is bit-identical to the unfused path.
-// TMEM: second-layer accumulators 2 M-tile regions x 3 blocks x C2 columns; first-layer tiles at 288 + 48 t.
+// TMEM: second-layer accumulators 2 M-tile regions x 4 blocks x C2 columns (384); first-layer tiles rotate
+// through 2 slots at 384 + 48 s.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 576;
 struct FusedArgs {
@@ -1043,8 +1044,11 @@ conv_fused12_kernel(const FusedArgs a) {
     constexpr uint32_t plane_bytes = (C1 / 8) * atom_stride;
     constexpr uint32_t plane_pitch = (plane_bytes + 127u) & ~127u;
     constexpr uint32_t kA1Bytes = NT1 * 4 * 128 * 16;
-    constexpr uint32_t N = C2, NBLK = 3, kRegion = NBLK * N, kL1Col = 2 * kRegion;
-    static_assert(kL1Col + NT1 * C1 <= 512, "TMEM budget");
+    // second-layer accumulators: 4 blocks per M-tile, so the block a new output starts in was drained a whole
+    // plane earlier (with 3 the MMA stream stalled on the epilogue once per plane); the first layer's three
+    // M-tiles per plane rotate through 2 accumulator slots
+    constexpr uint32_t N = C2, NBLK = 4, kRegion = NBLK * N, kL1Col = 2 * kRegion, kL1Slots = 2;
+    static_assert(kL1Col + kL1Slots * C1 <= 512, "TMEM budget");
     static_assert(RX <= RP && C1 % 16 == 0 && C2 % 16 == 0, "shape");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t w_region = (a.w2_bytes + 127u) & ~127u;
@@ -1063,9 +1067,9 @@ conv_fused12_kernel(const FusedArgs a) {
     uint64_t *a1_empty = bars + 6;           // [1]
     uint64_t *l1_full = bars + 7;            // [3]  first-layer accumulator tiles
     uint64_t *l1_empty = bars + 10;          // [3]
-    uint64_t *acc_full = bars + 13;          // [3]  second-layer accumulator blocks
-    uint64_t *acc_empty = bars + 16;         // [3]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+    uint64_t *acc_full = bars + 13;          // [4]  second-layer accumulator blocks
+    uint64_t *acc_empty = bars + 17;         // [4]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
@@ -1074,10 +1078,8 @@ conv_fused12_kernel(const FusedArgs a) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&plane_full[i], 4); mbar_init(&plane_empty[i], 1); }
         mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
-        }
+        for (int i = 0; i < 3; ++i) { mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x)
@@ -1123,15 +1125,16 @@ conv_fused12_kernel(const FusedArgs a) {
             mbar_wait(a1_full, pc1 & 1u);
 #pragma unroll 1
             for (int t = 0; t < NT1; ++t) {
-                mbar_wait(&l1_empty[t], (pc1 & 1u) ^ 1u);
+                const uint32_t g = pc1 * NT1 + (uint32_t)t, sl = g % kL1Slots, use = g / kL1Slots;
+                mbar_wait(&l1_empty[sl], (use & 1u) ^ 1u);
                 tc_fence_after();
                 if (leader) {
 #pragma unroll
                     for (int s = 0; s < 2; ++s)
-                        umma_bf16(tmem_base + kL1Col + (uint32_t)t * C1,
+                        umma_bf16(tmem_base + kL1Col + sl * C1,
                                   desc64(a1_lo0 + (uint32_t)t * (8192u >> 4) + s * (4096u >> 4), a1_hi),
                                   desc64(b1_lo0 + s * (uint32_t)(C1 * 2), b_hi), idesc_l1, s ? 1u : 0u);
-                    umma_commit(&l1_full[t]);
+                    umma_commit(&l1_full[sl]);
                 }
                 __syncwarp();
             }
@@ -1378,10 +1381,11 @@ conv_fused12_kernel(const FusedArgs a) {
                 uint8_t *pl = s_planes + slot * plane_pitch;
 #pragma unroll 1
                 for (int t = 0; t < NT1; ++t) {
-                    mbar_wait(&l1_full[t], pc & 1u);
+                    const uint32_t g = pc * NT1 + (uint32_t)t, sl = g % kL1Slots, use = g / kL1Slots;
+                    mbar_wait(&l1_full[sl], use & 1u);
                     tc_fence_after();
                     const int v = t * 128 + row;
-                    const uint32_t tcol = tmem_base + kL1Col + (uint32_t)t * C1 + ((uint32_t)(q * 32) << 16);
+                    const uint32_t tcol = tmem_base + kL1Col + sl * C1 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
                     for (int c0 = 0; c0 < C1; c0 += 16) {
                         uint32_t r[16];
@@ -1404,7 +1408,7 @@ conv_fused12_kernel(const FusedArgs a) {
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&l1_empty[t]);
+                    if (lane == 0) mbar_arrive(&l1_empty[sl]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
