@@ -149,6 +149,10 @@ struct ConvArgs {
     int pool;                        // fuse MaxPooling3D(2): `out` is the pooled tensor (edge dout/2)
     int max_blk;                     // cap on accumulator blocks per M-tile region (0: 256/cout)
     uint32_t tmem_cols;
+    // K-split: the input channels are contracted in several launches; fp32 partial sums live in HBM between them
+    int cin_atom_off;                // first channel atom of this launch's input-channel chunk
+    int acc_mode;                    // 0 normal, 1 first chunk (write partial), 2 middle (partial += acc), 3 last (finish)
+    float *partial;                  // (tile, cout/8, Dout_z, Dout, Dout, 8) fp32
 };
 
 // Epilogue of one M=128 accumulator tile (N = cout fp32 columns in TMEM):
@@ -255,6 +259,64 @@ __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int
     }
 }
 
+// K-split epilogue of one M=128 accumulator tile: partial sums of the input-channel chunks are kept as fp32
+// C8-blocked atoms (32 B) in HBM.  mode 1: partial = acc; 2: partial += acc; 3: out = bf16(relu(partial + acc + bias)).
+__device__ __forceinline__ void epilogue_tile_ksplit(uint32_t tmem_acc, int q, int lane, int cout, const float *s_bias,
+                                                     int relu, __nv_bfloat16 *__restrict__ out, float *__restrict__ partial,
+                                                     int mode, int tile, int dout, int z, int y0, int x0, int dout_z) {
+    const int row = q * 32 + lane;
+    const int y = y0 + (row >> 3), x = x0 + (row & 7);
+    const bool ok = (x < dout) && (y < dout);
+    const size_t cg_stride = (size_t)dout_z * dout * dout;
+    const size_t vox = (size_t)tile * (cout >> 3) * cg_stride + ((size_t)z * dout + y) * dout + x;
+    const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < cout; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tcol + (uint32_t)c0, r);
+        float4 pv[4];
+        if (ok && mode != 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 *pp = reinterpret_cast<const float4 *>(partial + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8);
+                pv[2 * h] = pp[0]; pv[2 * h + 1] = pp[1];
+            }
+        }
+        tmem_ld_wait();
+        if (!ok) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (mode != 1) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { v[4 * h] += pv[h].x; v[4 * h + 1] += pv[h].y; v[4 * h + 2] += pv[h].z; v[4 * h + 3] += pv[h].w; }
+        }
+        if (mode != 3) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 *pp = reinterpret_cast<float4 *>(partial + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8);
+                pp[0] = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+                pp[1] = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v0 = v[h * 8 + 2 * j] + s_bias[c0 + h * 8 + 2 * j];
+                    float v1 = v[h * 8 + 2 * j + 1] + s_bias[c0 + h * 8 + 2 * j + 1];
+                    if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                    pk[j] = *reinterpret_cast<uint32_t *>(&b2);
+                }
+                *reinterpret_cast<uint4 *>(out + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+}
+
 // Accumulator placement ("kd fusion").  The three kd taps of a 3x3x3 kernel read the SAME shifted A
 // tile of input plane p and feed three DIFFERENT output planes z = p, p-1, p-2.  Their accumulators
 // are laid out in TMEM so that they sit in adjacent N-column blocks in kd order; one
@@ -349,7 +411,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                     if (leader) {
                         mbar_expect_tx(&plane_full[slot], plane_bytes);
                         tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * TX * 8, yt * kTY,
-                                    z0 + p, tile * a.cin_atoms_total + sub * SUB_ATOMS);
+                                    z0 + p, tile * a.cin_atoms_total + a.cin_atom_off + sub * SUB_ATOMS);
                     }
                 }
         }
@@ -546,7 +608,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                     else
                         epilogue_tile_pool<4>(tacc, q, lane, s_bias, a.relu, a.out, tile, a.dout >> 1, z0 + zo, yt * kTY,
                                               xt * TX + m * 8, hold, a.dout_z >> 1);
-                } else
+                } else if (a.acc_mode)
+                epilogue_tile_ksplit(tacc, q, lane, a.cout, s_bias, a.relu, a.out, a.partial, a.acc_mode, tile,
+                                     a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.dout_z);
+                else
                 epilogue_tile(tacc, q, lane, a.cout, s_bias, a.relu, a.out, tile,
                               a.dout, z0 + zo, yt * kTY, xt * TX + m * 8, a.cout_total, a.cout_off, a.dout_z);
                 tc_fence_before();
@@ -1498,7 +1563,7 @@ static constexpr size_t kMaxDynSmem = 232448;   // 227 KB
 //   n_split  : the output channels are computed in n_split launches of n = cout/n_split columns
 //   nsub     : the input channels are streamed as nsub sub-planes of 16*ksteps channels
 //   tx       : patch width (16: two M-tiles per plane, 8: one)        ring: (sub-)plane ring depth
-struct ConvPlan { int n_split, n, nsub, ksteps, tx, ring; size_t smem; bool ok; bool rot; };
+struct ConvPlan { int n_split, n, nsub, ksteps, tx, ring; size_t smem; bool ok; bool rot; int k_split; };
 
 // rot: the packed weights hold 5 instead of 3 kd row blocks (see the ROT variant of conv_umma_kernel)
 static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring, bool rot) {
@@ -1537,8 +1602,28 @@ static double plan_cost(const ConvParams &c, const ConvPlan &p) {
     return cost;
 }
 
+// K-split plan: k_split launches over input-channel chunks, each with the full Cout (wide N), fp32 partial
+// sums round-trip through HBM between launches.  Cost per M-tile plane in cycles: per launch
+// max(MMA phase, partial traffic at ~23 B/clk/SM x 1.5 safety).
+static double ksplit_cost(const ConvParams &c, const ConvPlan &p) {
+    const int cc = c.cin / p.k_split;
+    const double N = 3.0 * p.n, units = 9.0 * (cc / 16);
+    int nblk = 256 / p.n; if (nblk > 8) nblk = 8;
+    const double a_reads = p.rot ? 1.0 + 2.0 / units : 1.0 + 2.0 / nblk + 2.0 / units;
+    const double smem_cyc = (a_reads * 4096.0 + N * 32.0) / 128.0, mma_cyc = N / 2.0;
+    const double mma = units * (smem_cyc > mma_cyc ? smem_cyc : mma_cyc);
+    const double pbytes = 128.0 * p.n * 4.0;            // one fp32 pass over an M-tile
+    double total = 0.0;
+    for (int g = 0; g < p.k_split; ++g) {
+        const double bytes = (g == 0 ? pbytes : g == p.k_split - 1 ? pbytes + 128.0 * p.n * 2.0 : 2.0 * pbytes);
+        const double hbm = 1.5 * bytes / 23.0;
+        total += mma > hbm ? mma : hbm;
+    }
+    return total * (p.ring == 2 ? 1.03 : 1.0) / (9.0 * (c.cin / 16)) ;   // per unit of the unsplit problem, like plan_cost
+}
+
 static ConvPlan plan_conv(const ConvParams &c) {
-    ConvPlan best{0, 0, 0, 0, 0, 0, 0, false, false};
+    ConvPlan best{0, 0, 0, 0, 0, 0, 0, false, false, 1};
     if (c.cin % 16 || c.cout % 16 || c.cout > 128 || (c.k != 1 && c.k != 3)) return best;
     static const int legacy = getenv("FPL_PLAN_LEGACY") ? atoi(getenv("FPL_PLAN_LEGACY")) : 0;
     int txs[2] = {16, 8};
@@ -1558,7 +1643,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
                         if (nsub > 1 && ring > 2) continue;
                         const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring, rot != 0);
                         if (sm > kMaxDynSmem) continue;
-                        const ConvPlan cand{split, n, nsub, ksteps, txs[ti], ring, sm, true, rot != 0};
+                        const ConvPlan cand{split, n, nsub, ksteps, txs[ti], ring, sm, true, rot != 0, 1};
                         // legacy: no split, single plane, wide patch, deep ring (loop order) -- first hit wins
                         if (legacy) return cand;
                         const double cost = plan_cost(c, cand);
@@ -1567,6 +1652,23 @@ static ConvPlan plan_conv(const ConvParams &c) {
                 }
             }
         }
+    // K-split candidates (3x3x3, no Cout split): taken only when clearly better than the best resident plan
+    static const int no_ksplit = getenv("FPL_NO_KSPLIT") ? 1 : 0;
+    if (best.ok && !legacy && !no_ksplit && c.k == 3 && c.cout <= 80) {
+        for (int ks_ = 2; ks_ <= 4; ks_ *= 2) {
+            if (c.cin % (16 * ks_)) continue;
+            const int cc = c.cin / ks_, ksteps = cc / 16;
+            if (!have_instance(3, ksteps, 16)) continue;
+            for (int rot = 1; rot >= 0; --rot)
+                for (int ring = 3; ring >= 2; --ring) {
+                    const size_t sm = plan_smem(3, cc, c.cout, 1, 16, ring, rot != 0);
+                    if (sm > kMaxDynSmem || (rot && 3 * c.cout > 256)) continue;
+                    const ConvPlan cand{1, c.cout, 1, ksteps, 16, ring, sm, true, rot != 0, ks_};
+                    const double cost = ksplit_cost(c, cand);
+                    if (cost < 0.8 * best_cost) { best = cand; best_cost = cost / 0.8; }
+                }
+        }
+    }
     return best;
 }
 
@@ -1603,10 +1705,13 @@ int pack_weights_umma(fpl_net *net) {
         const ConvPlan plan = plan_conv(c);
         if (!plan.ok) continue;
         // ROT plans store the kd row blocks as [kd0 kd1 kd2 kd0 kd1] (all three cyclic orders are windows)
-        const int ks = c.k, ksteps = c.cin / 16, n = plan.n, nkb = plan.rot ? 5 : ks;
-        std::vector<__nv_bfloat16> pk((size_t)ks * ks * nkb * c.cin * c.cout);
-        const size_t split_elems = (size_t)ks * ks * nkb * c.cin * n;
-        for (int g = 0; g < plan.n_split; ++g)
+        // one image per launch: n_split Cout splits (all input channels) or k_split input-channel chunks (all Cout)
+        const int ks = c.k, n = plan.n, nkb = plan.rot ? 5 : ks;
+        const int n_img = plan.n_split * plan.k_split, cc = c.cin / plan.k_split, ksteps = cc / 16;
+        std::vector<__nv_bfloat16> pk((size_t)ks * ks * nkb * cc * n * n_img);
+        const size_t img_elems = (size_t)ks * ks * nkb * cc * n;
+        for (int g = 0; g < n_img; ++g) {
+            const int co0 = plan.k_split > 1 ? 0 : g * n, ci0 = plan.k_split > 1 ? g * cc : 0;
             for (int kh = 0; kh < ks; ++kh)
                 for (int kw = 0; kw < ks; ++kw)
                     for (int s = 0; s < ksteps; ++s)
@@ -1615,12 +1720,13 @@ int pack_weights_umma(fpl_net *net) {
                                 for (int nn = 0; nn < n; ++nn)
                                     for (int e = 0; e < 8; ++e) {
                                         const int kd = kb % ks;
-                                        const int ci = 16 * s + 8 * h + e, co = g * n + nn;
+                                        const int ci = ci0 + 16 * s + 8 * h + e, co = co0 + nn;
                                         const int tap = (kd * ks + kh) * ks + kw;
                                         const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + co] * c.scale[co];
                                         const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
-                                        pk[g * split_elems + (((chunk * 2 + h) * nkb + kb) * n + nn) * 8 + e] = __float2bfloat16_rn(v);
+                                        pk[g * img_elems + (((chunk * 2 + h) * nkb + kb) * n + nn) * 8 + e] = __float2bfloat16_rn(v);
                                     }
+        }
         c.packed_bytes = pk.size() * sizeof(__nv_bfloat16);
         FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
         FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, pk.data(), c.packed_bytes, cudaMemcpyHostToDevice));
@@ -1634,6 +1740,11 @@ void free_packed_umma(fpl_net *net) {
         c.d_packed = nullptr; c.packed_bytes = 0;
     }
 }
+
+// activation buffer pool (defined below)
+struct PoolBuf { void *p; size_t cap; bool busy; };
+static std::vector<PoolBuf> g_bufs;
+static int pool_take(size_t bytes, cudaStream_t st);
 
 static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
                             int n_tiles, int din, int din_z, int relu, int pool, cudaStream_t st) {
@@ -1656,7 +1767,15 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FPL_ECUDA; }
     ConvArgs a;
     a.out = out;
-    a.w_bytes = (uint32_t)(c.packed_bytes / plan.n_split);
+    a.w_bytes = (uint32_t)(c.packed_bytes / (plan.n_split * plan.k_split));
+    a.cin_atom_off = 0; a.acc_mode = 0; a.partial = nullptr;
+    int partial_buf = -1;
+    if (plan.k_split > 1) {
+        FPL_REQUIRE(!pool, "conv_umma: pooled epilogue needs an unsplit plan");
+        partial_buf = pool_take((size_t)n_tiles * dout_z * dout * dout * c.cout * sizeof(float), st);
+        if (partial_buf < 0) return FPL_ENOMEM;
+        a.partial = (float *)g_bufs[partial_buf].p;
+    }
     a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.din_z = din_z; a.dout_z = dout_z;
     a.cin_atoms_total = cin_atoms; a.nsub = plan.nsub; a.cout = plan.n; a.cout_total = c.cout; a.ring = plan.ring;
     a.n_xt = (dout + plan.tx - 1) / plan.tx; a.n_yt = (dout + kTY - 1) / kTY;
@@ -1677,10 +1796,16 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
                    2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout_z * dout * dout);
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
-    for (int g = 0; g < plan.n_split; ++g) {
+    for (int g = 0; g < plan.n_split * plan.k_split; ++g) {
         a.w_packed = (const __nv_bfloat16 *)((const uint8_t *)c.d_packed + (size_t)g * a.w_bytes);
-        a.bias = c.d_bias + g * plan.n;
-        a.cout_off = g * plan.n;
+        if (plan.k_split > 1) {
+            a.bias = c.d_bias; a.cout_off = 0;
+            a.cin_atom_off = g * (c.cin / plan.k_split / 8);
+            a.acc_mode = g == 0 ? 1 : (g == plan.k_split - 1 ? 3 : 2);
+        } else {
+            a.bias = c.d_bias + g * plan.n;
+            a.cout_off = g * plan.n;
+        }
 #define FPL_LAUNCH_UMMA(KS_, KST_, TX_, ROT_)                                                                    \
         do {                                                                                                      \
             FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_, ROT_>,                           \
@@ -1706,6 +1831,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
 #undef FPL_LAUNCH_UMMA
         FPL_LAUNCH_CHECK(ctx);
     }
+    if (partial_buf >= 0) g_bufs[partial_buf].busy = false;     // stream-ordered: later launches may reuse it
     return FPL_OK;
 }
 
@@ -1727,9 +1853,6 @@ static int launch_conv_direct(fpl_ctx *ctx, const ConvParams &c, const __nv_bflo
 }
 
 // activation buffer pool (device): exact-size buffers, best fit, grow-only; one process = one GPU
-struct PoolBuf { void *p; size_t cap; bool busy; };
-static std::vector<PoolBuf> g_bufs;
-
 static int pool_take(size_t bytes, cudaStream_t st) {
     int best = -1;
     for (size_t i = 0; i < g_bufs.size(); ++i)

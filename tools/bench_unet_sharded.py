@@ -35,7 +35,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    net = fplnetwork.FplNetwork(getattr(fplmodels, a.model))
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        net = fplnetwork.FplNetwork(getattr(fplmodels, a.model))
     net.train_single.set_weights(bench.seeded_weights(a.model))
     net.set_precision("bf16")
     net._set_infer()
