@@ -1638,7 +1638,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
                 if (c.cout % (16 * split)) continue;
                 const int n = c.cout / split;
                 for (int rot = 1; rot >= 0; --rot) {
-                    if (rot && (c.k != 3 || txs[ti] != 16 || legacy || 3 * n > 256)) continue;
+                    if (rot && (c.k != 3 || txs[ti] != 16 || legacy || c.no_rot || 3 * n > 256)) continue;
                     for (int ring = 3; ring >= 2; --ring) {
                         if (nsub > 1 && ring > 2) continue;
                         const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring, rot != 0);
@@ -1654,7 +1654,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
         }
     // K-split candidates (3x3x3, no Cout split): taken only when clearly better than the best resident plan
     static const int no_ksplit = getenv("FPL_NO_KSPLIT") ? 1 : 0;
-    if (best.ok && !legacy && !no_ksplit && c.k == 3 && c.cout <= 80) {
+    if (best.ok && !legacy && !no_ksplit && !c.no_rot && c.k == 3 && c.cout <= 80) {
         for (int ks_ = 2; ks_ <= 4; ks_ *= 2) {
             if (c.cin % (16 * ks_)) continue;
             const int cc = c.cin / ks_, ksteps = cc / 16;
@@ -1678,7 +1678,17 @@ static int g_force_direct = 0;    // test hook: run every GEMM-shaped conv throu
 static int g_no_pool_fusion = 0;  // test hook: keep MaxPooling3D as its own kernel
 static int g_no_conv12_fusion = 0; // test hook: run the first two convolutions as separate kernels
 
+// first + second convolution suit conv_fused12_kernel (instantiated for 48/48 and 32/32 channels)
+static bool fusable12(const ConvParams &c1, const ConvParams &c2) {
+    return c1.cin == 1 && c1.k == 3 && (c1.cout == 48 || c1.cout == 32) && c2.k == 3 && c2.cin == c1.cout &&
+           c2.cout == c1.cout;
+}
+
 int pack_weights_umma(fpl_net *net) {
+    if (net->ops.size() >= 2 && net->ops[0].kind == OP_CONV && net->ops[1].kind == OP_CONV) {
+        ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
+        c2.no_rot = fusable12(c1, c2);
+    }
     for (ConvParams &c : net->convs) {
         if (c.cin == 1 && c.k == 3 && c.cout % 16 == 0) {   // first layer: K = 27 taps padded to 32
             std::vector<__nv_bfloat16> pk((size_t)2 * 2 * c.cout * 8);
@@ -1888,8 +1898,7 @@ bool umma_reads_volume(const fpl_net *net) {
     if (net->ops.size() < 2 || net->ops[0].kind != OP_CONV || net->ops[1].kind != OP_CONV) return false;
     const ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
     const ConvPlan p2 = plan_conv(c2);
-    return c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 && c2.cout == 48 &&
-           p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot;
+    return fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot && p2.k_split == 1;
 }
 
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
@@ -1915,8 +1924,8 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             // first + second convolution fused (conv_fused12_kernel): the first layer's output stays on chip
             const ConvParams &c1 = net->convs[o.conv_index], &c2 = net->convs[net->ops[1].conv_index];
             const ConvPlan p2 = plan_conv(c2);
-            const bool shape_ok = c1.cin == 1 && c1.k == 3 && c1.cout == 48 && c1.d_packed && c2.k == 3 && c2.cin == 48 &&
-                                  c2.cout == 48 && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot && d >= 8 && dzv >= 8;
+            const bool shape_ok = fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot &&
+                                  p2.k_split == 1 && d >= 8 && dzv >= 8;
             if (shape_ok) {
                 const int dout = d - 4, dout_z = dzv - 4;
                 const bool pool = !g_no_pool_fusion && net->ops.size() > 2 && net->ops[2].kind == OP_POOL &&
@@ -1942,14 +1951,20 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 if (vio) fa.vio = *vio;
                 const long long n_items = base_items * fa.n_zc;
                 int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
-                const size_t smem = ((c2.packed_bytes + 127) & ~size_t(127)) + 2 * 31104 + 3 * 8192 + 2 * 2 * 48 * 16 +
-                                    4 * 20 * 20 * 4 + 1024 + 512 + 256;
+                const int C = c1.cout;
+                const size_t smem = ((c2.packed_bytes + 127) & ~size_t(127)) + 2 * (size_t)(C / 8) * 324 * 16 + 3 * 8192 +
+                                    2 * 2 * C * 16 + 4 * 20 * 20 * 4 + 1024 + 512 + 256;
                 {
                     ProfScope prof(ctx, st, PROF_CONV3,
-                                   2.0 * 27 * 48 * 48 * (double)n_tiles * dout_z * dout * dout +
-                                   2.0 * 27 * 48 * (double)n_tiles * (dout_z + 2) * (dout + 2) * (dout + 2));
-                    FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    conv_fused12_kernel<48, 48><<<grid, kFusedThreads, smem, st>>>(fa);
+                                   2.0 * 27 * C * C * (double)n_tiles * dout_z * dout * dout +
+                                   2.0 * 27 * C * (double)n_tiles * (dout_z + 2) * (dout + 2) * (dout + 2));
+                    if (C == 48) {
+                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        conv_fused12_kernel<48, 48><<<grid, kFusedThreads, smem, st>>>(fa);
+                    } else {
+                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        conv_fused12_kernel<32, 32><<<grid, kFusedThreads, smem, st>>>(fa);
+                    }
                     FPL_LAUNCH_CHECK(ctx);
                 }
                 cur = nb; cur_is_skip = false;

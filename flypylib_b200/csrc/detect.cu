@@ -1079,6 +1079,50 @@ static int threshold_impl(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
 // either: the selection among true candidates is unchanged, and selected extras (value <= threshold)
 // are dropped when the rows are written (finish_rows_kernel).
 // ------------------------------------------------------------------------------------------------
+// level-1 histogram of the fused path: bin = top 11 bits of the monotone key.  Neighbouring voxels of the
+// smoothed map share their top bits, so a thread compares the RAW top bits with its previous voxel (2
+// instructions) and only converts / flushes a run when they change.
+__global__ void __launch_bounds__(512)
+hist1_kernel(const float *__restrict__ v, long long n, SelectState *s) {
+    __shared__ unsigned h[2048];
+    __shared__ unsigned nan_local;
+    for (int b = threadIdx.x; b < 2048; b += blockDim.x) h[b] = 0;
+    if (threadIdx.x == 0) nan_local = 0;
+    __syncthreads();
+    unsigned last = 0xffffffffu, run = 0, my_nan = 0;
+    auto flush = [&]() {
+        if (run) atomicAdd(&h[(last & 0x400u) ? ((~last) & 0x7ffu) : (last | 0x400u)], run);
+    };
+    auto feed = [&](float f) {
+        const unsigned top = __float_as_uint(f) >> 21;
+        if (f != f) ++my_nan;
+        if (top == last) { ++run; }
+        else { flush(); last = top; run = 1; }
+    };
+    const long long n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? (n >> 2) : 0;
+    const float4 *v4 = reinterpret_cast<const float4 *>(v);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 q0 = __ldg(v4 + i), q1 = __ldg(v4 + i + stride), q2 = __ldg(v4 + i + 2 * stride), q3 = __ldg(v4 + i + 3 * stride);
+        feed(q0.x); feed(q0.y); feed(q0.z); feed(q0.w);
+        feed(q1.x); feed(q1.y); feed(q1.z); feed(q1.w);
+        feed(q2.x); feed(q2.y); feed(q2.z); feed(q2.w);
+        feed(q3.x); feed(q3.y); feed(q3.z); feed(q3.w);
+    }
+    for (; i < n4; i += stride) {
+        const float4 q = __ldg(v4 + i);
+        feed(q.x); feed(q.y); feed(q.z); feed(q.w);
+    }
+    for (long long j = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += stride) feed(__ldg(v + j));
+    flush();
+    if (my_nan) atomicAdd(&nan_local, my_nan);
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2048; b += blockDim.x)
+        if (h[b]) atomicAdd(&s->hist[blockIdx.x % kHistSlots][b], (unsigned long long)h[b]);
+    if (threadIdx.x == 0 && nan_local) atomicAdd(&s->nan_count, (unsigned long long)nan_local);
+}
+
 __global__ void select_copy_kernel(const SelectState *src, SelectState *dst) {
     for (int b = threadIdx.x; b < 2048; b += blockDim.x) {       // dst was cleared by select_init_kernel
         unsigned long long c = 0ULL;
@@ -1195,15 +1239,17 @@ dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, 
                     // lower flat index wins ties: the left neighbour beats an equal value, the right one does not
                     bool c = fe >= cutoff_f && !(le >= fe) && !(re > fe);
                     // the z neighbours inside the brick are in this thread's registers: plane below first (lower index)
-                    if (c && k > 0) {
-                        const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
-                        c = !(a0 >= fe) && !(a1 >= fe) && !(a2 >= fe);
+                    if (c) {                                       // rare: keep it a branch, not predicated code
+                        if (k > 0) {
+                            const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
+                            c = !(a0 >= fe) && !(a1 >= fe) && !(a2 >= fe);
+                        }
+                        if (k < 7) {
+                            const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
+                            c = c && !(a0 > fe) && !(a1 > fe) && !(a2 > fe);
+                        }
+                        if (c) cmask |= 1ULL << (k * 8 + e);
                     }
-                    if (c && k < 7) {
-                        const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
-                        c = !(a0 > fe) && !(a1 > fe) && !(a2 > fe);
-                    }
-                    if (c) cmask |= 1ULL << (k * 8 + e);
                 }
             }
             if (x < d.X)
@@ -1248,7 +1294,6 @@ dense_pass2_kernel(const float *__restrict__ v, long long n, const unsigned *__r
     const unsigned lane = threadIdx.x & 31;
     const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
     const long long n8 = (n + 7) / 8;
-    HistFeed feed0, feed1;
     for (long long c0 = (long long)blockIdx.x * (kCh * 256); c0 < n8; c0 += (long long)gridDim.x * (kCh * 256)) {
         float f[kCh][8];
         unsigned valid[kCh];
@@ -1276,16 +1321,26 @@ dense_pass2_kernel(const float *__restrict__ v, long long n, const unsigned *__r
         for (int k = 0; k < kCh; ++k) {
             const long long i0 = (c0 + k * 256 + threadIdx.x) * 8;
             unsigned m = 0;
+            if (valid[k] == 0xffu && raw0 && !two) {           // the common case: 5 instructions per voxel
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (valid[k] & (1u << j)) {
+                for (int j = 0; j < 8; ++j) {
                     const float fe = f[k][j];
                     const unsigned bits = __float_as_uint(fe);
-                    if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0)) feed0.add(h3, (raw0 ? bits : f2key(fe)) & 1023u);
-                    if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
-                        feed1.add(h3 + 1024, (raw1 ? bits : f2key(fe)) & 1023u);
+                    if ((bits & msk0) == rpre0) atomicAdd(&h3[bits & 1023u], 1u);      // rare (22-bit class)
                     if (fe >= cutoff_f) m |= 1u << j;
                 }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j)
+                    if (valid[k] & (1u << j)) {
+                        const float fe = __ldg(v + i0 + j);        // re-read: no dynamic indexing of the register array
+                        const unsigned bits = __float_as_uint(fe);
+                        if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0)) atomicAdd(&h3[(raw0 ? bits : f2key(fe)) & 1023u], 1u);
+                        if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
+                            atomicAdd(&h3[1024 + ((raw1 ? bits : f2key(fe)) & 1023u)], 1u);
+                        if (fe >= cutoff_f) m |= 1u << j;
+                    }
+            }
             if (m) m &= ~((sup[i0 >> 5] >> (i0 & 31)) & 0xffu);     // i0 is a multiple of 8: one byte of one word
             mask[k] = m;
             cnt_me += __popc(m);
@@ -1317,8 +1372,6 @@ dense_pass2_kernel(const float *__restrict__ v, long long n, const unsigned *__r
                 }
         }
     }
-    feed0.flush(h3);
-    if (ns > 1) feed1.flush(h3 + 1024);
     __syncthreads();
     for (int i = threadIdx.x; i < ns * 1024; i += blockDim.x)
         if (h3[i]) atomicAdd(&st[i >> 10].hist[blockIdx.x % kHistSlots][i & 1023], (unsigned long long)h3[i]);
@@ -1550,7 +1603,7 @@ static int voxel2obj_fast(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
     {
         fpl::ProfScope prof(ctx, st, fpl::PROF_SELECT, 4.0 * (double)n);
         if (!level1_done) {                       // Gaussian ran through the generic kernel / sigma == 0
-            select_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_smooth, n, &d_states[0], 21, 2048, 1);
+            hist1_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_smooth, n, &d_states[0]);
             FPL_LAUNCH_CHECK(ctx);
         }
         if (ns > 1) { select_copy_kernel<<<1, 256, 0, st>>>(&d_states[0], &d_states[1]); FPL_LAUNCH_CHECK(ctx); }

@@ -28,6 +28,7 @@ struct ConvParams {                 // host copies (Keras order) + folded device
     // tcgen05 path
     void *d_packed = nullptr;       // operand-B image for the UMMA kernel (BN scale folded in)
     size_t packed_bytes = 0;
+    bool no_rot = false;            // second conv of the fused first+second kernel: split-window weight layout
 };
 
 // Tile grid of FplNetwork.infer (fplnetwork.py:146-160) and the optional direct volume I/O of a
