@@ -585,7 +585,7 @@ struct Counters {                       // device
     unsigned long long n_det;           // all selected
     unsigned long long overflow;
     unsigned long long ball_checks;
-    unsigned long long pad;
+    unsigned long long n_alive_owned;   // slab sessions: valid candidates inside the owned index range (this round)
 };
 
 // every thread takes 8 consecutive voxels (two 16-byte loads in flight), a warp reserves its output
@@ -677,7 +677,10 @@ __global__ void __launch_bounds__(256)
 nms_filter_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d,
                   const unsigned long long *__restrict__ a_idx, const float *__restrict__ a_val,
                   unsigned long long *b_idx, float *b_val, unsigned long long *w_idx, float *w_val,
-                  long long w_capacity, Counters *cnt) {
+                  long long w_capacity, Counters *cnt, unsigned long long own_lo = 0ULL,
+                  unsigned long long own_hi = ~0ULL) {
+    // [own_lo, own_hi): flat index range whose voxels this call may put on the worklist (slab sessions: the
+    // planes a rank owns; halo candidates stay in the list but are decided by their owner)
     const unsigned long long nA = cnt->n_cand;
     const unsigned lane = threadIdx.x & 31;
     for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < nA;
@@ -708,7 +711,9 @@ nms_filter_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup,
                     }
                 }
             }
-            is_work = !better;
+            const bool owned = idx >= own_lo && idx < own_hi;
+            is_work = !better && owned;
+            if (owned && own_hi != ~0ULL) atomicAdd(&cnt->n_alive_owned, 1ULL);
         }
         unsigned m_alive = __ballot_sync(0xffffffffu, alive);
         unsigned m_work = __ballot_sync(0xffffffffu, is_work);
@@ -901,7 +906,36 @@ nms_suppress_kernel(unsigned *sup, Dims d, int r, const unsigned long long *__re
 
 __global__ void round_reset_kernel(Counters *cnt) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        cnt->n_cand = cnt->n_next; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0;
+        cnt->n_cand = cnt->n_next; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0; cnt->n_alive_owned = 0;
+    }
+}
+
+// one block per point given by coordinates (may lie outside the volume: only the part of its ball inside counts)
+__global__ void __launch_bounds__(256)
+nms_suppress_zyx_kernel(unsigned *sup, Dims d, int r, const long long *__restrict__ zyx, long long n_pts) {
+    const int side = 2 * r + 1;
+    for (long long s = blockIdx.x; s < n_pts; s += gridDim.x) {
+        const long long z = zyx[3 * s], y = zyx[3 * s + 1], x = zyx[3 * s + 2];
+        for (int row = threadIdx.x; row < side * side; row += blockDim.x) {
+            int dz = row / side - r, dy = row % side - r;
+            int rem = r * r - dz * dz - dy * dy;
+            if (rem < 0) continue;
+            long long zz = z + dz, yy = y + dy;
+            if (zz < 0 || zz >= d.Z || yy < 0 || yy >= d.Y) continue;
+            int hw = isqrt_floor(rem);
+            long long x0 = x - hw < 0 ? 0 : x - hw;
+            long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
+            if (x1 < x0) continue;
+            unsigned long long q0 = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
+            unsigned long long q1 = ((unsigned long long)zz * d.Y + yy) * d.X + x1;
+            for (unsigned long long wd = q0 >> 5; wd <= (q1 >> 5); ++wd) {
+                unsigned long long lo = wd << 5;
+                unsigned b0 = q0 > lo ? (unsigned)(q0 - lo) : 0u;
+                unsigned b1 = q1 < lo + 31 ? (unsigned)(q1 - lo) : 31u;
+                unsigned mask = (b1 == 31u ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+                atomicOr(&sup[wd], mask);
+            }
+        }
     }
 }
 
@@ -1168,10 +1202,13 @@ __device__ __forceinline__ bool no_better_in_other_rows(const float *__restrict_
 // consecutive x per 256-wide chunk for all 8 z (32-byte vector loads, 8 rows in flight).  Stage 1 (unrolled,
 // registers only): brick maximum, level-2 histogram, candidates that survive the x-neighbour test.  Stage 2
 // (rare, rolled, out of line): the remaining 24 neighbours of those few voxels, re-read through L1/L2.
-__global__ void __launch_bounds__(256)
-dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, float *__restrict__ g,
-                   SelectState *st, int ns, unsigned long long *w_idx, float *w_val, long long w_cap,
-                   Counters *cnt) {
+// FAST: one order statistic whose level-1 class holds non-negative floats (the usual case) -- the class test is
+// two instructions on the raw bits; the generic variant handles two statistics and negative classes.
+template <bool FAST>
+__device__ __forceinline__ void dense_pass1_body(const float *__restrict__ v, Dims d, int gz, int gy, int gx,
+                                                 float *__restrict__ g, SelectState *st, int ns,
+                                                 unsigned long long *w_idx, float *w_val, long long w_cap,
+                                                 Counters *cnt) {
     extern __shared__ unsigned dsm[];
     float *s_max = reinterpret_cast<float *>(dsm);          // [gx]
     unsigned *h2 = dsm + ((gx + 31) & ~31);                 // [ns][2048]
@@ -1231,22 +1268,26 @@ dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, 
                     const float fe = f[k][e];                      // -inf outside the volume
                     m = fmaxf(m, fe);
                     const unsigned bits = __float_as_uint(fe);
-                    if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0))
-                        atomicAdd(&h2[((raw0 ? bits : f2key(fe)) >> 10) & 2047u], 1u);
-                    if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
-                        atomicAdd(&h2[2048 + (((raw1 ? bits : f2key(fe)) >> 10) & 2047u)], 1u);
+                    if (FAST) {
+                        if ((bits & msk0) == rpre0) atomicAdd(&h2[(bits >> 10) & 2047u], 1u);
+                    } else {
+                        if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0))
+                            atomicAdd(&h2[((raw0 ? bits : f2key(fe)) >> 10) & 2047u], 1u);
+                        if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
+                            atomicAdd(&h2[2048 + (((raw1 ? bits : f2key(fe)) >> 10) & 2047u)], 1u);
+                    }
                     const float le = e ? f[k][e - 1] : lf[k], re = e < 7 ? f[k][e + 1] : rt[k];
                     // lower flat index wins ties: the left neighbour beats an equal value, the right one does not
-                    bool c = fe >= cutoff_f && !(le >= fe) && !(re > fe);
+                    bool c = (fe >= cutoff_f) & !(le >= fe) & !(re > fe);       // & not &&: predicate logic, no branches
                     // the z neighbours inside the brick are in this thread's registers: plane below first (lower index)
                     if (c) {                                       // rare: keep it a branch, not predicated code
                         if (k > 0) {
                             const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
-                            c = !(a0 >= fe) && !(a1 >= fe) && !(a2 >= fe);
+                            c = !(a0 >= fe) & !(a1 >= fe) & !(a2 >= fe);
                         }
                         if (k < 7) {
                             const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
-                            c = c && !(a0 > fe) && !(a1 > fe) && !(a2 > fe);
+                            c = c & !(a0 > fe) & !(a1 > fe) & !(a2 > fe);
                         }
                         if (c) cmask |= 1ULL << (k * 8 + e);
                     }
@@ -1274,6 +1315,14 @@ dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, 
     }
     for (int i = threadIdx.x; i < ns * 2048; i += blockDim.x)
         if (h2[i]) atomicAdd(&st[i >> 11].hist[blockIdx.x % kHistSlots][i & 2047], (unsigned long long)h2[i]);
+}
+
+__global__ void __launch_bounds__(256)
+dense_pass1_kernel(const float *__restrict__ v, Dims d, int gz, int gy, int gx, float *__restrict__ g,
+                   SelectState *st, int ns, unsigned long long *w_idx, float *w_val, long long w_cap,
+                   Counters *cnt) {
+    if (ns == 1 && (st[0].prefix >> 31)) dense_pass1_body<true>(v, d, gz, gy, gx, g, st, ns, w_idx, w_val, w_cap, cnt);
+    else dense_pass1_body<false>(v, d, gz, gy, gx, g, st, ns, w_idx, w_val, w_cap, cnt);
 }
 
 // level-3 histogram + compaction of the still valid voxels above the level-2 cut-off (list A).
@@ -1380,6 +1429,27 @@ dense_pass2_kernel(const float *__restrict__ v, long long n, const unsigned *__r
 // between round 1 and dense pass 2: the worklist of round 1 is spent, list A starts empty
 __global__ void fast_reset_kernel(Counters *cnt) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { cnt->n_cand = 0; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0; }
+}
+
+__global__ void hist_add_kernel(unsigned long long *dst, const unsigned long long *src, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+}
+__global__ void idx_to_zyx_kernel(const unsigned long long *idx, long long n, Dims d, long long *zyx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long q = idx[i];
+        zyx[3 * i] = (long long)(q / ((unsigned long long)d.X * d.Y));
+        zyx[3 * i + 1] = (long long)((q / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        zyx[3 * i + 2] = (long long)(q % (unsigned long long)d.X);
+    }
+}
+__global__ void det_rows_kernel(const unsigned long long *idx, const float *val, long long n, Dims d, double *rows) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long q = idx[i];
+        rows[4 * i] = (double)(q / ((unsigned long long)d.X * d.Y));
+        rows[4 * i + 1] = (double)((q / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        rows[4 * i + 2] = (double)(q % (unsigned long long)d.X);
+        rows[4 * i + 3] = (double)val[i];
+    }
 }
 
 struct DetectBuffers {
@@ -1684,6 +1754,187 @@ static int voxel2obj_fast(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
     return FPL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// slab sessions: building blocks of the exact multi-GPU voxel2obj (semantics S2).  A rank holds the
+// smoothed map of the planes it owns plus an r-wide halo; it decides only for owned voxels, and after every
+// round the points selected by ALL ranks are applied to its suppression map -- so its validity map equals the
+// single-GPU one on its extended slab at the start of every round, and the union of the selections is the
+// single-GPU result.  Collectives (halo exchange, histogram all-reduce, per-round all-gather of the selected
+// points) are done by the host program (flypylib_b200/multi_gpu.py) between these calls.
+// ------------------------------------------------------------------------------------------------
+struct SlabSession {
+    fpl_ctx *ctx;
+    const float *smooth;            // extended slab (Ze,Y,X), caller-owned
+    Dims d; int r;
+    unsigned long long own_lo, own_hi;
+    DetectBuffers B;
+    void *mem;                      // one cudaMalloc behind all buffers
+    unsigned long long *a_idx, *b_idx; float *a_val, *b_val;
+    unsigned long long remaining;   // list A entries
+    long long rounds;
+};
+
+}  // namespace v2o
+}  // namespace fpl
+
+using namespace fpl::v2o;
+
+extern "C" {
+
+int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefix, uint32_t prefix_mask, int shift,
+                       int bins, uint64_t *d_hist, uint64_t *d_nan, void *stream) {
+    FPL_REQUIRE(ctx && d_v && d_hist && n >= 0 && bins > 0 && bins <= 2048, "fpl_v2o_hist_level: bad argument");
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    FPL_TRY(ctx->arena.reserve(sizeof(SelectState) + 4096));
+    ctx->arena.reset();
+    SelectState *s = (SelectState *)ctx->arena.take(sizeof(SelectState));
+    select_init_kernel<<<1, 256, 0, st>>>(s, 0ULL, 0ULL);
+    FPL_LAUNCH_CHECK(ctx);
+    SelectState hdr;            // prefix / mask of the class to histogram
+    FPL_CUDA_CHECK(cudaMemcpyAsync(&hdr, s, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    hdr.prefix = prefix; hdr.prefix_mask = prefix_mask;
+    FPL_CUDA_CHECK(cudaMemcpyAsync(s, &hdr, offsetof(SelectState, hist), cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        select_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_v, n, s, shift, bins, d_nan != nullptr);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    // fold the partial histograms: reuse select_copy_kernel's summation into slot 0 of a second state
+    FPL_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, 2048 * sizeof(uint64_t), st));
+    for (int sl = 0; sl < kHistSlots; ++sl) {
+        // 16 tiny adds; d_hist += slot
+        const unsigned long long *src = &s->hist[sl][0];
+        hist_add_kernel<<<8, 256, 0, st>>>((unsigned long long *)d_hist, src, 2048);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    if (d_nan) FPL_CUDA_CHECK(cudaMemcpyAsync(d_nan, &s->nan_count, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FPL_OK;
+}
+
+int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int64_t Y, int64_t X,
+                       const fpl_v2o_params *p, double threshold, int64_t own_lo, int64_t own_hi, int64_t list_cap,
+                       int64_t det_cap, void **session, int64_t *h_n_candidates, void *stream) {
+    FPL_REQUIRE(ctx && d_smooth_ext && session && own_lo >= 0 && own_hi >= own_lo && own_hi <= Ze && list_cap > 0 &&
+                det_cap > 0, "fpl_v2o_slab_begin: bad argument");
+    FPL_TRY(check_params(p, Ze, Y, X));
+    FPL_REQUIRE(p->obj_min_dist <= 27 + 4, "voxel2obj: radius outside the brick-grid limits");
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SlabSession *S = new SlabSession();
+    S->ctx = ctx; S->smooth = d_smooth_ext; S->d = Dims{Ze, Y, X}; S->r = p->obj_min_dist;
+    S->own_lo = (unsigned long long)own_lo * Y * X; S->own_hi = (unsigned long long)own_hi * Y * X;
+    S->rounds = 0; S->mem = nullptr;
+    // private arena for the session (several sessions may be alive on one device: single-GPU emulation in tests)
+    fpl::Arena saved = ctx->arena;
+    ctx->arena = fpl::Arena();
+    int rc = ctx->arena.reserve(detect_workspace_bytes(Ze, Y, X, list_cap, det_cap));
+    if (rc == FPL_OK) { ctx->arena.reset(); rc = take_detect_buffers(ctx, Ze, Y, X, list_cap, det_cap, S->B, st); }
+    S->mem = ctx->arena.base;
+    ctx->arena = saved;
+    if (rc != FPL_OK) { if (S->mem) cudaFree(S->mem); delete S; return rc; }
+    const long long n = Ze * Y * X;
+    compact_candidates_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth_ext, n, threshold, S->B.a_idx, S->B.a_val,
+                                                                list_cap, S->B.cnt);
+    FPL_LAUNCH_CHECK(ctx);
+    brick_max_kernel<<<S->B.gz * S->B.gy, 256, S->B.gx * sizeof(float), st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid);
+    FPL_LAUNCH_CHECK(ctx);
+    Counters *h_cnt = (Counters *)ctx->h_pinned;
+    FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_cnt->overflow) {
+        fpl::set_error("voxel2obj slab: candidate list overflow (%llu > %lld)", h_cnt->n_cand, (long long)list_cap);
+        cudaFree(S->mem); delete S;
+        return FPL_EOVERFLOW;
+    }
+    S->remaining = h_cnt->n_cand;
+    S->a_idx = S->B.a_idx; S->b_idx = S->B.b_idx; S->a_val = S->B.a_val; S->b_val = S->B.b_val;
+    if (h_n_candidates) *h_n_candidates = (int64_t)h_cnt->n_cand;
+    *session = S;
+    return FPL_OK;
+}
+
+// one round, decision half: worklist of the owned valid candidates -> ball check -> newly selected points.
+// d_sel_zyx receives their (z,y,x) in slab coordinates; *h_alive_owned = valid owned candidates at round start.
+int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64_t *h_n_sel, int64_t *h_alive_owned,
+                       void *stream) {
+    SlabSession *S = (SlabSession *)session;
+    FPL_REQUIRE(S && d_sel_zyx && h_n_sel && h_alive_owned, "fpl_v2o_slab_round: NULL argument");
+    fpl_ctx *ctx = S->ctx;
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Counters *h_cnt = (Counters *)ctx->h_pinned;
+    *h_n_sel = 0; *h_alive_owned = 0;
+    if (S->remaining == 0) return FPL_OK;
+    ++S->rounds;
+    long long fblocks = (long long)((S->remaining + 255) / 256);
+    if (fblocks > ctx->sm_count * 8) fblocks = ctx->sm_count * 8;
+    nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->a_idx, S->a_val, S->b_idx, S->b_val,
+                                                        S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, S->own_lo, S->own_hi);
+    FPL_LAUNCH_CHECK(ctx);
+    nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->r, S->B.grid, S->B.gz, S->B.gy, S->B.gx,
+                                                           S->B.w_idx, S->B.w_val, S->B.det_idx, S->B.det_val, S->B.sel_idx,
+                                                           S->B.det_cap, S->B.cnt, nullptr);
+    FPL_LAUNCH_CHECK(ctx);
+    FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_cnt->overflow) { fpl::set_error("voxel2obj slab: detection capacity too small"); return FPL_EOVERFLOW; }
+    FPL_REQUIRE((int64_t)h_cnt->n_sel_round <= sel_cap, "fpl_v2o_slab_round: selection buffer too small");
+    if (h_cnt->n_sel_round) {
+        idx_to_zyx_kernel<<<64, 256, 0, st>>>(S->B.sel_idx, (long long)h_cnt->n_sel_round, S->d, (long long *)d_sel_zyx);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    *h_n_sel = (int64_t)h_cnt->n_sel_round;
+    *h_alive_owned = (int64_t)h_cnt->n_alive_owned;
+    round_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
+    FPL_LAUNCH_CHECK(ctx);
+    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    S->remaining = h_cnt->n_next;
+    unsigned long long *ti = S->a_idx; S->a_idx = S->b_idx; S->b_idx = ti;
+    float *tv = S->a_val; S->a_val = S->b_val; S->b_val = tv;
+    return FPL_OK;
+}
+
+// one round, update half: suppress the balls of the points selected by all ranks (slab coordinates, may lie outside)
+int fpl_v2o_slab_suppress(void *session, const int64_t *d_zyx, int64_t n_pts, void *stream) {
+    SlabSession *S = (SlabSession *)session;
+    FPL_REQUIRE(S && (d_zyx || n_pts == 0), "fpl_v2o_slab_suppress: NULL argument");
+    if (n_pts <= 0) return FPL_OK;
+    FPL_CUDA_CHECK(cudaSetDevice(S->ctx->device));
+    nms_suppress_zyx_kernel<<<S->ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(S->B.sup, S->d, S->r, (const long long *)d_zyx, n_pts);
+    FPL_LAUNCH_CHECK(S->ctx);
+    return FPL_OK;
+}
+
+// detections of the owned planes: rows (z, y, x, conf) in slab coordinates, unordered
+int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h_count, int64_t *h_rounds, void *stream) {
+    SlabSession *S = (SlabSession *)session;
+    FPL_REQUIRE(S && h_count, "fpl_v2o_slab_end: NULL argument");
+    fpl_ctx *ctx = S->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = FPL_OK;
+    Counters *h_cnt = (Counters *)ctx->h_pinned;
+    if (cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) rc = FPL_ECUDA;
+    const long long n_det = rc == FPL_OK ? (long long)h_cnt->n_det : 0;
+    if (rc == FPL_OK && n_det > capacity) { fpl::set_error("fpl_v2o_slab_end: row buffer too small"); rc = FPL_EOVERFLOW; }
+    if (rc == FPL_OK && n_det > 0) {
+        det_rows_kernel<<<64, 256, 0, st>>>(S->B.det_idx, S->B.det_val, n_det, S->d, d_rows);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = FPL_ECUDA;
+    }
+    *h_count = n_det;
+    if (h_rounds) *h_rounds = S->rounds;
+    cudaFree(S->mem);
+    delete S;
+    return rc;
+}
+
+}  // extern "C"
+
+namespace fpl {
+namespace v2o {
 }  // namespace v2o
 }  // namespace fpl
 
