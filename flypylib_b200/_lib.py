@@ -61,6 +61,14 @@ _SIGNATURES = {
     "fpl_voxel2obj": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.POINTER(V2OParams), vp, ctypes.c_int64, c_i64p, c_f64p,
                                      c_i64p, vp]),
+    "fpl_v2o_hist_level": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
+                                          ctypes.c_int, vp, vp, vp]),
+    "fpl_v2o_slab_begin": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.POINTER(V2OParams), ctypes.c_double, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(vp), c_i64p, vp]),
+    "fpl_v2o_slab_round": (ctypes.c_int, [vp, vp, ctypes.c_int64, c_i64p, c_i64p, vp]),
+    "fpl_v2o_slab_suppress": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
+    "fpl_v2o_slab_end": (ctypes.c_int, [vp, vp, ctypes.c_int64, c_i64p, c_i64p, vp]),
     "fpl_net_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
     "fpl_net_destroy": (ctypes.c_int, [vp]),
     "fpl_net_info": (ctypes.c_int, [vp, c_i32p, c_i32p, c_i32p, c_i32p]),

@@ -1431,6 +1431,9 @@ __global__ void fast_reset_kernel(Counters *cnt) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { cnt->n_cand = 0; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0; }
 }
 
+__global__ void select_set_prefix_kernel(SelectState *s, unsigned prefix, unsigned mask) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { s->prefix = prefix; s->prefix_mask = mask; }
+}
 __global__ void hist_add_kernel(unsigned long long *dst, const unsigned long long *src, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
 }
@@ -1792,11 +1795,8 @@ int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefi
     SelectState *s = (SelectState *)ctx->arena.take(sizeof(SelectState));
     select_init_kernel<<<1, 256, 0, st>>>(s, 0ULL, 0ULL);
     FPL_LAUNCH_CHECK(ctx);
-    SelectState hdr;            // prefix / mask of the class to histogram
-    FPL_CUDA_CHECK(cudaMemcpyAsync(&hdr, s, offsetof(SelectState, hist), cudaMemcpyDeviceToHost, st));
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-    hdr.prefix = prefix; hdr.prefix_mask = prefix_mask;
-    FPL_CUDA_CHECK(cudaMemcpyAsync(s, &hdr, offsetof(SelectState, hist), cudaMemcpyHostToDevice, st));
+    select_set_prefix_kernel<<<1, 32, 0, st>>>(s, prefix, prefix_mask);      // the class to histogram
+    FPL_LAUNCH_CHECK(ctx);
     if (n > 0) {
         select_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_v, n, s, shift, bins, d_nan != nullptr);
         FPL_LAUNCH_CHECK(ctx);

@@ -103,3 +103,244 @@ def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigm
         return merge_detections([rows])
     parts = allgather_detections(torch.from_numpy(np.ascontiguousarray(rows)).to(image_dev.device), group)
     return merge_detections([p.cpu().numpy() for p in parts])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Exact global voxel2obj on z-slabs (semantics S2): the result is bit-identical to ONE
+# voxel2obj call on the whole volume (flypylib/fplobjdetect.py:132-257), whatever the number of ranks.
+#   1. halo exchange of the probability map: r + lw planes per cut (lw = Gaussian half width), so that every
+#      rank can smooth its owned planes plus an r-wide halo exactly;
+#   2. the 97th percentile of the WHOLE padded volume: three radix levels, each a per-rank histogram of the
+#      owned planes + a sum all-reduce of 2048 counters (the border zeros of the padded volume enter as a count);
+#   3. greedy NMS as rounds: every rank decides only for the voxels it owns; the points selected in a round
+#      are all-gathered and every rank suppresses all balls that reach into its extended slab -- its validity
+#      map then equals the single-GPU one at the start of every round;
+#   4. all-gather of the owned detections, global order (conf desc, flat index asc), buffer crop, offset.
+# The collectives are tiny (KBs per round); `_DistCollectives` maps them to torch.distributed (NCCL on the
+# GPU box), `_LocalCollectives` runs all ranks in one process on one GPU (tests).
+# ---------------------------------------------------------------------------------------------------
+class _DistCollectives(object):
+    """One local rank; collectives over torch.distributed (device tensors -> NCCL)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.local_ranks = [self.rank]
+
+    def halo(self, slabs, ranges, Z, h):
+        import torch
+        dist = self.dist
+        slab, (z0, z1) = slabs[0], ranges[0]
+        all_ranges = [None] * self.world
+        dist.all_gather_object(all_ranges, (z0, z1), group=self.group)
+        e0, e1 = max(0, z0 - h), min(Z, z1 + h)
+        ext = torch.empty((e1 - e0,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+        ext[z0 - e0:z1 - e0] = slab
+        ops = []
+        for peer, (p0, p1) in enumerate(all_ranges):
+            if peer == self.rank or p1 <= p0:
+                continue
+            pe0, pe1 = max(0, p0 - h), min(Z, p1 + h)
+            lo, hi = max(z0, pe0), min(z1, pe1)                 # my planes the peer's extended slab needs
+            if hi > lo:
+                ops.append(dist.P2POp(dist.isend, slab[lo - z0:hi - z0].contiguous(), peer, group=self.group))
+            lo, hi = max(p0, e0), min(p1, e1)                   # the peer's planes my extended slab needs
+            if hi > lo:
+                ops.append(dist.P2POp(dist.irecv, ext[lo - e0:hi - e0], peer, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return [(ext, e0)]
+
+    def allreduce(self, tensors):
+        self.dist.all_reduce(tensors[0], group=self.group)
+        return tensors
+
+    def allgather(self, tensors):
+        import torch
+        t = tensors[0]
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        counts = [torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(counts, n, group=self.group)
+        m = max(1, max(int(c.item()) for c in counts))
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        bufs = [torch.zeros_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(bufs, pad, group=self.group)
+        return [torch.cat([b[:int(c.item())] for b, c in zip(bufs, counts)], 0)]
+
+
+class _LocalCollectives(object):
+    """All ranks in this process (same device): the collectives are plain tensor operations."""
+
+    def __init__(self, world):
+        self.world, self.rank, self.local_ranks = world, 0, list(range(world))
+
+    def halo(self, slabs, ranges, Z, h):
+        import torch
+        full = torch.cat(slabs, 0)
+        base = ranges[0][0]
+        out = []
+        for (z0, z1) in ranges:
+            e0, e1 = max(0, z0 - h), min(Z, z1 + h)
+            out.append((full[e0 - base:e1 - base].contiguous(), e0))
+        return out
+
+    def allreduce(self, tensors):
+        total = sum(tensors[1:], tensors[0].clone())
+        return [total.clone() for _ in tensors]
+
+    def allgather(self, tensors):
+        import torch
+        cat = torch.cat(tensors, 0)
+        return [cat.clone() for _ in tensors]
+
+
+def _key2f(k):
+    k = np.uint32(k)
+    u = (k & np.uint32(0x7fffffff)) if (k & np.uint32(0x80000000)) else ~k
+    return np.array([u], dtype=np.uint32).view(np.float32)[0]
+
+
+def _scan_level(hist, rank, prefix, mask, shift, bins, extra_zeros):
+    """One radix-select level on the host (the device version is select_scan_kernel in csrc/detect.cu):
+    add the implicit border zeros to the class of +0.0, find the bin holding `rank`."""
+    h = np.asarray(hist, dtype=np.uint64).copy()
+    zkey = 0x80000000
+    if (zkey & mask) == prefix:
+        h[(zkey >> shift) & (bins - 1)] += np.uint64(extra_zeros)
+    cum = np.cumsum(h[:bins].astype(object))
+    sel = int(np.searchsorted(np.array([int(c) for c in cum], dtype=object), rank, side='right'))
+    sel = min(sel, bins - 1)
+    before = int(cum[sel - 1]) if sel else 0
+    return rank - before, prefix | (sel << shift), mask | ((bins - 1) << shift)
+
+
+def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volume_offset=(0, 0, 0), buffer_sz=0,
+                     thd=0, coll=None, return_stats=False):
+    """voxel2obj of the whole (Z,Y,X) map whose planes [z0,z1) are held by different ranks; bit-identical to
+    the single call.  ``pred_slabs`` / ``ranges``: CUDA float32 slabs and their (z0,z1) for the LOCAL ranks
+    (one entry with torch.distributed, all ranks with ``_LocalCollectives``).  Every rank returns the full
+    ``{'locs','conf'}`` dict."""
+    import ctypes
+    import torch
+    from . import _lib, fplobjdetect as P
+    if coll is None:
+        coll = _DistCollectives()
+    lib = _lib.lib()
+    nl = len(pred_slabs)
+    Y, X = int(pred_slabs[0].shape[1]), int(pred_slabs[0].shape[2])
+    dev = pred_slabs[0].device
+    devi = dev.index
+    ctx = _lib.context(devi)
+    st = _lib.current_stream_ptr(devi)
+    p, _keep = P._make_params((Z, Y, X), obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+    r, lw = int(p.obj_min_dist), max(int(p.lw), 0)
+    empty = {'locs': np.zeros((0, 3)), 'conf': np.zeros(0)}
+    stats = {'threshold': float('nan'), 'rounds': 0}
+
+    def done(out):
+        return (out, stats) if return_stats else out
+
+    with torch.cuda.device(devi):
+        # 1. halo exchange + exact smoothing of [z0-r, z1+r)
+        ext = coll.halo([s.contiguous() for s in pred_slabs], ranges, Z, r + lw)
+        smooth, s_lo = [], []
+        for (e, e0), (z0, z1) in zip(ext, ranges):
+            d_s = torch.empty_like(e)
+            if e.shape[0] > 0:
+                _lib.check(lib.fpl_v2o_smooth(ctx.handle, e.data_ptr(), int(e.shape[0]), Y, X, ctypes.byref(p),
+                                              d_s.data_ptr(), st), "fpl_v2o_smooth")
+            s0, s1 = max(0, z0 - r), min(Z, z1 + r)
+            smooth.append(d_s[s0 - e0:s1 - e0]); s_lo.append(s0)
+        del ext
+        # 2. global percentile (np.percentile of the padded volume): three all-reduced radix levels
+        n_pad = (Z + 2 * r) * (Y + 2 * r) * (X + 2 * r)
+        extra = n_pad - Z * Y * X
+        targets = [int(p.rank_lo)] + ([int(p.rank_hi)] if p.rank_hi != p.rank_lo else [])
+        states = [[t, 0, 0] for t in targets]                       # [rank, prefix, mask]
+        for li, (shift, bins) in enumerate(((21, 2048), (10, 2048), (0, 1024))):
+            for stt in states:
+                hs, nans = [], []
+                for sm, lo, (z0, z1) in zip(smooth, s_lo, ranges):
+                    own = sm[z0 - lo:z1 - lo]
+                    h = torch.zeros(2048, dtype=torch.int64, device=dev)
+                    nn = torch.zeros(1, dtype=torch.int64, device=dev)
+                    _lib.check(lib.fpl_v2o_hist_level(ctx.handle, own.data_ptr(), int(own.numel()), stt[1], stt[2], shift, bins,
+                                                      h.data_ptr(), nn.data_ptr() if li == 0 else None, st), "fpl_v2o_hist_level")
+                    hs.append(torch.cat([h, nn]))
+                tot = coll.allreduce(hs)[0].cpu().numpy()
+                if li == 0 and int(tot[2048]) > 0:                  # NaNs: percentile is NaN, nothing is selected
+                    return done(empty)
+                stt[0], stt[1], stt[2] = _scan_level(tot[:2048], stt[0], stt[1], stt[2], shift, bins, extra)
+        a, b = _key2f(states[0][1]), _key2f(states[-1][1])
+        g = np.float32(p.gamma)
+        dlt = np.float32(b - a)
+        res = np.float32(a + np.float32(dlt * g))
+        if g >= np.float32(0.5):
+            res = np.float32(b - np.float32(dlt * np.float32(np.float32(1.0) - g)))
+        pr = float(res)
+        thresh = float('nan') if (pr != pr or p.thd != p.thd) else max(pr, float(p.thd))
+        stats['threshold'] = thresh
+        # 3. NMS rounds
+        cand_bound = max(1, n_pad - targets[0])
+        sessions, sel_bufs = [], []
+        for sm, lo, (z0, z1) in zip(smooth, s_lo, ranges):
+            ze = int(sm.shape[0])
+            if ze == 0 or z1 <= z0:
+                sessions.append(None); sel_bufs.append(None); continue
+            cap = P._default_capacity((ze, Y, X), r)
+            h = ctypes.c_void_p()
+            ncand = ctypes.c_int64()
+            _lib.check(lib.fpl_v2o_slab_begin(ctx.handle, sm.data_ptr(), ze, Y, X, ctypes.byref(p), thresh, z0 - lo, z1 - lo,
+                                              int(min(ze * Y * X, cand_bound)), cap, ctypes.byref(h), ctypes.byref(ncand), st),
+                       "fpl_v2o_slab_begin")
+            sessions.append(h); sel_bufs.append(torch.empty((cap, 3), dtype=torch.int64, device=dev))
+        while True:
+            sels, alive = [], []
+            for h, buf, lo in zip(sessions, sel_bufs, s_lo):
+                if h is None:
+                    sels.append(torch.zeros((0, 3), dtype=torch.int64, device=dev)); alive.append(0); continue
+                n_sel, n_alive = ctypes.c_int64(), ctypes.c_int64()
+                _lib.check(lib.fpl_v2o_slab_round(h, buf.data_ptr(), int(buf.shape[0]), ctypes.byref(n_sel),
+                                                  ctypes.byref(n_alive), st), "fpl_v2o_slab_round")
+                pts = buf[:n_sel.value].clone()
+                pts[:, 0] += lo                                         # global z
+                sels.append(pts); alive.append(n_alive.value)
+            tot_alive = coll.allreduce([torch.tensor([a_], dtype=torch.int64, device=dev) for a_ in alive])
+            if int(tot_alive[0].item()) == 0:
+                break
+            stats['rounds'] += 1
+            gathered = coll.allgather(sels)
+            if int(gathered[0].shape[0]) == 0:
+                raise RuntimeError("voxel2obj_global: NMS round made no progress (internal error)")
+            for h, lo, pts in zip(sessions, s_lo, gathered):
+                if h is None:
+                    continue
+                loc = pts.clone()
+                loc[:, 0] -= lo
+                _lib.check(lib.fpl_v2o_slab_suppress(h, loc.data_ptr(), int(loc.shape[0]), st), "fpl_v2o_slab_suppress")
+        # 4. owned detections -> global list
+        rows = []
+        for h, lo, sm in zip(sessions, s_lo, smooth):
+            if h is None:
+                rows.append(torch.zeros((0, 4), dtype=torch.float64, device=dev)); continue
+            cap = P._default_capacity((int(sm.shape[0]), Y, X), r)
+            out = torch.empty((cap, 4), dtype=torch.float64, device=dev)
+            cnt, rounds = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(lib.fpl_v2o_slab_end(h, out.data_ptr(), cap, ctypes.byref(cnt), ctypes.byref(rounds), st),
+                       "fpl_v2o_slab_end")
+            o = out[:cnt.value].clone()
+            o[:, 0] += lo
+            rows.append(o)
+        allrows = coll.allgather(rows)[0].cpu().numpy()
+    if allrows.shape[0] == 0:
+        return done(empty)
+    z, y, x, c = allrows[:, 0], allrows[:, 1], allrows[:, 2], allrows[:, 3]
+    order = np.lexsort((x, y, z, -c))                                   # conf desc, flat index asc
+    z, y, x, c = z[order], y[order], x[order], c[order]
+    bx, by, bz = (int(p.buffer_xyz[i]) for i in range(3))
+    keep = (x >= bx) & (y >= by) & (z >= bz) & (x < X - bx) & (y < Y - by) & (z < Z - bz)
+    locs = np.stack([x[keep] + p.offset_xyz[0], y[keep] + p.offset_xyz[1], z[keep] + p.offset_xyz[2]], 1)
+    return done({'locs': locs, 'conf': c[keep].copy()})

@@ -111,6 +111,34 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
                   const fpl_v2o_params *p, double *d_dets, int64_t capacity, int64_t *h_count,
                   double *h_threshold, int64_t *h_stats, void *stream);
 
+/* --- exact multi-GPU voxel2obj (semantics S2): building blocks for z-slab ranks.  The host
+ * program (flypylib_b200/multi_gpu.py:voxel2obj_global) does the collectives between these calls: halo
+ * exchange of the probability map, all-reduce of the radix histograms (np.percentile over the WHOLE padded
+ * volume, fplobjdetect.py:183), all-gather of the points selected in each round of the greedy loop (:187-231). */
+
+/* Histogram of ((key >> shift) & (bins-1)) over the values whose monotone key matches prefix under prefix_mask
+ * (one level of the radix select).  d_hist: 2048 uint64 (device); d_nan (optional): NaN count (device). */
+int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefix, uint32_t prefix_mask,
+                       int shift, int bins, uint64_t *d_hist, uint64_t *d_nan, void *stream);
+
+/* Open a session on an extended slab (Ze,Y,X) of the smoothed map: planes [own_lo, own_hi) are owned by this
+ * rank, the rest is halo (>= obj_min_dist planes towards every neighbouring rank).  Candidates = values >
+ * threshold.  *session is released by fpl_v2o_slab_end. */
+int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int64_t Y, int64_t X,
+                       const fpl_v2o_params *p, double threshold, int64_t own_lo, int64_t own_hi,
+                       int64_t list_cap, int64_t det_cap, void **session, int64_t *h_n_candidates,
+                       void *stream);
+/* Decision half of one round: owned valid candidates without a better valid voxel in their ball are selected;
+ * their (z,y,x) slab coordinates go to d_sel_zyx (device, sel_cap x 3 int64). */
+int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64_t *h_n_sel,
+                       int64_t *h_alive_owned, void *stream);
+/* Update half: suppress the balls of the points selected by ALL ranks (slab coordinates; points outside the
+ * slab are legal, only the part of their ball inside counts). */
+int fpl_v2o_slab_suppress(void *session, const int64_t *d_zyx, int64_t n_pts, void *stream);
+/* Close: rows (z, y, x, conf) of the owned detections in slab coordinates, unordered. */
+int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h_count, int64_t *h_rounds,
+                     void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * network: model builders + FplNetwork.infer         (flypylib/fplmodels.py, fplnetwork.py:99-189)
  * ------------------------------------------------------------------------------------------- */
