@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_global_v2o_gpu.py -x -q > gpurun_out/q_tests.log 2>&1
-timeout 600 python -m pytest tests/test_voxel2obj_gpu.py -x -q > gpurun_out/q_tests2.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/check_global_v2o.py --size 512 > gpurun_out/s_global_n2.json 2> gpurun_out/s_global_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 tools/check_global_v2o.py --size 640 --kind uniform > gpurun_out/s_global_n2u.json 2> gpurun_out/s_global_n2u.err
 exit 0
