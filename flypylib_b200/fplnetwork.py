@@ -145,6 +145,59 @@ class FplNetwork:
                                                 _lib.current_stream_ptr(dev)), "fpl_net_infer_volume")
         return pred
 
+    def infer_host(self, image_host, normalize=None, out=None, image_dev=None, chunk_layers=4):
+        """``infer`` on a HOST tensor (pinned memory for true overlap) with the host->device copy pipelined
+        behind the computation: the volume is cut into chunks of ``chunk_layers`` reference tile layers in z;
+        chunk c+1 is copied on a side stream while chunk c runs.  Every chunk is an independent sub-volume whose
+        first plane lies on the reference tile grid, so its interior equals the corresponding planes of the
+        whole-volume ``infer`` (same tiles, same zero padding at the far edge).  Returns a CUDA float32 tensor.
+        ``image_dev`` (optional) receives the device copy of the volume."""
+        import torch
+        assert self.infer_network is not None, 'network has not been trained'
+        if image_host.dim() != 3:
+            raise ValueError("image must be 3-D (Z,Y,X)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        Z, Y, X = (int(v) for v in image_host.shape)
+        off, out_sz = int(self.rf_offset[0]), int(self.infer_sz[0]) - 2 * int(self.rf_offset[0])
+        n_layers = 0 if Z <= 2 * off else -(-(Z - 2 * off) // out_sz)
+        if image_dev is None:
+            image_dev = torch.empty((Z, Y, X), dtype=image_host.dtype, device=dev)
+        pred = out if out is not None else torch.empty((Z, Y, X), dtype=torch.float32, device=dev)
+        if n_layers <= chunk_layers:
+            image_dev.copy_(image_host, non_blocking=True)
+            return self.infer_device(image_dev, normalize=normalize, out=pred)
+        side = getattr(self, "_copy_stream", None)
+        if side is None:
+            side = self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)                      # image_dev / pred may still be in use by earlier work
+        chunks, copied = [], 0
+        for k0 in range(0, n_layers, chunk_layers):
+            k1 = min(n_layers, k0 + chunk_layers)
+            in0, in1 = k0 * out_sz, (Z if k1 == n_layers else k1 * out_sz + 2 * off)
+            with torch.cuda.stream(side):
+                if in1 > copied:
+                    image_dev[copied:in1].copy_(image_host[copied:in1], non_blocking=True)
+                    copied = in1
+                ev = side.record_event()
+            chunks.append((k0, k1, in0, in1, ev))
+        pred[:off].zero_()
+        pred[Z - off:].zero_()
+        for k0, k1, in0, in1, ev in chunks:
+            main.wait_event(ev)
+            tmp = self.infer_device(image_dev[in0:in1], normalize=normalize,
+                                    out=self._chunk_buffer(in1 - in0, Y, X, dev))
+            lo, hi = in0 + off, (Z - off if k1 == n_layers else k1 * out_sz + off)
+            pred[lo:hi].copy_(tmp[off:off + (hi - lo)])
+        return pred
+
+    def _chunk_buffer(self, z, Y, X, dev):
+        import torch
+        buf = getattr(self, "_chunk_pred", None)
+        if buf is None or buf.numel() < z * Y * X or buf.device != dev:
+            buf = self._chunk_pred = torch.empty(z * Y * X, dtype=torch.float32, device=dev)
+        return buf[:z * Y * X].view(z, Y, X)
+
     def infer(self, image):
         """fplnetwork.py:136-189: probability map (float32, image.shape) of a 3-D image."""
         import torch

@@ -189,3 +189,23 @@ def test_bf16_detection_agreement_random_init_stress():
     gt, pd = _detections("vgg_like2", w, vol, "fp32"), _detections("vgg_like2", w, vol, "bf16")
     assert gt["conf"].size > 20
     assert _f1(fplobjdetect.obj_pr(pd["locs"], gt["locs"], 27.0)) >= 0.97
+
+
+@pytest.mark.parametrize("arch,shape", [("vgg_like2", (420, 130, 150)), ("unet_like2", (520, 110, 120))])
+def test_infer_host_pipelined_equals_infer_device(arch, shape):
+    """FplNetwork.infer_host (H2D copy pipelined chunk by chunk behind the computation) == infer_device on the
+    whole volume, bit for bit (every chunk starts on the reference tile grid)."""
+    import torch
+    import bench
+    from flypylib_b200 import fplmodels, fplnetwork
+    net = fplnetwork.FplNetwork(getattr(fplmodels, arch))
+    net.train_single.set_weights(bench.seeded_weights(arch))
+    net.set_precision("bf16")
+    net._set_infer()
+    net.tile_multiplier = 1 if arch == "unet_like2" else 4
+    host = torch.from_numpy(cases.em_volume(shape, seed=8)).pin_memory()
+    want = net.infer_device(host.cuda(), normalize=(128.0, 33.0))
+    for chunk_layers in (2, 3):
+        got = net.infer_host(host, normalize=(128.0, 33.0), chunk_layers=chunk_layers)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (arch, chunk_layers)

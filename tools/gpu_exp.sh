@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python __graft_entry__.py smoke > gpurun_out/u_smoke.log 2>&1
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/bench_unet_sharded.py --size 2048 > gpurun_out/u_unet2048_n2.json 2> gpurun_out/u_unet2048_n2.err
+timeout 900 python -m pytest tests/test_umma_gpu.py -x -q -k "pipelined" > gpurun_out/v_tests.log 2>&1
+timeout 600 python bench.py --no-cpu-baseline 2>gpurun_out/v_bench.err | tail -1 > gpurun_out/v_bench.json
 exit 0
