@@ -72,3 +72,70 @@ def test_allgather_detections_gloo_world2():
     res.sort()
     assert res[0][1] == res[1][1] == [(3, 4), (0, 4)]      # one rank contributes an empty list
     assert res[0][2] == res[1][2] and res[0][2] == sorted(res[0][2], reverse=True)
+
+
+# ---- exact-global voxel2obj (S2): host logic and collectives -------------------------------------------
+def test_radix_scan_levels_select_order_statistics():
+    """multi_gpu._scan_level (host half of the all-reduced radix select) finds the same order statistic as a
+    sort, including the implicit border zeros of the padded volume."""
+    rng = np.random.default_rng(0)
+    v = np.concatenate([np.abs(rng.standard_normal(150000)) * 0.3, -rng.random(5000), np.zeros(300)]).astype(np.float32)
+
+    def f2key(a):
+        u = a.view(np.uint32)
+        return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+
+    keys = f2key(v)
+    extra = 40000
+    allv = np.sort(np.concatenate([v, np.zeros(extra, np.float32)]))
+    for target in [0, 4999, 5000, 30000, 45299, 45300, 120000, v.size + extra - 1]:
+        rank, prefix, mask = target, 0, 0
+        for shift, bins in ((21, 2048), (10, 2048), (0, 1024)):
+            sel = (keys & np.uint32(mask)) == np.uint32(prefix)
+            h = np.bincount(((keys[sel] >> np.uint32(shift)) & np.uint32(bins - 1)).astype(np.int64), minlength=2048)
+            rank, prefix, mask = multi_gpu._scan_level(h, rank, prefix, mask, shift, bins, extra)
+        assert mask == 0xffffffff
+        got = multi_gpu._key2f(prefix)
+        assert got == allv[target] or (got == 0 and allv[target] == 0), (target, got, allv[target])
+
+
+def _coll_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coll = multi_gpu._DistCollectives()
+        Z, h = 23, 4
+        full = torch.arange(Z * 3 * 2, dtype=torch.float32).view(Z, 3, 2)
+        cuts = [(0, 3), (3, 5), (5, 23)][:world] if world == 3 else [(0, 9), (9, 23)]
+        z0, z1 = cuts[rank]
+        (ext, e0), = coll.halo([full[z0:z1].contiguous()], [(z0, z1)], Z, h)
+        ok_halo = e0 == max(0, z0 - h) and torch.equal(ext, full[e0:min(Z, z1 + h)])
+        tot = coll.allreduce([torch.tensor([rank + 1, 10 * (rank + 1)])])[0].tolist()
+        rows = torch.full((rank + 1, 3), rank, dtype=torch.int64)
+        gathered = coll.allgather([rows])[0]
+        q.put((rank, bool(ok_halo), tot, gathered.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_s2_collectives_gloo(world):
+    """Halo exchange (slabs thinner than the halo: several peers feed one extended slab), sum all-reduce and
+    variable-length all-gather of multi_gpu._DistCollectives over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 300 + world
+    procs = [ctx.Process(target=_coll_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s = sum(range(1, world + 1))
+    want_rows = [[r, r, r] for r in range(world) for _ in range(r + 1)]
+    for rank, ok_halo, tot, gathered in res:
+        assert ok_halo, rank
+        assert tot == [s, 10 * s]
+        assert gathered == want_rows
