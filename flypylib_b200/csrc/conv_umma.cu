@@ -1654,6 +1654,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
         }
     // K-split candidates (3x3x3, no Cout split): taken only when clearly better than the best resident plan
     static const int no_ksplit = getenv("FPL_NO_KSPLIT") ? 1 : 0;
+    static const double ks_margin = getenv("FPL_KSPLIT_MARGIN") ? atof(getenv("FPL_KSPLIT_MARGIN")) : 0.8;
     if (best.ok && !legacy && !no_ksplit && !c.no_rot && c.k == 3 && c.cout <= 80) {
         for (int ks_ = 2; ks_ <= 4; ks_ *= 2) {
             if (c.cin % (16 * ks_)) continue;
@@ -1665,7 +1666,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
                     if (sm > kMaxDynSmem || (rot && 3 * c.cout > 256)) continue;
                     const ConvPlan cand{1, c.cout, 1, ksteps, 16, ring, sm, true, rot != 0, ks_};
                     const double cost = ksplit_cost(c, cand);
-                    if (cost < 0.8 * best_cost) { best = cand; best_cost = cost / 0.8; }
+                    if (cost < ks_margin * best_cost) { best = cand; best_cost = cost / ks_margin; }
                 }
         }
     }

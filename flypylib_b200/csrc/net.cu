@@ -35,6 +35,35 @@ static int build_graph(fpl_net *n) {
                  conv(3, 96, 32), conv(1, 32, 32), final_(32)};
             n->info = {24, 9, 1, 100, false};
             break;
+        case FPL_ARCH_BASELINE:      // fplmodels.py:73-100
+            g = {conv(3, 1, 32), pool(), conv(3, 32, 32), pool(), conv(3, 32, 32), conv(1, 32, 64), final_(64)};
+            n->info = {18, 7, 4, 102, true};
+            break;
+        case FPL_ARCH_UNET_LIKE:     // fplmodels.py:206-256
+            g = {conv(3, 1, 32), conv(1, 32, 32), save(0), pool(), conv(3, 32, 64), conv(1, 64, 64), save(1),
+                 pool(), conv(1, 64, 128), upcat(1, 0), conv(3, 192, 64), conv(1, 64, 64), upcat(0, 4),
+                 conv(3, 96, 32), conv(1, 32, 32), final_(32)};
+            n->info = {18, 6, 1, 102, false};
+            break;
+        case FPL_ARCH_UNET_LIKE3:    // fplmodels.py:306-357
+            g = {conv(3, 1, 32), conv(3, 32, 32), save(0), pool(), conv(3, 32, 64), conv(3, 64, 64), save(1),
+                 pool(), conv(3, 64, 128), conv(1, 128, 128), upcat(1, 2), conv(3, 192, 64), conv(1, 64, 64),
+                 upcat(0, 10), conv(3, 96, 32), conv(1, 32, 32), final_(32)};
+            n->info = {32, 13, 1, 100, false};
+            break;
+        case FPL_ARCH_UNET_LIKE4:    // fplmodels.py:359-410
+            g = {conv(3, 1, 32), conv(3, 32, 32), save(0), pool(), conv(3, 32, 64), conv(3, 64, 64), save(1),
+                 pool(), conv(3, 64, 128), conv(3, 128, 128), upcat(1, 4), conv(3, 192, 64), conv(1, 64, 64),
+                 upcat(0, 14), conv(3, 96, 32), conv(1, 32, 32), final_(32)};
+            n->info = {40, 17, 1, 100, false};
+            break;
+        case FPL_ARCH_UNET_LIKE4B:   // fplmodels.py:412-467
+            g = {conv(3, 1, 32), conv(3, 32, 32), save(0), pool(), conv(3, 32, 64), conv(1, 64, 32), conv(3, 32, 64),
+                 save(1), pool(), conv(1, 64, 48), conv(3, 48, 128), conv(1, 128, 48), conv(3, 48, 128),
+                 conv(1, 128, 48), upcat(1, 4), conv(3, 112, 64), conv(1, 64, 64), upcat(0, 14), conv(3, 96, 32),
+                 conv(1, 32, 32), final_(32)};
+            n->info = {40, 17, 1, 100, false};
+            break;
         default:
             set_error("fpl_net_create: unknown architecture %d", n->arch);
             return FPL_EINVAL;

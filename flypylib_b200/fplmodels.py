@@ -25,6 +25,21 @@ _ARCH = {
     "unet_like2": dict(id=_lib.ARCH_UNET_LIKE2, rf=(24, 9, 1), infer_sz=100, final_bias=False,
                        convs=[(3, 1, 32), (3, 32, 32), (3, 32, 64), (3, 64, 64), (1, 64, 128), (3, 192, 64),
                               (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
+    "baseline_model": dict(id=_lib.ARCH_BASELINE, rf=(18, 7, 4), infer_sz=102, final_bias=True,
+                           convs=[(3, 1, 32), (3, 32, 32), (3, 32, 32), (1, 32, 64)], final_cin=64),
+    "unet_like": dict(id=_lib.ARCH_UNET_LIKE, rf=(18, 6, 1), infer_sz=102, final_bias=False,
+                      convs=[(3, 1, 32), (1, 32, 32), (3, 32, 64), (1, 64, 64), (1, 64, 128), (3, 192, 64),
+                             (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
+    "unet_like3": dict(id=_lib.ARCH_UNET_LIKE3, rf=(32, 13, 1), infer_sz=100, final_bias=False,
+                       convs=[(3, 1, 32), (3, 32, 32), (3, 32, 64), (3, 64, 64), (3, 64, 128), (1, 128, 128),
+                              (3, 192, 64), (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
+    "unet_like4": dict(id=_lib.ARCH_UNET_LIKE4, rf=(40, 17, 1), infer_sz=100, final_bias=False,
+                       convs=[(3, 1, 32), (3, 32, 32), (3, 32, 64), (3, 64, 64), (3, 64, 128), (3, 128, 128),
+                              (3, 192, 64), (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
+    "unet_like4b": dict(id=_lib.ARCH_UNET_LIKE4B, rf=(40, 17, 1), infer_sz=100, final_bias=False,
+                        convs=[(3, 1, 32), (3, 32, 32), (3, 32, 64), (1, 64, 32), (3, 32, 64), (1, 64, 48),
+                               (3, 48, 128), (1, 128, 48), (3, 48, 128), (1, 128, 48), (3, 112, 64), (1, 64, 64),
+                               (3, 96, 32), (1, 32, 32)], final_cin=32),
 }
 
 _PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "tf32": _lib.PREC_TF32}
@@ -255,3 +270,40 @@ def unet_like2(in_sz=24):
                     'optimizer': 'adam',
                     'metrics': [masked_accuracy, lb0l1err, lb1l1err]}
     return Model("unet_like2", in_sz), (24, 9, 1), 100, compile_args
+
+
+def masked_binary_crossentropy(y_true, y_pred):     # fplmodels.py:52-60, named for compile_args only
+    raise NotImplementedError("training losses are outside the B200 inference hot path")
+
+
+def baseline_model(in_sz=None):
+    """returns simple baseline model (flypylib/fplmodels.py:73-100)"""
+    return Model("baseline_model", in_sz), (18, 7, 4), 102, None
+
+
+def unet_like(in_sz=18):
+    """construct a u-net style network (flypylib/fplmodels.py:206-256)"""
+    compile_args = {'loss': masked_binary_crossentropy, 'optimizer': 'adam',
+                    'metrics': [masked_accuracy, lb0l1err, lb1l1err]}
+    return Model("unet_like", in_sz), (18, 6, 1), 102, compile_args
+
+
+def unet_like3(in_sz=32):
+    """construct a u-net style network (flypylib/fplmodels.py:306-357)"""
+    compile_args = {'loss': masked_focal_loss, 'optimizer': 'adam',
+                    'metrics': [masked_accuracy, lb0l1err, lb1l1err]}
+    return Model("unet_like3", in_sz), (32, 13, 1), 100, compile_args
+
+
+def unet_like4(in_sz=40):
+    """construct a u-net style network (flypylib/fplmodels.py:359-410)"""
+    compile_args = {'loss': masked_focal_loss, 'optimizer': 'adam',
+                    'metrics': [masked_accuracy, lb0l1err, lb1l1err]}
+    return Model("unet_like4", in_sz), (40, 17, 1), 100, compile_args
+
+
+def unet_like4b(in_sz=40):
+    """construct a u-net style network (flypylib/fplmodels.py:412-467)"""
+    compile_args = {'loss': masked_focal_loss, 'optimizer': 'adam',
+                    'metrics': [masked_accuracy, lb0l1err, lb1l1err]}
+    return Model("unet_like4b", in_sz), (40, 17, 1), 100, compile_args

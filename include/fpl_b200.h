@@ -147,6 +147,12 @@ int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h
 #define FPL_ARCH_VGG_LIKE    1
 #define FPL_ARCH_VGG_LIKE2   2
 #define FPL_ARCH_UNET_LIKE2  3
+/* further builders of flypylib/fplmodels.py (same layer vocabulary): :73-100, :206-256, :306-357, :359-410, :412-467 */
+#define FPL_ARCH_BASELINE    4
+#define FPL_ARCH_UNET_LIKE   5
+#define FPL_ARCH_UNET_LIKE3  6
+#define FPL_ARCH_UNET_LIKE4  7
+#define FPL_ARCH_UNET_LIKE4B 8
 
 /* arithmetic of the conv stack */
 #define FPL_PREC_FP32  0   /* CUDA-core fp32 direct convolution (validation path)            */

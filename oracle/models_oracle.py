@@ -41,6 +41,34 @@ ARCHS = {
                     ("C", 3, 192, 64), ("C", 1, 64, 64), ("U", "conv1", 6),
                     ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
                    (24, 9, 1), 100, False),
+    # further builders with the same layer vocabulary: fplmodels.py:73-100, :206-256, :306-357, :359-410, :412-467
+    "baseline_model": ([("C", 3, 1, 32), ("P",), ("C", 3, 32, 32), ("P",), ("C", 3, 32, 32), ("C", 1, 32, 64), ("F", 64)],
+                       (18, 7, 4), 102, True),
+    "unet_like": ([("C", 3, 1, 32), ("C", 1, 32, 32), ("S", "conv1"), ("P",),
+                   ("C", 3, 32, 64), ("C", 1, 64, 64), ("S", "conv2"), ("P",),
+                   ("C", 1, 64, 128), ("U", "conv2", 0),
+                   ("C", 3, 192, 64), ("C", 1, 64, 64), ("U", "conv1", 4),
+                   ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
+                  (18, 6, 1), 102, False),
+    "unet_like3": ([("C", 3, 1, 32), ("C", 3, 32, 32), ("S", "conv1"), ("P",),
+                    ("C", 3, 32, 64), ("C", 3, 64, 64), ("S", "conv2"), ("P",),
+                    ("C", 3, 64, 128), ("C", 1, 128, 128), ("U", "conv2", 2),
+                    ("C", 3, 192, 64), ("C", 1, 64, 64), ("U", "conv1", 10),
+                    ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
+                   (32, 13, 1), 100, False),
+    "unet_like4": ([("C", 3, 1, 32), ("C", 3, 32, 32), ("S", "conv1"), ("P",),
+                    ("C", 3, 32, 64), ("C", 3, 64, 64), ("S", "conv2"), ("P",),
+                    ("C", 3, 64, 128), ("C", 3, 128, 128), ("U", "conv2", 4),
+                    ("C", 3, 192, 64), ("C", 1, 64, 64), ("U", "conv1", 14),
+                    ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
+                   (40, 17, 1), 100, False),
+    "unet_like4b": ([("C", 3, 1, 32), ("C", 3, 32, 32), ("S", "conv1"), ("P",),
+                     ("C", 3, 32, 64), ("C", 1, 64, 32), ("C", 3, 32, 64), ("S", "conv2"), ("P",),
+                     ("C", 1, 64, 48), ("C", 3, 48, 128), ("C", 1, 128, 48), ("C", 3, 48, 128), ("C", 1, 128, 48),
+                     ("U", "conv2", 4),
+                     ("C", 3, 112, 64), ("C", 1, 64, 64), ("U", "conv1", 14),
+                     ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
+                    (40, 17, 1), 100, False),
 }
 
 

@@ -27,7 +27,9 @@ def _predict(arch, s, w, x, precision, force_direct=False):
 
 
 @pytest.mark.parametrize("arch,s,n", [("vgg_like2", 36, 2), ("vgg_like2", 52, 3), ("vgg_like", 38, 2),
-                                      ("unet_like2", 36, 2), ("vgg_like2", 100, 1)])
+                                      ("unet_like2", 36, 2), ("vgg_like2", 100, 1), ("baseline_model", 38, 2),
+                                      ("unet_like", 30, 2), ("unet_like3", 44, 2), ("unet_like4", 52, 1),
+                                      ("unet_like4b", 52, 1)])
 def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
     w = M.random_weights(arch, seed=11)
     x = np.random.default_rng(s).standard_normal((n, s, s, s)).astype(np.float32)
