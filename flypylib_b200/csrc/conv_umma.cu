@@ -1317,7 +1317,7 @@ conv_fused12_kernel(const FusedArgs a) {
         // (flat v = y1*18 + x1) are written as im2col rows of A1; a task = two x-adjacent voxels.
         const int bt = threadIdx.x - 320;             // 0..127
         constexpr int kPer = (RY * RX + 127) / 128;   // raw elements per thread and plane (4)
-        constexpr int kTasks = SY * (SX / 2);         // 162
+        constexpr int kTasks = (SY / 2) * SX;         // 162 y-pairs
         uint32_t pc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int t = item;
@@ -1389,22 +1389,22 @@ conv_fused12_kernel(const FusedArgs a) {
                 mbar_wait(a1_empty, (pc & 1u) ^ 1u);
 #pragma unroll 1
                 for (int task = bt; task < kTasks; task += 128) {
-                    const int y1 = task / (SX / 2), x1 = (task - y1 * (SX / 2)) * 2;
-                    float f[3][3][4];
+                    // a task = two y-adjacent voxels (y1, x1), (y1+1, x1); consecutive lanes take consecutive x, so
+                    // the raw-plane loads (4-byte stride) and the 16-byte im2col stores (16-byte stride) of a warp
+                    // are bank-conflict free (x-adjacent pairs cost 2x the shared-memory wavefronts, profiles/)
+                    const int yp = task / SX, x1 = task - yp * SX, y1 = 2 * yp;
+                    float f[3][4][3];
 #pragma unroll
                     for (int kd = 0; kd < 3; ++kd) {
                         const float *pl = s_rawp + ((z0 + p + kd) % kRing) * RY * RP + y1 * RP + x1;
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
-                            const float2 va = *reinterpret_cast<const float2 *>(pl + kh * RP);
-                            const float2 vb = *reinterpret_cast<const float2 *>(pl + kh * RP + 2);
-                            f[kd][kh][0] = va.x; f[kd][kh][1] = va.y; f[kd][kh][2] = vb.x; f[kd][kh][3] = vb.y;
+                        for (int r4 = 0; r4 < 4; ++r4) {
+                            f[kd][r4][0] = pl[r4 * RP]; f[kd][r4][1] = pl[r4 * RP + 1]; f[kd][r4][2] = pl[r4 * RP + 2];
                         }
                     }
-                    const int v0 = y1 * SX + x1;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const int v = v0 + j;
+                        const int v = (y1 + j) * SX + x1;
                         uint8_t *arow = s_a1 + (v >> 7) * 8192 + (v & 127) * 16;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -1415,7 +1415,7 @@ conv_fused12_kernel(const FusedArgs a) {
 #pragma unroll
                                 for (int u = 0; u < 2; ++u) {
                                     const int tp = 8 * k + 2 * e2 + u;
-                                    pv[u] = tp < 27 ? f[tp / 9][(tp / 3) % 3][j + tp % 3] : (tp < 29 ? 1.f : 0.f);
+                                    pv[u] = tp < 27 ? f[tp / 9][j + (tp / 3) % 3][tp % 3] : (tp < 29 ? 1.f : 0.f);
                                 }
                                 __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[0], pv[1]);
                                 pk[e2] = *reinterpret_cast<uint32_t *>(&b2);
