@@ -1263,33 +1263,49 @@ __device__ __forceinline__ void dense_pass1_body(const float *__restrict__ v, Di
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
+                // branch-free per-voxel part: brick maximum, "in the level-2 class" mask, x-neighbour test mask
+                unsigned inb = 0, cx = 0;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float fe = f[k][e];                      // -inf outside the volume
                     m = fmaxf(m, fe);
                     const unsigned bits = __float_as_uint(fe);
-                    if (FAST) {
-                        if ((bits & msk0) == rpre0) atomicAdd(&h2[(bits >> 10) & 2047u], 1u);
-                    } else {
-                        if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0))
-                            atomicAdd(&h2[((raw0 ? bits : f2key(fe)) >> 10) & 2047u], 1u);
-                        if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
-                            atomicAdd(&h2[2048 + (((raw1 ? bits : f2key(fe)) >> 10) & 2047u)], 1u);
-                    }
+                    const bool hit = FAST ? ((bits & msk0) == rpre0)
+                                          : ((raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0)) ||
+                                             (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1))));
+                    inb |= (hit ? 1u : 0u) << e;
                     const float le = e ? f[k][e - 1] : lf[k], re = e < 7 ? f[k][e + 1] : rt[k];
                     // lower flat index wins ties: the left neighbour beats an equal value, the right one does not
-                    bool c = (fe >= cutoff_f) & !(le >= fe) & !(re > fe);       // & not &&: predicate logic, no branches
-                    // the z neighbours inside the brick are in this thread's registers: plane below first (lower index)
-                    if (c) {                                       // rare: keep it a branch, not predicated code
-                        if (k > 0) {
-                            const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
-                            c = !(a0 >= fe) & !(a1 >= fe) & !(a2 >= fe);
+                    const bool c = fe >= cutoff_f && fe > le && fe >= re;        // (NaN maps never get here: nan_count)
+                    cx |= (c ? 1u : 0u) << e;
+                }
+                if (inb | cx) {                                    // rare: one branch per row of 8 voxels
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float fe = f[k][e];
+                        if (inb & (1u << e)) {
+                            const unsigned bits = __float_as_uint(fe);
+                            if (FAST) atomicAdd(&h2[(bits >> 10) & 2047u], 1u);
+                            else {
+                                if (raw0 ? ((bits & msk0) == rpre0) : ((f2key(fe) & msk0) == pre0))
+                                    atomicAdd(&h2[((raw0 ? bits : f2key(fe)) >> 10) & 2047u], 1u);
+                                if (two && (raw1 ? ((bits & msk1) == rpre1) : ((f2key(fe) & msk1) == pre1)))
+                                    atomicAdd(&h2[2048 + (((raw1 ? bits : f2key(fe)) >> 10) & 2047u)], 1u);
+                            }
                         }
-                        if (k < 7) {
-                            const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
-                            c = c & !(a0 > fe) & !(a1 > fe) & !(a2 > fe);
+                        if (cx & (1u << e)) {
+                            // the z neighbours inside the brick are in this thread's registers: plane below first (lower index)
+                            bool c = true;
+                            if (k > 0) {
+                                const float a0 = e ? f[k - 1][e - 1] : lf[k - 1], a1 = f[k - 1][e], a2 = e < 7 ? f[k - 1][e + 1] : rt[k - 1];
+                                c = !(a0 >= fe) && !(a1 >= fe) && !(a2 >= fe);
+                            }
+                            if (k < 7) {
+                                const float a0 = e ? f[k + 1][e - 1] : lf[k + 1], a1 = f[k + 1][e], a2 = e < 7 ? f[k + 1][e + 1] : rt[k + 1];
+                                c = c && !(a0 > fe) && !(a1 > fe) && !(a2 > fe);
+                            }
+                            if (c) cmask |= 1ULL << (k * 8 + e);
                         }
-                        if (c) cmask |= 1ULL << (k * 8 + e);
                     }
                 }
             }

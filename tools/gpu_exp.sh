@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=${1:-8}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 3 --warmup 3 2> gpurun_out/z3_bench_n$N.err | tail -1 > gpurun_out/z3_bench_n$N.json
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 tools/bench_unet_sharded.py --size 2048 2> gpurun_out/z3_unet_n$N.err | tail -1 > gpurun_out/z3_unet_n$N.json
+timeout 1200 python -m pytest tests/test_voxel2obj_gpu.py tests/test_global_v2o_gpu.py -x -q > gpurun_out/a3_tests.log 2>&1
+timeout 600 python tools/bench_voxel2obj.py --size 1024 --steps 3 > gpurun_out/a3_v2o_1024.json 2> gpurun_out/a3.err
+timeout 600 python tools/bench_voxel2obj.py --size 1024 --steps 3 --kind uniform > gpurun_out/a3_v2o_1024u.json 2> gpurun_out/a3u.err
 exit 0
