@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_voxel2obj_gpu.py tests/test_global_v2o_gpu.py -x -q > gpurun_out/a3_tests.log 2>&1
-timeout 600 python tools/bench_voxel2obj.py --size 1024 --steps 3 > gpurun_out/a3_v2o_1024.json 2> gpurun_out/a3.err
-timeout 600 python tools/bench_voxel2obj.py --size 1024 --steps 3 --kind uniform > gpurun_out/a3_v2o_1024u.json 2> gpurun_out/a3u.err
+C512="python bench.py --size 512 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gauss_strided|gauss_contig|hist1|dense_pass1|dense_pass2" -c 6 -o gpurun_out/r01d_prof_detect -f $C512 > /dev/null 2>&1
+ncu -i gpurun_out/r01d_prof_detect.ncu-rep --page raw --csv > gpurun_out/r01d_prof_detect_raw.csv 2>/dev/null
+rm -f gpurun_out/r01d_prof_detect.ncu-rep
 exit 0

@@ -8,7 +8,7 @@ timeout 300 $C512 > gpurun_out/${tag}_plain512.log 2>&1 || exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${tag}_launches_512.csv $C512 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_fused12_kernel -s 1 -c 1 -o gpurun_out/${tag}_prof_fused12 -f $C512 > /dev/null 2>&1
 ncu -i gpurun_out/${tag}_prof_fused12.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_fused12_raw.csv 2>/dev/null
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gauss_strided|gauss_contig|dense_pass1|dense_pass2|select_hist|nms_filter|nms_ballcheck" -s 7 -c 9 -o gpurun_out/${tag}_prof_detect -f $C512 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gauss_strided|gauss_contig|hist1|dense_pass1|dense_pass2" -c 6 -o gpurun_out/${tag}_prof_detect -f $C512 > /dev/null 2>&1
 ncu -i gpurun_out/${tag}_prof_detect.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_detect_raw.csv 2>/dev/null
 timeout 600 python tools/bench_voxel2obj.py --size 2048 > gpurun_out/${tag}_v2o_2048.json 2>/dev/null
 timeout 600 python tools/bench_voxel2obj.py --size 2048 --kind uniform > gpurun_out/${tag}_v2o_2048u.json 2>/dev/null
