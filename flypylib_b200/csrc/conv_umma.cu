@@ -1096,7 +1096,10 @@ struct FusedArgs {
     VolumeIO vio;
 };
 
-template <int C1, int C2>
+// ROT: the second convolution uses the rotating-window scheme of conv_umma_kernel<.., ROT> (3 blocks per M-tile,
+// weights packed with 5 kd row blocks, barriers per M-tile, M-tiles issued one after the other); used where the
+// 5/3 larger weight image fits beside the rings (32/32 channels), not for 48/48.
+template <int C1, int C2, bool ROT>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 conv_fused12_kernel(const FusedArgs a) {
     constexpr int KS = 3, KSTEPS = C1 / 16, TX = 16;
@@ -1112,7 +1115,7 @@ conv_fused12_kernel(const FusedArgs a) {
     // second-layer accumulators: 4 blocks per M-tile, so the block a new output starts in was drained a whole
     // plane earlier (with 3 the MMA stream stalled on the epilogue once per plane); the first layer's three
     // M-tiles per plane rotate through 2 accumulator slots
-    constexpr uint32_t N = C2, NBLK = 4, kRegion = NBLK * N, kL1Col = 2 * kRegion, kL1Slots = 2;
+    constexpr uint32_t N = C2, NBLK = ROT ? 3 : 4, kRegion = NBLK * N, kL1Col = 2 * kRegion, kL1Slots = 2;
     static_assert(kL1Col + kL1Slots * C1 <= 512, "TMEM budget");
     static_assert(RX <= RP && C1 % 16 == 0 && C2 % 16 == 0, "shape");
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1132,9 +1135,9 @@ conv_fused12_kernel(const FusedArgs a) {
     uint64_t *a1_empty = bars + 6;           // [1]
     uint64_t *l1_full = bars + 7;            // [3]  first-layer accumulator tiles
     uint64_t *l1_empty = bars + 10;          // [3]
-    uint64_t *acc_full = bars + 13;          // [4]  second-layer accumulator blocks
-    uint64_t *acc_empty = bars + 17;         // [4]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
+    uint64_t *acc_full = bars + 13;          // [8]  second-layer accumulator blocks (ROT: [2 M-tiles][3])
+    uint64_t *acc_empty = bars + 21;         // [8]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 30);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.n_tiles * a.n_yt * a.n_xt * a.n_zc;
@@ -1144,7 +1147,7 @@ conv_fused12_kernel(const FusedArgs a) {
         for (int i = 0; i < 2; ++i) { mbar_init(&plane_full[i], 4); mbar_init(&plane_empty[i], 1); }
         mbar_init(a1_full, 4); mbar_init(a1_empty, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&l1_full[i], 1); mbar_init(&l1_empty[i], 4); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], ROT ? 4 : 8); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x)
@@ -1177,8 +1180,10 @@ conv_fused12_kernel(const FusedArgs a) {
         const uint32_t a_hi = (SX * 16u >> 4) | (1u << 14);
         const uint32_t b_hi = (128u >> 4) | (1u << 14);
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
-        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * KS) << 16);
-        const uint32_t b_step16 = N * KS * 2u;
+        const uint32_t idesc_3 = make_idesc_bf16(128, (int)(3u * N));
+        constexpr uint32_t kKB = ROT ? 5u : (uint32_t)KS;           // kd row blocks per weight chunk
+        const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | ((N * kKB) << 16);
+        const uint32_t b_step16 = N * kKB * 2u;
         const uint32_t a1_hi = (128u >> 4) | (1u << 14);
         const uint32_t a1_lo0 = (smem_u32(s_a1) >> 4) | ((2048u >> 4) << 16);
         const uint32_t b1_lo0 = (smem_u32(s_w1) >> 4) | ((uint32_t)C1 << 16);
@@ -1214,6 +1219,62 @@ conv_fused12_kernel(const FusedArgs a) {
             const int np = nz + KS - 1;
             issue_l1();
             issue_l1();                              // np >= 3 always
+            if constexpr (ROT) {
+#pragma unroll 1
+            for (int ip = 0; ip < np; ++ip, ++pc2) {
+                const uint32_t slot = pc2 & 1u, ph = (pc2 >> 1) & 1u;
+                const int kd_lo = ip - (nz - 1) > 0 ? ip - (nz - 1) : 0;
+                const int kd_hi = ip < KS - 1 ? ip : KS - 1;
+                const bool full = kd_lo == 0 && kd_hi == KS - 1;
+                const uint32_t A0 = ac0 + (uint32_t)ip;            // output fed through kd = 0
+                const uint32_t r = A0 % NBLK;
+                const uint32_t win = ((r + 1u) % 3u) * N;          // rotating window, see conv_umma_kernel<.., ROT>
+                mbar_wait(&plane_full[slot], ph);
+                tc_fence_after();
+                const uint32_t a_pl = a_lo0 + slot * (plane_pitch >> 4);
+#pragma unroll 1
+                for (int m = 0; m < 2; ++m) {
+                    if (kd_lo == 0) mbar_wait(&acc_empty[m * 3 + (2u - r)], ((A0 / NBLK) & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t d_reg = tmem_base + (uint32_t)m * kRegion;
+#pragma unroll 1
+                        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                            for (int kw = 0; kw < KS; ++kw) {
+                                uint32_t b_lo = b_lo0 + (uint32_t)((kh * KS + kw) * KSTEPS) * b_step16;
+#pragma unroll
+                                for (int s = 0; s < KSTEPS; ++s) {
+                                    const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4) +
+                                                          (uint32_t)m * 8u;
+                                    const uint64_t ad = desc64(a_lo, a_hi);
+                                    const bool first = kh == 0 && kw == 0 && s == 0;
+                                    if (full && !first) {
+                                        umma_bf16(d_reg, ad, desc64(b_lo + win, b_hi), idesc_3, 1u);
+                                    } else {
+#pragma unroll
+                                        for (int kd = 0; kd < KS; ++kd)
+                                            if (kd >= kd_lo && kd <= kd_hi) {
+                                                const uint32_t bl = 2u - (r + 3u - (uint32_t)kd) % 3u;
+                                                umma_bf16(d_reg + bl * N, ad, desc64(b_lo + (uint32_t)kd * N, b_hi), idesc_1,
+                                                          (first && kd == 0) ? 0u : 1u);
+                                            }
+                                    }
+                                    b_lo += b_step16;
+                                }
+                            }
+                        if (ip >= KS - 1) {
+                            const uint32_t Ad = ac0 + (uint32_t)(ip - (KS - 1));
+                            umma_commit(&acc_full[m * 3 + (2u - Ad % NBLK)]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (leader) umma_commit(&plane_empty[slot]);
+                __syncwarp();
+                if (ip + 2 < np) issue_l1();          // first-layer plane ip+2 behind this plane's MMAs
+            }
+            } else {
 #pragma unroll 1
             for (int ip = 0; ip < np; ++ip, ++pc2) {
                 const uint32_t slot = pc2 & 1u, ph = (pc2 >> 1) & 1u;
@@ -1277,6 +1338,7 @@ conv_fused12_kernel(const FusedArgs a) {
                 __syncwarp();
                 if (ip + 2 < np) issue_l1();          // first-layer plane ip+2 behind this plane's MMAs
             }
+            }
             ac0 += (uint32_t)nz;
         }
     } else if (warp < 10) {
@@ -1297,7 +1359,8 @@ conv_fused12_kernel(const FusedArgs a) {
             const int nz = min(a.zc_len, a.dout_z - z0);
             for (int zo = 0; zo < nz; ++zo, ++A) {
                 const uint32_t bl = NBLK - 1u - (A % NBLK), ph = (A / NBLK) & 1u;
-                mbar_wait(&acc_full[bl], ph);
+                const uint32_t bar_i = ROT ? (uint32_t)m * 3u + bl : bl;
+                mbar_wait(&acc_full[bar_i], ph);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)m * kRegion + bl * N;
                 if (a.pool)
@@ -1308,7 +1371,7 @@ conv_fused12_kernel(const FusedArgs a) {
                                   C2, 0, a.dout_z);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[bl]);
+                if (lane == 0) mbar_arrive(&acc_empty[bar_i]);
             }
         }
     } else if (warp < 14) {
@@ -1688,7 +1751,7 @@ static bool fusable12(const ConvParams &c1, const ConvParams &c2) {
 int pack_weights_umma(fpl_net *net) {
     if (net->ops.size() >= 2 && net->ops[0].kind == OP_CONV && net->ops[1].kind == OP_CONV) {
         ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
-        c2.no_rot = fusable12(c1, c2);
+        c2.no_rot = fusable12(c1, c2) && c1.cout == 48;       // the 32/32 instance of the fused kernel is ROT
     }
     for (ConvParams &c : net->convs) {
         if (c.cin == 1 && c.k == 3 && c.cout % 16 == 0) {   // first layer: K = 27 taps padded to 32
@@ -1899,7 +1962,8 @@ bool umma_reads_volume(const fpl_net *net) {
     if (net->ops.size() < 2 || net->ops[0].kind != OP_CONV || net->ops[1].kind != OP_CONV) return false;
     const ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
     const ConvPlan p2 = plan_conv(c2);
-    return fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot && p2.k_split == 1;
+    return fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 && p2.rot == (c1.cout == 32) &&
+           p2.k_split == 1;
 }
 
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
@@ -1925,8 +1989,8 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             // first + second convolution fused (conv_fused12_kernel): the first layer's output stays on chip
             const ConvParams &c1 = net->convs[o.conv_index], &c2 = net->convs[net->ops[1].conv_index];
             const ConvPlan p2 = plan_conv(c2);
-            const bool shape_ok = fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 && !p2.rot &&
-                                  p2.k_split == 1 && d >= 8 && dzv >= 8;
+            const bool shape_ok = fusable12(c1, c2) && c1.d_packed && p2.ok && p2.n_split == 1 && p2.nsub == 1 &&
+                                  p2.rot == (c1.cout == 32) && p2.k_split == 1 && d >= 8 && dzv >= 8;
             if (shape_ok) {
                 const int dout = d - 4, dout_z = dzv - 4;
                 const bool pool = !g_no_pool_fusion && net->ops.size() > 2 && net->ops[2].kind == OP_POOL &&
@@ -1960,11 +2024,11 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                                    2.0 * 27 * C * C * (double)n_tiles * dout_z * dout * dout +
                                    2.0 * 27 * C * (double)n_tiles * (dout_z + 2) * (dout + 2) * (dout + 2));
                     if (C == 48) {
-                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<48, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        conv_fused12_kernel<48, 48><<<grid, kFusedThreads, smem, st>>>(fa);
+                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<48, 48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        conv_fused12_kernel<48, 48, false><<<grid, kFusedThreads, smem, st>>>(fa);
                     } else {
-                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        conv_fused12_kernel<32, 32><<<grid, kFusedThreads, smem, st>>>(fa);
+                        FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_fused12_kernel<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        conv_fused12_kernel<32, 32, true><<<grid, kFusedThreads, smem, st>>>(fa);
                     }
                     FPL_LAUNCH_CHECK(ctx);
                 }
