@@ -48,6 +48,78 @@ conv_fp32_kernel(const float *__restrict__ in, const float *__restrict__ w,
     }
 }
 
+// Register/shared-memory tiled variant for Cin % 16 == 0 (every layer but the first): a block computes
+// 64 x-voxels x R rows x all Cout; a thread owns 2 voxels (x, x+32) x 16 output channels.  The weights of one
+// (tap, Cin chunk) are staged in shared memory once per block and read as broadcast float4; the activations are
+// read as float4 over 4 input channels.  Same FMA order per output as conv_fp32_kernel (taps outer, channels
+// inner) -> bit-identical results, ~2 loads per 16 FMAs instead of 17.
+template <int K>
+__global__ void __launch_bounds__(512)
+conv_fp32_tiled_kernel(const float *__restrict__ in, const float *__restrict__ w,
+                       const float *__restrict__ scale, const float *__restrict__ bias,
+                       float *__restrict__ out, int n_tiles, int din, int cin, int cout, int relu, int chunk) {
+    __shared__ __align__(16) float sw[32 * 128];
+    const int dout = din - (K - 1);
+    const int R = blockDim.z;
+    const int xb = (dout + 63) / 64, yb = (dout + R - 1) / R;
+    long long bid = blockIdx.x;
+    const int x0 = (int)(bid % xb) * 64 + threadIdx.x; bid /= xb;
+    const int y = (int)(bid % yb) * R + threadIdx.z; bid /= yb;
+    const int z = (int)(bid % dout); bid /= dout;
+    const int t = (int)bid;
+    const int co0 = threadIdx.y * 16;
+    const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, nthr = blockDim.x * blockDim.y * blockDim.z;
+    const bool yok = y < dout;
+    const bool ok0 = yok && x0 < dout, ok1 = yok && x0 + 32 < dout;
+    // clamped coordinates keep every load in bounds; results of invalid voxels are simply not stored
+    const int yc = yok ? y : dout - 1, xa = x0 < dout ? x0 : dout - 1, xb1 = x0 + 32 < dout ? x0 + 32 : dout - 1;
+    float acc0[16], acc1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    const float *tin = in + (size_t)t * din * din * din * cin;
+    for (int kd = 0; kd < K; ++kd)
+        for (int kh = 0; kh < K; ++kh)
+            for (int kw = 0; kw < K; ++kw) {
+                const size_t rowbase = ((size_t)(z + kd) * din + (yc + kh)) * din;
+                const float *ip0 = tin + (rowbase + xa + kw) * cin;
+                const float *ip1 = tin + (rowbase + xb1 + kw) * cin;
+                const float *wt = w + (size_t)((kd * K + kh) * K + kw) * cin * cout;
+                for (int c0 = 0; c0 < cin; c0 += chunk) {
+                    __syncthreads();
+                    for (int i = tid * 4; i < chunk * cout; i += nthr * 4)
+                        *reinterpret_cast<float4 *>(&sw[i]) = __ldg(reinterpret_cast<const float4 *>(wt + (size_t)c0 * cout + i));
+                    __syncthreads();
+#pragma unroll 2
+                    for (int ci = 0; ci < chunk; ci += 4) {
+                        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(ip0 + c0 + ci));
+                        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(ip1 + c0 + ci));
+                        const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 *wr = reinterpret_cast<const float4 *>(&sw[(ci + q) * cout + co0]);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 wv = wr[j4];
+                                acc0[4 * j4 + 0] = fmaf(av0[q], wv.x, acc0[4 * j4 + 0]); acc1[4 * j4 + 0] = fmaf(av1[q], wv.x, acc1[4 * j4 + 0]);
+                                acc0[4 * j4 + 1] = fmaf(av0[q], wv.y, acc0[4 * j4 + 1]); acc1[4 * j4 + 1] = fmaf(av1[q], wv.y, acc1[4 * j4 + 1]);
+                                acc0[4 * j4 + 2] = fmaf(av0[q], wv.z, acc0[4 * j4 + 2]); acc1[4 * j4 + 2] = fmaf(av1[q], wv.z, acc1[4 * j4 + 2]);
+                                acc0[4 * j4 + 3] = fmaf(av0[q], wv.w, acc0[4 * j4 + 3]); acc1[4 * j4 + 3] = fmaf(av1[q], wv.w, acc1[4 * j4 + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+    const size_t obase = (size_t)t * dout * dout * dout + ((size_t)z * dout + yc) * dout;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float sc = scale[co0 + j], bi = bias[co0 + j];
+        float v0 = fmaf(acc0[j], sc, bi), v1 = fmaf(acc1[j], sc, bi);
+        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        if (ok0) out[(obase + x0) * cout + co0 + j] = v0;
+        if (ok1) out[(obase + x0 + 32) * cout + co0 + j] = v1;
+    }
+}
+
 // MaxPooling3D((2,2,2)), floor.
 __global__ void __launch_bounds__(256)
 pool_fp32_kernel(const float *__restrict__ in, float *__restrict__ out, int n_tiles, int din, int c) {
@@ -123,7 +195,15 @@ static int launch_conv(fpl_ctx *ctx, const float *in, const ConvParams &c, float
     const int xb = (dout + 31) / 32;
     const long long blocks = (long long)n_tiles * dout * dout * xb;
     FPL_REQUIRE(blocks < 2147483647LL, "conv_fp32: grid too large");
-    if (c.cout % 8 == 0 && c.cout / 8 <= 8) {
+    if (c.cin % 16 == 0 && c.cout % 16 == 0 && c.cout <= 128 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(c.d_kernel) & 15) == 0) {
+        const int g = c.cout / 16;
+        int rows = 512 / (32 * g); if (rows > 4) rows = 4; if (rows < 1) rows = 1;
+        const long long tb = (long long)n_tiles * dout * ((dout + rows - 1) / rows) * ((dout + 63) / 64);
+        FPL_REQUIRE(tb < 2147483647LL, "conv_fp32: grid too large");
+        conv_fp32_tiled_kernel<K><<<(unsigned)tb, dim3(32, g, rows), 0, st>>>(in, c.d_kernel, c.d_scale, c.d_bias, out, n_tiles,
+                                                                           din, c.cin, c.cout, relu, c.cin % 32 == 0 ? 32 : 16);
+    } else if (c.cout % 8 == 0 && c.cout / 8 <= 8) {
         dim3 block(32, c.cout / 8);
         conv_fp32_kernel<K, 8><<<(unsigned)blocks, block, 0, st>>>(in, c.d_kernel, c.d_scale, c.d_bias, out,
                                                                   n_tiles, din, c.cin, c.cout, relu);
