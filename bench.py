@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="volume edge (default: configs[1], 1024)")
     ap.add_argument("--model", default="vgg_like2", choices=["vgg_like", "vgg_like2", "unet_like2"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--tile-mult", type=int, default=None,
                     help="VGG only: evaluate super-tiles of this many reference tiles per axis "
                          "(bit-identical to the reference grid; default 4 for the VGGs, 1 for the U-Net)")

@@ -261,6 +261,8 @@ __device__ __forceinline__ void epilogue_tile_pool(uint32_t tmem_acc, int q, int
 
 // K-split epilogue of one M=128 accumulator tile: partial sums of the input-channel chunks are kept as fp32
 // C8-blocked atoms (32 B) in HBM.  mode 1: partial = acc; 2: partial += acc; 3: out = bf16(relu(partial + acc + bias)).
+// mode 4 (hi/lo path): as 3, but the fp32 result v is stored as two bf16 tensors hi = bf16(v), lo = bf16(v - hi)
+// in channel groups [0, cout/8) and [cout/8, cout/4) of a tensor with 2*cout channels.
 __device__ __forceinline__ void epilogue_tile_ksplit(uint32_t tmem_acc, int q, int lane, int cout, const float *s_bias,
                                                      int relu, __nv_bfloat16 *__restrict__ out, float *__restrict__ partial,
                                                      int mode, int tile, int dout, int z, int y0, int x0, int dout_z) {
@@ -291,7 +293,25 @@ __device__ __forceinline__ void epilogue_tile_ksplit(uint32_t tmem_acc, int q, i
 #pragma unroll
             for (int h = 0; h < 4; ++h) { v[4 * h] += pv[h].x; v[4 * h + 1] += pv[h].y; v[4 * h + 2] += pv[h].z; v[4 * h + 3] += pv[h].w; }
         }
-        if (mode != 3) {
+        if (mode == 4) {
+            const size_t ovox = (size_t)tile * (cout >> 2) * cg_stride + ((size_t)z * dout + y) * dout + x;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v0 = v[h * 8 + 2 * j] + s_bias[c0 + h * 8 + 2 * j];
+                    float v1 = v[h * 8 + 2 * j + 1] + s_bias[c0 + h * 8 + 2 * j + 1];
+                    if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+                    ph[j] = *reinterpret_cast<const uint32_t *>(&hi); pl[j] = *reinterpret_cast<const uint32_t *>(&lo);
+                }
+                *reinterpret_cast<uint4 *>(out + (ovox + (size_t)((c0 >> 3) + h) * cg_stride) * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4 *>(out + (ovox + (size_t)((cout >> 3) + (c0 >> 3) + h) * cg_stride) * 8) =
+                    make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+        } else if (mode != 3) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float4 *pp = reinterpret_cast<float4 *>(partial + (vox + (size_t)((c0 >> 3) + h) * cg_stride) * 8);
@@ -1718,7 +1738,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
     // K-split candidates (3x3x3, no Cout split): taken only when clearly better than the best resident plan
     static const int no_ksplit = getenv("FPL_NO_KSPLIT") ? 1 : 0;
     static const double ks_margin = getenv("FPL_KSPLIT_MARGIN") ? atof(getenv("FPL_KSPLIT_MARGIN")) : 0.8;
-    if (best.ok && !legacy && !no_ksplit && !c.no_rot && c.k == 3 && c.cout <= 80) {
+    if (best.ok && !legacy && !no_ksplit && !c.no_ksplit && !c.no_rot && c.k == 3 && c.cout <= 80) {
         for (int ks_ = 2; ks_ <= 4; ks_ *= 2) {
             if (c.cin % (16 * ks_)) continue;
             const int cc = c.cin / ks_, ksteps = cc / 16;
@@ -1748,7 +1768,10 @@ static bool fusable12(const ConvParams &c1, const ConvParams &c2) {
            c2.cout == c1.cout;
 }
 
+static int pack_weights_hilo(fpl_net *net);
+
 int pack_weights_umma(fpl_net *net) {
+    if (net->precision == FPL_PREC_TF32) return pack_weights_hilo(net);
     if (net->ops.size() >= 2 && net->ops[0].kind == OP_CONV && net->ops[1].kind == OP_CONV) {
         ConvParams &c1 = net->convs[net->ops[0].conv_index], &c2 = net->convs[net->ops[1].conv_index];
         c2.no_rot = fusable12(c1, c2) && c1.cout == 48;       // the 32/32 instance of the fused kernel is ROT
@@ -1811,8 +1834,38 @@ int pack_weights_umma(fpl_net *net) {
 void free_packed_umma(fpl_net *net) {
     for (ConvParams &c : net->convs) {
         if (c.d_packed) cudaFree(c.d_packed);
-        c.d_packed = nullptr; c.packed_bytes = 0;
+        if (c.d_packed_lo) cudaFree(c.d_packed_lo);
+        c.d_packed = nullptr; c.d_packed_lo = nullptr; c.packed_bytes = 0; c.hilo_chunk = 0;
     }
+}
+
+// instantiation table of conv_umma_kernel
+static int dispatch_umma(const ConvPlan &plan, int ks, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmap,
+                         const ConvArgs &a) {
+#define FPL_LAUNCH_UMMA(KS_, KST_, TX_, ROT_)                                                                    \
+        do {                                                                                                      \
+            FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_, ROT_>,                           \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            conv_umma_kernel<KS_, KST_, TX_, ROT_><<<grid, kThreads, smem, st>>>(tmap, a);                        \
+        } while (0)
+    const int kst = plan.ksteps;
+    if (plan.rot && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, true);
+    else if (plan.rot && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, true);
+    else if (plan.rot && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, true);
+    else if (plan.rot && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, true);
+    else if (ks == 3 && plan.tx == 16 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, false);
+    else if (ks == 3 && plan.tx == 16 && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, false);
+    else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, false);
+    else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, false);
+    else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8, false);
+    else if (ks == 3 && plan.tx == 8 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 8, false);
+    else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16, false);
+    else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16, false);
+    else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16, false);
+    else if (ks == 1 && kst == 6) FPL_LAUNCH_UMMA(1, 6, 16, false);
+    else { set_error("conv_umma: no instantiation for k=%d ksteps=%d tx=%d", ks, kst, plan.tx); return FPL_EINVAL; }
+#undef FPL_LAUNCH_UMMA
+    return FPL_OK;
 }
 
 // activation buffer pool (defined below)
@@ -1880,29 +1933,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
             a.bias = c.d_bias + g * plan.n;
             a.cout_off = g * plan.n;
         }
-#define FPL_LAUNCH_UMMA(KS_, KST_, TX_, ROT_)                                                                    \
-        do {                                                                                                      \
-            FPL_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<KS_, KST_, TX_, ROT_>,                           \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-            conv_umma_kernel<KS_, KST_, TX_, ROT_><<<grid, kThreads, smem, st>>>(tmap, a);                        \
-        } while (0)
-        const int kst = plan.ksteps;
-        if (plan.rot && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, true);
-        else if (plan.rot && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, true);
-        else if (plan.rot && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, true);
-        else if (plan.rot && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, true);
-        else if (ks == 3 && plan.tx == 16 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, false);
-        else if (ks == 3 && plan.tx == 16 && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, false);
-        else if (ks == 3 && plan.tx == 16 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, false);
-        else if (ks == 3 && plan.tx == 16 && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, false);
-        else if (ks == 3 && plan.tx == 8 && kst == 4) FPL_LAUNCH_UMMA(3, 4, 8, false);
-        else if (ks == 3 && plan.tx == 8 && kst == 3) FPL_LAUNCH_UMMA(3, 3, 8, false);
-        else if (ks == 1 && kst == 2) FPL_LAUNCH_UMMA(1, 2, 16, false);
-        else if (ks == 1 && kst == 3) FPL_LAUNCH_UMMA(1, 3, 16, false);
-        else if (ks == 1 && kst == 4) FPL_LAUNCH_UMMA(1, 4, 16, false);
-        else if (ks == 1 && kst == 6) FPL_LAUNCH_UMMA(1, 6, 16, false);
-        else { set_error("conv_umma: no instantiation for k=%d ksteps=%d tx=%d", ks, kst, plan.tx); return FPL_EINVAL; }
-#undef FPL_LAUNCH_UMMA
+        FPL_TRY(dispatch_umma(plan, ks, grid, smem, st, tmap, a));
         FPL_LAUNCH_CHECK(ctx);
     }
     if (partial_buf >= 0) g_bufs[partial_buf].busy = false;     // stream-ordered: later launches may reuse it
@@ -1955,6 +1986,313 @@ static int pool_take(size_t bytes, cudaStream_t st) {
     return best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// High-precision tensor-core path (FPL_PREC_TF32 slot of the ABI): "bf16 x 3".
+// Every activation tensor is kept as TWO bf16 tensors hi = bf16(v), lo = bf16(v - hi) (channel groups
+// [0,C/8) and [C/8,C/4) of one C8-blocked tensor with 2C channels); every weight likewise as w_hi, w_lo.
+// A convolution is the sum of three bf16 contractions  hi*w_hi + lo*w_hi + hi*w_lo  (the dropped lo*w_lo
+// term is ~2^-18 relative), each run by the same conv_umma_kernel as a K-split launch over the fp32
+// partial-sum buffer; the last launch adds the bias, applies ReLU and splits the fp32 result again.
+// Products of bf16 pairs are exact in fp32 and the accumulation is fp32, so the result carries ~16 mantissa
+// bits end to end -- more than TF32's 10 -- at a third of the bf16 path's MMA rate (vs the CUDA-core fp32
+// path: two orders of magnitude faster).  First layer (Cin = 1) and the 1-channel output layer run on CUDA
+// cores in fp32.  Cubic staged tiles only (no fused first+second kernel, no direct volume I/O).
+// ------------------------------------------------------------------------------------------------
+static std::vector<__nv_bfloat16> pack_image(const ConvParams &c, const ConvPlan &plan, int ci0, int cc, bool lo_part) {
+    const int ks = c.k, n = c.cout, nkb = plan.rot ? 5 : ks, ksteps = cc / 16;
+    std::vector<__nv_bfloat16> pk((size_t)ks * ks * nkb * cc * n);
+    for (int kh = 0; kh < ks; ++kh)
+        for (int kw = 0; kw < ks; ++kw)
+            for (int s = 0; s < ksteps; ++s)
+                for (int h = 0; h < 2; ++h)
+                    for (int kb = 0; kb < nkb; ++kb)
+                        for (int nn = 0; nn < n; ++nn)
+                            for (int e = 0; e < 8; ++e) {
+                                const int kd = kb % ks, ci = ci0 + 16 * s + 8 * h + e;
+                                const int tap = (kd * ks + kh) * ks + kw;
+                                const float v = c.kernel[((size_t)tap * c.cin + ci) * c.cout + nn] * c.scale[nn];
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                                const size_t chunk = ((size_t)(kh * ks + kw) * ksteps + s);
+                                pk[(((chunk * 2 + h) * nkb + kb) * n + nn) * 8 + e] =
+                                    lo_part ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+                            }
+    return pk;
+}
+
+// chunk plan of a hi/lo convolution: resident weights, all Cout in one launch
+static ConvPlan hilo_plan(const ConvParams &c, int cc) {
+    ConvParams chunk;
+    chunk.k = c.k; chunk.cin = cc; chunk.cout = c.cout; chunk.no_ksplit = true;
+    ConvPlan p = plan_conv(chunk);
+    if (p.ok && p.n_split != 1) p.ok = false;
+    return p;
+}
+
+static int pack_weights_hilo(fpl_net *net) {
+    for (ConvParams &c : net->convs) {
+        if (c.cin % 16 || c.cout % 16) continue;            // first layer / output layer: CUDA cores
+        int cc = 0;
+        const int cands[4] = {48, 32, 16, 64};
+        for (int i = 0; i < 4 && !cc; ++i)
+            if (c.cin % cands[i] == 0 && hilo_plan(c, cands[i]).ok) cc = cands[i];
+        FPL_REQUIRE(cc > 0, "hi/lo path: no chunk plan for k=%d Cin=%d Cout=%d", c.k, c.cin, c.cout);
+        const ConvPlan plan = hilo_plan(c, cc);
+        const int n_chunks = c.cin / cc;
+        std::vector<__nv_bfloat16> hi, lo;
+        for (int g = 0; g < n_chunks; ++g) {
+            std::vector<__nv_bfloat16> a = pack_image(c, plan, g * cc, cc, false), b = pack_image(c, plan, g * cc, cc, true);
+            hi.insert(hi.end(), a.begin(), a.end()); lo.insert(lo.end(), b.begin(), b.end());
+        }
+        c.hilo_chunk = cc;
+        c.packed_bytes = hi.size() * sizeof(__nv_bfloat16);
+        FPL_CUDA_CHECK(cudaMalloc(&c.d_packed, c.packed_bytes));
+        FPL_CUDA_CHECK(cudaMalloc(&c.d_packed_lo, c.packed_bytes));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_packed, hi.data(), c.packed_bytes, cudaMemcpyHostToDevice));
+        FPL_CUDA_CHECK(cudaMemcpy(c.d_packed_lo, lo.data(), c.packed_bytes, cudaMemcpyHostToDevice));
+    }
+    return FPL_OK;
+}
+
+__device__ __forceinline__ void store_hilo8(__nv_bfloat16 *hi_p, __nv_bfloat16 *lo_p, const float (&v)[8]) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[2 * j] - __low2float(hi), v[2 * j + 1] - __high2float(hi));
+        ph[j] = *reinterpret_cast<const uint32_t *>(&hi); pl[j] = *reinterpret_cast<const uint32_t *>(&lo);
+    }
+    *reinterpret_cast<uint4 *>(hi_p) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4 *>(lo_p) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+__device__ __forceinline__ void load_hilo8(const uint4 *hi_p, const uint4 *lo_p, float (&v)[8]) {
+    const uint4 a = __ldg(hi_p), b = __ldg(lo_p);
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&ua[j]), l2 = *reinterpret_cast<const __nv_bfloat162 *>(&ub[j]);
+        v[2 * j] = __low2float(h2) + __low2float(l2); v[2 * j + 1] = __high2float(h2) + __high2float(l2);
+    }
+}
+
+// first layer in fp32 on CUDA cores: one thread = one voxel x one group of 8 output channels
+__global__ void __launch_bounds__(256)
+first_hilo_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ scale,
+                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int n_tiles, int din, int cout) {
+    const int dout = din - 2, cg_n = cout / 8;
+    const long long vox_n = (long long)dout * dout * dout, total = (long long)n_tiles * cg_n * vox_n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long v = i;
+        const int x = (int)(v % dout); v /= dout;
+        const int y = (int)(v % dout); v /= dout;
+        const int z = (int)(v % dout); v /= dout;
+        const int cg = (int)(v % cg_n), t = (int)(v / cg_n);
+        const float *ip = in + (size_t)t * din * din * din;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float a = __ldg(ip + ((size_t)(z + kd) * din + (y + kh)) * din + (x + kw));
+                    const float *wp = w + (size_t)((kd * 3 + kh) * 3 + kw) * cout + cg * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, __ldg(wp + j), acc[j]);
+                }
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(acc[j], scale[cg * 8 + j], bias[cg * 8 + j]), 0.f);
+        const size_t o = (size_t)z * dout * dout + (size_t)y * dout + x;
+        store_hilo8(out + (((size_t)t * 2 * cg_n + cg) * vox_n + o) * 8, out + (((size_t)t * 2 * cg_n + cg_n + cg) * vox_n + o) * 8, r);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pool_hilo_kernel(const uint4 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int n_tiles, int cg_n, int din) {
+    const int dout = din / 2;
+    const long long vin = (long long)din * din * din, vout = (long long)dout * dout * dout, total = (long long)n_tiles * cg_n * vout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long v = i;
+        const int x = (int)(v % dout); v /= dout;
+        const int y = (int)(v % dout); v /= dout;
+        const int z = (int)(v % dout); v /= dout;
+        const int cg = (int)(v % cg_n), t = (int)(v / cg_n);
+        const uint4 *hp = in + ((size_t)t * 2 * cg_n + cg) * vin, *lp = in + ((size_t)t * 2 * cg_n + cg_n + cg) * vin;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int dz = 0; dz < 2; ++dz)
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    const size_t q = ((size_t)(2 * z + dz) * din + (2 * y + dy)) * din + (2 * x + dx);
+                    float f[8];
+                    load_hilo8(hp + q, lp + q, f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+                }
+        const size_t o = ((size_t)z * dout + y) * dout + x;
+        store_hilo8(out + (((size_t)t * 2 * cg_n + cg) * vout + o) * 8, out + (((size_t)t * 2 * cg_n + cg_n + cg) * vout + o) * 8, m);
+    }
+}
+
+// concatenate([UpSampling3D(2)(a), Cropping3D(crop)(skip)]): hi groups of both first, then lo groups of both
+__global__ void __launch_bounds__(256)
+upcat_hilo_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *__restrict__ skip, int ds, int cgs,
+                  int crop, uint4 *__restrict__ out, int n_tiles) {
+    const int dout = 2 * da, cgo = cga + cgs;
+    const long long vo = (long long)dout * dout * dout, total = (long long)n_tiles * 2 * cgo * vo;
+    const long long va = (long long)da * da * da, vs = (long long)ds * ds * ds;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long v = i;
+        const int x = (int)(v % dout); v /= dout;
+        const int y = (int)(v % dout); v /= dout;
+        const int z = (int)(v % dout); v /= dout;
+        const int g2 = (int)(v % (2 * cgo)), t = (int)(v / (2 * cgo));
+        const int half = g2 / cgo, g = g2 % cgo;                 // half 0: hi, 1: lo
+        uint4 r;
+        if (g < cga) r = __ldg(a + ((size_t)t * 2 * cga + half * cga + g) * va + ((size_t)(z / 2) * da + y / 2) * da + x / 2);
+        else r = __ldg(skip + ((size_t)t * 2 * cgs + half * cgs + (g - cga)) * vs + ((size_t)(z + crop) * ds + y + crop) * ds + x + crop);
+        out[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+final_hilo_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, float bias, float *__restrict__ out,
+                  int n_tiles, int d, int cg_n, int stride) {
+    const long long vox = (long long)d * d * d, total = (long long)n_tiles * vox;
+    const int dout = d * stride;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / vox);
+        const long long o = i - (long long)t * vox;
+        float acc = 0.f;
+        for (int cg = 0; cg < cg_n; ++cg) {
+            float f[8];
+            load_hilo8(in + ((size_t)t * 2 * cg_n + cg) * vox + o, in + ((size_t)t * 2 * cg_n + cg_n + cg) * vox + o, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(f[j], __ldg(w + cg * 8 + j), acc);
+        }
+        acc += bias;
+        const float pr = 1.f / (1.f + expf(-acc));
+        const int x = (int)(o % d), y = (int)((o / d) % d), z = (int)(o / ((long long)d * d));
+        float *op = out + (size_t)t * dout * dout * dout;
+        for (int ez = 0; ez < stride; ++ez)
+            for (int ey = 0; ey < stride; ++ey)
+                for (int ex = 0; ex < stride; ++ex)
+                    op[((size_t)(z * stride + ez) * dout + (y * stride + ey)) * dout + (x * stride + ex)] = pr;
+    }
+}
+
+// one hi/lo convolution: (Cin/chunk) x 3 K-split launches of conv_umma_kernel over the fp32 partial buffer
+static int launch_conv_hilo(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_tiles,
+                            int din, int relu, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FPL_ECUDA; }
+    const int cc = c.hilo_chunk, n_chunks = c.cin / cc;
+    const ConvPlan plan = hilo_plan(c, cc);
+    FPL_REQUIRE(cc > 0 && plan.ok, "hi/lo conv: no plan for k=%d Cin=%d Cout=%d", c.k, c.cin, c.cout);
+    const int ks = c.k, dout = din - (ks - 1);
+    const int sx = plan.tx + ks - 1, sy = kTY + ks - 1;
+    const int atoms_total = 2 * c.cin / 8;                       // hi atoms, then lo atoms
+    CUtensorMap tmap;
+    cuuint64_t gdim[4] = {(cuuint64_t)din * 8, (cuuint64_t)din, (cuuint64_t)din, (cuuint64_t)n_tiles * atoms_total};
+    cuuint64_t gstride[3] = {(cuuint64_t)din * 16, (cuuint64_t)din * din * 16, (cuuint64_t)din * din * din * 16};
+    cuuint32_t box[4] = {(cuuint32_t)sx * 8, (cuuint32_t)sy, 1, (cuuint32_t)(2 * plan.ksteps)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FPL_ECUDA; }
+    const int pbuf = pool_take((size_t)n_tiles * dout * dout * dout * c.cout * sizeof(float), st);
+    if (pbuf < 0) return FPL_ENOMEM;
+    ConvArgs a;
+    a.out = out; a.bias = c.d_bias; a.partial = (float *)g_bufs[pbuf].p;
+    a.w_bytes = (uint32_t)(c.packed_bytes / n_chunks);
+    a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.din_z = din; a.dout_z = dout;
+    a.cin_atoms_total = atoms_total; a.nsub = plan.nsub; a.cout = c.cout; a.cout_total = c.cout; a.cout_off = 0; a.ring = plan.ring;
+    a.n_xt = (dout + plan.tx - 1) / plan.tx; a.n_yt = (dout + kTY - 1) / kTY;
+    const long long base_items = (long long)n_tiles * a.n_xt * a.n_yt;
+    int n_zc = (int)((4LL * ctx->sm_count + base_items - 1) / base_items);
+    if (n_zc < 1) n_zc = 1;
+    int zc_len = (dout + n_zc - 1) / n_zc;
+    if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
+    a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
+    a.relu = relu; a.pool = 0; a.max_blk = 0; a.tmem_cols = 512;
+    const long long n_items = base_items * a.n_zc;
+    int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
+    ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
+                   3.0 * 2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
+    const int n_launch = 3 * n_chunks;
+    int li = 0;
+    for (int g = 0; g < n_chunks; ++g)
+        for (int term = 0; term < 3; ++term, ++li) {             // hi*w_hi, lo*w_hi, hi*w_lo
+            const uint8_t *img = (const uint8_t *)(term == 2 ? c.d_packed_lo : c.d_packed) + (size_t)g * a.w_bytes;
+            a.w_packed = (const __nv_bfloat16 *)img;
+            a.cin_atom_off = g * (cc / 8) + (term == 1 ? c.cin / 8 : 0);
+            a.acc_mode = li == 0 ? 1 : (li == n_launch - 1 ? 4 : 2);
+            FPL_TRY(dispatch_umma(plan, ks, grid, plan.smem, st, tmap, a));
+            FPL_LAUNCH_CHECK(ctx);
+        }
+    g_bufs[pbuf].busy = false;
+    return FPL_OK;
+}
+
+static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
+    fpl_ctx *ctx = net->ctx;
+    for (PoolBuf &b : g_bufs) b.busy = false;
+    auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
+    int cur = -1, skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
+    bool cur_is_skip = false;
+    int d = in_sz, c = 1;
+    const int stream_blocks = ctx->sm_count * 8;
+    for (size_t oi = 0; oi < net->ops.size(); ++oi) {
+        const Op &o = net->ops[oi];
+        if (o.kind == OP_CONV) {
+            const ConvParams &cp = net->convs[o.conv_index];
+            const int dout = d - (o.k - 1);
+            const int nb = pool_take((size_t)n_tiles * dout * dout * dout * 2 * cp.cout * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
+            __nv_bfloat16 *dst = (__nv_bfloat16 *)g_bufs[nb].p;
+            if (cp.cin == 1) {
+                FPL_REQUIRE(cp.k == 3 && cp.cout % 8 == 0, "hi/lo path: unsupported first layer");
+                ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
+                first_hilo_kernel<<<stream_blocks, 256, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d, cp.cout);
+                FPL_LAUNCH_CHECK(ctx);
+            } else {
+                FPL_REQUIRE(cp.d_packed && cp.d_packed_lo, "hi/lo path: layer k=%d Cin=%d Cout=%d has no packed weights", cp.k, cp.cin, cp.cout);
+                FPL_TRY(launch_conv_hilo(ctx, cp, (const __nv_bfloat16 *)g_bufs[cur].p, dst, n_tiles, d, 1, st));
+            }
+            if (!cur_is_skip) release(cur);
+            cur = nb; cur_is_skip = false; d = dout; c = o.cout;
+        } else if (o.kind == OP_POOL) {
+            const int nb = pool_take((size_t)n_tiles * (d / 2) * (d / 2) * (d / 2) * 2 * c * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * 2 * c * 2.0 * d * d * d * 1.125);
+            pool_hilo_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, (__nv_bfloat16 *)g_bufs[nb].p, n_tiles, c / 8, d);
+            FPL_LAUNCH_CHECK(ctx);
+            if (!cur_is_skip) release(cur);
+            cur = nb; cur_is_skip = false; d /= 2;
+        } else if (o.kind == OP_SAVE) {
+            skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_c[o.slot] = c; cur_is_skip = true;
+        } else if (o.kind == OP_UPCAT) {
+            const int nb = pool_take((size_t)n_tiles * 8 * d * d * d * 2 * (c + skip_c[o.slot]) * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * 2 * (c + skip_c[o.slot]) * 2.0 * 8.0 * d * d * d * 2);
+            upcat_hilo_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, d, c / 8, (const uint4 *)g_bufs[skip_buf[o.slot]].p,
+                                                            skip_d[o.slot], skip_c[o.slot] / 8, o.crop, (uint4 *)g_bufs[nb].p, n_tiles);
+            FPL_LAUNCH_CHECK(ctx);
+            if (!cur_is_skip) release(cur);
+            release(skip_buf[o.slot]);
+            cur = nb; cur_is_skip = false; d *= 2; c += skip_c[o.slot];
+        } else if (o.kind == OP_FINAL) {
+            const ConvParams &cp = net->convs[o.conv_index];
+            ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * d * d * d * (c * 4.0 + 4.0));
+            final_hilo_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, cp.d_kernel, cp.bias[0], d_out, n_tiles, d,
+                                                            c / 8, net->info.rf_stride);
+            FPL_LAUNCH_CHECK(ctx);
+        }
+    }
+    return FPL_OK;
+}
+
 // true when forward_umma will take the fused first+second convolution path, whose builders can read the
 // input tile straight from the (uint8 / float32) volume -- no float32 tile staging needed
 bool umma_reads_volume(const fpl_net *net) {
@@ -1966,11 +2304,17 @@ bool umma_reads_volume(const fpl_net *net) {
            p2.k_split == 1;
 }
 
+static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st);
+
 int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st,
                  const VolumeIO *vio, int in_z) {
     fpl_ctx *ctx = net->ctx;
+    if (net->precision == FPL_PREC_TF32) {
+        FPL_REQUIRE(vio == nullptr && (in_z <= 0 || in_z == in_sz), "forward_umma: the hi/lo path runs on cubic staged tiles");
+        return forward_hilo(net, d_tiles, n_tiles, in_sz, d_out, st);
+    }
     if (net->precision != FPL_PREC_BF16) {
-        set_error("forward_umma: only the bf16 tcgen05 path is built (precision %d requested)", net->precision);
+        set_error("forward_umma: unknown tensor-core precision %d", net->precision);
         return FPL_ESTATE;
     }
     if (in_z <= 0) in_z = in_sz;

@@ -364,7 +364,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     // one thinner slab.  Used when the x/y tile counts are similar and the largest activation of a slab
     // (first conv output, 96 B per voxel) fits comfortably in HBM.
     bool slab_mode = false;
-    if (m > 1 && net->precision != FPL_PREC_FP32 && zb == 0 && ze == g.nz && !g_no_slab_mode) {
+    if (m > 1 && net->precision == FPL_PREC_BF16 && zb == 0 && ze == g.nz && !g_no_slab_mode) {
         const int nxy = g.ny > g.nx ? g.ny : g.nx, nmin = g.ny < g.nx ? g.ny : g.nx;
         int mz = m < g.nz ? m : g.nz;
         const double xy_bytes = 96.0 * ((double)nxy * g.out_sz + 2 * off) * ((double)nxy * g.out_sz + 2 * off);
@@ -430,8 +430,8 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
         if (ph.batch > ph.n) ph.batch = (int)ph.n;
         size_t ie = (size_t)ph.grid.in_z * ph.grid.in_sz * ph.grid.in_sz * ph.batch;
         size_t oe = (size_t)ph.grid.out_z * ph.grid.out_sz * ph.grid.out_sz * ph.batch;
-        if (net->precision != FPL_PREC_FP32 && !g_no_direct_io) oe = 1;      // the final layer scatters directly
-        if (net->precision != FPL_PREC_FP32 && !g_no_direct_io && umma_reads_volume(net)) ie = 1;
+        if (net->precision == FPL_PREC_BF16 && !g_no_direct_io) oe = 1;      // the final layer scatters directly
+        if (net->precision == FPL_PREC_BF16 && !g_no_direct_io && umma_reads_volume(net)) ie = 1;
         if (ie > need_in) need_in = ie;
         if (oe > need_out) need_out = oe;
     }
@@ -455,7 +455,7 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
             // tcgen05 path: the final layer scatters straight into the prediction volume; the input tile is
             // staged by the gather kernel (float32, L2 resident) unless the fused first+second convolution
             // kernel runs, whose builders read the volume directly in the shadow of the MMAs
-            const bool fused_scatter = net->precision != FPL_PREC_FP32 && !g_no_direct_io;
+            const bool fused_scatter = net->precision == FPL_PREC_BF16 && !g_no_direct_io;
             // ... and when the first two convolutions run fused, its builders gather straight from the volume
             const bool direct_in = fused_scatter && umma_reads_volume(net);
             if (!direct_in) {

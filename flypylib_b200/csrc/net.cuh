@@ -29,6 +29,10 @@ struct ConvParams {                 // host copies (Keras order) + folded device
     void *d_packed = nullptr;       // operand-B image for the UMMA kernel (BN scale folded in)
     size_t packed_bytes = 0;
     bool no_rot = false;            // second conv of the fused first+second kernel: split-window weight layout
+    bool no_ksplit = false;         // planner: resident-weight plans only (chunk convolutions of the hi/lo path)
+    // hi/lo (bf16x3) path: per input-channel chunk one image of bf16(w) and one of bf16(w - bf16(w))
+    void *d_packed_lo = nullptr;
+    int hilo_chunk = 0;             // input channels per chunk
 };
 
 // Tile grid of FplNetwork.infer (fplnetwork.py:146-160) and the optional direct volume I/O of a

@@ -211,3 +211,34 @@ def test_infer_host_pipelined_equals_infer_device(arch, shape):
         got = net.infer_host(host, normalize=(128.0, 33.0), chunk_layers=chunk_layers)
         torch.cuda.synchronize()
         assert torch.equal(got, want), (arch, chunk_layers)
+
+
+@pytest.mark.parametrize("arch,s,n", [("vgg_like2", 36, 2), ("vgg_like2", 52, 2), ("vgg_like", 38, 2), ("unet_like2", 36, 2),
+                                      ("baseline_model", 38, 1), ("unet_like", 30, 2)])
+def test_hilo_tensor_core_path_vs_float64_oracle(arch, s, n):
+    """precision 'tf32' = the high-precision tensor-core path (bf16 hi/lo split, three bf16 contractions per
+    convolution, fp32 accumulate): probability maps within 2e-3 of the float64 oracle (north_star bound for
+    the fp32/TF32 path); measured ~1e-5."""
+    w = M.random_weights(arch, seed=11)
+    x = np.random.default_rng(s).standard_normal((n, s, s, s)).astype(np.float32)
+    got = _predict(arch, s, w, x, "tf32")
+    want = M.forward(arch, w, x)
+    assert got.shape == want.shape
+    e = np.abs(got.astype(np.float64) - want).max()
+    assert e < 2e-4, "hi/lo path vs float64 oracle: %g" % e
+
+
+def test_hilo_infer_volume_vs_reference_tiling():
+    from flypylib_b200 import fplmodels, fplnetwork
+    import torch
+    net = fplnetwork.FplNetwork(fplmodels.vgg_like2)
+    w = M.random_weights("vgg_like2", seed=99)
+    net.train_single.set_weights(w)
+    net.set_precision("tf32")
+    net._set_infer()
+    net.tile_multiplier = 2
+    img = ((cases.em_volume((190, 185, 200), seed=5).astype(np.float32) - 128.0) / 33.0).astype(np.float32)
+    got = net.infer(img)
+    ref_net = M.TorchNet("vgg_like2", w, dtype=torch.float32)
+    want = M.infer_tiler(img, ref_net, net.infer_sz, net.rf_offset, n_gpu=1)
+    assert np.abs(got - want).max() < 2e-4
