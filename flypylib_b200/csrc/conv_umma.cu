@@ -2074,35 +2074,50 @@ __device__ __forceinline__ void load_hilo8(const uint4 *hi_p, const uint4 *lo_p,
     }
 }
 
-// first layer in fp32 on CUDA cores: one thread = one voxel x one group of 8 output channels
+// first layer in fp32 on CUDA cores: one thread = one voxel x CG groups of 8 output channels; the folded
+// weights sit in shared memory (broadcast float4 reads), threads run along x (coalesced loads and 16-byte stores)
+template <int CG>
 __global__ void __launch_bounds__(256)
 first_hilo_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ scale,
-                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int n_tiles, int din, int cout) {
-    const int dout = din - 2, cg_n = cout / 8;
-    const long long vox_n = (long long)dout * dout * dout, total = (long long)n_tiles * cg_n * vox_n;
+                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int n_tiles, int din) {
+    constexpr int COUT = CG * 8;
+    __shared__ __align__(16) float sw[27 * COUT];
+    __shared__ float ssc[COUT], sbi[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ssc[i] = scale[i]; sbi[i] = bias[i]; }
+    __syncthreads();
+    const int dout = din - 2;
+    const long long vox_n = (long long)dout * dout * dout, total = (long long)n_tiles * vox_n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long v = i;
-        const int x = (int)(v % dout); v /= dout;
-        const int y = (int)(v % dout); v /= dout;
-        const int z = (int)(v % dout); v /= dout;
-        const int cg = (int)(v % cg_n), t = (int)(v / cg_n);
-        const float *ip = in + (size_t)t * din * din * din;
-        float acc[8];
+        const int t = (int)(i / vox_n);
+        const long long o = i - (long long)t * vox_n;
+        const int x = (int)(o % dout), y = (int)((o / dout) % dout), z = (int)(o / ((long long)dout * dout));
+        const float *ip = in + (size_t)t * din * din * din + ((size_t)z * din + y) * din + x;
+        float acc[COUT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+#pragma unroll 1
         for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
             for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const float a = __ldg(ip + ((size_t)(z + kd) * din + (y + kh)) * din + (x + kw));
-                    const float *wp = w + (size_t)((kd * 3 + kh) * 3 + kw) * cout + cg * 8;
+                    const float a = __ldg(ip + ((size_t)kd * din + kh) * din + kw);
+                    const float4 *wp = reinterpret_cast<const float4 *>(&sw[((kd * 3 + kh) * 3 + kw) * COUT]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, __ldg(wp + j), acc[j]);
+                    for (int j4 = 0; j4 < COUT / 4; ++j4) {
+                        const float4 wv = wp[j4];
+                        acc[4 * j4] = fmaf(a, wv.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(a, wv.y, acc[4 * j4 + 1]);
+                        acc[4 * j4 + 2] = fmaf(a, wv.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(a, wv.w, acc[4 * j4 + 3]);
+                    }
                 }
-        float r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(acc[j], scale[cg * 8 + j], bias[cg * 8 + j]), 0.f);
-        const size_t o = (size_t)z * dout * dout + (size_t)y * dout + x;
-        store_hilo8(out + (((size_t)t * 2 * cg_n + cg) * vox_n + o) * 8, out + (((size_t)t * 2 * cg_n + cg_n + cg) * vox_n + o) * 8, r);
+        for (int cg = 0; cg < CG; ++cg) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(acc[cg * 8 + j], ssc[cg * 8 + j], sbi[cg * 8 + j]), 0.f);
+            store_hilo8(out + (((size_t)t * 2 * CG + cg) * vox_n + o) * 8, out + (((size_t)t * 2 * CG + CG + cg) * vox_n + o) * 8, r);
+        }
     }
 }
 
@@ -2252,9 +2267,12 @@ static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_
             if (nb < 0) return FPL_ENOMEM;
             __nv_bfloat16 *dst = (__nv_bfloat16 *)g_bufs[nb].p;
             if (cp.cin == 1) {
-                FPL_REQUIRE(cp.k == 3 && cp.cout % 8 == 0, "hi/lo path: unsupported first layer");
+                FPL_REQUIRE(cp.k == 3 && (cp.cout == 48 || cp.cout == 32), "hi/lo path: unsupported first layer");
                 ProfScope prof(ctx, st, PROF_FIRST, 2.0 * 27 * cp.cout * (double)n_tiles * dout * dout * dout);
-                first_hilo_kernel<<<stream_blocks, 256, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d, cp.cout);
+                if (cp.cout == 48)
+                    first_hilo_kernel<6><<<stream_blocks, 256, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
+                else
+                    first_hilo_kernel<4><<<stream_blocks, 256, 0, st>>>(d_tiles, cp.d_kernel, cp.d_scale, cp.d_bias, dst, n_tiles, d);
                 FPL_LAUNCH_CHECK(ctx);
             } else {
                 FPL_REQUIRE(cp.d_packed && cp.d_packed_lo, "hi/lo path: layer k=%d Cin=%d Cout=%d has no packed weights", cp.k, cp.cin, cp.cout);

@@ -157,7 +157,8 @@ int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h
 /* arithmetic of the conv stack */
 #define FPL_PREC_FP32  0   /* CUDA-core fp32 direct convolution (validation path)            */
 #define FPL_PREC_BF16  1   /* tcgen05 kind::f16 implicit GEMM, bf16 operands, fp32 accumulate */
-#define FPL_PREC_TF32  2   /* tcgen05 kind::tf32 implicit GEMM                                */
+#define FPL_PREC_TF32  2   /* high-precision tensor-core path: bf16 hi/lo split operands, 3 bf16 contractions
+                            * per convolution, fp32 accumulate (~16 mantissa bits, >= TF32 accuracy)        */
 
 /* Build a network object for `arch`; replaces the Keras graph construction in the builders and
  * FplNetwork._set_infer (fplnetwork.py:99-110: the x rf_stride nearest up-sampling of the VGG
