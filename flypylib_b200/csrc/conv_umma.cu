@@ -153,6 +153,9 @@ struct ConvArgs {
     int cin_atom_off;                // first channel atom of this launch's input-channel chunk
     int acc_mode;                    // 0 normal, 1 first chunk (write partial), 2 middle (partial += acc), 3 last (finish)
     float *partial;                  // (tile, cout/8, Dout_z, Dout, Dout, 8) fp32
+    // hi/lo path: the nsub sub-planes are the hi and the lo part of the same channels and share ONE weight image
+    int shared_w;                    // 1: weights are indexed without the sub-plane offset
+    int sub_stride;                  // channel atoms between consecutive sub-planes (0: contiguous, 2*KSTEPS)
 };
 
 // Epilogue of one M=128 accumulator tile (N = cout fp32 columns in TMEM):
@@ -431,7 +434,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                     if (leader) {
                         mbar_expect_tx(&plane_full[slot], plane_bytes);
                         tma_load_4d(s_planes + slot * plane_pitch, &tmap_in, &plane_full[slot], xt * TX * 8, yt * kTY,
-                                    z0 + p, tile * a.cin_atoms_total + a.cin_atom_off + sub * SUB_ATOMS);
+                                    z0 + p, tile * a.cin_atoms_total + a.cin_atom_off + sub * (a.sub_stride ? a.sub_stride : SUB_ATOMS));
                     }
                 }
         }
@@ -445,7 +448,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
         const uint32_t a_lo0 = (smem_u32(s_planes) >> 4) | ((atom_stride >> 4) << 16);
         const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | ((N * KS) << 16);   // LBO = KS*Cout*16 bytes
         const uint32_t b_step16 = N * KS * 2u;                            // one (kh,kw,kstep) chunk = KS*Cout*32 bytes
-        const uint32_t kt = (uint32_t)(nsub * KSTEPS);                    // K steps per tap over all sub-planes
+        const uint32_t kt = (uint32_t)((a.shared_w ? 1 : nsub) * KSTEPS);   // K steps per tap in the weight image
+        const uint32_t wsub = a.shared_w ? 0u : (uint32_t)KSTEPS;           // weight K-step offset per sub-plane
         mbar_wait(w_full, 0);
         uint32_t pc = 0, ac0 = 0;
         if constexpr (ROT) {
@@ -482,7 +486,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                                 for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
                                     for (int kw = 0; kw < KS; ++kw) {
-                                        uint32_t b_lo = b_lo0r + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)(sub * KSTEPS)) * b_step16r;
+                                        uint32_t b_lo = b_lo0r + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)sub * wsub) * b_step16r;
 #pragma unroll
                                         for (int s = 0; s < KSTEPS; ++s) {
                                             const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4) +
@@ -554,7 +558,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs a) 
                         for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
                             for (int kw = 0; kw < KS; ++kw) {
-                                uint32_t b_lo = b_lo0 + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)(sub * KSTEPS)) * b_step16;
+                                uint32_t b_lo = b_lo0 + ((uint32_t)(kh * KS + kw) * kt + (uint32_t)sub * wsub) * b_step16;
 #pragma unroll
                                 for (int s = 0; s < KSTEPS; ++s) {
                                     const uint32_t a_lo = a_pl + (uint32_t)(kh * SX + kw) + (uint32_t)(2 * s) * (atom_stride >> 4);
@@ -1895,7 +1899,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     ConvArgs a;
     a.out = out;
     a.w_bytes = (uint32_t)(c.packed_bytes / (plan.n_split * plan.k_split));
-    a.cin_atom_off = 0; a.acc_mode = 0; a.partial = nullptr;
+    a.cin_atom_off = 0; a.acc_mode = 0; a.partial = nullptr; a.shared_w = 0; a.sub_stride = 0;
     int partial_buf = -1;
     if (plan.k_split > 1) {
         FPL_REQUIRE(!pool, "conv_umma: pooled epilogue needs an unsplit plan");
@@ -2230,20 +2234,31 @@ static int launch_conv_hilo(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     int zc_len = (dout + n_zc - 1) / n_zc;
     if (zc_len < 8) zc_len = dout < 8 ? dout : 8;
     a.zc_len = zc_len; a.n_zc = (dout + zc_len - 1) / zc_len;
-    a.relu = relu; a.pool = 0; a.max_blk = 0; a.tmem_cols = 512;
+    a.relu = relu; a.pool = 0; a.max_blk = 0; a.tmem_cols = 512; a.shared_w = 0; a.sub_stride = 0;
     const long long n_items = base_items * a.n_zc;
     int grid = ctx->sm_count; if (grid > n_items) grid = (int)n_items;
     ProfScope prof(ctx, st, ks == 3 ? PROF_CONV3 : PROF_CONV1,
                    3.0 * 2.0 * ks * ks * ks * c.cin * c.cout * (double)n_tiles * dout * dout * dout);
-    const int n_launch = 3 * n_chunks;
+    // per chunk two launches: (hi, lo) x w_hi as two sub-planes sharing one weight image (their sum stays in TMEM),
+    // then hi x w_lo; the fp32 partial sums pass through HBM between launches
+    const bool fuse = plan.nsub == 1 && plan_smem(ks, cc, c.cout, 1, plan.tx, 2, plan.rot) <= kMaxDynSmem;
+    const size_t smem_fused = plan_smem(ks, cc, c.cout, 1, plan.tx, 2, plan.rot);
+    const int per_chunk = fuse ? 2 : 3, n_launch = per_chunk * n_chunks;
     int li = 0;
     for (int g = 0; g < n_chunks; ++g)
-        for (int term = 0; term < 3; ++term, ++li) {             // hi*w_hi, lo*w_hi, hi*w_lo
-            const uint8_t *img = (const uint8_t *)(term == 2 ? c.d_packed_lo : c.d_packed) + (size_t)g * a.w_bytes;
+        for (int term = 0; term < per_chunk; ++term, ++li) {
+            const bool lo_w = term == per_chunk - 1;              // last term of a chunk: hi x w_lo
+            const uint8_t *img = (const uint8_t *)(lo_w ? c.d_packed_lo : c.d_packed) + (size_t)g * a.w_bytes;
             a.w_packed = (const __nv_bfloat16 *)img;
-            a.cin_atom_off = g * (cc / 8) + (term == 1 ? c.cin / 8 : 0);
             a.acc_mode = li == 0 ? 1 : (li == n_launch - 1 ? 4 : 2);
-            FPL_TRY(dispatch_umma(plan, ks, grid, plan.smem, st, tmap, a));
+            if (fuse && term == 0) {
+                a.cin_atom_off = g * (cc / 8); a.nsub = 2; a.ring = 2; a.shared_w = 1; a.sub_stride = c.cin / 8;
+                FPL_TRY(dispatch_umma(plan, ks, grid, smem_fused, st, tmap, a));
+            } else {
+                a.cin_atom_off = g * (cc / 8) + ((!fuse && term == 1) ? c.cin / 8 : 0);
+                a.nsub = plan.nsub; a.ring = plan.ring; a.shared_w = 0; a.sub_stride = 0;
+                FPL_TRY(dispatch_umma(plan, ks, grid, plan.smem, st, tmap, a));
+            }
             FPL_LAUNCH_CHECK(ctx);
         }
     g_bufs[pbuf].busy = false;
