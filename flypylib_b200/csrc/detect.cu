@@ -893,12 +893,15 @@ nms_suppress_kernel(unsigned *sup, Dims d, int r, const unsigned long long *__re
             long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
             unsigned long long q0 = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
             unsigned long long q1 = ((unsigned long long)zz * d.Y + yy) * d.X + x1;
-            for (unsigned long long wd = q0 >> 5; wd <= (q1 >> 5); ++wd) {
-                unsigned long long lo = wd << 5;
+            // 64-bit words: a row of <= 2r+1 voxels touches at most two of them (the bitmap is 8-byte aligned
+            // and padded to a multiple of 64 bits)
+            unsigned long long *sup64 = reinterpret_cast<unsigned long long *>(sup);
+            for (unsigned long long wd = q0 >> 6; wd <= (q1 >> 6); ++wd) {
+                unsigned long long lo = wd << 6;
                 unsigned b0 = q0 > lo ? (unsigned)(q0 - lo) : 0u;
-                unsigned b1 = q1 < lo + 31 ? (unsigned)(q1 - lo) : 31u;
-                unsigned mask = (b1 == 31u ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
-                atomicOr(&sup[wd], mask);
+                unsigned b1 = q1 < lo + 63 ? (unsigned)(q1 - lo) : 63u;
+                unsigned long long mask = (b1 == 63u ? ~0ULL : ((1ULL << (b1 + 1)) - 1ULL)) & ~((1ULL << b0) - 1ULL);
+                atomicOr(&sup64[wd], mask);
             }
         }
     }
@@ -928,12 +931,15 @@ nms_suppress_zyx_kernel(unsigned *sup, Dims d, int r, const long long *__restric
             if (x1 < x0) continue;
             unsigned long long q0 = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
             unsigned long long q1 = ((unsigned long long)zz * d.Y + yy) * d.X + x1;
-            for (unsigned long long wd = q0 >> 5; wd <= (q1 >> 5); ++wd) {
-                unsigned long long lo = wd << 5;
+            // 64-bit words: a row of <= 2r+1 voxels touches at most two of them (the bitmap is 8-byte aligned
+            // and padded to a multiple of 64 bits)
+            unsigned long long *sup64 = reinterpret_cast<unsigned long long *>(sup);
+            for (unsigned long long wd = q0 >> 6; wd <= (q1 >> 6); ++wd) {
+                unsigned long long lo = wd << 6;
                 unsigned b0 = q0 > lo ? (unsigned)(q0 - lo) : 0u;
-                unsigned b1 = q1 < lo + 31 ? (unsigned)(q1 - lo) : 31u;
-                unsigned mask = (b1 == 31u ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
-                atomicOr(&sup[wd], mask);
+                unsigned b1 = q1 < lo + 63 ? (unsigned)(q1 - lo) : 63u;
+                unsigned long long mask = (b1 == 63u ? ~0ULL : ((1ULL << (b1 + 1)) - 1ULL)) & ~((1ULL << b0) - 1ULL);
+                atomicOr(&sup64[wd], mask);
             }
         }
     }
@@ -1493,7 +1499,7 @@ static size_t detect_workspace_bytes(int64_t Z, int64_t Y, int64_t X, long long 
     const long long n = Z * Y * X;
     size_t b = 0;
     auto add = [&](size_t x) { b += (x + 255) & ~size_t(255); };
-    add(((size_t)n + 31) / 32 * 4);
+    add(((size_t)n + 63) / 64 * 8);
     add(list_cap * 8); add(list_cap * 8); add(list_cap * 4); add(list_cap * 4);   // A, B
     add(list_cap * 8); add(list_cap * 4);                                          // worklist
     add(det_cap * 8); add(det_cap * 4); add(det_cap * 8);                          // det, sel
@@ -1509,7 +1515,7 @@ static int take_detect_buffers(fpl_ctx *ctx, int64_t Z, int64_t Y, int64_t X, lo
     const long long n = Z * Y * X;
     fpl::Arena &A = ctx->arena;
     B.list_cap = list_cap; B.det_cap = det_cap;
-    B.sup_words = ((size_t)n + 31) / 32;
+    B.sup_words = ((size_t)n + 63) / 64 * 2;          // whole 64-bit words (nms_suppress uses 64-bit atomics)
     B.sup = (unsigned *)A.take(B.sup_words * 4);
     B.a_idx = (unsigned long long *)A.take(list_cap * 8);
     B.b_idx = (unsigned long long *)A.take(list_cap * 8);
