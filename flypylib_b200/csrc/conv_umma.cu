@@ -1662,7 +1662,7 @@ static size_t plan_smem(int ks, int cin, int n, int nsub, int tx, int ring, bool
 }
 
 static bool have_instance(int ks, int ksteps, int tx) {
-    if (ks == 3 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
+    if (ks == 3 && tx == 16) return ksteps == 1 || ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;   // 1: ROT only
     if (ks == 3 && tx == 8) return ksteps == 4 || ksteps == 3;
     if (ks == 1 && tx == 16) return ksteps == 2 || ksteps == 3 || ksteps == 4 || ksteps == 6;
     return false;
@@ -1726,6 +1726,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
                 const int n = c.cout / split;
                 for (int rot = 1; rot >= 0; --rot) {
                     if (rot && (c.k != 3 || txs[ti] != 16 || legacy || c.no_rot || 3 * n > 256)) continue;
+                    if (!rot && ksteps == 1) continue;           // 16-channel sub-planes exist as a ROT instance only
                     for (int ring = 3; ring >= 2; --ring) {
                         if (nsub > 1 && ring > 2) continue;
                         const size_t sm = plan_smem(c.k, c.cin, n, nsub, txs[ti], ring, rot != 0);
@@ -1750,7 +1751,7 @@ static ConvPlan plan_conv(const ConvParams &c) {
             for (int rot = 1; rot >= 0; --rot)
                 for (int ring = 3; ring >= 2; --ring) {
                     const size_t sm = plan_smem(3, cc, c.cout, 1, 16, ring, rot != 0);
-                    if (sm > kMaxDynSmem || (rot && 3 * c.cout > 256)) continue;
+                    if (sm > kMaxDynSmem || (rot && 3 * c.cout > 256) || (!rot && ksteps == 1)) continue;
                     const ConvPlan cand{1, c.cout, 1, ksteps, 16, ring, sm, true, rot != 0, ks_};
                     const double cost = ksplit_cost(c, cand);
                     if (cost < ks_margin * best_cost) { best = cand; best_cost = cost / ks_margin; }
@@ -1853,7 +1854,8 @@ static int dispatch_umma(const ConvPlan &plan, int ks, int grid, size_t smem, cu
             conv_umma_kernel<KS_, KST_, TX_, ROT_><<<grid, kThreads, smem, st>>>(tmap, a);                        \
         } while (0)
     const int kst = plan.ksteps;
-    if (plan.rot && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, true);
+    if (plan.rot && kst == 1) FPL_LAUNCH_UMMA(3, 1, 16, true);
+    else if (plan.rot && kst == 3) FPL_LAUNCH_UMMA(3, 3, 16, true);
     else if (plan.rot && kst == 2) FPL_LAUNCH_UMMA(3, 2, 16, true);
     else if (plan.rot && kst == 4) FPL_LAUNCH_UMMA(3, 4, 16, true);
     else if (plan.rot && kst == 6) FPL_LAUNCH_UMMA(3, 6, 16, true);
