@@ -144,8 +144,15 @@ __device__ __forceinline__ float exact_output(const double (&x)[kRun + 2 * LW], 
 // to round identically.  Exactness never rests on the fast chain.
 template <int LW>
 __device__ __forceinline__ void run_from_window(const double (&x)[kRun + 2 * LW], const Taps &taps,
-                                                float (&res)[kRun], bool nonneg, unsigned cert,
+                                                float (&res)[kRun], unsigned cert,
                                                 const float *win, int wstride) {
+    bool nonneg = false;
+    if (cert) {                      // the certificate needs non-negative inputs: check the sign bits of the window
+        unsigned sgn = 0;
+#pragma unroll
+        for (int k = 0; k < kRun + 2 * LW; ++k) sgn |= __float_as_uint(win[k * wstride]);
+        nonneg = (sgn >> 31) == 0u;
+    }
     if (cert && nonneg) {
         unsigned bad = 0;
 #pragma unroll
@@ -251,15 +258,10 @@ gauss_strided_kernel(const float *__restrict__ in, float *__restrict__ out, long
         const int base = (ty * kRunsPerThread + run) * kRun;
         if (n0 + base >= n) break;
         double x[kRun + 2 * LW];
-        unsigned sgn = 0;
 #pragma unroll
-        for (int k = 0; k < kRun + 2 * LW; ++k) {
-            const float tv = tile[base + k][tx];
-            sgn |= __float_as_uint(tv);
-            x[k] = (double)tv;
-        }
+        for (int k = 0; k < kRun + 2 * LW; ++k) x[k] = (double)tile[base + k][tx];
         float res[kRun];
-        run_from_window<LW>(x, taps, res, (sgn >> 31) == 0u, cert, &tile[base][tx], kLines);
+        run_from_window<LW>(x, taps, res, cert, &tile[base][tx], kLines);
         if (live) {
 #pragma unroll
             for (int q = 0; q < kRun; ++q)
@@ -350,14 +352,9 @@ gauss_contig_kernel(const float *__restrict__ in, float *__restrict__ out, long 
     for (int run = 0; run < kRunsPerThread; ++run) {
         const int base = (ty * kRunsPerThread + run) * kRun;
         double x[kRun + 2 * LW];
-        unsigned sgn = 0;
 #pragma unroll
-        for (int k = 0; k < kRun + 2 * LW; ++k) {
-            const float tv = tile[(base + k) * kPitch + tx];
-            sgn |= __float_as_uint(tv);
-            x[k] = (double)tv;
-        }
-        run_from_window<LW>(x, taps, res[run], (sgn >> 31) == 0u, cert, &tile[base * kPitch + tx], kPitch);
+        for (int k = 0; k < kRun + 2 * LW; ++k) x[k] = (double)tile[(base + k) * kPitch + tx];
+        run_from_window<LW>(x, taps, res[run], cert, &tile[base * kPitch + tx], kPitch);
     }
     __syncthreads();
 #pragma unroll
