@@ -117,8 +117,8 @@ __global__ void gauss_generic_kernel(const float *__restrict__ in, float *__rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kLines = 64;
 constexpr int kGroups = 2;          // 128-thread blocks: more, finer-grained blocks per SM overlap load and FP64 phases
-constexpr int kRun = 8;
-constexpr int kRunsPerThread = 4;
+constexpr int kRun = 16;
+constexpr int kRunsPerThread = 2;
 constexpr int kTN = kGroups * kRunsPerThread * kRun;   // 64 outputs along the axis per block
 
 // Exact SciPy chain of one output: tmp = x0*w0; tmp += (x[-j] + x[+j]) * w[j], every operation rounded.
