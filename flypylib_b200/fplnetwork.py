@@ -7,6 +7,7 @@ tiles are gathered, evaluated and scattered on the GPU by ``fpl_net_infer_volume
 staging batch, no host loops).
 """
 import ctypes
+import pickle
 
 import numpy as np
 
@@ -43,6 +44,21 @@ class multi_gpu_callback(object):
         self.model_to_save.save('%s_%03d.h5' % (self.save_prefix, epoch))
 
 
+def _weights_path(filepath):
+    """Weight container next to the pickled network.  The reference writes ``<filepath>.keras.h5`` through
+    Keras/h5py (fplnetwork.py:82-83); h5py is not available here, so the same arrays (Model.get_weights()
+    order) go to ``<filepath>.keras.npz``."""
+    return filepath + '.keras.npz'
+
+
+def load_network(filepath):
+    """fplnetwork.py:32-44: un-pickle an FplNetwork written by ``save_network`` and restore its weights."""
+    with open(filepath, 'rb') as fn:
+        network = pickle.load(fn)
+    network._restore_models(_weights_path(filepath))
+    return network
+
+
 class FplNetwork:
     """deep learning/CNN class wrapping a B200 network (reference: wraps a keras model)
 
@@ -72,6 +88,32 @@ class FplNetwork:
         self.train_network.compile(**compile_args)
         self.compile_args = compile_args
         self.tile_multiplier = 1
+
+    # ------------------------------------------------------------------------------------------
+    def save_network(self, filepath):
+        """fplnetwork.py:81-97: weights to the side file, the network object (builder, receptive-field info,
+        compile_args, ...) pickled to ``filepath``; the live networks are kept."""
+        self.train_single.save(_weights_path(filepath))
+        with open(filepath, 'wb') as fn:
+            pickle.dump(self, fn)
+
+    def __getstate__(self):
+        keep = dict(self.__dict__)
+        keep['_precision'] = self.train_single.precision if self.train_single is not None else None
+        for k in ('train_network', 'train_single', 'infer_network', '_copy_stream', '_chunk_pred'):
+            keep[k] = None
+        return keep
+
+    def _restore_models(self, weights_file):
+        precision = self.__dict__.pop('_precision', None)
+        self.train_single, _, _, _ = self.model()
+        self.train_network = self.train_single
+        if precision:
+            self.train_single.set_precision(precision)
+        with np.load(weights_file) as z:
+            self.train_single.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
+        self.train_network.compile(**self.compile_args)
+        self._set_infer()
 
     # ------------------------------------------------------------------------------------------
     def _set_infer(self):

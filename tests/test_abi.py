@@ -67,3 +67,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_save_network_load_network_roundtrip(tmp_path):
+    """fplnetwork.save_network / load_network (reference fplnetwork.py:32-44, 81-97): the pickled network and
+    its weight side file restore builder, receptive-field info, compile_args and weights (host-only, no GPU)."""
+    import numpy as np
+    from flypylib_b200 import fplmodels, fplnetwork
+    net = fplnetwork.FplNetwork(fplmodels.unet_like2)
+    rng = np.random.default_rng(3)
+    w = [rng.standard_normal(a.shape).astype(np.float32) for a in net.train_single.get_weights()]
+    net.train_single.set_weights(w)
+    net.set_precision("tf32")
+    net._set_infer()
+    net.tile_multiplier = 1
+    path = str(tmp_path / "net.p")
+    net.save_network(path)
+    assert net.infer_network is not None                      # the live network is untouched
+    back = fplnetwork.load_network(path)
+    assert back.rf_size == net.rf_size and back.rf_offset == net.rf_offset and back.infer_sz == net.infer_sz
+    assert back.compile_args.keys() == net.compile_args.keys()
+    assert back.train_single.precision == "tf32" and back.infer_network.precision == "tf32"
+    for a, b in zip(back.infer_network.get_weights(), w):
+        assert np.array_equal(a, b)
