@@ -451,3 +451,45 @@ def full_roi_inference(data_source, dvid_uuid, dvid_roi, network, thd, working_d
         with open('%s/all.p' % working_dir, 'wb') as f_out:
             pickle.dump(obj, f_out)
     return obj
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluate_substacks (flypylib/fplobjdetect.py:459-512): infer + voxel2obj + PR curve per substack.
+# The reference forks one process per substack for the post-processing; a CUDA context does not
+# survive fork and voxel2obj is now faster than the fork, so the work runs inline.
+# ---------------------------------------------------------------------------------------------
+def _get_labels(seg, tt):
+    """Segment label under every detection (fplobjdetect.py:459-461); locs are (x,y,z), seg is (Z,Y,X)."""
+    tt_ind = tt['locs'].astype(int)
+    return seg[tt_ind[:, 2], tt_ind[:, 1], tt_ind[:, 0]]
+
+
+def evaluate_substacks(network, substacks, thds, obj_min_dist=27, smoothing_sigma=5, volume_offset=(0, 0, 0),
+                       buffer_sz=5, allow_mult=False):
+    """Precision/recall of ``network`` on annotated substacks (fplobjdetect.py:484-512).
+
+    ``substacks``: sequence of ``(image, groundtruth_json[, seg])`` -- image as accepted by
+    ``network.infer`` (array), ground truth as a json file (or json text) in either wire format, optional
+    segmentation array (Z,Y,X) for label-constrained matching (the reference takes an h5 path; h5py is not
+    available).  Returns ``(aggregate_pr(results), results)`` with one PR_Result per substack, in order."""
+    from . import fplsynapses
+    results = []
+    for ss in substacks:
+        image = ss[0]
+        if hasattr(network, 'infer_device') and not isinstance(image, str):
+            import torch
+            dev_img = image if isinstance(image, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32))
+            pred = network.infer_device(dev_img.cuda())
+            shape = tuple(pred.shape)
+        else:
+            pred = network.infer(image)
+            shape = pred.shape
+        out = voxel2obj(pred, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz)
+        gt = fplsynapses.load_from_json(ss[1], shape, buffer_sz)
+        lbls_pd = lbls_gt = None
+        if len(ss) >= 3 and ss[2] is not None:
+            seg = np.asarray(ss[2])
+            lbls_pd, lbls_gt = _get_labels(seg, out), _get_labels(seg, gt)
+        results.append(obj_pr_curve(out, gt, obj_min_dist, thds, lbls_pd, lbls_gt, allow_mult=allow_mult))
+    return aggregate_pr(results), results

@@ -167,3 +167,31 @@ def test_full_roi_inference_gpu_end_to_end(tmp_path):
     assert np.array_equal(out["locs"], np.concatenate(locs)) and np.array_equal(out["conf"], np.concatenate(conf))
     lo = np.array([0, 0, 0]); hi = np.array([160, 140, 150])
     assert np.all(out["locs"] >= lo) and np.all(out["locs"] < hi)
+
+
+def test_evaluate_substacks_inline(tmp_path, monkeypatch):
+    """evaluate_substacks (fplobjdetect.py:484-512): per-substack PR curves and their aggregate; checked against
+    the pieces called by hand (oracle voxel2obj standing in for the CUDA one, fake network)."""
+    from flypylib_b200 import fplsynapses
+    monkeypatch.setattr(F, "voxel2obj", _oracle_v2o)
+    net = FakeNet()
+    thds = np.array([0.0, 0.5, 0.6, 0.9])
+    subs, expected = [], []
+    for seed in (1, 2):
+        img = ((cases.em_volume((40, 44, 48), seed=seed).astype(np.float32) - 128.0) / 33.0)
+        pred = net.infer(img)
+        dets = _oracle_v2o(pred, 5, 1.5, (0, 0, 0), 4, 0)
+        keep = np.arange(dets["conf"].size) % 3 != 0               # ground truth = two thirds of the detections
+        gt = {"locs": dets["locs"][keep] + 1.0, "conf": dets["conf"][keep]}
+        jf = str(tmp_path / ("gt%d.json" % seed))
+        fplsynapses.tbars_to_json_format(gt, json_file=jf)
+        subs.append((img, jf))
+        expected.append(F.obj_pr_curve(dets, fplsynapses.load_from_json(jf, pred.shape, 4), 5, thds))
+    agg, results = F.evaluate_substacks(net, subs, thds, obj_min_dist=5, smoothing_sigma=1.5, buffer_sz=4)
+    assert len(results) == 2
+    for r, e in zip(results, expected):
+        for k in ("num_tp", "tot_pred", "tot_gt", "pp", "rr"):
+            assert np.array_equal(getattr(r, k), getattr(e, k)), k
+    want = F.aggregate_pr(expected)
+    assert np.array_equal(agg.num_tp, want.num_tp) and np.array_equal(agg.pp, want.pp)
+    assert agg.num_tp[0] > 0
