@@ -493,3 +493,72 @@ def evaluate_substacks(network, substacks, thds, obj_min_dist=27, smoothing_sigm
             lbls_pd, lbls_gt = _get_labels(seg, out), _get_labels(seg, gt)
         results.append(obj_pr_curve(out, gt, obj_min_dist, thds, lbls_pd, lbls_gt, allow_mult=allow_mult))
     return aggregate_pr(results), results
+
+
+# ---------------------------------------------------------------------------------------------
+# gen_batches (flypylib/fplobjdetect.py:27-130): the patch generator that feeds FplNetwork.train
+# (BASELINE config 5).  Host-side numpy; same sampling and augmentation, same order of np.random calls
+# (so a seeded run reproduces the reference's batches bit for bit).  h5py is not available: every
+# training volume is given as arrays instead of hdf5 file names.
+# ---------------------------------------------------------------------------------------------
+def gen_batches(train_data, context_sz, batch_sz, is_mask=False):
+    """generator that yields ``(data, labels)`` training batches for ``fit_generator``.
+
+    ``train_data``: sequence of ``(image, labels, mask)`` arrays of equal 3-D shape (the reference takes
+    ``(image.h5, prefix)`` and reads ``<prefix>labels.h5`` / ``<prefix>mask.h5``).  ``context_sz``: patch
+    size; ``batch_sz``: examples per batch, alternating label 0 / label 1 positions drawn with replacement
+    from the masked-in voxels at least half a patch away from the faces.  Augmentation per example:
+    rot90 in the last two axes (0-3 times), flip of the last axis, flip of the first axis.
+    ``data`` is float32 ``(batch,) + context_sz + (1,)``; ``labels`` uint8 ``(batch,1,1,1,1)`` or, with
+    ``is_mask``, ``(batch,6,6,6,1)`` label patches in which masked-out voxels carry label 2.  As in the
+    reference the two arrays are re-used between yields."""
+    n_per_class = int(round(batch_sz / 2))
+    context_rr = tuple(int(round(cc / 2)) for cc in context_sz)
+    ims, lls, mms, locs = [], [], [], []
+    for tr in train_data:
+        ims.append(np.asarray(tr[0]))
+        lls.append(np.array(tr[1]))
+        mm = np.array(tr[2])
+        mm[:context_rr[0], :, :] = 0; mm[:, :context_rr[1], :] = 0; mm[:, :, :context_rr[2]] = 0
+        mm[-context_rr[0]:, :, :] = 0; mm[:, -context_rr[1]:, :] = 0; mm[:, :, -context_rr[2]:] = 0
+        mms.append(mm)
+        locs.append([((lls[-1] == cc) & (mm == 1)).nonzero() for cc in range(2)])
+        if is_mask:
+            lls[-1][(mm == 0).nonzero()] = 2
+    train_idx, n_train = 0, len(train_data)
+    data = np.zeros((batch_sz, context_sz[0], context_sz[1], context_sz[2], 1), dtype='float32')
+    labels = np.zeros((batch_sz, 6, 6, 6, 1) if is_mask else (batch_sz, 1, 1, 1, 1), dtype='uint8')
+    while True:
+        im, ll = ims[train_idx], lls[train_idx]
+        for cc in range(2):
+            pos = locs[train_idx][cc]
+            if len(pos[0]) == 0:            # class absent in this volume: keep the previous examples
+                continue
+            pick = np.random.choice(len(pos[0]), n_per_class, True)
+            for ii in range(n_per_class):
+                xx, yy, zz = pos[0][pick[ii]], pos[1][pick[ii]], pos[2][pick[ii]]
+                ex = ii * 2 + cc
+                data[ex, :, :, :, 0] = im[xx - context_rr[0]:xx + context_rr[0], yy - context_rr[1]:yy + context_rr[1],
+                                          zz - context_rr[2]:zz + context_rr[2]]
+                if is_mask:
+                    labels[ex, :, :, :, 0] = ll[xx - 3:xx + 3, yy - 3:yy + 3, zz - 3:zz + 3]
+                else:
+                    labels[ex, 0] = ll[xx, yy, zz]
+        aug_rot = np.floor(4 * np.random.rand(batch_sz))
+        aug_ref = np.floor(2 * np.random.rand(batch_sz))
+        aug_fpz = np.floor(2 * np.random.rand(batch_sz))
+        for ii in range(batch_sz):
+            if aug_rot[ii]:
+                data[ii, :, :, :, 0] = np.rot90(data[ii, :, :, :, 0], int(aug_rot[ii]), (1, 2))
+                if is_mask:
+                    labels[ii, :, :, :, 0] = np.rot90(labels[ii, :, :, :, 0], int(aug_rot[ii]), (1, 2))
+            if aug_ref[ii]:
+                data[ii, :, :, :, 0] = np.flip(data[ii, :, :, :, 0], 2)
+                if is_mask:
+                    labels[ii, :, :, :, 0] = np.flip(labels[ii, :, :, :, 0], 2)
+            if aug_fpz[ii]:
+                data[ii, :, :, :, 0] = np.flip(data[ii, :, :, :, 0], 0)
+                if is_mask:
+                    labels[ii, :, :, :, 0] = np.flip(labels[ii, :, :, :, 0], 0)
+        yield data, labels
+        train_idx = (train_idx + 1) % n_train

@@ -187,9 +187,50 @@ def golden_substack_images(ref):
     np.savez_compressed(os.path.join(HERE, "substack_golden.npz"), **out)
 
 
+def gen_batches_volumes():
+    """Two small training volumes (image float32, labels {0,1}, mask {0,1}) for the gen_batches goldens."""
+    vols = []
+    for seed in (31, 32):
+        rng = np.random.default_rng(seed)
+        shape = (26, 24, 28)
+        im = rng.standard_normal(shape).astype(np.float32)
+        ll = (rng.random(shape) < 0.08).astype(np.uint8)
+        mm = (rng.random(shape) < 0.85).astype(np.uint8)
+        vols.append((im, ll, mm))
+    return vols
+
+
+def golden_gen_batches(ref):
+    """Reference gen_batches (fplobjdetect.py:27-130) run unmodified with an in-memory stand-in for h5py.File."""
+    vols = gen_batches_volumes()
+    store = {}
+    for i, (im, ll, mm) in enumerate(vols):
+        store["im%d.h5" % i] = im; store["p%d_labels.h5" % i] = ll; store["p%d_mask.h5" % i] = mm
+
+    class FakeFile(object):
+        def __init__(self, name, mode="r"):
+            self.name = name
+
+        def __getitem__(self, key):
+            return store[self.name].copy()
+
+    ref.fplobjdetect.h5py.File = FakeFile
+    out = {}
+    train = tuple(("im%d.h5" % i, "p%d_" % i) for i in range(len(vols)))
+    for tag, ctx, bs, is_mask in [("cls", (8, 8, 8), 6, False), ("mask", (10, 10, 10), 4, True)]:
+        np.random.seed(1234)
+        g = ref.fplobjdetect.gen_batches(train, ctx, bs, is_mask=is_mask)
+        for k in range(3):
+            d, l = next(g)
+            out["%s/data%d" % (tag, k)] = d.copy(); out["%s/labels%d" % (tag, k)] = l.copy()
+    np.savez_compressed(os.path.join(HERE, "gen_batches_golden.npz"), **out)
+    print("gen_batches goldens:", sorted(out)[:4], "...")
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
     golden_voxel2obj(ref)
     golden_infer_tiler(ref)
     golden_eval(ref)
     golden_substack_images(ref)
+    golden_gen_batches(ref)

@@ -102,3 +102,18 @@ def test_load_from_json_matches_reference(key, src, kw):
         g, w = np.asarray(got[k]), want[k]
         assert g.shape == w.shape, k
         assert [None if x is None else x for x in g.tolist()] == w.tolist(), k
+
+
+@pytest.mark.parametrize("tag,ctx,bs,is_mask", [("cls", (8, 8, 8), 6, False), ("mask", (10, 10, 10), 4, True)])
+def test_gen_batches_matches_reference(tag, ctx, bs, is_mask):
+    """gen_batches (fplobjdetect.py:27-130): with the same np.random seed the batches equal those of the
+    unmodified reference bit for bit (tests/golden/make_golden.py:golden_gen_batches)."""
+    from tests.golden import make_golden
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "gen_batches_golden.npz"))
+    np.random.seed(1234)
+    g = F.gen_batches(make_golden.gen_batches_volumes(), ctx, bs, is_mask=is_mask)
+    for k in range(3):
+        d, l = next(g)
+        assert d.dtype == np.float32 and l.dtype == np.uint8
+        assert np.array_equal(d, gold["%s/data%d" % (tag, k)]), (tag, k)
+        assert np.array_equal(l, gold["%s/labels%d" % (tag, k)]), (tag, k)
