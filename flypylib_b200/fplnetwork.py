@@ -44,6 +44,18 @@ class multi_gpu_callback(object):
         self.model_to_save.save('%s_%03d.h5' % (self.save_prefix, epoch))
 
 
+def get_custom_objects(compile_args):
+    """fplnetwork.py:19-30: name -> function map of the non-string loss and metrics in compile_args (what
+    Keras' load_model needs as custom_objects; kept so that scripts calling it keep working)."""
+    custom_objects = {}
+    if not isinstance(compile_args['loss'], str):
+        custom_objects[compile_args['loss'].__name__] = compile_args['loss']
+    for mm in compile_args['metrics']:
+        if not isinstance(mm, str):
+            custom_objects[mm.__name__] = mm
+    return custom_objects
+
+
 def _weights_path(filepath):
     """Weight container next to the pickled network.  The reference writes ``<filepath>.keras.h5`` through
     Keras/h5py (fplnetwork.py:82-83); h5py is not available here, so the same arrays (Model.get_weights()

@@ -562,3 +562,10 @@ def gen_batches(train_data, context_sz, batch_sz, is_mask=False):
                     labels[ii, :, :, :, 0] = np.flip(labels[ii, :, :, :, 0], 0)
         yield data, labels
         train_idx = (train_idx + 1) % n_train
+
+
+def get_out_sz(in_sz):
+    """output edge of a u-net style net for an input sub-volume edge (flypylib/fplobjdetect.py:514-522)"""
+    import math
+    bottleneck_sz = int(math.floor(math.floor((in_sz - 2) / 2) - 2) / 2)
+    return (bottleneck_sz * 2 - 2) * 2 - 2
