@@ -683,7 +683,7 @@ nms_filter_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup,
     for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < nA;
          i0 += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long i = i0 + threadIdx.x;
-        bool alive = false, is_work = false;
+        bool alive = false, is_work = false, owned_alive = false;
         unsigned long long idx = 0; float val = 0.f;
         if (i < nA) {
             idx = a_idx[i]; val = a_val[i];
@@ -708,9 +708,12 @@ nms_filter_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup,
                     }
                 }
             }
-            const bool owned = idx >= own_lo && idx < own_hi;
-            is_work = !better && owned;
-            if (owned && own_hi != ~0ULL) atomicAdd(&cnt->n_alive_owned, 1ULL);
+            owned_alive = idx >= own_lo && idx < own_hi;
+            is_work = !better && owned_alive;
+        }
+        if (own_hi != ~0ULL) {                           // slab sessions: valid owned candidates, one atomic per warp
+            const unsigned m_own = __ballot_sync(0xffffffffu, owned_alive);
+            if (lane == 0 && m_own) atomicAdd(&cnt->n_alive_owned, (unsigned long long)__popc(m_own));
         }
         unsigned m_alive = __ballot_sync(0xffffffffu, alive);
         unsigned m_work = __ballot_sync(0xffffffffu, is_work);
