@@ -311,8 +311,11 @@ def main():
     if os.path.exists(tpath):       # dram bytes per launch of the dominant kernel from the committed ncu capture
         traffic = json.load(open(tpath))
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf"], "traffic": traffic,
-                "kernel": "conv_umma_kernel<3> (tcgen05 implicit GEMM, 3x3x3 conv)",
+                "frac": achieved / pk["tf"],
+                # DRAM bytes (read + write) of ONE launch of the dominant kernel in the committed ncu --set full
+                # capture (profiles/, a 512^3 run: its launches are 1/8 of this run's); details alongside
+                "traffic": (traffic or {}).get("dram_bytes_total"), "traffic_detail": traffic,
+                "kernel": "conv_fused12_kernel + conv_umma_kernel<3> (tcgen05 implicit GEMM, 3x3x3 convolutions)",
                 "launches": int(cnt3 / max(1, args.steps)), "ms_per_step": ms3 / args.steps,
                 "peak_source": "%s bf16 sustained" % pk["src"]}
     families = {k: {"ms_per_step": v[0] / args.steps, "launch_groups": int(v[2] / max(1, args.steps))}
