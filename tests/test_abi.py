@@ -90,3 +90,27 @@ def test_save_network_load_network_roundtrip(tmp_path):
     assert back.train_single.precision == "tf32" and back.infer_network.precision == "tf32"
     for a, b in zip(back.infer_network.get_weights(), w):
         assert np.array_equal(a, b)
+
+
+def test_error_behaviour_of_the_python_shims():
+    """Errors raised before any GPU work, as the reference raises them: un-built network (fplnetwork.py:141-142),
+    wrong input rank / dtype, out-of-scope branches."""
+    import numpy as np
+    import pytest
+    from flypylib_b200 import fplmodels, fplnetwork, fplobjdetect
+    net = fplnetwork.FplNetwork(fplmodels.vgg_like)
+    with pytest.raises(AssertionError, match="network has not been trained"):
+        net.infer(np.zeros((8, 8, 8), np.float32))
+    with pytest.raises(NotImplementedError):
+        net.infer("volume.h5")
+    with pytest.raises(ValueError):
+        fplobjdetect.voxel2obj(np.zeros((4, 4), np.float32), 3, 1.0)
+    with pytest.raises(TypeError):
+        fplobjdetect.voxel2obj(np.zeros((4, 4, 4), np.float64), 3, 1.0)
+    with pytest.raises(NotImplementedError):
+        fplobjdetect.voxel2obj(np.zeros((4, 4, 4), np.float32), 3, 1.0, seg=np.zeros((4, 4, 4)))
+    with pytest.raises(ValueError):
+        fplmodels.vgg_like()[0].set_weights([np.zeros(3, np.float32)])
+    m = fplmodels.vgg_like2()[0]
+    assert m.count_params() == 265777                      # 264 048 conv weights + BN + final bias (SURVEY 8a)
+    assert fplmodels.unet_like2()[1] == (24, 9, 1) and fplmodels.vgg_like()[2] == 102
