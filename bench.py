@@ -48,6 +48,8 @@ def parse():
                          "(bit-identical to the reference grid; default 4 for the VGGs, 1 for the U-Net)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (cfg1 / cfg4 at N=1, cfg3 at N>1, e2e_dropin)")
     return ap.parse_args()
 
 
@@ -60,21 +62,29 @@ def peaks():
     return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
 
 
-def synth_volume_device(size, seed, device):
-    """EM-like uint8 volume generated on the device (not timed): smooth unit-variance noise -> 128+33*n."""
+def synth_volume_planes(size, z_lo, z_hi, seed, device, block=64):
+    """Planes [z_lo, z_hi) of THE synthetic EM-like uint8 volume (not timed), generated on the device.  The volume is
+    defined block by block (64 planes, seed + block index), so any rank can produce exactly its own planes of the one
+    global volume: smooth unit-variance noise -> 128 + 33 * n."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    out = torch.empty((size, size, size), dtype=torch.uint8, device=device)
-    slab = 64
+    out = torch.empty((z_hi - z_lo, size, size), dtype=torch.uint8, device=device)
     k = torch.ones((1, 1, 3, 3, 3), device=device) / 27.0
-    for z0 in range(0, size, slab):
-        z1 = min(size, z0 + slab)
-        a = torch.randn((1, 1, z1 - z0 + 4, size + 4, size + 4), generator=g, device=device)
+    for bi in range(z_lo // block, -(-z_hi // block)):
+        b0, b1 = bi * block, min(size, (bi + 1) * block)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 100003 + bi)
+        a = torch.randn((1, 1, b1 - b0 + 4, size + 4, size + 4), generator=g, device=device)
         a = torch.nn.functional.conv3d(torch.nn.functional.conv3d(a, k), k)
         a = a / a.std()
-        out[z0:z1] = (128 + 33 * a[0, 0, :z1 - z0, :size, :size]).clamp_(0, 255).to(torch.uint8)
+        blk = (128 + 33 * a[0, 0, :b1 - b0, :size, :size]).clamp_(0, 255).to(torch.uint8)
+        lo, hi = max(b0, z_lo), min(b1, z_hi)
+        out[lo - z_lo:hi - z_lo] = blk[lo - b0:hi - b0]
+        del a, blk
     return out
+
+
+def synth_volume_device(size, seed, device):
+    return synth_volume_planes(size, 0, size, seed, device)
 
 
 def seeded_weights(arch, seed=4321):
@@ -171,12 +181,36 @@ def cpu_baseline(arch, n_tiles=24, v2o_edge=320):
                       "on a %d^3 map (%.1f s)" % (n_tiles, infer_sz, out_edge, arch, t_fwd, v2o_edge, t_v2o)}
 
 
+def cpu_cfg1():
+    """BASELINE configs[0] in full, not extrapolated: vgg_like on a 256^3 volume through the reference tiler
+    (27 tiles of 102^3, torch-CPU fp32 restatement of the Keras graph) + voxel2obj (C restatement) on the whole map."""
+    import torch
+    from oracle import models_oracle as M
+    from oracle import voxel2obj_oracle as O
+    from tests.golden import cases
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, rf, infer_sz, _ = M.ARCHS["vgg_like"]
+    img = ((cases.em_volume((256, 256, 256), seed=1234).astype(np.float32) - NORM[0]) / NORM[1]).astype(np.float32)
+    net = M.TorchNet("vgg_like", seeded_weights("vgg_like"), dtype=torch.float32)
+    t0 = time.perf_counter()
+    pred = M.infer_tiler(img, net, (infer_sz,) * 3, (rf[1],) * 3, n_gpu=1)
+    t1 = time.perf_counter()
+    out = O.voxel2obj(pred, DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0), DET["buffer_sz"], DET["thd"], impl="c")
+    t2 = time.perf_counter()
+    return {"workload": "vgg_like inference + voxel2obj on a synthetic 256^3 volume (BASELINE configs[0]), whole "
+                        "workload, not extrapolated", "value": 256 ** 3 / (t2 - t0) / 1e6, "unit": UNIT,
+            "s_infer": t1 - t0, "s_voxel2obj": t2 - t1, "cores": cores, "kind": "port",
+            "detections": int(out["conf"].size)}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement of the reference path (Keras/TF are not installable
     here, so the arithmetic is the oracle port) on the box's host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     vals, last = [], None
     t_all0 = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -189,13 +223,116 @@ def run_reference(args):
     ms = (args.size ** 3 / (v * 1e6)) * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s inference + voxel2obj on a synthetic %d^3 uint8 EM volume "
                                    "(ms_per_step extrapolated from the bounded sample)" % (args.model, args.size)},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
+            "gpu_launches": 0}
+    if not args.no_extras:
+        try:
+            line["cfg1"] = cpu_cfg1()
+        except Exception as e:      # noqa: BLE001 -- an extra leg must never take the main line down
+            line["cfg1"] = {"error": repr(e)[:200]}
+    line["wall_s"] = time.perf_counter() - t_all0
     print(json.dumps(line))
+
+
+def build_net(model, precision, tile_mult):
+    import contextlib
+    from flypylib_b200 import fplmodels, fplnetwork
+    with contextlib.redirect_stdout(sys.stderr):    # model.summary() (fplnetwork.py:58) must not precede the JSON line
+        net = fplnetwork.FplNetwork(getattr(fplmodels, model))
+    net.train_single.set_weights(seeded_weights(model))
+    net.set_precision(precision)
+    net._set_infer()
+    net.tile_multiplier = tile_mult if tile_mult is not None else (1 if model.startswith("unet") else 4)
+    return net
+
+
+def timed(fn, steps, sync):
+    """steps calls of fn between two CUDA events on the current stream, device synchronised on both sides."""
+    import torch
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    r = None
+    for _ in range(steps):
+        r = fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / steps, (time.perf_counter() - w0) * 1e3 / steps, r
+
+
+def leg_cfg1(dev, sync):
+    """BASELINE configs[0] on the GPU: vgg_like + voxel2obj on the 256^3 volume the CPU arm runs in full."""
+    import torch
+    from flypylib_b200 import fplobjdetect
+    from tests.golden import cases
+    net = build_net("vgg_like", "bf16", 4)
+    host = torch.from_numpy(cases.em_volume((256, 256, 256), seed=1234)).pin_memory()
+    vol = torch.empty_like(host, device=dev)
+
+    def step():
+        vol.copy_(host, non_blocking=True)
+        pred = net.infer_device(vol, normalize=NORM)
+        return fplobjdetect.voxel2obj_device(pred, DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0),
+                                             DET["buffer_sz"], DET["thd"])
+    for _ in range(3):
+        step()
+    ms, wall, out = timed(step, 5, sync)
+    ms = max(ms, wall)
+    return {"workload": "vgg_like (bf16) inference + voxel2obj on a synthetic 256^3 volume (BASELINE configs[0]), "
+                        "pinned host uint8 -> H2D -> infer -> voxel2obj -> D2H list", "value": 256 ** 3 / (ms * 1e-3) / 1e6,
+            "unit": UNIT, "ms_per_step": ms, "detections": int(out["conf"].size)}
+
+
+def leg_cfg4(dev, sync, ctx, pk, size=2048):
+    """BASELINE configs[3]: standalone voxel2obj on a precomputed size^3 float32 probability map in HBM."""
+    import torch
+    from flypylib_b200 import fplobjdetect
+    from tools import bench_voxel2obj
+    pm = bench_voxel2obj.synth_map(size, 99, "blobs", dev)
+
+    def step():
+        return fplobjdetect.voxel2obj_device(pm, 27, 5, (0, 0, 0), 30, 0, return_stats=True)
+    for _ in range(2):
+        step()
+    ctx.profile_begin()
+    ms, _, (out, st) = timed(step, 3, sync)
+    prof = ctx.profile_end()
+    achieved = 12.0 * size ** 3 / (ms * 1e-3) / 1e9
+    return {"workload": "voxel2obj(r=27, sigma=5, buffer=30) on a synthetic %d^3 float32 probability map resident in HBM "
+                        "(BASELINE configs[3])" % size, "value": size ** 3 / (ms * 1e-3) / 1e6, "unit": UNIT,
+            "ms_per_step": ms, "detections": int(out["conf"].size), "path": st.get("path"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm"], "algorithmic_bytes_per_voxel": 12},
+            "families": {k: round(v[0] / 3, 3) for k, v in prof.items() if v[2]}}
+
+
+def leg_cfg3(dev, sync, world, rank, size=2048):
+    """BASELINE configs[2]: unet_like2 on ONE synthetic size^3 volume, z-slab sharded at tile-layer granularity with
+    receptive-field halos over the ranks, exact-global voxel2obj, detections on every rank."""
+    import torch
+    from flypylib_b200 import multi_gpu
+    net = build_net("unet_like2", "bf16", 1)
+    plans = multi_gpu.shard_plan(size, int(net.rf_offset[0]), net.slab_granularity(), world)
+    (in0, in1), own = plans[rank]
+    slab = synth_volume_planes(size, in0, in1, 4321, dev)
+
+    def step():
+        return multi_gpu.detect_volume_sharded(net, slab, size, plans, NORM, DET["obj_min_dist"], DET["smoothing_sigma"],
+                                               (0, 0, 0), DET["buffer_sz"], DET["thd"])
+    step()
+    ms, _, out = timed(step, 1, sync)
+    t = torch.tensor([ms], device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+    return {"workload": "unet_like2 (bf16) inference + exact-global voxel2obj on ONE synthetic %d^3 uint8 volume, z-slab "
+                        "sharded over %d GPUs at tile-layer granularity (BASELINE configs[2])" % (size, world),
+            "value": size ** 3 / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world,
+            "detections": int(out["conf"].size), "planes_per_rank": [p[1][1] - p[1][0] for p in plans]}
 
 
 def main():
@@ -204,7 +341,7 @@ def main():
         return run_reference(args)
     import torch
     import torch.distributed as dist
-    from flypylib_b200 import fplmodels, fplnetwork, fplobjdetect, multi_gpu, _lib
+    from flypylib_b200 import fplobjdetect, multi_gpu, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,92 +354,105 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):    # model.summary() (fplnetwork.py:58) must not precede the JSON line
-        net = fplnetwork.FplNetwork(getattr(fplmodels, args.model))
-    net.train_single.set_weights(seeded_weights(args.model))
-    net.set_precision(args.precision)
-    net._set_infer()
-    if args.tile_mult is None:
-        args.tile_mult = 1 if args.model == "unet_like2" else 4
-    net.tile_multiplier = args.tile_mult
+    net = build_net(args.model, args.precision, args.tile_mult)
+    args.tile_mult = net.tile_multiplier
     ctx = _lib.context(local)
-
     size = args.size
-    vol = synth_volume_device(size, 1234 + rank, dev)
-    pred = torch.empty((size, size, size), dtype=torch.float32, device=dev)
-
-    def step():
-        net.infer_device(vol, normalize=NORM, out=pred)
-        out = fplobjdetect.voxel2obj_device(pred, DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0),
-                                            DET["buffer_sz"], DET["thd"])
-        if world > 1:       # the only collective of the path: all-gather of the detection lists (NCCL)
-            rows = torch.from_numpy(np.concatenate([out["locs"], out["conf"][:, None]], 1)).to(dev)
-            parts = multi_gpu.allgather_detections(rows)
-            return sum(int(p.shape[0]) for p in parts)
-        return out["conf"].size
+    det = (DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0), DET["buffer_sz"], DET["thd"])
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- the workload: ONE synthetic size^3 volume.  N = 1: resident on the GPU.  N > 1: z-slab sharded over the
+    # ranks (strong scaling): every rank holds the planes its slab needs (slab + 2*rf_offset halo)
+    if world == 1:
+        vol = synth_volume_device(size, 1234, dev)
+        pred = torch.empty((size, size, size), dtype=torch.float32, device=dev)
+        h2d_bytes = int(vol.numel())
+
+        def step():
+            net.infer_device(vol, normalize=NORM, out=pred)
+            return fplobjdetect.voxel2obj_device(pred, *det)
+    else:
+        plans = multi_gpu.shard_plan(size, int(net.rf_offset[0]), net.slab_granularity(), world)
+        (in0, in1), _own = plans[rank]
+        vol = synth_volume_planes(size, in0, in1, 1234, dev)
+        h2d_bytes = int(sum((p[0][1] - p[0][0]) * size * size for p in plans))
+
+        def step():
+            # forward: slab + receptive-field halo, no communication; detection: exact-global voxel2obj (halo planes
+            # over NCCL P2P, all-reduced radix histograms, per-round all-gather of the selected points) -> the
+            # single-GPU detection list on every rank
+            return multi_gpu.detect_volume_sharded(net, vol, size, plans, NORM, *det)
+
     for _ in range(args.warmup):
-        n_det = step()
+        out = step()
     sync()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count()
     ctx.profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        n_det = step()
-    e1.record()
-    sync()
-    elapsed_ms = e0.elapsed_time(e1)
+    ms_per_step, _, out = timed(step, args.steps, sync)
     prof = ctx.profile_end()
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t)
-    ms_per_step = elapsed_ms / args.steps
-    value = world * size ** 3 / (ms_per_step * 1e-3) / 1e6
+    ms_per_step = max_over_ranks(ms_per_step)
+    n_det = int(out["conf"].size)
+    value = size ** 3 / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end: pinned host uint8 volume -> H2D -> infer -> voxel2obj -> D2H detection list
-    e2e = None
+    e2e = e2e_dropin = None
     if not args.no_e2e:
-        host = torch.empty((size, size, size), dtype=torch.uint8).pin_memory()
+        host = torch.empty(tuple(vol.shape), dtype=torch.uint8).pin_memory()
         host.copy_(vol)
-        dvol = torch.empty_like(vol)
-        d2h = 0
-        net.infer_host(host, normalize=NORM, out=pred, image_dev=dvol)      # untimed: sizes the chunk buffers
-        sync()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        t0.record()
-        for _ in range(args.steps):
-            # public API with a HOST volume: the H2D copy is pipelined behind the convolutions chunk by chunk
-            net.infer_host(host, normalize=NORM, out=pred, image_dev=dvol)
-            out = fplobjdetect.voxel2obj_device(pred, DET["obj_min_dist"], DET["smoothing_sigma"], (0, 0, 0),
-                                                DET["buffer_sz"], DET["thd"])
-            d2h = out["conf"].size * 32
-        t1.record()
-        sync()
-        wall = (time.perf_counter() - w0) * 1e3
-        e_ms = max(t0.elapsed_time(t1), wall) / args.steps
-        if world > 1:
-            t = torch.tensor([e_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t)
-        e2e = {"value": world * size ** 3 / (e_ms * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int(size ** 3), "d2h_bytes_per_step": int(d2h)}
+        if world == 1:
+            dvol = torch.empty_like(vol)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+            def e2e_step():
+                # public API with a HOST volume: the H2D copy is pipelined behind the convolutions chunk by chunk
+                net.infer_host(host, normalize=NORM, out=pred, image_dev=dvol)
+                return fplobjdetect.voxel2obj_device(pred, *det)
+        else:
+            def e2e_step():
+                vol.copy_(host, non_blocking=True)
+                return step()
+        e2e_step()                                          # untimed: sizes the buffers
+        e_ms, e_wall, out_e = timed(e2e_step, args.steps, sync)
+        e_ms = max_over_ranks(max(e_ms, e_wall))
+        e2e = {"value": size ** 3 / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": int(out_e["conf"].size * 32)}
+        del host
+        if world == 1 and not args.no_extras and args.precision == "bf16":
+            # the literal reference call sequence (fplnetwork.py:136, fplobjdetect.py:132): normalised float32 ndarray
+            # -> infer -> float32 ndarray -> voxel2obj(ndarray) -> dict; pageable host memory, 4 B/voxel each way
+            try:
+                del dvol
+                img = ((vol.cpu().numpy().astype(np.float32) - np.float32(NORM[0])) / np.float32(NORM[1]))
+
+                def dropin_step():
+                    p = net.infer(img)
+                    return fplobjdetect.voxel2obj(p, *det)
+                dropin_step()
+                t0 = time.perf_counter()
+                out_d = dropin_step()
+                d_ms = (time.perf_counter() - t0) * 1e3
+                e2e_dropin = {"value": size ** 3 / (d_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": d_ms,
+                              "h2d_bytes_per_step": int(8 * size ** 3), "d2h_bytes_per_step": int(4 * size ** 3 + out_d["conf"].size * 32),
+                              "call": "voxel2obj(FplNetwork.infer(float32 ndarray)) with pageable numpy arrays both ways",
+                              "identical_to_device_path": bool(np.array_equal(out_d["conf"], out["conf"]) and
+                                                               np.array_equal(out_d["locs"], out["locs"]))}
+                del img
+            except Exception as e:      # noqa: BLE001
+                e2e_dropin = {"error": repr(e)[:200]}
+
     pk = peaks()
     ms3, work3, cnt3 = prof["conv3"]
     achieved = (work3 / (ms3 * 1e-3) / 1e12) if ms3 > 0 else 0.0
@@ -315,7 +465,8 @@ def main():
                 # DRAM bytes (read + write) of ONE launch of the dominant kernel in the committed ncu --set full
                 # capture (profiles/, a 512^3 run: its launches are 1/8 of this run's); details alongside
                 "traffic": (traffic or {}).get("dram_bytes_total"), "traffic_detail": traffic,
-                "kernel": "conv_fused12_kernel + conv_umma_kernel<3> (tcgen05 implicit GEMM, 3x3x3 convolutions)",
+                "kernel": "conv_fused12_kernel + conv_umma_kernel<3> (tcgen05 implicit GEMM, 3x3x3 convolutions)"
+                          + (" on rank 0" if world > 1 else ""),
                 "launches": int(cnt3 / max(1, args.steps)), "ms_per_step": ms3 / args.steps,
                 "peak_source": "%s bf16 sustained" % pk["src"]}
     families = {k: {"ms_per_step": v[0] / args.steps, "launch_groups": int(v[2] / max(1, args.steps))}
@@ -323,19 +474,60 @@ def main():
     g_ms, g_work, _ = prof["gauss"]
     if g_ms > 0:
         families["gauss"]["hbm_frac_algorithmic"] = (g_work / (g_ms * 1e-3) / 1e9) / pk["hbm"]
+    if world == 1:
+        how = ("synthetic %d^3 uint8 EM volume resident in HBM, random-init weights, reference tile grid evaluated as "
+               "z-slab tiles of %d reference layers" % (size, args.tile_mult))
+    else:
+        how = ("ONE synthetic %d^3 uint8 EM volume z-slab sharded over %d GPUs (cuts every %d planes, 2*rf_offset halo, no "
+               "forward communication), exact-global voxel2obj: same detection list as N=1 on every rank"
+               % (size, world, net.slab_granularity()))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "%s (%s, tcgen05 implicit GEMM) inference + voxel2obj(r=27, sigma=5, buffer=15) on a "
-                                   "synthetic %d^3 uint8 EM volume per GPU, random-init weights, reference tile grid evaluated as %d^3-tile super-tiles"
-                                   % (args.model, args.precision, size, args.tile_mult),
-                       "l2": "inputs larger than L2 (1 GiB uint8 volume, 4 GiB probability map per step)",
-                       "detections_per_step": int(n_det)},
+            "config": {"workload": "%s (%s, tcgen05 implicit GEMM) inference + voxel2obj(r=27, sigma=5, buffer=15) on a %s"
+                                   % (args.model, args.precision, how),
+                       "l2": "inputs larger than L2 (%.2f GiB uint8 volume, %.1f GiB probability map per GPU and step)"
+                             % (vol.numel() / 2 ** 30, 4.0 * size ** 3 / world / 2 ** 30),
+                       "detections_per_step": n_det},
             "roofline": roofline, "families": families, "gpu_launches": int(launches / max(1, args.steps)),
             "clocks": clocks, "e2e": e2e}
+    if e2e_dropin is not None:
+        line["e2e_dropin"] = e2e_dropin
+
+    # ---- extra legs (never allowed to take the main line down): the other BASELINE configs, driver-visible
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
+    if not args.no_extras and args.model == "vgg_like2" and args.precision == "bf16" and size == 1024:
+        import threading
+        watchdog = threading.Timer(240.0, lambda: (line.setdefault("extras_error", "extra legs timed out"), emit(),
+                                                   os._exit(0)))
+        watchdog.daemon = True
+        watchdog.start()
+        del vol, out
+        if world == 1:
+            del pred
+        net.infer_network.close(); net.train_single.close()
+        torch.cuda.empty_cache()
+        ctx.release_workspace()
+        try:
+            if world == 1:
+                line["cfg1"] = leg_cfg1(dev, sync)
+                ctx.release_workspace(); torch.cuda.empty_cache()
+                line["cfg4"] = leg_cfg4(dev, sync, ctx, pk)
+            else:
+                line["cfg3"] = leg_cfg3(dev, sync, world, rank)
+        except Exception as e:      # noqa: BLE001
+            line["extras_error"] = repr(e)[:300]
+        watchdog.cancel()
+        if world > 1 and "extras_error" in line:        # ranks may be out of step: no further collectives
+            emit()
+            os._exit(0)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.model)
-    print(json.dumps(line))
+    emit()
     if world > 1:
         dist.destroy_process_group()
 

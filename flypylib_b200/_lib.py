@@ -50,6 +50,7 @@ _SIGNATURES = {
     "fpl_ctx_destroy": (ctypes.c_int, [vp]),
     "fpl_ctx_workspace_bytes": (ctypes.c_int, [vp, c_i64p]),
     "fpl_ctx_launch_count": (ctypes.c_int, [vp, c_i64p]),
+    "fpl_ctx_release_workspace": (ctypes.c_int, [vp]),
     "fpl_ctx_profile_begin": (ctypes.c_int, [vp]),
     "fpl_ctx_profile_end": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
     "fpl_v2o_smooth": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -89,6 +90,9 @@ _SIGNATURES = {
     "fpl_net_infer_volume": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, vp, vp]),
+    "fpl_net_infer_slab": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, vp, vp]),
 }
 
 
@@ -142,6 +146,9 @@ class Context:
         v = ctypes.c_int64()
         check(lib().fpl_ctx_workspace_bytes(self.handle, ctypes.byref(v)))
         return v.value
+
+    def release_workspace(self):
+        check(lib().fpl_ctx_release_workspace(self.handle), "fpl_ctx_release_workspace")
 
     def profile_begin(self):
         check(lib().fpl_ctx_profile_begin(self.handle), "fpl_ctx_profile_begin")

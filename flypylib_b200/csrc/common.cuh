@@ -59,6 +59,8 @@ namespace fpl {
 enum ProfTag { PROF_CONV3 = 0, PROF_CONV1 = 1, PROF_FIRST = 2, PROF_NETAUX = 3, PROF_GAUSS = 4,
                PROF_SELECT = 5, PROF_NMS = 6, PROF_TILER = 7, PROF_NTAGS = 8 };
 struct ProfRec { cudaEvent_t a, b; int tag; double work; };
+// one activation buffer of the tcgen05 forward pass (conv_umma.cu: pool_take)
+struct PoolBuf { void *p; size_t cap; bool busy; };
 }  // namespace fpl
 
 struct fpl_ctx {
@@ -71,6 +73,7 @@ struct fpl_ctx {
     bool profiling = false;
     std::vector<fpl::ProfRec> prof;
     std::vector<cudaEvent_t> prof_free;
+    std::vector<fpl::PoolBuf> act_pool;   // activation buffers of the networks of this context (this device)
 };
 
 namespace fpl {

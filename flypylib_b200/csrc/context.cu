@@ -93,6 +93,8 @@ int fpl_ctx_destroy(fpl_ctx *ctx) {
     if (!ctx) return FPL_OK;
     cudaSetDevice(ctx->device);
     ctx->arena.release();
+    for (auto &b : ctx->act_pool) cudaFree(b.p);
+    ctx->act_pool.clear();
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -103,6 +105,16 @@ int fpl_ctx_destroy(fpl_ctx *ctx) {
 int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes) {
     FPL_REQUIRE(ctx && bytes, "fpl_ctx_workspace_bytes: NULL argument");
     *bytes = (int64_t)ctx->arena.cap;
+    return FPL_OK;
+}
+
+int fpl_ctx_release_workspace(fpl_ctx *ctx) {
+    FPL_REQUIRE(ctx, "fpl_ctx_release_workspace: NULL ctx");
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    FPL_CUDA_CHECK(cudaDeviceSynchronize());
+    ctx->arena.release();
+    for (auto &b : ctx->act_pool) cudaFree(b.p);
+    ctx->act_pool.clear();
     return FPL_OK;
 }
 

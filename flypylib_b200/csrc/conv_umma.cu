@@ -1874,10 +1874,8 @@ static int dispatch_umma(const ConvPlan &plan, int ks, int grid, size_t smem, cu
     return FPL_OK;
 }
 
-// activation buffer pool (defined below)
-struct PoolBuf { void *p; size_t cap; bool busy; };
-static std::vector<PoolBuf> g_bufs;
-static int pool_take(size_t bytes, cudaStream_t st);
+// activation buffer pool: lives in the context (one pool per device, fpl_ctx::act_pool); defined below
+static int pool_take(fpl_ctx *ctx, size_t bytes, cudaStream_t st);
 
 static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat16 *in, __nv_bfloat16 *out,
                             int n_tiles, int din, int din_z, int relu, int pool, cudaStream_t st) {
@@ -1905,9 +1903,9 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
     int partial_buf = -1;
     if (plan.k_split > 1) {
         FPL_REQUIRE(!pool, "conv_umma: pooled epilogue needs an unsplit plan");
-        partial_buf = pool_take((size_t)n_tiles * dout_z * dout * dout * c.cout * sizeof(float), st);
+        partial_buf = pool_take(ctx, (size_t)n_tiles * dout_z * dout * dout * c.cout * sizeof(float), st);
         if (partial_buf < 0) return FPL_ENOMEM;
-        a.partial = (float *)g_bufs[partial_buf].p;
+        a.partial = (float *)ctx->act_pool[partial_buf].p;
     }
     a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.din_z = din_z; a.dout_z = dout_z;
     a.cin_atoms_total = cin_atoms; a.nsub = plan.nsub; a.cout = plan.n; a.cout_total = c.cout; a.ring = plan.ring;
@@ -1942,7 +1940,7 @@ static int launch_conv_umma(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
         FPL_TRY(dispatch_umma(plan, ks, grid, smem, st, tmap, a));
         FPL_LAUNCH_CHECK(ctx);
     }
-    if (partial_buf >= 0) g_bufs[partial_buf].busy = false;     // stream-ordered: later launches may reuse it
+    if (partial_buf >= 0) ctx->act_pool[partial_buf].busy = false;     // stream-ordered: later launches may reuse it
     return FPL_OK;
 }
 
@@ -1963,8 +1961,11 @@ static int launch_conv_direct(fpl_ctx *ctx, const ConvParams &c, const __nv_bflo
     return FPL_OK;
 }
 
-// activation buffer pool (device): exact-size buffers, best fit, grow-only; one process = one GPU
-static int pool_take(size_t bytes, cudaStream_t st) {
+// activation buffer pool (device): exact-size buffers, best fit, grow-only.  It belongs to the context, i.e. to
+// one device; a context runs its networks on ONE stream at a time (buffers are recycled in stream order, see
+// include/fpl_b200.h "Conventions").
+static int pool_take(fpl_ctx *ctx, size_t bytes, cudaStream_t st) {
+    std::vector<PoolBuf> &g_bufs = ctx->act_pool;
     int best = -1;
     for (size_t i = 0; i < g_bufs.size(); ++i)
         if (!g_bufs[i].busy && g_bufs[i].cap >= bytes && (best < 0 || g_bufs[i].cap < g_bufs[best].cap)) best = (int)i;
@@ -2222,10 +2223,10 @@ static int launch_conv_hilo(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return FPL_ECUDA; }
-    const int pbuf = pool_take((size_t)n_tiles * dout * dout * dout * c.cout * sizeof(float), st);
+    const int pbuf = pool_take(ctx, (size_t)n_tiles * dout * dout * dout * c.cout * sizeof(float), st);
     if (pbuf < 0) return FPL_ENOMEM;
     ConvArgs a;
-    a.out = out; a.bias = c.d_bias; a.partial = (float *)g_bufs[pbuf].p;
+    a.out = out; a.bias = c.d_bias; a.partial = (float *)ctx->act_pool[pbuf].p;
     a.w_bytes = (uint32_t)(c.packed_bytes / n_chunks);
     a.n_tiles = n_tiles; a.din = din; a.dout = dout; a.din_z = din; a.dout_z = dout;
     a.cin_atoms_total = atoms_total; a.nsub = plan.nsub; a.cout = c.cout; a.cout_total = c.cout; a.cout_off = 0; a.ring = plan.ring;
@@ -2263,12 +2264,13 @@ static int launch_conv_hilo(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
             }
             FPL_LAUNCH_CHECK(ctx);
         }
-    g_bufs[pbuf].busy = false;
+    ctx->act_pool[pbuf].busy = false;
     return FPL_OK;
 }
 
 static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
     fpl_ctx *ctx = net->ctx;
+    std::vector<PoolBuf> &g_bufs = ctx->act_pool;
     for (PoolBuf &b : g_bufs) b.busy = false;
     auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
     int cur = -1, skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
@@ -2280,7 +2282,7 @@ static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_
         if (o.kind == OP_CONV) {
             const ConvParams &cp = net->convs[o.conv_index];
             const int dout = d - (o.k - 1);
-            const int nb = pool_take((size_t)n_tiles * dout * dout * dout * 2 * cp.cout * 2, st);
+            const int nb = pool_take(ctx, (size_t)n_tiles * dout * dout * dout * 2 * cp.cout * 2, st);
             if (nb < 0) return FPL_ENOMEM;
             __nv_bfloat16 *dst = (__nv_bfloat16 *)g_bufs[nb].p;
             if (cp.cin == 1) {
@@ -2298,7 +2300,7 @@ static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_
             if (!cur_is_skip) release(cur);
             cur = nb; cur_is_skip = false; d = dout; c = o.cout;
         } else if (o.kind == OP_POOL) {
-            const int nb = pool_take((size_t)n_tiles * (d / 2) * (d / 2) * (d / 2) * 2 * c * 2, st);
+            const int nb = pool_take(ctx, (size_t)n_tiles * (d / 2) * (d / 2) * (d / 2) * 2 * c * 2, st);
             if (nb < 0) return FPL_ENOMEM;
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * 2 * c * 2.0 * d * d * d * 1.125);
             pool_hilo_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, (__nv_bfloat16 *)g_bufs[nb].p, n_tiles, c / 8, d);
@@ -2308,7 +2310,7 @@ static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_
         } else if (o.kind == OP_SAVE) {
             skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_c[o.slot] = c; cur_is_skip = true;
         } else if (o.kind == OP_UPCAT) {
-            const int nb = pool_take((size_t)n_tiles * 8 * d * d * d * 2 * (c + skip_c[o.slot]) * 2, st);
+            const int nb = pool_take(ctx, (size_t)n_tiles * 8 * d * d * d * 2 * (c + skip_c[o.slot]) * 2, st);
             if (nb < 0) return FPL_ENOMEM;
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * 2 * (c + skip_c[o.slot]) * 2.0 * 8.0 * d * d * d * 2);
             upcat_hilo_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, d, c / 8, (const uint4 *)g_bufs[skip_buf[o.slot]].p,
@@ -2353,6 +2355,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         return FPL_ESTATE;
     }
     if (in_z <= 0) in_z = in_sz;
+    std::vector<PoolBuf> &g_bufs = ctx->act_pool;
     for (PoolBuf &b : g_bufs) b.busy = false;
     auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
     int cur = -1;                 // pool buffer holding the current activation (-1: the fp32 input tiles)
@@ -2376,7 +2379,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                                   dout % 2 == 0 && dout_z % 2 == 0;
                 const size_t out_bytes = pool ? (size_t)n_tiles * (dout_z / 2) * (dout / 2) * (dout / 2) * c2.cout * 2
                                               : (size_t)n_tiles * dout_z * dout * dout * c2.cout * 2;
-                const int nb = pool_take(out_bytes, st);
+                const int nb = pool_take(ctx, out_bytes, st);
                 if (nb < 0) return FPL_ENOMEM;
                 FusedArgs fa;
                 fa.in = d_tiles; fa.w1_packed = (const __nv_bfloat16 *)c1.d_packed;
@@ -2428,7 +2431,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                                    plan_conv(cp).n_split == 1;
             const size_t out_bytes = fuse_pool ? (size_t)n_tiles * (dout_z / 2) * (dout / 2) * (dout / 2) * cp.cout * 2
                                                : (size_t)n_tiles * dout_z * dout * dout * cp.cout * 2;
-            const int nb = pool_take(out_bytes, st);
+            const int nb = pool_take(ctx, out_bytes, st);
             if (nb < 0) return FPL_ENOMEM;
             __nv_bfloat16 *dst = (__nv_bfloat16 *)g_bufs[nb].p;
             if (cp.cin == 1) {
@@ -2481,7 +2484,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             if (fuse_pool) { d /= 2; dzv /= 2; skip_next_pool = true; }
         } else if (o.kind == OP_POOL) {
             if (skip_next_pool) { skip_next_pool = false; continue; }
-            const int nb = pool_take((size_t)n_tiles * (dzv / 2) * (d / 2) * (d / 2) * c * 2, st);
+            const int nb = pool_take(ctx, (size_t)n_tiles * (dzv / 2) * (d / 2) * (d / 2) * c * 2, st);
             if (nb < 0) return FPL_ENOMEM;
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * c * 2.0 * dzv * d * d * 1.125);
             pool_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, (uint4 *)g_bufs[nb].p,
@@ -2495,7 +2498,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             cur_is_skip = true;
         } else if (o.kind == OP_UPCAT) {
             FPL_REQUIRE(dzv == d, "forward_umma: the U-Net runs on cubic tiles");
-            const int nb = pool_take((size_t)n_tiles * 8 * d * d * d * (c + skip_c[o.slot]) * 2, st);
+            const int nb = pool_take(ctx, (size_t)n_tiles * 8 * d * d * d * (c + skip_c[o.slot]) * 2, st);
             if (nb < 0) return FPL_ENOMEM;
             ProfScope prof(ctx, st, PROF_NETAUX, (double)n_tiles * (c + skip_c[o.slot]) * 2.0 * 8.0 * d * d * d * 2);
             upcat_blocked_kernel<<<stream_blocks, 256, 0, st>>>((const uint4 *)g_bufs[cur].p, d, c / 8,

@@ -1456,8 +1456,12 @@ __global__ void fast_reset_kernel(Counters *cnt) {
 __global__ void select_set_prefix_kernel(SelectState *s, unsigned prefix, unsigned mask) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { s->prefix = prefix; s->prefix_mask = mask; }
 }
-__global__ void hist_add_kernel(unsigned long long *dst, const unsigned long long *src, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+__global__ void hist_fold_kernel(const SelectState *s, unsigned long long *dst) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < 2048; b += gridDim.x * blockDim.x) {
+        unsigned long long c = 0ULL;
+        for (int sl = 0; sl < kHistSlots; ++sl) c += s->hist[sl][b];
+        dst[b] = c;
+    }
 }
 __global__ void idx_to_zyx_kernel(const unsigned long long *idx, long long n, Dims d, long long *zyx) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1823,14 +1827,8 @@ int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefi
         select_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>(d_v, n, s, shift, bins, d_nan != nullptr);
         FPL_LAUNCH_CHECK(ctx);
     }
-    // fold the partial histograms: reuse select_copy_kernel's summation into slot 0 of a second state
-    FPL_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, 2048 * sizeof(uint64_t), st));
-    for (int sl = 0; sl < kHistSlots; ++sl) {
-        // 16 tiny adds; d_hist += slot
-        const unsigned long long *src = &s->hist[sl][0];
-        hist_add_kernel<<<8, 256, 0, st>>>((unsigned long long *)d_hist, src, 2048);
-        FPL_LAUNCH_CHECK(ctx);
-    }
+    hist_fold_kernel<<<8, 256, 0, st>>>(s, (unsigned long long *)d_hist);      // sum of the partial histograms
+    FPL_LAUNCH_CHECK(ctx);
     if (d_nan) FPL_CUDA_CHECK(cudaMemcpyAsync(d_nan, &s->nan_count, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     FPL_CUDA_CHECK(cudaStreamSynchronize(st));
     return FPL_OK;

@@ -319,9 +319,11 @@ int fpl_net_forward_tiles(fpl_net *net, const float *d_tiles, int32_t n_tiles, i
     return forward_umma(net, d_tiles, n_tiles, in_sz, d_out, st);
 }
 
-int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
-                         float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
-                         int32_t z_tile_end, float *d_pred, void *stream) {
+// clear_lo / clear_hi: whether the rf_offset-wide border planes at the low / high z end of d_pred belong to this
+// call (whole volume: both; a z-slab of a larger volume: only where the slab touches the volume's end)
+static int infer_volume_impl(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
+                             float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
+                             int32_t z_tile_end, float *d_pred, bool clear_lo, bool clear_hi, void *stream) {
     FPL_REQUIRE(net && d_image && d_pred, "fpl_net_infer_volume: NULL argument");
     if (net->precision < 0) { fpl::set_error("network has not been trained"); return FPL_ESTATE; }
     FPL_REQUIRE(Z > 0 && Y > 0 && X > 0, "fpl_net_infer_volume: empty image");
@@ -344,9 +346,10 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     int ze = (z_tile_end < 0 || z_tile_end > g.nz) ? g.nz : z_tile_end;
     // only this rank's rows of pred are cleared/written when a z-range is given
     {
-        long long z0 = (zb == 0) ? 0 : (long long)zb * g.out_sz + off;
-        long long z1 = (ze == g.nz) ? Z : (long long)ze * g.out_sz + off;
+        long long z0 = (zb == 0) ? (clear_lo ? 0 : off) : (long long)zb * g.out_sz + off;
+        long long z1 = (ze == g.nz) ? (clear_hi ? Z : Z - off) : (long long)ze * g.out_sz + off;
         if (z1 > Z) z1 = Z;
+        if (z0 > Z) z0 = Z;
         if (z1 > z0)
             FPL_CUDA_CHECK(cudaMemsetAsync(d_pred + z0 * Y * X, 0, sizeof(float) * (size_t)(z1 - z0) * Y * X, st));
     }
@@ -487,6 +490,30 @@ int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, flo
     if (rc != FPL_OK) return rc;
     FPL_CUDA_CHECK(cudaGetLastError());
     return FPL_OK;
+}
+
+int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
+                         float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
+                         int32_t z_tile_end, float *d_pred, void *stream) {
+    return infer_volume_impl(net, d_image, image_is_u8, norm_mean, norm_std, Z, Y, X, z_tile_begin, z_tile_end,
+                             d_pred, true, true, stream);
+}
+
+int fpl_net_infer_slab(fpl_net *net, const void *d_image_slab, int image_is_u8, float norm_mean, float norm_std,
+                       int64_t Z, int64_t z0, int64_t z1, int64_t Y, int64_t X, float *d_pred_slab, void *stream) {
+    FPL_REQUIRE(net && d_image_slab && d_pred_slab, "fpl_net_infer_slab: NULL argument");
+    FPL_REQUIRE(z0 >= 0 && z1 > z0 && z1 <= Z, "fpl_net_infer_slab: bad plane range [%lld,%lld) of %lld",
+                (long long)z0, (long long)z1, (long long)Z);
+    const int off = net->info.rf_offset, out = net->info.infer_sz - 2 * off;
+    // cut granularity: the VGG nets are shift-equivariant by rf_stride, so any multiple of it reproduces the
+    // whole-volume values; the U-Net output depends on the tile phase, so cuts must lie on the reference grid
+    const int gran = net->info.rf_stride != 1 ? net->info.rf_stride : out;
+    FPL_REQUIRE(z0 % gran == 0, "fpl_net_infer_slab: first plane %lld is not a multiple of %d", (long long)z0, gran);
+    FPL_REQUIRE(z1 == Z || (z1 - z0 > 2 * off && (z1 - z0 - 2 * off) % gran == 0),
+                "fpl_net_infer_slab: an inner slab must hold 2*rf_offset + k*%d planes (got %lld)", gran,
+                (long long)(z1 - z0));
+    return infer_volume_impl(net, d_image_slab, image_is_u8, norm_mean, norm_std, z1 - z0, Y, X, 0, -1, d_pred_slab,
+                             z0 == 0, z1 == Z, stream);
 }
 
 }  // extern "C"

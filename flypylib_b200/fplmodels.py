@@ -62,6 +62,14 @@ def lb1l1err(y_true, y_pred):
     raise NotImplementedError("training metrics are outside the B200 inference hot path")
 
 
+def _rank():
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except ImportError:
+        return 0
+
+
 class Model(object):
     """Handle on one network: weights on the host in Keras order + a lazily created device net."""
 
@@ -119,6 +127,16 @@ class Model(object):
             new.append(w)
         self._weights = new
         self._net_dirty = True
+        if getattr(self, "_trainer", None) is not None:      # weights set from outside: the trainer's flat copy
+            self._trainer.load_from_model()                  # (and its Adam moments) would be stale
+
+    def _set_weights_from_trainer(self, weights):
+        """Trainer -> model write-back at the end of an epoch: same as set_weights, but the trainer stays as it is."""
+        tr, self._trainer = getattr(self, "_trainer", None), None
+        try:
+            self.set_weights(weights)
+        finally:
+            self._trainer = tr
 
     def count_params(self):
         return int(sum(int(np.prod(s)) for s in self.weight_shapes()))
@@ -231,8 +249,9 @@ class Model(object):
             tr.sync_to_model()
             if verbose:
                 print("Epoch %d/%d - loss: %.4f - acc: %.4f" % (epoch + 1, epochs, logs["loss"], logs["acc"]))
-            for cb in (callbacks or []):
-                cb.on_epoch_end(epoch, logs)
+            if _rank() == 0:                # one log / checkpoint writer (the replicas hold identical weights)
+                for cb in (callbacks or []):
+                    cb.on_epoch_end(epoch, logs)
         return history
 
     def save(self, path):

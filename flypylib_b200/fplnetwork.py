@@ -112,7 +112,7 @@ class FplNetwork:
     def __getstate__(self):
         keep = dict(self.__dict__)
         keep['_precision'] = self.train_single.precision if self.train_single is not None else None
-        for k in ('train_network', 'train_single', 'infer_network', '_copy_stream', '_chunk_pred'):
+        for k in ('train_network', 'train_single', 'infer_network', '_copy_stream'):
             keep[k] = None
         return keep
 
@@ -164,50 +164,93 @@ class FplNetwork:
         self.train_network.compile(**self.compile_args)
 
     def make_infer_parallel(self, n_gpu):
-        """fplnetwork.py:130-134.  The reference replicates the graph on n_gpu towers inside one
-        process; here n_gpu is the number of ranks (one process per GPU, torch.distributed) over which
-        ``infer`` shards the tile layers -- see multi_gpu.infer_volume_sharded."""
+        """fplnetwork.py:130-134.  The reference replicates the graph on n_gpu towers inside one process
+        (flypylib/multi_gpu.py:20-61) and feeds one tile per tower and predict step; here n_gpu is the number
+        of ranks (one process per GPU, torch.distributed) over which ``infer`` shards the volume as z-slabs
+        (``multi_gpu.shard_plan`` + ``infer_slab_device``).  With n_gpu > 1 ``torch.distributed`` must be
+        initialised with that world size before ``infer`` is called."""
         self._set_infer()
         self.n_gpu = n_gpu
 
     # ------------------------------------------------------------------------------------------
+    def _check_built(self):
+        assert self.infer_network is not None, 'network has not been trained'
+        assert self.infer_network.input_shape[1:-1] == self.infer_sz, \
+            'network input shape does not match expected infer_sz'
+
+    def slab_granularity(self):
+        """Plane granularity of z cuts that keep ``infer`` bit-identical to the whole-volume call: rf_stride for
+        the VGG builders (shift-equivariant), the reference tile pitch for the U-Nets (tile phase matters)."""
+        stride = int(self.rf_stride[0])
+        return stride if stride != 1 else int(self.infer_sz[0]) - 2 * int(self.rf_offset[0])
+
+    def infer_slab_device(self, image_slab, Z, z0, normalize=None, pred=None, pred_z0=None):
+        """Planes [z0, z0 + len(image_slab)) of a (Z,Y,X) volume as one slab (fpl_net_infer_slab): writes the
+        prediction planes [z0+off, z1-off) -- plus the zero border planes when the slab touches an end of the
+        volume -- into ``pred``, a CUDA float32 tensor whose plane 0 is plane ``pred_z0`` of the prediction volume
+        (default: a fresh tensor covering exactly the written planes).  Returns (pred, first, last) with
+        [first,last) the written plane range."""
+        import torch
+        self._check_built()
+        if image_slab.dim() != 3:
+            raise ValueError("image slab must be 3-D (z,Y,X)")
+        is_u8 = image_slab.dtype == torch.uint8
+        if not is_u8 and image_slab.dtype != torch.float32:
+            image_slab = image_slab.float()
+        if is_u8 and normalize is None:
+            raise ValueError("uint8 input needs normalize=(mean, std)")
+        image_slab = image_slab.contiguous()
+        zs, Y, X = (int(v) for v in image_slab.shape)
+        Z, z0 = int(Z), int(z0)
+        z1 = z0 + zs
+        off = int(self.rf_offset[0])
+        first = 0 if z0 == 0 else z0 + off
+        last = Z if z1 == Z else z1 - off
+        if last < first:
+            last = first
+        if pred is None:
+            pred = torch.empty((last - first, Y, X), dtype=torch.float32, device=image_slab.device)
+            pred_z0 = first
+        if pred_z0 is None:
+            pred_z0 = 0
+        if not (pred.is_contiguous() and pred.dtype == torch.float32 and tuple(pred.shape[1:]) == (Y, X)):
+            raise ValueError("pred must be a contiguous float32 (planes,Y,X) tensor")
+        if first < pred_z0 or last > pred_z0 + int(pred.shape[0]):
+            raise ValueError("pred does not cover the written planes [%d,%d)" % (first, last))
+        dev = image_slab.device.index
+        net = self.infer_network.device_net(dev)
+        lib = _lib.lib()
+        _lib.check(lib.fpl_net_set_tile_multiplier(net, int(self.tile_multiplier)), "fpl_net_set_tile_multiplier")
+        mean, std = (float(normalize[0]), float(normalize[1])) if normalize is not None else (0.0, 1.0)
+        # address of plane z0 of the prediction volume inside `pred` (only [first,last) is touched)
+        p_slab = pred.data_ptr() + (z0 - int(pred_z0)) * Y * X * 4
+        with torch.cuda.device(dev):
+            _lib.check(lib.fpl_net_infer_slab(net, image_slab.data_ptr(), 1 if is_u8 else 0, mean, std, Z, z0, z1,
+                                              Y, X, ctypes.c_void_p(p_slab), _lib.current_stream_ptr(dev)),
+                       "fpl_net_infer_slab")
+        return pred, first, last
+
     def infer_device(self, image_dev, normalize=None, out=None):
         """``infer`` on a CUDA tensor (Z,Y,X): float32 (already normalised) or uint8 with
         ``normalize=(mean, std)`` applied on the fly.  Returns a CUDA float32 tensor."""
         import torch
-        assert self.infer_network is not None, 'network has not been trained'
-        assert self.infer_network.input_shape[1:-1] == self.infer_sz, \
-            'network input shape does not match expected infer_sz'
+        self._check_built()
         if image_dev.dim() != 3:
             raise ValueError("image must be 3-D (Z,Y,X)")
-        is_u8 = image_dev.dtype == torch.uint8
-        if not is_u8 and image_dev.dtype != torch.float32:
-            image_dev = image_dev.float()
-        if is_u8 and normalize is None:
-            raise ValueError("uint8 input needs normalize=(mean, std)")
-        image_dev = image_dev.contiguous()
-        dev = image_dev.device.index
-        net = self.infer_network.device_net(dev)
-        lib = _lib.lib()
-        _lib.check(lib.fpl_net_set_tile_multiplier(net, int(self.tile_multiplier)), "fpl_net_set_tile_multiplier")
         Z, Y, X = (int(s) for s in image_dev.shape)
         pred = out if out is not None else torch.empty((Z, Y, X), dtype=torch.float32, device=image_dev.device)
-        mean, std = (float(normalize[0]), float(normalize[1])) if normalize is not None else (0.0, 1.0)
-        with torch.cuda.device(dev):
-            _lib.check(lib.fpl_net_infer_volume(net, image_dev.data_ptr(), 1 if is_u8 else 0, mean, std,
-                                                Z, Y, X, 0, -1, pred.data_ptr(),
-                                                _lib.current_stream_ptr(dev)), "fpl_net_infer_volume")
+        self.infer_slab_device(image_dev, Z, 0, normalize=normalize, pred=pred, pred_z0=0)
         return pred
 
     def infer_host(self, image_host, normalize=None, out=None, image_dev=None, chunk_layers=4):
         """``infer`` on a HOST tensor (pinned memory for true overlap) with the host->device copy pipelined
         behind the computation: the volume is cut into chunks of ``chunk_layers`` reference tile layers in z;
-        chunk c+1 is copied on a side stream while chunk c runs.  Every chunk is an independent sub-volume whose
-        first plane lies on the reference tile grid, so its interior equals the corresponding planes of the
-        whole-volume ``infer`` (same tiles, same zero padding at the far edge).  Returns a CUDA float32 tensor.
-        ``image_dev`` (optional) receives the device copy of the volume."""
+        chunk c+1 is copied on a side stream while chunk c runs.  Every chunk is a slab whose first plane lies
+        on the reference tile grid (``infer_slab_device``), so it writes exactly the planes of the whole-volume
+        ``infer`` straight into the result -- no staging buffer, no extra device copies.  Returns a CUDA float32
+        tensor.  ``image_dev`` (optional) receives the device copy of the volume."""
         import torch
-        assert self.infer_network is not None, 'network has not been trained'
+        self._check_built()
         if image_host.dim() != 3:
             raise ValueError("image must be 3-D (Z,Y,X)")
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -234,37 +277,71 @@ class FplNetwork:
                     image_dev[copied:in1].copy_(image_host[copied:in1], non_blocking=True)
                     copied = in1
                 ev = side.record_event()
-            chunks.append((k0, k1, in0, in1, ev))
-        pred[:off].zero_()
-        pred[Z - off:].zero_()
-        for k0, k1, in0, in1, ev in chunks:
+            chunks.append((in0, in1, ev))
+        for in0, in1, ev in chunks:
             main.wait_event(ev)
-            tmp = self.infer_device(image_dev[in0:in1], normalize=normalize,
-                                    out=self._chunk_buffer(in1 - in0, Y, X, dev))
-            lo, hi = in0 + off, (Z - off if k1 == n_layers else k1 * out_sz + off)
-            pred[lo:hi].copy_(tmp[off:off + (hi - lo)])
+            self.infer_slab_device(image_dev[in0:in1], Z, in0, normalize=normalize, pred=pred, pred_z0=0)
         return pred
 
-    def _chunk_buffer(self, z, Y, X, dev):
-        import torch
-        buf = getattr(self, "_chunk_pred", None)
-        if buf is None or buf.numel() < z * Y * X or buf.device != dev:
-            buf = self._chunk_pred = torch.empty(z * Y * X, dtype=torch.float32, device=dev)
-        return buf[:z * Y * X].view(z, Y, X)
-
     def infer(self, image):
-        """fplnetwork.py:136-189: probability map (float32, image.shape) of a 3-D image."""
+        """fplnetwork.py:136-189: probability map (float32, image.shape) of a 3-D image.
+
+        With ``make_infer_parallel(n_gpu > 1)`` and torch.distributed initialised (one process per GPU) every
+        rank evaluates its z-slab and the prediction planes are all-gathered, so every rank returns the whole map
+        -- bit-identical to the single-GPU result."""
         import torch
         if isinstance(image, str):
             raise NotImplementedError("h5 file input needs h5py, which is not available; pass an array")
-        assert self.infer_network is not None, \
-            'network has not been trained'
-        assert self.infer_network.input_shape[1:-1] == self.infer_sz, \
-            'network input shape does not match expected infer_sz'
+        self._check_built()
+        world = self._world()
         if isinstance(image, torch.Tensor):
             dev = image if image.is_cuda else image.cuda()
-            return self.infer_device(dev)
+            return self.infer_device(dev) if world == 1 else self._infer_gathered(dev)
         image = np.asarray(image)
         _lib.context()
+        if world > 1:
+            return self._infer_gathered(image).cpu().numpy()
         dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).cuda()
         return self.infer_device(dev).cpu().numpy()
+
+    def _world(self):
+        if self.n_gpu <= 1:
+            return 1
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("make_infer_parallel(%d): initialise torch.distributed (one process per GPU) "
+                               "before calling infer" % self.n_gpu)
+        if dist.get_world_size() != self.n_gpu:
+            raise RuntimeError("make_infer_parallel(%d) but the process group has %d ranks"
+                               % (self.n_gpu, dist.get_world_size()))
+        return self.n_gpu
+
+    def _infer_gathered(self, image):
+        """Sharded infer + all-gather of the prediction planes (every rank passes the same whole image)."""
+        import torch
+        import torch.distributed as dist
+        from . import multi_gpu
+        world, rank = dist.get_world_size(), dist.get_rank()
+        Z, Y, X = (int(v) for v in image.shape)
+        plans = multi_gpu.shard_plan(Z, int(self.rf_offset[0]), self.slab_granularity(), world)
+        (in0, in1), (own0, own1) = plans[rank]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if isinstance(image, torch.Tensor):
+            slab = image[in0:in1].to(dev)
+            if slab.dtype != torch.float32:
+                slab = slab.float()
+        else:
+            slab = torch.from_numpy(np.ascontiguousarray(image[in0:in1], dtype=np.float32)).to(dev)
+        own = torch.zeros((0, Y, X), dtype=torch.float32, device=dev)
+        if in1 > in0:
+            own, first, last = self.infer_slab_device(slab, Z, in0)
+            assert (first, last) == (own0, own1), ((first, last), (own0, own1))
+        width = max(p[1][1] - p[1][0] for p in plans)
+        pad = torch.zeros((max(width, 1), Y, X), dtype=torch.float32, device=dev)
+        pad[:own.shape[0]] = own
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        pred = torch.empty((Z, Y, X), dtype=torch.float32, device=dev)
+        for part, (_, (o0, o1)) in zip(parts, plans):
+            pred[o0:o1] = part[:o1 - o0]
+        return pred

@@ -360,8 +360,10 @@ def fri_postprocess(pred, working_dir, obj_min_dist, smoothing_sigma, substack, 
         out = voxel2obj(pred, obj_min_dist, smoothing_sigma,
                         (substack.x - buffer_sz, substack.y - buffer_sz, substack.z - buffer_sz),
                         buffer_sz, thd)
-    with open(ff, 'wb') as f_out:
+    tmp = '%s.tmp.%d' % (ff, os.getpid())          # atomic: a resuming / neighbouring rank never reads half a pickle
+    with open(tmp, 'wb') as f_out:
         pickle.dump(out, f_out)
+    os.replace(tmp, ff)
     return ff
 
 
@@ -399,12 +401,21 @@ def full_roi_inference(data_source, dvid_uuid, dvid_roi, network, thd, working_d
     except ImportError:
         dist = None
 
+    # which substacks are already on disk is decided ONCE, by rank 0, before any rank writes: ranks that scanned on
+    # their own could see each other's fresh pickles, deal the rest differently and leave substacks unprocessed
+    done_idx = None
+    if rank == 0:
+        done_idx = [si for si, rr in enumerate(roi[0]) if os.path.isfile(fri_filename(working_dir, rr))]
+    if world > 1:
+        box = [done_idx]
+        dist.broadcast_object_list(box, src=0)
+        done_idx = box[0]
+    done_set = set(done_idx)
     results = {}                    # substack index -> (locs, conf)
     pending = []
     for si, rr in enumerate(roi[0]):
-        ff = fri_filename(working_dir, rr)
-        if os.path.isfile(ff):
-            with open(ff, 'rb') as f_in:
+        if si in done_set:
+            with open(fri_filename(working_dir, rr), 'rb') as f_in:
                 obj = pickle.load(f_in)
             results[si] = (obj['locs'], obj['conf'])
             continue
@@ -443,6 +454,9 @@ def full_roi_inference(data_source, dvid_uuid, dvid_roi, network, thd, working_d
             for si, l, c in part:
                 results[si] = (l, c)
 
+    missing = [si for si in range(len(roi[0])) if si not in results]
+    if missing:
+        raise RuntimeError("full_roi_inference: substacks %s were not processed" % missing[:8])
     order = sorted(results)
     locs = np.concatenate([np.asarray(results[si][0]).reshape(-1, 3) for si in order]) if order else np.zeros((0, 3))
     conf = np.concatenate([np.asarray(results[si][1]).reshape(-1) for si in order]) if order else np.zeros(0)

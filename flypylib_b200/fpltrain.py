@@ -34,10 +34,28 @@ class Trainer(object):
         flat = np.concatenate([w.ravel() for w in model.get_weights()]).astype(np.float32)
         assert flat.size == n_p.value, (flat.size, n_p.value)
         self.params = torch.from_numpy(flat).to(self.dev)
+        self.broadcast_params()
         self.grads = torch.zeros_like(self.params)
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.bn_batch = torch.zeros(n_bn.value, dtype=torch.float32, device=self.dev)
+        self.step_count = 0
+
+    def broadcast_params(self):
+        """Every replica must start from rank 0's weights (each rank drew its own glorot initialisation): the
+        reference's towers share ONE set of variables (flypylib/multi_gpu.py:20-61)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.params, 0)
+
+    def load_from_model(self):
+        """Re-read the flat parameters from the model (after Model.set_weights / a checkpoint restore) and reset the
+        Adam moments."""
+        import torch
+        flat = np.concatenate([w.ravel() for w in self.model.get_weights()]).astype(np.float32)
+        self.params.copy_(torch.from_numpy(flat))
+        self.broadcast_params()
+        self.m.zero_(); self.v.zero_()
         self.step_count = 0
 
     def forward_backward(self, x, labels, global_batch, seed):
@@ -103,7 +121,7 @@ class Trainer(object):
             n = int(np.prod(s))
             out.append(flat[o:o + n].reshape(s).copy())
             o += n
-        self.model.set_weights(out)
+        self.model._set_weights_from_trainer(out)
 
     def close(self):
         if self.handle:

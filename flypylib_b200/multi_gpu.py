@@ -40,6 +40,36 @@ def slab_for_layers(begin, end, size, rf_offset, out_sz):
     return (z0, z1), (p0, p1)
 
 
+def shard_plan(Z, rf_offset, granularity, world_size):
+    """z-slab sharding of ONE (Z,Y,X) volume over world_size ranks for ``FplNetwork.infer``: the
+    prediction planes [off, Z-off) are cut into groups of ``granularity`` planes (``FplNetwork.slab_granularity``:
+    rf_stride for the VGGs, the tile pitch for the U-Nets), the groups are dealt contiguously
+    (``partition_layers``), and rank r reads the image planes its groups need -- its slab plus a 2*rf_offset
+    receptive-field halo, nothing is recomputed beyond that.  Returns per rank
+    ``((in0, in1), (own0, own1))``: image planes to read and prediction planes owned; the owned ranges partition
+    [0, Z) (the first / last non-empty rank also owns the zero border planes), which is what
+    ``voxel2obj_global`` expects.  Ranks without work get empty ranges."""
+    Z, off, gran = int(Z), int(rf_offset), int(granularity)
+    span = Z - 2 * off
+    n_groups = 0 if span <= 0 else -(-span // gran)
+    if n_groups == 0:                       # thinner than the receptive field: rank 0 returns the all-zero map
+        return [((0, Z), (0, Z))] + [((Z, Z), (Z, Z))] * (world_size - 1)
+    parts = partition_layers(n_groups, world_size)
+    busy = [r for r, (a, b) in enumerate(parts) if b > a]
+    plans = []
+    for r, (g0, g1) in enumerate(parts):
+        if g1 <= g0:
+            edge = Z if r > busy[-1] else 0
+            plans.append(((edge, edge), (edge, edge)))
+            continue
+        in0 = g0 * gran
+        in1 = Z if r == busy[-1] else g1 * gran + 2 * off
+        own0 = 0 if r == busy[0] else in0 + off
+        own1 = Z if r == busy[-1] else in1 - off
+        plans.append(((in0, in1), (own0, own1)))
+    return plans
+
+
 def allgather_detections(rows, group=None):
     """All-gather variable-length detection lists.  rows: (K,4) float64 tensor (x,y,z,conf) on the
     device the process group works on.  Returns the list of per-rank (K_r,4) tensors."""
@@ -105,6 +135,29 @@ def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigm
     return merge_detections([p.cpu().numpy() for p in parts])
 
 
+def detect_volume_sharded(network, image_slab, Z, plans, normalize, obj_min_dist, smoothing_sigma,
+                          volume_offset=(0, 0, 0), buffer_sz=0, thd=0, group=None, return_stats=False):
+    """The whole T-bar path on ONE (Z,Y,X) volume sharded as z-slabs over the ranks of ``group`` (one process per
+    GPU): replaces the reference's tower replication (flypylib/multi_gpu.py:20-61, fplnetwork.py:130-134) followed
+    by a single ``voxel2obj``.  ``image_slab`` holds this rank's planes ``plans[rank][0]`` (``shard_plan``).
+    Forward pass: ``FplNetwork.infer_slab_device`` -- receptive-field halo only, no communication.  Detection:
+    ``voxel2obj_global`` (exact-global semantics): every rank returns the detection list of the single-GPU
+    call, bit for bit."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    (in0, in1), (own0, own1) = plans[rank]
+    Y, X = int(image_slab.shape[1]), int(image_slab.shape[2])
+    if in1 > in0:
+        pred, first, last = network.infer_slab_device(image_slab, Z, in0, normalize=normalize)
+        assert (first, last) == (own0, own1), ((first, last), (own0, own1))
+    else:
+        pred = torch.zeros((0, Y, X), dtype=torch.float32, device=image_slab.device)
+    coll = _DistCollectives(group, all_ranges=[p[1] for p in plans])
+    return voxel2obj_global([pred], [(own0, own1)], Z, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd,
+                            coll=coll, return_stats=return_stats)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Exact global voxel2obj on z-slabs (SURVEY 8e, semantics S2): the result is bit-identical to ONE
 # voxel2obj call on the whole volume (flypylib/fplobjdetect.py:132-257), whatever the number of ranks.
@@ -122,18 +175,24 @@ def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigm
 class _DistCollectives(object):
     """One local rank; collectives over torch.distributed (device tensors -> NCCL)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, all_ranges=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.local_ranks = [self.rank]
+        self.all_ranges = [tuple(r) for r in all_ranges] if all_ranges is not None else None
 
     def halo(self, slabs, ranges, Z, h):
         import torch
         dist = self.dist
         slab, (z0, z1) = slabs[0], ranges[0]
-        all_ranges = [None] * self.world
-        dist.all_gather_object(all_ranges, (z0, z1), group=self.group)
+        all_ranges = self.all_ranges
+        if all_ranges is None:                                  # callers that know the plan pass it (no collective)
+            all_ranges = [None] * self.world
+            dist.all_gather_object(all_ranges, (z0, z1), group=self.group)
+        assert tuple(all_ranges[self.rank]) == (z0, z1)
+        if z1 <= z0:                                            # a rank without planes takes no part in the exchange
+            return [(slab, z0)]
         e0, e1 = max(0, z0 - h), min(Z, z1 + h)
         ext = torch.empty((e1 - e0,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
         ext[z0 - e0:z1 - e0] = slab
@@ -157,18 +216,28 @@ class _DistCollectives(object):
         self.dist.all_reduce(tensors[0], group=self.group)
         return tensors
 
-    def allgather(self, tensors):
+    def allgather(self, tensors, scalars=None):
+        """Concatenation of every rank's rows; with ``scalars`` also the sum of one integer per rank (the row
+        counts and the scalars travel in the same small all-gather)."""
         import torch
         t = tensors[0]
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        counts = [torch.zeros_like(n) for _ in range(self.world)]
-        self.dist.all_gather(counts, n, group=self.group)
-        m = max(1, max(int(c.item()) for c in counts))
-        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        bufs = [torch.zeros_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(bufs, pad, group=self.group)
-        return [torch.cat([b[:int(c.item())] for b, c in zip(bufs, counts)], 0)]
+        head = torch.tensor([t.shape[0], int(scalars[0]) if scalars is not None else 0], dtype=torch.int64,
+                            device=t.device)
+        heads = torch.empty(self.world * 2, dtype=torch.int64, device=t.device)
+        self.dist.all_gather_into_tensor(heads, head, group=self.group)
+        heads = heads.view(self.world, 2).cpu().numpy()
+        counts, total = [int(c) for c in heads[:, 0]], int(heads[:, 1].sum())
+        m = max(counts)
+        if m == 0:
+            out = [t[:0].clone()]
+        else:
+            pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[:t.shape[0]] = t
+            bufs = torch.empty(self.world * pad.numel(), dtype=t.dtype, device=t.device)
+            self.dist.all_gather_into_tensor(bufs, pad.view(-1), group=self.group)
+            bufs = bufs.view((self.world, m) + tuple(t.shape[1:]))
+            out = [torch.cat([bufs[r, :c] for r, c in enumerate(counts)], 0)]
+        return out if scalars is None else (out, total)
 
 
 class _LocalCollectives(object):
@@ -191,10 +260,11 @@ class _LocalCollectives(object):
         total = sum(tensors[1:], tensors[0].clone())
         return [total.clone() for _ in tensors]
 
-    def allgather(self, tensors):
+    def allgather(self, tensors, scalars=None):
         import torch
         cat = torch.cat(tensors, 0)
-        return [cat.clone() for _ in tensors]
+        out = [cat.clone() for _ in tensors]
+        return out if scalars is None else (out, int(sum(int(v) for v in scalars)))
 
 
 def _key2f(k):
@@ -261,16 +331,22 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
         targets = [int(p.rank_lo)] + ([int(p.rank_hi)] if p.rank_hi != p.rank_lo else [])
         states = [[t, 0, 0] for t in targets]                       # [rank, prefix, mask]
         for li, (shift, bins) in enumerate(((21, 2048), (10, 2048), (0, 1024))):
+            seen = {}                                               # the two order statistics usually share a class
             for stt in states:
-                hs, nans = [], []
-                for sm, lo, (z0, z1) in zip(smooth, s_lo, ranges):
-                    own = sm[z0 - lo:z1 - lo]
-                    h = torch.zeros(2048, dtype=torch.int64, device=dev)
-                    nn = torch.zeros(1, dtype=torch.int64, device=dev)
-                    _lib.check(lib.fpl_v2o_hist_level(ctx.handle, own.data_ptr(), int(own.numel()), stt[1], stt[2], shift, bins,
-                                                      h.data_ptr(), nn.data_ptr() if li == 0 else None, st), "fpl_v2o_hist_level")
-                    hs.append(torch.cat([h, nn]))
-                tot = coll.allreduce(hs)[0].cpu().numpy()
+                key = (stt[1], stt[2])
+                if key not in seen:
+                    hs = []
+                    for sm, lo, (z0, z1) in zip(smooth, s_lo, ranges):
+                        own = sm[z0 - lo:z1 - lo]
+                        h = torch.zeros(2049, dtype=torch.int64, device=dev)
+                        if own.numel():
+                            _lib.check(lib.fpl_v2o_hist_level(ctx.handle, own.data_ptr(), int(own.numel()), stt[1], stt[2],
+                                                              shift, bins, h.data_ptr(),
+                                                              h.data_ptr() + 2048 * 8 if li == 0 else None, st),
+                                       "fpl_v2o_hist_level")
+                        hs.append(h)
+                    seen[key] = coll.allreduce(hs)[0].cpu().numpy()
+                tot = seen[key]
                 if li == 0 and int(tot[2048]) > 0:                  # NaNs: percentile is NaN, nothing is selected
                     return done(empty)
                 stt[0], stt[1], stt[2] = _scan_level(tot[:2048], stt[0], stt[1], stt[2], shift, bins, extra)
@@ -308,11 +384,10 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
                 pts = buf[:n_sel.value].clone()
                 pts[:, 0] += lo                                         # global z
                 sels.append(pts); alive.append(n_alive.value)
-            tot_alive = coll.allreduce([torch.tensor([a_], dtype=torch.int64, device=dev) for a_ in alive])
-            if int(tot_alive[0].item()) == 0:
+            gathered, tot_alive = coll.allgather(sels, scalars=alive)
+            if tot_alive == 0:
                 break
             stats['rounds'] += 1
-            gathered = coll.allgather(sels)
             if int(gathered[0].shape[0]) == 0:
                 raise RuntimeError("voxel2obj_global: NMS round made no progress (internal error)")
             for h, lo, pts in zip(sessions, s_lo, gathered):

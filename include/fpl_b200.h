@@ -15,7 +15,10 @@
  *   - pointers named d_* are DEVICE pointers (sm_100a B200 global memory) owned by the caller;
  *     h_* are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *   - the library allocates only inside an explicit fpl_ctx (grow-only workspace arena,
- *     packed weights); fpl_ctx_destroy frees everything.
+ *     activation buffer pool, packed weights); fpl_ctx_destroy frees everything.
+ *   - one fpl_ctx per (process, device).  Calls on one context are stream-ordered: its workspace and
+ *     activation buffers are recycled in launch order, so use ONE stream at a time per context
+ *     (synchronise before switching streams).
  *   - volumes are C-order (Z,Y,X); detections are rows (x, y, z, conf) of float64, exactly the
  *     columns of the reference's obj_pred array (flypylib/fplobjdetect.py:211,233-257).
  *   - there is NO CPU fallback: every compute entry point fails with FPL_ENODEV when no sm_100
@@ -53,6 +56,9 @@ int fpl_ctx_create(int device, fpl_ctx **out);
 int fpl_ctx_destroy(fpl_ctx *ctx);
 /* bytes currently held by the context's workspace arena */
 int fpl_ctx_workspace_bytes(fpl_ctx *ctx, int64_t *bytes);
+/* give the grow-only workspace arena and the activation buffer pool back to the driver (they regrow on demand);
+ * synchronises the device.  For callers that alternate between very different problem sizes. */
+int fpl_ctx_release_workspace(fpl_ctx *ctx);
 /* number of kernel launches issued by this context since creation (bench.py "gpu_launches") */
 int fpl_ctx_launch_count(fpl_ctx *ctx, int64_t *launches);
 
@@ -203,6 +209,20 @@ int fpl_net_forward_tiles(fpl_net *net, const float *d_tiles, int32_t n_tiles, i
 int fpl_net_infer_volume(fpl_net *net, const void *d_image, int image_is_u8, float norm_mean,
                          float norm_std, int64_t Z, int64_t Y, int64_t X, int32_t z_tile_begin,
                          int32_t z_tile_end, float *d_pred, void *stream);
+
+/* One z-slab of a larger volume: the multi-GPU / streaming form of fpl_net_infer_volume.  The reference
+ * replicates the graph on n_gpu towers and feeds one tile per tower and predict step
+ * (flypylib/multi_gpu.py:20-61, fplnetwork.py:130-134,175-176); here every rank (or every chunk of a host
+ * volume) evaluates the planes [z0,z1) of the (Z,Y,X) image as one slab and writes ITS planes of the one
+ * prediction volume: [z0+rf_offset, z1-rf_offset), plus the zero border [0,rf_offset) when z0 == 0 and
+ * [Z-rf_offset,Z) when z1 == Z.  The values equal those of the whole-volume call bit for bit provided the cuts
+ * lie on the network's grid: z0 a multiple of rf_stride (VGG builders, shift-equivariant) or of
+ * infer_sz-2*rf_offset (U-Net builders: tile phase matters), and an inner slab holds 2*rf_offset + k*that
+ * many planes (checked).  d_image_slab / d_pred_slab point at plane z0 of the image / prediction volume;
+ * only the planes listed above are written, so slabs of neighbouring calls may share one buffer. */
+int fpl_net_infer_slab(fpl_net *net, const void *d_image_slab, int image_is_u8, float norm_mean,
+                       float norm_std, int64_t Z, int64_t z0, int64_t z1, int64_t Y, int64_t X,
+                       float *d_pred_slab, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * data-parallel training step of the VGG builders (BASELINE config 5)

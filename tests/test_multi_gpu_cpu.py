@@ -114,6 +114,16 @@ def _coll_worker(rank, world, port, q):
         tot = coll.allreduce([torch.tensor([rank + 1, 10 * (rank + 1)])])[0].tolist()
         rows = torch.full((rank + 1, 3), rank, dtype=torch.int64)
         gathered = coll.allgather([rows])[0]
+        (g2,), total = coll.allgather([rows[:0]], scalars=[rank + 5])      # nobody has rows; scalars still summed
+        assert g2.shape == (0, 3) and total == sum(r + 5 for r in range(world))
+        (g3,), total3 = coll.allgather([rows], scalars=[1])
+        assert torch.equal(g3, gathered) and total3 == world
+        # a rank without planes (more ranks than slabs) takes no part in the halo exchange; plan known up front
+        cuts2 = [(0, 12), (12, 23), (23, 23)][:world] if world == 3 else [(0, 23), (23, 23)]
+        coll2 = multi_gpu._DistCollectives(all_ranges=cuts2)
+        a0, a1 = cuts2[rank]
+        (ext2, f0), = coll2.halo([full[a0:a1].contiguous()], [(a0, a1)], Z, h)
+        ok_halo = ok_halo and (a1 == a0 or (f0 == max(0, a0 - h) and torch.equal(ext2, full[f0:min(Z, a1 + h)])))
         q.put((rank, bool(ok_halo), tot, gathered.tolist()))
     finally:
         dist.destroy_process_group()
@@ -139,3 +149,31 @@ def test_s2_collectives_gloo(world):
         assert ok_halo, rank
         assert tot == [s, 10 * s]
         assert gathered == want_rows
+
+
+def test_shard_plan_partitions_the_volume():
+    """multi_gpu.shard_plan: owned prediction planes partition [0,Z); every rank reads its planes plus a
+    2*rf_offset halo; cuts lie on the network grid (SURVEY 8e 'Forward pass')."""
+    for Z, off, gran, world in [(1024, 10, 4, 8), (1024, 10, 4, 2), (2048, 9, 82, 8), (256, 7, 4, 4), (333, 10, 4, 5),
+                                (30, 10, 4, 4), (15, 10, 4, 2), (270, 9, 82, 3), (100, 9, 82, 2)]:
+        plans = multi_gpu.shard_plan(Z, off, gran, world)
+        assert len(plans) == world
+        pos = 0
+        for (in0, in1), (own0, own1) in plans:
+            if own1 == own0:
+                assert in1 == in0
+                continue
+            assert own0 == pos
+            pos = own1
+            assert in0 % gran == 0 and in0 <= own0 and in1 >= own1
+            if in0 > 0:
+                assert own0 == in0 + off
+            if in1 < Z:
+                assert own1 == in1 - off and (in1 - in0 - 2 * off) % gran == 0
+        assert pos == Z
+    # the north-star split: unet_like2 on 2048^3 over 8 ranks = whole tile layers 4,3,3,3,3,3,3,3; 18 halo planes
+    plans = multi_gpu.shard_plan(2048, 9, 82, 8)
+    assert [(p[0][1] - p[0][0] - 18 + 81) // 82 for p in plans] == [4, 3, 3, 3, 3, 3, 3, 3]
+    # VGG on 1024^3: 251 groups of 4 planes -> 32/31 groups per rank (balance 0.98)
+    plans = multi_gpu.shard_plan(1024, 10, 4, 8)
+    assert sorted({p[1][1] - p[1][0] for p in plans[1:-1]}) == [124, 128]

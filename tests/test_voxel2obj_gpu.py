@@ -213,3 +213,15 @@ def test_gaussian_certified_chain_is_bit_exact(margin):
                 assert np.array_equal(s_gpu.view(np.uint32), interior.view(np.uint32)), (i, r, sigma)
     finally:
         lib.fpl_debug_gauss_cert(0)
+
+
+@pytest.mark.parametrize("shape,kind,classic", [((416, 512, 448), "blobs", False), ((416, 512, 448), "blobs", True),
+                                                ((352, 384, 400), "uniform", False)])
+def test_scale_runner_vs_c_oracle(shape, kind, classic):
+    """tools/check_v2o_scale.py (the runner behind profiles/r02_v2o_scale_*.json: the 1024^3 bench map and a map with
+    more than 2^32 voxels) on shapes the C oracle finishes in well under a minute: reference parameters, threshold,
+    list, order and confidences bit for bit, on the default and on the classic path."""
+    from tools import check_v2o_scale
+    res = check_v2o_scale.compare(shape, kind, 7, 27, 5.0, 15, 0.0, classic=classic)
+    assert res["detections_oracle"] > 20
+    assert res["threshold_identical"] and res["locs_identical"] and res["conf_identical"], res
