@@ -406,6 +406,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_per_step = max_over_ranks(ms_per_step)
     n_det = int(out["conf"].size)
+    import hashlib      # same list at every N (strong scaling on one volume, exact-global detection): compare across runs
+    det_sha = hashlib.sha256(np.ascontiguousarray(out["locs"]).tobytes() + np.ascontiguousarray(out["conf"]).tobytes()).hexdigest()[:16]
     value = size ** 3 / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end: pinned host uint8 volume -> H2D -> infer -> voxel2obj -> D2H detection list
@@ -489,7 +491,7 @@ def main():
                                    % (args.model, args.precision, how),
                        "l2": "inputs larger than L2 (%.2f GiB uint8 volume, %.1f GiB probability map per GPU and step)"
                              % (vol.numel() / 2 ** 30, 4.0 * size ** 3 / world / 2 ** 30),
-                       "detections_per_step": n_det},
+                       "detections_per_step": n_det, "detections_sha256_16": det_sha},
             "roofline": roofline, "families": families, "gpu_launches": int(launches / max(1, args.steps)),
             "clocks": clocks, "e2e": e2e}
     if e2e_dropin is not None:

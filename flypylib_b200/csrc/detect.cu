@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <vector>
 
 namespace fpl {
 namespace v2o {
@@ -979,6 +981,40 @@ __global__ void bitonic_step_kernel(unsigned *skey, unsigned long long *sidx, lo
     }
 }
 
+// all steps with j < 2048 of the bitonic network, for k in [k_first, k_last], on 2048-element chunks held in shared
+// memory (one launch instead of up to 66 tiny ones; the chunks are aligned, so partners i ^ j stay inside a chunk)
+constexpr int kBitonicChunk = 2048;
+__global__ void __launch_bounds__(1024)
+bitonic_local_kernel(unsigned *skey, unsigned long long *sidx, long long n_pow2, long long k_first, long long k_last) {
+    __shared__ unsigned s_key[kBitonicChunk];
+    __shared__ unsigned long long s_idx[kBitonicChunk];
+    for (long long base = (long long)blockIdx.x * kBitonicChunk; base < n_pow2; base += (long long)gridDim.x * kBitonicChunk) {
+        for (int i = threadIdx.x; i < kBitonicChunk; i += blockDim.x)
+            if (base + i < n_pow2) { s_key[i] = skey[base + i]; s_idx[i] = sidx[base + i]; }
+        __syncthreads();
+        for (long long k = k_first; k <= k_last; k <<= 1) {
+            long long j0 = k >> 1;
+            if (j0 >= kBitonicChunk) j0 = kBitonicChunk >> 1;
+            for (long long j = j0; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < kBitonicChunk; i += blockDim.x) {
+                    const int l = i ^ (int)j;
+                    if (l > i && base + l < n_pow2) {
+                        const unsigned ka = s_key[i], kb = s_key[l];
+                        const unsigned long long ia = s_idx[i], ib = s_idx[l];
+                        const bool up = ((base + i) & k) == 0;
+                        const bool swap = up ? det_before(kb, ib, ka, ia) : det_before(ka, ia, kb, ib);
+                        if (swap) { s_key[i] = kb; s_key[l] = ka; s_idx[i] = ib; s_idx[l] = ia; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < kBitonicChunk; i += blockDim.x)
+            if (base + i < n_pow2) { skey[base + i] = s_key[i]; sidx[base + i] = s_idx[i]; }
+        __syncthreads();
+    }
+}
+
 // fplobjdetect.py:233-253: columns (x,y,z,conf) float64; coordinates are already "un-padded"
 // (interior indices); keep rows with b <= coord < size-b (buffer in x,y,z order); add the offset.
 // Order-preserving compaction by one block.
@@ -1605,11 +1641,19 @@ static int finish_detections(fpl_ctx *ctx, DetectBuffers &B, unsigned long long 
     int sblocks = (int)((np2 + 255) / 256); if (sblocks > grid_stream) sblocks = grid_stream;
     sort_prepare_kernel<<<sblocks, 256, 0, st>>>(B.det_idx, B.det_val, (long long)n_det, np2, B.skey, B.sidx);
     FPL_LAUNCH_CHECK(ctx);
-    for (long long k = 2; k <= np2; k <<= 1)
-        for (long long j = k >> 1; j > 0; j >>= 1) {
+    // bitonic network: everything up to k = 2048 in one launch (chunks in shared memory); for larger k the steps with
+    // j >= 2048 run on global memory, the rest of that k again in one shared-memory launch
+    int lblocks = (int)((np2 + kBitonicChunk - 1) / kBitonicChunk); if (lblocks > grid_stream) lblocks = grid_stream;
+    bitonic_local_kernel<<<lblocks, 1024, 0, st>>>(B.skey, B.sidx, np2, 2, np2 < kBitonicChunk ? np2 : kBitonicChunk);
+    FPL_LAUNCH_CHECK(ctx);
+    for (long long k = 2 * kBitonicChunk; k <= np2; k <<= 1) {
+        for (long long j = k >> 1; j >= kBitonicChunk; j >>= 1) {
             bitonic_step_kernel<<<sblocks, 256, 0, st>>>(B.skey, B.sidx, np2, j, k);
             FPL_LAUNCH_CHECK(ctx);
         }
+        bitonic_local_kernel<<<lblocks, 1024, 0, st>>>(B.skey, B.sidx, np2, k, k);
+        FPL_LAUNCH_CHECK(ctx);
+    }
     finish_rows_kernel<<<1, 1024, 0, st>>>(B.skey, B.sidx, (long long)n_det, d, p->buffer_xyz[0],
                                            p->buffer_xyz[1], p->buffer_xyz[2], p->offset_xyz[0],
                                            p->offset_xyz[1], p->offset_xyz[2], d_dets, capacity,
@@ -1782,6 +1826,8 @@ static int voxel2obj_fast(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_
     *done = true;
     return FPL_OK;
 }
+
+#include "detect_approx.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // slab sessions: building blocks of the exact multi-GPU voxel2obj (semantics S2).  A rank holds the
@@ -2033,8 +2079,9 @@ int fpl_v2o_detect(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, in
 }
 
 static int g_v2o_classic = 0;
-// test hook: run fpl_voxel2obj through the classic (five dense passes) path
-int fpl_debug_v2o_classic(int on) { g_v2o_classic = on; return FPL_OK; }
+// test hook: 0 = default (two-tier path when the map qualifies, else the fused exact path), 1 = classic exact path
+// (five dense passes), 2 = fused exact path only (never the two-tier path)
+int fpl_debug_v2o_classic(int mode) { g_v2o_classic = mode; return FPL_OK; }
 
 int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,
                   const fpl_v2o_params *p, double *d_dets, int64_t capacity, int64_t *h_count,
@@ -2051,11 +2098,25 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
     // 22-bit radix class upwards) -> some slack on top of the exact candidate bound
     long long list_cap = cand_cap + cand_cap / 8 + 65536;
     if (list_cap > (long long)n) list_cap = (long long)n;
-    const bool try_fast = !g_v2o_classic && r > 0;
+    const bool try_fast = g_v2o_classic != 1 && r > 0;
+    const bool try_approx = g_v2o_classic == 0 && r > 0;
     size_t need = 2 * (n * sizeof(float) + 512) + 2 * sizeof(SelectState) + sizeof(ThreshOut) + 4096 + 2048 +
                   detect_workspace_bytes(Z, Y, X, try_fast ? list_cap : cand_cap, capacity > 0 ? capacity : 1);
+    if (try_approx) need += (size_t)n / 16 + ((size_t)1 << 24);     // lattice sample, band / narrow / ambiguity lists
     FPL_TRY(ctx->arena.reserve(need));
     ctx->arena.reset();
+    if (try_approx) {
+        // two-tier path: fp32 smoothing with a proven bound, exact values only where a decision needs them
+        SelectState *st2 = (SelectState *)ctx->arena.take(2 * sizeof(SelectState));
+        ThreshOut *tout2 = (ThreshOut *)ctx->arena.take(sizeof(ThreshOut));
+        FPL_REQUIRE(st2 && tout2, "voxel2obj: workspace sizing error");
+        bool done = false;
+        FPL_TRY(voxel2obj_approx(ctx, d_pred, Z, Y, X, p, st2, tout2, list_cap, d_dets, capacity, h_count, h_threshold,
+                                 h_stats, st, &done));
+        if (done) return FPL_OK;
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+        ctx->arena.reset();                 // did not qualify / certificate failed: exact path from scratch
+    }
     float *smooth = (float *)ctx->arena.take(n * sizeof(float));
     float *tmp = (float *)ctx->arena.take(n * sizeof(float));
     SelectState *states = (SelectState *)ctx->arena.take(2 * sizeof(SelectState));

@@ -122,8 +122,12 @@ def voxel2obj_device(pred_dev, obj_min_dist, smoothing_sigma, volume_offset=(0, 
         rows = dets[:count.value].cpu().numpy()
     out = {'locs': rows[:, :3].copy(), 'conf': rows[:, 3].copy()}
     if return_stats:
+        # stats[6]: which path of fpl_voxel2obj produced the result (all three are bit-identical by construction)
+        path = {2: 'two-tier', 1: 'fused-exact'}.get(int(stats[6]), 'classic-exact')
         return out, {'threshold': thresh.value, 'candidates': stats[0], 'rounds': stats[1],
-                     'ball_checks': stats[2], 'selected': stats[3]}
+                     'ball_checks': stats[2], 'selected': stats[3], 'path': path,
+                     'exact_recomputed': int(stats[4]) if path == 'two-tier' else None,
+                     'ambiguous_ball_checks': int(stats[7]) if path == 'two-tier' else None}
     return out
 
 

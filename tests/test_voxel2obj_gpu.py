@@ -64,15 +64,16 @@ def test_stages_bit_exact_vs_oracle_and_golden(case, generic):
     assert np.array_equal(rows[:, 3], GOLD[name + "/conf"])
 
 
-@pytest.fixture(params=["fused", "classic"])
+@pytest.fixture(params=["default", "fused", "classic"])
 def v2o_path(request):
-    """fpl_voxel2obj has two detection paths: the fused one (level-1 select histogram inside the Gaussian
-    x pass, two dense passes, NMS on a candidate superset) and the classic one it falls back to when the
-    superset does not fit its lists.  Every drop-in parity test runs through both."""
+    """fpl_voxel2obj has three detection paths: the two-tier one (fp32 smoothing with a proven bound, exact values
+    only where a decision needs them; the default whenever the map qualifies), the fused exact one (exact smoothing,
+    three dense passes, NMS on a candidate superset) and the classic exact one it falls back to when the superset
+    does not fit its lists.  Every drop-in parity test runs through all three."""
     from flypylib_b200 import _lib
     lib = _lib.lib()
     lib.fpl_debug_v2o_classic.argtypes = [ctypes.c_int]
-    lib.fpl_debug_v2o_classic(1 if request.param == "classic" else 0)
+    lib.fpl_debug_v2o_classic({"default": 0, "classic": 1, "fused": 2}[request.param])
     yield request.param
     lib.fpl_debug_v2o_classic(0)
 
@@ -215,13 +216,47 @@ def test_gaussian_certified_chain_is_bit_exact(margin):
         lib.fpl_debug_gauss_cert(0)
 
 
-@pytest.mark.parametrize("shape,kind,classic", [((416, 512, 448), "blobs", False), ((416, 512, 448), "blobs", True),
-                                                ((352, 384, 400), "uniform", False)])
-def test_scale_runner_vs_c_oracle(shape, kind, classic):
+@pytest.mark.parametrize("shape,kind,mode", [((416, 512, 448), "blobs", 0), ((416, 512, 448), "blobs", 1),
+                                             ((416, 512, 448), "blobs", 2), ((352, 384, 400), "uniform", 0)])
+def test_scale_runner_vs_c_oracle(shape, kind, mode):
     """tools/check_v2o_scale.py (the runner behind profiles/r02_v2o_scale_*.json: the 1024^3 bench map and a map with
     more than 2^32 voxels) on shapes the C oracle finishes in well under a minute: reference parameters, threshold,
     list, order and confidences bit for bit, on the default and on the classic path."""
     from tools import check_v2o_scale
-    res = check_v2o_scale.compare(shape, kind, 7, 27, 5.0, 15, 0.0, classic=classic)
+    res = check_v2o_scale.compare(shape, kind, 7, 27, 5.0, 15, 0.0, mode=mode)
     assert res["detections_oracle"] > 20
+    assert res["gpu_path"] == {0: "two-tier", 1: "classic-exact", 2: "fused-exact"}[mode], res["gpu_path"]
     assert res["threshold_identical"] and res["locs_identical"] and res["conf_identical"], res
+
+
+@pytest.mark.parametrize("shape,kind,r,sigma,thd", [
+    ((128, 128, 128), "blobs", 27, 5.0, 0), ((96, 100, 132), "uniform", 27, 5.0, 0), ((120, 90, 101), "blobs", 9, 2.0, 0),
+    ((100, 96, 96), "uniform", 8, 4.0, 0.51), ((90, 110, 70), "blobs", 6, 1.5, 0.02), ((64, 64, 200), "uniform", 5, 1.0, 0),
+])
+def test_two_tier_path_runs_and_is_bit_exact(shape, kind, r, sigma, thd):
+    """The default path on maps that qualify (non-negative, lw <= r) IS the two-tier path (stats say so), and its
+    threshold / list / order / confidences equal the C oracle's bit for bit; odd x extents take the scalar staging."""
+    import torch
+    from flypylib_b200 import fplobjdetect
+    pm = cases.prob_map(shape, 5, kind, peaks_per_50cube=20.0)
+    got, st = fplobjdetect.voxel2obj_device(torch.from_numpy(pm).cuda(), r, sigma, (0, 0, 0), 3, thd, return_stats=True)
+    assert st["path"] == "two-tier", st
+    want, s, t = O.voxel2obj(pm, r, sigma, (0, 0, 0), 3, thd, impl="c", return_intermediates=True)
+    assert st["threshold"] == float(t)
+    assert thd or want["conf"].size > 3
+    assert np.array_equal(got["locs"], want["locs"]) and np.array_equal(got["conf"], want["conf"])
+
+
+def test_two_tier_path_declines_what_it_cannot_certify():
+    """Negative or non-finite inputs, lw > r, ties / plateaus: the exact paths take over (and stay bit-exact)."""
+    import torch
+    from flypylib_b200 import fplobjdetect
+    rng = np.random.default_rng(3)
+    neg = (rng.standard_normal((64, 64, 64)) * 0.3).astype(np.float32)
+    for pm, r, sigma in [(neg, 6, 1.5), (cases.prob_map((64, 64, 64), 4, "blobs"), 3, 4.0),
+                         (cases.prob_map((80, 80, 80), 4, "ties"), 6, 1.5), (cases.prob_map((64, 64, 64), 8, "saturated"), 4, 1.0)]:
+        got, st = fplobjdetect.voxel2obj_device(torch.from_numpy(pm).cuda(), r, sigma, (0, 0, 0), 0, 0, return_stats=True)
+        want = O.voxel2obj(pm, r, sigma, (0, 0, 0), 0, 0, impl="c")
+        assert np.array_equal(got["locs"], want["locs"]) and np.array_equal(got["conf"], want["conf"]), st
+    got, st = fplobjdetect.voxel2obj_device(torch.from_numpy(neg).cuda(), 6, 1.5, (0, 0, 0), 0, 0, return_stats=True)
+    assert st["path"] != "two-tier"

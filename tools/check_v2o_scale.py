@@ -53,7 +53,8 @@ def synth_map(shape, seed, kind, dev):
     return out
 
 
-def compare(shape, kind, seed, r, sigma, buf, thd, classic=False):
+def compare(shape, kind, seed, r, sigma, buf, thd, classic=False, mode=None):
+    """mode: 0 default (two-tier when the map qualifies), 1 classic exact, 2 fused exact"""
     import ctypes
     import torch
     from flypylib_b200 import fplobjdetect, _lib
@@ -64,7 +65,8 @@ def compare(shape, kind, seed, r, sigma, buf, thd, classic=False):
     torch.cuda.synchronize()
     lib = _lib.lib()
     lib.fpl_debug_v2o_classic.argtypes = [ctypes.c_int]
-    lib.fpl_debug_v2o_classic(1 if classic else 0)
+    mode = (1 if classic else 0) if mode is None else int(mode)
+    lib.fpl_debug_v2o_classic(mode)
     try:
         got, st = fplobjdetect.voxel2obj_device(pm, r, sigma, (0, 0, 0), buf, thd, return_stats=True)    # warm-up
         torch.cuda.synchronize()
@@ -94,10 +96,10 @@ def compare(shape, kind, seed, r, sigma, buf, thd, classic=False):
     same_conf = bool(got["conf"].shape == want["conf"].shape and np.array_equal(got["conf"], want["conf"]))
     n_cand = int(np.count_nonzero(s > t))
     return {"shape": list(shape), "kind": kind, "seed": seed, "r": r, "sigma": sigma, "buffer": buf, "thd": thd,
-            "gpu_path": "classic" if classic else "default", "voxels": n_vox, "padded_voxels": n_pad,
+            "gpu_path": st.get("path"), "voxels": n_vox, "padded_voxels": n_pad,
             "voxels_over_2p32": n_vox > 2 ** 32, "threshold_gpu": st["threshold"], "threshold_oracle": float(t),
             "detections_gpu": int(got["conf"].size), "detections_oracle": int(want["conf"].size),
-            "candidates_oracle": n_cand, "gpu_stats": {k: (int(v) if not isinstance(v, float) else v) for k, v in st.items()},
+            "candidates_oracle": n_cand, "gpu_stats": {k: (v if isinstance(v, (float, str)) or v is None else int(v)) for k, v in st.items()},
             "max_flat_index_gpu": int((got["locs"][:, 2] * shape[1] * shape[2] + got["locs"][:, 1] * shape[2]
                                        + got["locs"][:, 0]).max()) if got["conf"].size else -1,
             "threshold_identical": same_thresh, "locs_identical": same_locs, "conf_identical": same_conf,
@@ -116,9 +118,10 @@ def main():
     ap.add_argument("--buffer", type=int, default=15)
     ap.add_argument("--thd", type=float, default=0.0)
     ap.add_argument("--classic", action="store_true", help="force the classic (five dense passes) GPU path")
+    ap.add_argument("--mode", type=int, default=None, help="0 default (two-tier), 1 classic exact, 2 fused exact")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    res = compare(tuple(a.shape), a.kind, a.seed, a.r, a.sigma, a.buffer, a.thd, classic=a.classic)
+    res = compare(tuple(a.shape), a.kind, a.seed, a.r, a.sigma, a.buffer, a.thd, classic=a.classic, mode=a.mode)
     line = json.dumps(res)
     print(line)
     if a.out:
