@@ -379,9 +379,19 @@ def main():
         pred = torch.empty((size, size, size), dtype=torch.float32, device=dev)
         h2d_bytes = int(vol.numel())
 
+        v2o_stats = {}
+
         def step():
             net.infer_device(vol, normalize=NORM, out=pred)
-            return fplobjdetect.voxel2obj_device(pred, *det)
+            out, st = fplobjdetect.voxel2obj_device(pred, *det, return_stats=True)
+            v2o_stats.update(st)
+            if st.get("two_tier_declined", 0) > 0 and "decline_info" not in v2o_stats:
+                import ctypes
+                info = (ctypes.c_longlong * 8)()
+                _lib.lib().fpl_debug_v2o_decline_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+                code = _lib.lib().fpl_debug_v2o_decline_info(ctx.handle, info)
+                v2o_stats["decline_info"] = [int(code)] + [int(v) for v in info]
+            return out
     else:
         plans = multi_gpu.shard_plan(size, int(net.rf_offset[0]), net.slab_granularity(), world)
         (in0, in1), _own = plans[rank]
@@ -405,6 +415,12 @@ def main():
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms_per_step = max_over_ranks(ms_per_step)
+    s2_stages = None
+    if world > 1:       # one extra, untimed step with a device synchronisation at every stage boundary: where the
+        #                 exact-global detection spends its time on rank 0 (the forward pass is the rest of the step)
+        _o, st_ = multi_gpu.detect_volume_sharded(net, vol, size, plans, NORM, *det, return_stats='stages')
+        s2_stages = {k: round(v, 3) for k, v in st_['stage_ms'].items()}       # 'setup' = the forward pass of this rank
+        s2_stages['rounds'] = st_['rounds']
     n_det = int(out["conf"].size)
     import hashlib      # same list at every N (strong scaling on one volume, exact-global detection): compare across runs
     det_sha = hashlib.sha256(np.ascontiguousarray(out["locs"]).tobytes() + np.ascontiguousarray(out["conf"]).tobytes()).hexdigest()[:16]
@@ -491,11 +507,14 @@ def main():
                                    % (args.model, args.precision, how),
                        "l2": "inputs larger than L2 (%.2f GiB uint8 volume, %.1f GiB probability map per GPU and step)"
                              % (vol.numel() / 2 ** 30, 4.0 * size ** 3 / world / 2 ** 30),
-                       "detections_per_step": n_det, "detections_sha256_16": det_sha},
+                       "detections_per_step": n_det, "detections_sha256_16": det_sha,
+                       "voxel2obj_path": (v2o_stats.get("path"), v2o_stats.get("two_tier_declined"), v2o_stats.get("decline_info")) if world == 1 else "exact-global (slab sessions)"},
             "roofline": roofline, "families": families, "gpu_launches": int(launches / max(1, args.steps)),
             "clocks": clocks, "e2e": e2e}
     if e2e_dropin is not None:
         line["e2e_dropin"] = e2e_dropin
+    if s2_stages is not None:
+        line["detection_stages_ms_rank0"] = s2_stages
 
     # ---- extra legs (never allowed to take the main line down): the other BASELINE configs, driver-visible
     def emit():

@@ -70,6 +70,8 @@ _SIGNATURES = {
                                           ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(vp), c_i64p, vp]),
     "fpl_v2o_slab_round": (ctypes.c_int, [vp, vp, ctypes.c_int64, c_i64p, c_i64p, vp]),
     "fpl_v2o_slab_suppress": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
+    "fpl_v2o_slab_round_pack": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, vp]),
+    "fpl_v2o_slab_apply_blocks": (ctypes.c_int, [vp, vp, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, vp]),
     "fpl_v2o_slab_end": (ctypes.c_int, [vp, vp, ctypes.c_int64, c_i64p, c_i64p, vp]),
     "fpl_net_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
     "fpl_net_destroy": (ctypes.c_int, [vp]),

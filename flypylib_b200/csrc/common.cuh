@@ -74,6 +74,10 @@ struct fpl_ctx {
     std::vector<fpl::ProfRec> prof;
     std::vector<cudaEvent_t> prof_free;
     std::vector<fpl::PoolBuf> act_pool;   // activation buffers of the networks of this context (this device)
+    int v2o_decline = 0;                  // why the last fpl_voxel2obj left the two-tier path (0 = it did not)
+    long long v2o_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // counters behind the decline (diagnosis)
+    int v2o_skip = 0, v2o_fail_streak = 0; // adaptive: calls that go straight to the exact path after declines
+    std::vector<fpl::PoolBuf> slab_cache; // workspace blocks of finished voxel2obj slab sessions, reused by the next
 };
 
 namespace fpl {

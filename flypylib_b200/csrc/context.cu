@@ -95,6 +95,8 @@ int fpl_ctx_destroy(fpl_ctx *ctx) {
     ctx->arena.release();
     for (auto &b : ctx->act_pool) cudaFree(b.p);
     ctx->act_pool.clear();
+    for (auto &b : ctx->slab_cache) cudaFree(b.p);
+    ctx->slab_cache.clear();
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -115,6 +117,8 @@ int fpl_ctx_release_workspace(fpl_ctx *ctx) {
     ctx->arena.release();
     for (auto &b : ctx->act_pool) cudaFree(b.p);
     ctx->act_pool.clear();
+    for (auto &b : ctx->slab_cache) cudaFree(b.p);
+    ctx->slab_cache.clear();
     return FPL_OK;
 }
 

@@ -1517,6 +1517,63 @@ __global__ void det_rows_kernel(const unsigned long long *idx, const float *val,
     }
 }
 
+// ---- exchange blocks of the exact multi-GPU rounds: row 0 = (n_selected, alive_owned, overflow), rows 1.. = (z,y,x) of the
+// points this rank selected in the round, z global.  One fixed-size block per rank -> ONE all-gather per round, no host
+// round trip between decision and suppression.
+__global__ void slab_pack_kernel(const unsigned long long *sel_idx, const Counters *cnt, Dims d, long long z_offset,
+                                 long long *block, long long sel_cap, int first, unsigned long long n_first) {
+    const unsigned long long n = cnt->n_sel_round;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        block[0] = (long long)n;
+        block[1] = first ? (long long)n_first : (long long)cnt->n_alive_owned;
+        block[2] = (long long)cnt->overflow + ((long long)n > sel_cap ? 1 : 0);
+    }
+    const unsigned long long m = n < (unsigned long long)sel_cap ? n : (unsigned long long)sel_cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long q = sel_idx[i];
+        block[3 * (1 + i)] = (long long)(q / ((unsigned long long)d.X * d.Y)) + z_offset;
+        block[3 * (1 + i) + 1] = (long long)((q / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        block[3 * (1 + i) + 2] = (long long)(q % (unsigned long long)d.X);
+    }
+}
+
+// suppress the balls of the points of all ranks' blocks (blocks are (1 + sel_cap) rows apart); z_offset: global -> slab
+__global__ void __launch_bounds__(256)
+nms_suppress_blocks_kernel(unsigned *sup, Dims d, int r, const long long *__restrict__ blocks, int n_blocks, long long sel_cap,
+                           long long z_offset) {
+    const int side = 2 * r + 1;
+    for (int b = 0; b < n_blocks; ++b) {
+        const long long *blk = blocks + (long long)b * 3 * (1 + sel_cap);
+        long long n_pts = blk[0];
+        if (n_pts > sel_cap) n_pts = sel_cap;
+        for (long long s = blockIdx.x; s < n_pts; s += gridDim.x) {
+            const long long z = blk[3 * (1 + s)] - z_offset, y = blk[3 * (1 + s) + 1], x = blk[3 * (1 + s) + 2];
+            if (z + r < 0 || z - r >= d.Z) continue;             // ball does not reach this slab
+            for (int row = threadIdx.x; row < side * side; row += blockDim.x) {
+                int dz = row / side - r, dy = row % side - r;
+                int rem = r * r - dz * dz - dy * dy;
+                if (rem < 0) continue;
+                long long zz = z + dz, yy = y + dy;
+                if (zz < 0 || zz >= d.Z || yy < 0 || yy >= d.Y) continue;
+                int hw = isqrt_floor(rem);
+                long long x0 = x - hw < 0 ? 0 : x - hw;
+                long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
+                if (x1 < x0) continue;
+                unsigned long long q0 = ((unsigned long long)zz * d.Y + yy) * d.X + x0;
+                unsigned long long q1 = ((unsigned long long)zz * d.Y + yy) * d.X + x1;
+                unsigned long long *sup64 = reinterpret_cast<unsigned long long *>(sup);
+                for (unsigned long long wd = q0 >> 6; wd <= (q1 >> 6); ++wd) {
+                    unsigned long long lo = wd << 6;
+                    unsigned b0 = q0 > lo ? (unsigned)(q0 - lo) : 0u;
+                    unsigned b1 = q1 < lo + 63 ? (unsigned)(q1 - lo) : 63u;
+                    unsigned long long mask = (b1 == 63u ? ~0ULL : ((1ULL << (b1 + 1)) - 1ULL)) & ~((1ULL << b0) - 1ULL);
+                    atomicOr(&sup64[wd], mask);
+                }
+            }
+        }
+    }
+}
+
 struct DetectBuffers {
     unsigned *sup; size_t sup_words;
     unsigned long long *a_idx, *b_idx, *w_idx, *det_idx, *sel_idx, *sidx;
@@ -1843,10 +1900,13 @@ struct SlabSession {
     Dims d; int r;
     unsigned long long own_lo, own_hi;
     DetectBuffers B;
-    void *mem;                      // one cudaMalloc behind all buffers
+    void *mem; size_t mem_cap;      // one device block behind all buffers (recycled through fpl_ctx::slab_cache)
     unsigned long long *a_idx, *b_idx; float *a_val, *b_val;
-    unsigned long long remaining;   // list A entries
+    unsigned long long remaining;   // list A entries (from round 2 on)
     long long rounds;
+    ApproxState *state;             // cut-off of the dense pass / the compaction (exact: smallest float above the threshold)
+    bool first;                     // round 1 works on the local-maximum worklist of the dense pass
+    unsigned long long n_first;     // its size
 };
 
 }  // namespace v2o
@@ -1896,28 +1956,56 @@ int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int6
     // private arena for the session (several sessions may be alive on one device: single-GPU emulation in tests)
     fpl::Arena saved = ctx->arena;
     ctx->arena = fpl::Arena();
-    int rc = ctx->arena.reserve(detect_workspace_bytes(Ze, Y, X, list_cap, det_cap));
+    const size_t want = detect_workspace_bytes(Ze, Y, X, list_cap, det_cap) + sizeof(ApproxState) + 256;
+    for (size_t i = 0; i < ctx->slab_cache.size(); ++i)            // blocks of finished sessions are kept for the next one
+        if (ctx->slab_cache[i].cap >= want) {
+            ctx->arena.base = (char *)ctx->slab_cache[i].p; ctx->arena.cap = ctx->slab_cache[i].cap;
+            ctx->slab_cache.erase(ctx->slab_cache.begin() + i);
+            break;
+        }
+    int rc = ctx->arena.reserve(want);
     if (rc == FPL_OK) { ctx->arena.reset(); rc = take_detect_buffers(ctx, Ze, Y, X, list_cap, det_cap, S->B, st); }
-    S->mem = ctx->arena.base;
+    S->mem = ctx->arena.base; S->mem_cap = ctx->arena.cap;
     ctx->arena = saved;
     if (rc != FPL_OK) { if (S->mem) cudaFree(S->mem); delete S; return rc; }
-    const long long n = Ze * Y * X;
-    compact_candidates_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth_ext, n, threshold, S->B.a_idx, S->B.a_val,
-                                                                list_cap, S->B.cnt);
-    FPL_LAUNCH_CHECK(ctx);
-    brick_max_kernel<<<S->B.gz * S->B.gy, 256, S->B.gx * sizeof(float), st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid);
-    FPL_LAUNCH_CHECK(ctx);
+    // One dense pass instead of "compact every candidate, then test each against its 26 neighbours": brick maxima + the
+    // owned voxels above the threshold that no 26-neighbour exceeds = the worklist of round 1 (nothing is suppressed
+    // yet, so "valid and no better valid neighbour" is "local maximum"; ties are left to the exact ball check).
+    // The candidate list for the later rounds is gathered after the first suppression, brick by brick.
+    S->state = (ApproxState *)((char *)S->mem + detect_workspace_bytes(Ze, Y, X, list_cap, det_cap));
+    ApproxState hs;
+    memset(&hs, 0, sizeof(hs));
+    {   // candidates are  (double)v > threshold  and  v > 0  (fplobjdetect.py:184, :205): as a float cut-off
+        float c = (float)threshold;
+        if (threshold != threshold) c = INFINITY;
+        else if (!((double)c > threshold)) c = nextafterf(c, INFINITY);
+        while ((double)nextafterf(c, -INFINITY) > threshold) c = nextafterf(c, -INFINITY);
+        if (!(c > 0.f)) c = 1.401298464324817e-45f;
+        hs.cutA = c; hs.Lb = INFINITY; hs.Hb = INFINITY;
+    }
+    FPL_CUDA_CHECK(cudaMemcpyAsync(S->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    FPL_CUDA_CHECK(cudaMemsetAsync(S->B.grid, 0, brick_grid_bytes(Ze, Y, X), st));
+    {
+        const long long items = Ze * ((Y + kP1Strip - 1) / kP1Strip) * ((X + kP1Cols - 1) / kP1Cols);
+        long long g1 = (items + 3) / 4;
+        if (g1 > (long long)ctx->sm_count * 64) g1 = (long long)ctx->sm_count * 64;
+        approx_pass1_kernel<<<(unsigned)g1, 128, 0, st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid, S->state, nullptr, nullptr, 0,
+                                                          S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, (int)own_lo, (int)own_hi);
+        FPL_LAUNCH_CHECK(ctx);
+    }
     Counters *h_cnt = (Counters *)ctx->h_pinned;
     FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     FPL_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_cnt->overflow) {
-        fpl::set_error("voxel2obj slab: candidate list overflow (%llu > %lld)", h_cnt->n_cand, (long long)list_cap);
+        fpl::set_error("voxel2obj slab: worklist overflow (%llu > %lld)", h_cnt->n_work, (long long)list_cap);
         cudaFree(S->mem); delete S;
         return FPL_EOVERFLOW;
     }
-    S->remaining = h_cnt->n_cand;
+    S->first = true;
+    S->n_first = h_cnt->n_work;
+    S->remaining = h_cnt->n_work;
     S->a_idx = S->B.a_idx; S->b_idx = S->B.b_idx; S->a_val = S->B.a_val; S->b_val = S->B.b_val;
-    if (h_n_candidates) *h_n_candidates = (int64_t)h_cnt->n_cand;
+    if (h_n_candidates) *h_n_candidates = (int64_t)h_cnt->n_work;
     *session = S;
     return FPL_OK;
 }
@@ -1933,13 +2021,29 @@ int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64
     cudaStream_t st = (cudaStream_t)stream;
     Counters *h_cnt = (Counters *)ctx->h_pinned;
     *h_n_sel = 0; *h_alive_owned = 0;
-    if (S->remaining == 0) return FPL_OK;
+    const bool first = S->first;
+    if (!first && S->rounds == 1) {
+        // entering round 2: every rank's round-1 balls are in the suppression map now -> gather the candidates that
+        // are still valid (bricks whose maximum reaches the cut-off only), owned planes and halo alike
+        fast_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        approx_compact_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(S->smooth, S->d, S->B.grid, S->B.gz, S->B.gy, S->B.gx, S->B.sup, S->state,
+                                                                  S->a_idx, S->a_val, S->B.list_cap, S->B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h_cnt->overflow) { fpl::set_error("voxel2obj slab: candidate list overflow"); return FPL_EOVERFLOW; }
+        S->remaining = h_cnt->n_cand;
+    }
+    if (S->remaining == 0 && !first) { ++S->rounds; return FPL_OK; }
     ++S->rounds;
-    long long fblocks = (long long)((S->remaining + 255) / 256);
-    if (fblocks > ctx->sm_count * 8) fblocks = ctx->sm_count * 8;
-    nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->a_idx, S->a_val, S->b_idx, S->b_val,
-                                                        S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, S->own_lo, S->own_hi);
-    FPL_LAUNCH_CHECK(ctx);
+    if (!first) {
+        long long fblocks = (long long)((S->remaining + 255) / 256);
+        if (fblocks > ctx->sm_count * 8) fblocks = ctx->sm_count * 8;
+        nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->a_idx, S->a_val, S->b_idx, S->b_val,
+                                                            S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, S->own_lo, S->own_hi);
+        FPL_LAUNCH_CHECK(ctx);
+    }
     nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->r, S->B.grid, S->B.gz, S->B.gy, S->B.gx,
                                                            S->B.w_idx, S->B.w_val, S->B.det_idx, S->B.det_val, S->B.sel_idx,
                                                            S->B.det_cap, S->B.cnt, nullptr);
@@ -1953,10 +2057,11 @@ int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64
         FPL_LAUNCH_CHECK(ctx);
     }
     *h_n_sel = (int64_t)h_cnt->n_sel_round;
-    *h_alive_owned = (int64_t)h_cnt->n_alive_owned;
+    // round 1: "alive" = owned local maxima above the threshold (zero on every rank <=> there is no candidate at all)
+    *h_alive_owned = first ? (int64_t)S->n_first : (int64_t)h_cnt->n_alive_owned;
     round_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
     FPL_LAUNCH_CHECK(ctx);
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (first) { S->first = false; return FPL_OK; }
     S->remaining = h_cnt->n_next;
     unsigned long long *ti = S->a_idx; S->a_idx = S->b_idx; S->b_idx = ti;
     float *tv = S->a_val; S->a_val = S->b_val; S->b_val = tv;
@@ -1970,6 +2075,59 @@ int fpl_v2o_slab_suppress(void *session, const int64_t *d_zyx, int64_t n_pts, vo
     if (n_pts <= 0) return FPL_OK;
     FPL_CUDA_CHECK(cudaSetDevice(S->ctx->device));
     nms_suppress_zyx_kernel<<<S->ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(S->B.sup, S->d, S->r, (const long long *)d_zyx, n_pts);
+    FPL_LAUNCH_CHECK(S->ctx);
+    return FPL_OK;
+}
+
+// One round without a host round trip: decision half -> exchange block (header + selected points, z global).  The
+// caller all-gathers the blocks of all ranks (one collective) and hands them to fpl_v2o_slab_apply_blocks.
+int fpl_v2o_slab_round_pack(void *session, int64_t *d_block, int64_t sel_cap, int64_t z_offset, void *stream) {
+    SlabSession *S = (SlabSession *)session;
+    FPL_REQUIRE(S && d_block && sel_cap > 0, "fpl_v2o_slab_round_pack: bad argument");
+    fpl_ctx *ctx = S->ctx;
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool first = S->first;
+    const int grid_stream = ctx->sm_count * 8;
+    if (!first && S->rounds == 1) {         // entering round 2: gather the candidates that survived every rank's round 1
+        fast_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+        approx_compact_kernel<<<grid_stream, 256, 0, st>>>(S->smooth, S->d, S->B.grid, S->B.gz, S->B.gy, S->B.gx, S->B.sup, S->state,
+                                                       S->a_idx, S->a_val, S->B.list_cap, S->B.cnt);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    ++S->rounds;
+    if (!first) {
+        nms_filter_kernel<<<grid_stream, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->a_idx, S->a_val, S->b_idx, S->b_val,
+                                                     S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, S->own_lo, S->own_hi);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    nms_ballcheck_kernel<<<grid_stream, 256, 0, st>>>(S->smooth, S->B.sup, S->d, S->r, S->B.grid, S->B.gz, S->B.gy, S->B.gx,
+                                                     S->B.w_idx, S->B.w_val, S->B.det_idx, S->B.det_val, S->B.sel_idx,
+                                                     S->B.det_cap, S->B.cnt, nullptr);
+    FPL_LAUNCH_CHECK(ctx);
+    slab_pack_kernel<<<64, 256, 0, st>>>(S->B.sel_idx, S->B.cnt, S->d, (long long)z_offset, (long long *)d_block, (long long)sel_cap,
+                                         first ? 1 : 0, S->n_first);
+    FPL_LAUNCH_CHECK(ctx);
+    round_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
+    FPL_LAUNCH_CHECK(ctx);
+    if (first) S->first = false;
+    else {
+        unsigned long long *ti = S->a_idx; S->a_idx = S->b_idx; S->b_idx = ti;
+        float *tv = S->a_val; S->a_val = S->b_val; S->b_val = tv;
+    }
+    return FPL_OK;
+}
+
+// Update half for the gathered blocks of all ranks (n_blocks x (1 + sel_cap) x 3 int64, z global; z_offset = global z of
+// this slab's plane 0).
+int fpl_v2o_slab_apply_blocks(void *session, const int64_t *d_blocks, int32_t n_blocks, int64_t sel_cap, int64_t z_offset,
+                              void *stream) {
+    SlabSession *S = (SlabSession *)session;
+    FPL_REQUIRE(S && d_blocks && n_blocks > 0 && sel_cap > 0, "fpl_v2o_slab_apply_blocks: bad argument");
+    FPL_CUDA_CHECK(cudaSetDevice(S->ctx->device));
+    nms_suppress_blocks_kernel<<<S->ctx->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(S->B.sup, S->d, S->r, (const long long *)d_blocks,
+                                                                                       n_blocks, (long long)sel_cap, (long long)z_offset);
     FPL_LAUNCH_CHECK(S->ctx);
     return FPL_OK;
 }
@@ -1992,7 +2150,8 @@ int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h
     }
     *h_count = n_det;
     if (h_rounds) *h_rounds = S->rounds;
-    cudaFree(S->mem);
+    if (rc == FPL_OK && ctx->slab_cache.size() < 4) ctx->slab_cache.push_back(fpl::PoolBuf{S->mem, S->mem_cap, false});
+    else cudaFree(S->mem);
     delete S;
     return rc;
 }
@@ -2078,6 +2237,20 @@ int fpl_v2o_detect(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, in
                        h_stats, st);
 }
 
+// test / diagnosis hook: why the last fpl_voxel2obj on ctx left the two-tier path (codes: detect_approx.cuh; 0 = it ran,
+// -1 = skipped by the adaptive back-off); reset_backoff != 0 also clears the back-off state
+int fpl_debug_v2o_decline_reason(fpl_ctx *ctx, int reset_backoff) {
+    if (!ctx) return -2;
+    if (reset_backoff) { ctx->v2o_skip = 0; ctx->v2o_fail_streak = 0; }
+    return ctx->v2o_decline;
+}
+
+int fpl_debug_v2o_decline_info(fpl_ctx *ctx, long long *out8) {
+    if (!ctx || !out8) return -2;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->v2o_info[i];
+    return ctx->v2o_decline;
+}
+
 static int g_v2o_classic = 0;
 // test hook: 0 = default (two-tier path when the map qualifies, else the fused exact path), 1 = classic exact path
 // (five dense passes), 2 = fused exact path only (never the two-tier path)
@@ -2102,10 +2275,16 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
     const bool try_approx = g_v2o_classic == 0 && r > 0;
     size_t need = 2 * (n * sizeof(float) + 512) + 2 * sizeof(SelectState) + sizeof(ThreshOut) + 4096 + 2048 +
                   detect_workspace_bytes(Z, Y, X, try_fast ? list_cap : cand_cap, capacity > 0 ? capacity : 1);
-    if (try_approx) need += (size_t)n / 16 + ((size_t)1 << 24);     // lattice sample, band / narrow / ambiguity lists
+    if (try_approx) need += (size_t)n / 16 + ((size_t)1 << 24) + ((size_t)128 << 20);     // lattice sample, band / narrow / ambiguity lists, exact-value scratch
     FPL_TRY(ctx->arena.reserve(need));
     ctx->arena.reset();
-    if (try_approx) {
+    if (try_approx && ctx->v2o_skip > 0) {
+        // adaptive: the last call(s) on this context did not qualify (a kind of map whose certificates fail, e.g. a value
+        // distribution so tight that too many voxels sit within the bound of the percentile) -- do not pay for the
+        // attempt every time; retry after 16, 32, 64, 64, .. calls
+        --ctx->v2o_skip;
+        ctx->v2o_decline = -1;
+    } else if (try_approx) {
         // two-tier path: fp32 smoothing with a proven bound, exact values only where a decision needs them
         SelectState *st2 = (SelectState *)ctx->arena.take(2 * sizeof(SelectState));
         ThreshOut *tout2 = (ThreshOut *)ctx->arena.take(sizeof(ThreshOut));
@@ -2113,9 +2292,13 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
         bool done = false;
         FPL_TRY(voxel2obj_approx(ctx, d_pred, Z, Y, X, p, st2, tout2, list_cap, d_dets, capacity, h_count, h_threshold,
                                  h_stats, st, &done));
-        if (done) return FPL_OK;
+        if (done) { ctx->v2o_fail_streak = 0; return FPL_OK; }
         FPL_CUDA_CHECK(cudaStreamSynchronize(st));
         ctx->arena.reset();                 // did not qualify / certificate failed: exact path from scratch
+        if (ctx->v2o_decline > 5) {         // a data-dependent decline cost a Gaussian pass: back off
+            if (ctx->v2o_fail_streak < 3) ++ctx->v2o_fail_streak;
+            ctx->v2o_skip = 8 << ctx->v2o_fail_streak;          // 16, 32, 64, 64, .. calls go straight to the exact path
+        }
     }
     float *smooth = (float *)ctx->arena.take(n * sizeof(float));
     float *tmp = (float *)ctx->arena.take(n * sizeof(float));

@@ -72,9 +72,18 @@ __device__ float exact_point(const float *__restrict__ pred, const Dims &d, int 
         float res = 0.f;
         if (yy >= 0 && yy < d.Y && xx >= 0 && xx < d.X) {
             const float *col = pred + yy * d.X + xx;
-            auto at = [&](long long zz) -> double { return (zz >= 0 && zz < d.Z) ? (double)__ldg(col + zz * plane) : 0.0; };
-            double tmp = __dmul_rn(at(z), taps.w[lw]);
-            for (int j = -lw; j < 0; ++j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(z + j), at(z - j)), taps.w[lw + j]));
+            // all loads of the column first (independent: one memory latency), then the dependent FP64 chain
+            auto at = [&](long long zz) -> float { return (zz >= 0 && zz < d.Z) ? __ldg(col + zz * plane) : 0.f; };
+            float lo_v[kApxMaxLw], hi_v[kApxMaxLw];
+#pragma unroll
+            for (int k = 0; k < kApxMaxLw; ++k) {
+                lo_v[k] = k < lw ? at(z - lw + k) : 0.f;
+                hi_v[k] = k < lw ? at(z + lw - k) : 0.f;
+            }
+            double tmp = __dmul_rn((double)at(z), taps.w[lw]);
+#pragma unroll
+            for (int k = 0; k < kApxMaxLw; ++k)
+                if (k < lw) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)lo_v[k], (double)hi_v[k]), taps.w[k]));
             res = (float)tmp;
         }
         T1[c] = res;
@@ -94,20 +103,86 @@ __device__ float exact_point(const float *__restrict__ pred, const Dims &d, int 
     return (float)tmp;
 }
 
-// one block per list entry: out[i] = exact_point(idx[i])
+// Exact values of a LIST of voxels (the percentile's narrow band, the detections): the same chain as exact_point, but
+// as three flat kernels -- one thread per (voxel, column) for the z pass, per (voxel, x offset) for the y pass, per voxel
+// for the x pass -- so that the per-voxel dependency chain is hidden by parallelism instead of paid per block.
+// t1: n * (2lw+1)^2 floats, t2: n * (2lw+1) floats of scratch.
+constexpr int kExactBatch = 1 << 16;
 __global__ void __launch_bounds__(256)
-exact_list_kernel(const float *__restrict__ pred, Dims d, int lw, Taps taps, const unsigned long long *__restrict__ idx,
-                  const unsigned long long *__restrict__ n_ptr, float *__restrict__ out) {
-    extern __shared__ float ex_sm[];
-    const unsigned long long n = *n_ptr;
-    for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+exact_z_kernel(const float *__restrict__ pred, Dims d, int lw, Taps taps, const unsigned long long *__restrict__ idx,
+               long long n, float *__restrict__ t1) {
+    const int W = 2 * lw + 1, W2 = W * W;
+    const long long plane = d.Y * d.X, total = n * W2;
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
+        const long long i = gi / W2;
+        const int c = (int)(gi - i * W2);
         const unsigned long long q = idx[i];
-        const long long x = (long long)(q % (unsigned long long)d.X);
-        const long long y = (long long)((q / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        const long long x = (long long)(q % (unsigned long long)d.X) + (c % W - lw);
+        const long long y = (long long)((q / (unsigned long long)d.X) % (unsigned long long)d.Y) + (c / W - lw);
         const long long z = (long long)(q / ((unsigned long long)d.X * d.Y));
-        const float s = exact_point(pred, d, lw, taps, z, y, x, ex_sm);
-        if (threadIdx.x == 0) out[i] = s;
+        float res = 0.f;
+        if (y >= 0 && y < d.Y && x >= 0 && x < d.X) {
+            const float *col = pred + y * d.X + x;
+            auto at = [&](long long zz) -> float { return (zz >= 0 && zz < d.Z) ? __ldg(col + zz * plane) : 0.f; };
+            float lo_v[kApxMaxLw], hi_v[kApxMaxLw];
+#pragma unroll
+            for (int k = 0; k < kApxMaxLw; ++k) {
+                lo_v[k] = k < lw ? at(z - lw + k) : 0.f;
+                hi_v[k] = k < lw ? at(z + lw - k) : 0.f;
+            }
+            double tmp = __dmul_rn((double)at(z), taps.w[lw]);
+#pragma unroll
+            for (int k = 0; k < kApxMaxLw; ++k)
+                if (k < lw) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)lo_v[k], (double)hi_v[k]), taps.w[k]));
+            res = (float)tmp;
+        }
+        t1[gi] = res;
     }
+}
+// in: n x rows x W (filter along rows, i.e. stride W) -> out: n x W; rows == W
+__global__ void __launch_bounds__(256)
+exact_y_kernel(const float *__restrict__ t1, int lw, Taps taps, long long n, float *__restrict__ t2) {
+    const int W = 2 * lw + 1;
+    const long long total = n * W;
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
+        const long long i = gi / W;
+        const int dx = (int)(gi - i * W);
+        const float *src = t1 + i * W * W + dx;
+        double tmp = __dmul_rn((double)src[lw * W], taps.w[lw]);
+        for (int k = 0; k < lw; ++k)
+            tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)src[k * W], (double)src[(2 * lw - k) * W]), taps.w[k]));
+        t2[gi] = (float)tmp;
+    }
+}
+__global__ void __launch_bounds__(256)
+exact_x_kernel(const float *__restrict__ t2, int lw, Taps taps, long long n, float *__restrict__ out) {
+    const int W = 2 * lw + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float *src = t2 + i * W;
+        double tmp = __dmul_rn((double)src[lw], taps.w[lw]);
+        for (int k = 0; k < lw; ++k)
+            tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn((double)src[k], (double)src[2 * lw - k]), taps.w[k]));
+        out[i] = (float)tmp;
+    }
+}
+
+static int exact_list(fpl_ctx *ctx, const float *d_pred, Dims d, int lw, const Taps &taps, const unsigned long long *idx,
+                      long long n, float *out, float *t1, float *t2, cudaStream_t st) {
+    const int W = 2 * lw + 1;
+    for (long long b0 = 0; b0 < n; b0 += kExactBatch) {
+        const long long nb = n - b0 < kExactBatch ? n - b0 : kExactBatch;
+        long long blocks = (nb * W * W + 255) / 256;
+        if (blocks > (long long)ctx->sm_count * 64) blocks = (long long)ctx->sm_count * 64;
+        exact_z_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_pred, d, lw, taps, idx + b0, nb, t1);
+        FPL_LAUNCH_CHECK(ctx);
+        long long b2 = (nb * W + 255) / 256; if (b2 > (long long)ctx->sm_count * 32) b2 = (long long)ctx->sm_count * 32;
+        exact_y_kernel<<<(unsigned)b2, 256, 0, st>>>(t1, lw, taps, nb, t2);
+        FPL_LAUNCH_CHECK(ctx);
+        long long b3 = (nb + 255) / 256;
+        exact_x_kernel<<<(unsigned)b3, 256, 0, st>>>(t2, lw, taps, nb, out + b0);
+        FPL_LAUNCH_CHECK(ctx);
+    }
+    return FPL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -311,133 +386,174 @@ __global__ void approx_band_kernel(const SelectState *lo, const SelectState *hi,
     s->cutA = cut;
 }
 
+// how many sample values lie inside [Lb, Hb]: x 64 = the expected size of the band list.  A map whose values crowd
+// around the percentile within the bound (tight distributions) is handed to the exact path before the dense pass.
+__global__ void __launch_bounds__(256)
+approx_sample_count_kernel(const float *__restrict__ sample, long long n_s, const ApproxState *S, unsigned long long *count) {
+    const float Lb = S->Lb, Hb = S->Hb;
+    unsigned c = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_s; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(sample + i);
+        c += (v >= Lb && v <= Hb) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // the ONE dense pass over A: count of voxels below the band, list of the voxels inside it, 8^3 brick maxima, and the
 // worklist of the first NMS round -- voxels >= cutA that no 26-neighbour certainly beats.  Warps are independent (no
-// shared memory, no barriers): a warp takes (plane z, group of 4 rows) items; a lane 4 consecutive x per 128-wide
-// chunk for the 4 rows plus one halo row on each side (6 x 16-byte loads in flight per thread, ~56 registers, so
-// 32+ warps per SM hide the memory latency).  The in-plane test is a separable 3x3 maximum in registers; the few
+// shared memory, no barriers).  A warp takes (plane z, strip of 32 rows) items and walks down the rows with a rolling
+// 3-row window; a lane owns 4 consecutive x (one 16-byte load per row), lanes 0 and 31 only feed their neighbours'
+// x +- 1 tests, so a warp produces 120 columns per pass and needs no edge loads.  The rows of the next group of 4 are
+// in flight while the current group is processed.  Per voxel: separable 3x3 maximum from registers + shuffles; the few
 // survivors fetch their 18 neighbours of the planes above / below through L1/L2.  Brick maxima are combined with
-// integer atomicMax on the (zero-initialised) grid: the values are non-negative floats.
+// integer atomicMax on the zero-initialised grid (the values are non-negative floats).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kP1Rows = 4;
-__global__ void __launch_bounds__(128, 6)
+constexpr int kP1Strip = 32, kP1Cols = 120, kP1Group = 4;
+__global__ void __launch_bounds__(128, 5)
 approx_pass1_kernel(const float *__restrict__ A, Dims d, int gy, int gx, float *__restrict__ g,
                     ApproxState *S, unsigned long long *band_idx, float *band_val, long long band_cap,
-                    unsigned long long *w_idx, float *w_val, long long w_cap, Counters *cnt) {
+                    unsigned long long *w_idx, float *w_val, long long w_cap, Counters *cnt, int own_z0, int own_z1) {
+    // planes [own_z0, own_z1) are owned (z-slab ranks: the rest is halo -- it feeds the neighbourhood tests and the brick
+    // maxima, but is neither counted, listed nor put on the worklist)
     const float Lb = S->Lb, Hb = S->Hb, cutA = S->cutA;
     const float lowA = fminf(Lb, cutA);                     // (a thd above the percentile lifts cutA over the band)
     const int lane = threadIdx.x & 31;
     const int X = (int)d.X, Y = (int)d.Y, Z = (int)d.Z;
     const bool vec_ok = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const long long plane = d.Y * d.X;
-    const int ygroups = (Y + kP1Rows - 1) / kP1Rows;
-    const long long n_items = (long long)Z * ygroups;
+    const int strips = (Y + kP1Strip - 1) / kP1Strip, xchunks = (X + kP1Cols - 1) / kP1Cols;
+    const long long n_items = (long long)Z * strips * xchunks;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const bool lane_owns = lane >= 1 && lane <= 30;
     unsigned long long n_below = 0;
     for (long long it = warp0; it < n_items; it += n_warps) {
-        const int z = (int)(it / ygroups), y0 = (int)(it - (long long)z * ygroups) * kP1Rows;
+        // x chunk fastest, then strip, then plane: concurrently running warps share halo rows / planes in L1/L2
+        const int xcI = (int)(it % xchunks);
+        const int sI = (int)((it / xchunks) % strips);
+        const int z = (int)(it / ((long long)xchunks * strips));
+        const int x = xcI * kP1Cols - 4 + 4 * lane, y0 = sI * kP1Strip;
+        const int y_end = min(y0 + kP1Strip, Y);            // rows [y0, y_end) are produced
         const float *pz = A + (long long)z * plane;
-        for (int xc = 0; xc < X; xc += 128) {
-            const int x = xc + 4 * lane;
-            float v[kP1Rows + 2][4];
-#pragma unroll
-            for (int rr = 0; rr < kP1Rows + 2; ++rr) {
-                const int yy = y0 - 1 + rr;
-                const bool rok = yy >= 0 && yy < Y && x < X;
+        const bool owned = z >= own_z0 && z < own_z1;       // warp-uniform
+        const bool col_ok = x >= 0 && x < X;
+        auto load_row = [&](int yy, float (&o)[4]) {
+            if (yy >= 0 && yy < Y && col_ok) {
                 const float *rp = pz + (long long)yy * X + x;
-                if (rok && vec_ok) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rp));
-                    v[rr][0] = q.x; v[rr][1] = q.y; v[rr][2] = q.z; v[rr][3] = q.w;
-                } else {
+                if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4 *>(rp)); o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
+                else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[rr][e] = (rok && x + e < X) ? __ldg(rp + e) : -INFINITY;
+                    for (int e = 0; e < 4; ++e) o[e] = x + e < X ? __ldg(rp + e) : -INFINITY;
                 }
+            } else { o[0] = o[1] = o[2] = o[3] = -INFINITY; }
+        };
+        float pv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};          // values of the previous row
+        float m3pp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, m3p[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float bm = 0.f;                                     // running brick maximum (8 rows)
+        float nxt[kP1Group][4];
+#pragma unroll
+        for (int k = 0; k < kP1Group; ++k) load_row(y0 - 1 + k, nxt[k]);
+        // rows y0-1 .. y_end (inclusive) are consumed; row yy-1 is produced when row yy arrives
+        for (int yb = y0 - 1; yb <= y_end; yb += kP1Group) {
+            float cur[kP1Group][4];
+#pragma unroll
+            for (int k = 0; k < kP1Group; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cur[k][e] = nxt[k][e];
+            if (yb + kP1Group <= y_end) {
+#pragma unroll
+                for (int k = 0; k < kP1Group; ++k) load_row(yb + kP1Group + k, nxt[k]);
             }
-            // 3-wide maximum along x (neighbouring lanes hold the neighbouring columns)
-            float m3[kP1Rows + 2][4];
+            unsigned surv = 0, bandm = 0;                   // bit 4 k + e: output row yb + k - 1, column x + e
 #pragma unroll
-            for (int rr = 0; rr < kP1Rows + 2; ++rr) {
-                float lf = __shfl_up_sync(0xffffffffu, v[rr][3], 1), rt = __shfl_down_sync(0xffffffffu, v[rr][0], 1);
-                if (lane == 0 || lane == 31) {
-                    const int yy = y0 - 1 + rr;
-                    const bool rok = yy >= 0 && yy < Y;
-                    const float *rp = pz + (long long)yy * X;
-                    if (lane == 0) lf = (rok && x >= 1 && x - 1 < X) ? __ldg(rp + x - 1) : -INFINITY;
-                    else rt = (rok && x + 4 < X) ? __ldg(rp + x + 4) : -INFINITY;
-                }
-                m3[rr][0] = fmaxf(fmaxf(lf, v[rr][0]), v[rr][1]);
-                m3[rr][1] = fmaxf(fmaxf(v[rr][0], v[rr][1]), v[rr][2]);
-                m3[rr][2] = fmaxf(fmaxf(v[rr][1], v[rr][2]), v[rr][3]);
-                m3[rr][3] = fmaxf(fmaxf(v[rr][2], v[rr][3]), rt);
-            }
-            float m = 0.f;
-            unsigned cand = 0, nb = 0;
-#pragma unroll
-            for (int rr = 1; rr <= kP1Rows; ++rr)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float f = v[rr][e];                   // -inf outside the volume
-                    m = fmaxf(m, f);
-                    nb += (f < Lb && f >= 0.f) ? 1u : 0u;       // (-inf = outside is not counted)
-                    cand |= (f >= lowA ? 1u : 0u) << ((rr - 1) * 4 + e);
-                }
-            n_below += nb;
-            if (cand) {
-                unsigned surv = 0;
-#pragma unroll
-                for (int rr = 1; rr <= kP1Rows; ++rr)
+            for (int k = 0; k < kP1Group; ++k) {
+                const int yy = yb + k;                      // the row that arrives; row yy - 1 is decided now
+                if (yy > y_end) break;                      // warp-uniform
+                const float lf = __shfl_up_sync(0xffffffffu, cur[k][3], 1), rt = __shfl_down_sync(0xffffffffu, cur[k][0], 1);
+                float m3c[4];
+                m3c[0] = fmaxf(fmaxf(lf, cur[k][0]), cur[k][1]);
+                m3c[1] = fmaxf(fmaxf(cur[k][0], cur[k][1]), cur[k][2]);
+                m3c[2] = fmaxf(fmaxf(cur[k][1], cur[k][2]), cur[k][3]);
+                m3c[3] = fmaxf(fmaxf(cur[k][2], cur[k][3]), rt);
+                const int yo = yy - 1;                      // output row
+                if (yo >= y0) {
+                    unsigned cand = 0, nb = 0;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const unsigned bit = 1u << ((rr - 1) * 4 + e);
-                        const float f = v[rr][e];
-                        const float m9 = fmaxf(fmaxf(m3[rr - 1][e], m3[rr][e]), m3[rr + 1][e]);
-                        // nobody in the plane certainly beats it (equal / near-equal neighbours are left to the ball check)
-                        if ((cand & bit) && f >= cutA && !(m9 > f * kApxUp)) surv |= bit;
-                        if ((cand & bit) && f >= Lb && f <= Hb) {
-                            const unsigned long long pos = atomicAdd(&S->n_band, 1ULL);
-                            const unsigned long long idx = (unsigned long long)((long long)z * plane + (long long)(y0 + rr - 1) * X + x + e);
-                            if ((long long)pos < band_cap) { band_idx[pos] = idx; band_val[pos] = f; }
-                            else atomicAdd(&S->overflow, 1ULL);
-                        }
+                        const float f = pv[e];                  // -inf outside the volume
+                        bm = fmaxf(bm, f);
+                        nb += (f < Lb && f >= 0.f) ? 1u : 0u;
+                        cand |= (f >= lowA ? 1u : 0u) << e;
                     }
-#pragma unroll 1
-                while (surv) {
-                    const int b = __ffs((int)surv) - 1;
-                    surv &= surv - 1u;
-                    const int yy = y0 + (b >> 2), xx = x + (b & 3);
-                    const unsigned long long idx = (unsigned long long)((long long)z * plane + (long long)yy * X + xx);
-                    const float val = __ldg(A + idx);
-                    const float hi = val * kApxUp;
-                    bool ok = true;
+                    if (owned && lane_owns) {
+                        n_below += nb;
+                        if (cand) {
 #pragma unroll
-                    for (int dz = -1; dz <= 1; dz += 2) {
-                        const int zz = z + dz;
-                        if (zz < 0 || zz >= Z) continue;
-#pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy) {
-                            const int y2 = yy + dy;
-                            if (y2 < 0 || y2 >= Y) continue;
-                            const float *rp = A + (long long)zz * plane + (long long)y2 * X;
-#pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int x2 = xx + dx;
-                                if (x2 >= 0 && x2 < X && __ldg(rp + x2) > hi) ok = false;
+                            for (int e = 0; e < 4; ++e) {
+                                const float f = pv[e];
+                                const float m9 = fmaxf(fmaxf(m3pp[e], m3p[e]), m3c[e]);
+                                // band member / nobody in the plane certainly beats it (near-equal neighbours are left to
+                                // the ball check): both are rare and handled after the group, out of the unrolled code
+                                if ((cand & (1u << e)) && f >= Lb && f <= Hb) bandm |= 1u << (4 * k + e);
+                                if ((cand & (1u << e)) && f >= cutA && !(m9 > f * kApxUp)) surv |= 1u << (4 * k + e);
                             }
                         }
                     }
-                    if (ok) {
-                        const unsigned long long pos = atomicAdd(&cnt->n_work, 1ULL);
-                        if ((long long)pos < w_cap) { w_idx[pos] = idx; w_val[pos] = val; }
-                        else atomicAdd(&cnt->overflow, 1ULL);
+                    // brick maximum: flushed every 8 rows (strips start on brick boundaries); lanes (odd, odd+1) share a brick
+                    if ((yo & (kBrick - 1)) == kBrick - 1 || yo == y_end - 1) {
+                        const float other = __shfl_down_sync(0xffffffffu, bm, 1);
+                        if ((lane & 1) && lane <= 29 && col_ok && fmaxf(bm, other) > 0.f)
+                            atomicMax(reinterpret_cast<int *>(g + ((size_t)(z / kBrick) * gy + yo / kBrick) * gx + x / kBrick),
+                                      __float_as_int(fmaxf(bm, other)));
+                        bm = 0.f;
                     }
                 }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { pv[e] = cur[k][e]; m3pp[e] = m3p[e]; m3p[e] = m3c[e]; }
             }
-            // brick maximum: two lanes share a brick (8 x); rows / planes of a brick are combined by the atomic
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            if ((lane & 1) == 0 && x < X && m > 0.f)
-                atomicMax(reinterpret_cast<int *>(g + ((size_t)(z / kBrick) * gy + y0 / kBrick) * gx + x / kBrick), __float_as_int(m));
+#pragma unroll 1
+            while (bandm) {
+                const int b = __ffs((int)bandm) - 1;
+                bandm &= bandm - 1u;
+                const unsigned long long idx = (unsigned long long)((long long)z * plane + (long long)(yb + (b >> 2) - 1) * X + x + (b & 3));
+                const unsigned long long pos = atomicAdd(&S->n_band, 1ULL);
+                if ((long long)pos < band_cap) { band_idx[pos] = idx; band_val[pos] = __ldg(A + idx); }
+                else atomicAdd(&S->overflow, 1ULL);
+            }
+#pragma unroll 1
+            while (surv) {
+                const int b = __ffs((int)surv) - 1;
+                surv &= surv - 1u;
+                const int yo = yb + (b >> 2) - 1, xx = x + (b & 3);
+                const unsigned long long idx = (unsigned long long)((long long)z * plane + (long long)yo * X + xx);
+                const float val = __ldg(A + idx);
+                const float hi = val * kApxUp;
+                bool ok = true;                             // the 18 neighbours of the planes above / below
+#pragma unroll
+                for (int dz = -1; dz <= 1; dz += 2) {
+                    const int zz = z + dz;
+                    if (zz < 0 || zz >= Z) continue;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int y2 = yo + dy;
+                        if (y2 < 0 || y2 >= Y) continue;
+                        const float *rp = A + (long long)zz * plane + (long long)y2 * X;
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int x2 = xx + dx;
+                            if (x2 >= 0 && x2 < X && __ldg(rp + x2) > hi) ok = false;
+                        }
+                    }
+                }
+                if (ok) {
+                    const unsigned long long pos = atomicAdd(&cnt->n_work, 1ULL);
+                    if ((long long)pos < w_cap) { w_idx[pos] = idx; w_val[pos] = val; }
+                    else atomicAdd(&cnt->overflow, 1ULL);
+                }
+            }
         }
     }
 #pragma unroll
@@ -551,32 +667,61 @@ __device__ __forceinline__ int approx_list_bricks(const float *__restrict__ g, i
     return min(*s_n, 1024);
 }
 
-// one block per worklist entry.  Outcome per entry p: some valid voxel of the ball certainly beats it -> nothing;
-// every other valid voxel of the ball is certainly worse -> selected; otherwise -> ambiguous list (exact resolve).
+// one WARP per worklist entry (no block barriers: entries are independent).  Outcome per entry p: some valid voxel of
+// the ball certainly beats it -> nothing; every other valid voxel of the ball is certainly worse -> selected;
+// otherwise -> ambiguous list (exact resolve).  A voxel that matters has A >= A(p)(1 - 4 eps), so only bricks whose
+// maximum reaches that are scanned (the brick grid stays in L2); for an isolated peak that is its own blob.
+constexpr int kBcListCap = 768;                             // >= 9^3 bricks can touch a ball of radius <= 31
 __global__ void __launch_bounds__(256)
 approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d, int r,
                         const float *__restrict__ g, int gy, int gx, const unsigned long long *__restrict__ w_idx,
                         const float *__restrict__ w_val, unsigned long long *det_idx, float *det_val,
                         unsigned long long *sel_idx, long long det_capacity, Counters *cnt, ApproxState *S,
                         unsigned long long *amb_idx, unsigned long long own_lo, unsigned long long own_hi) {
-    __shared__ int s_list[1024];
-    __shared__ int s_n, found, amb;
+    __shared__ int s_list_all[8][kBcListCap];
     const unsigned long long nW = cnt->n_work;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_list = s_list_all[warp];
     const int r2 = r * r;
     const float cutA = S->cutA;
-    for (unsigned long long w = blockIdx.x; w < nW; w += gridDim.x) {
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * 8 + warp, wstride = (unsigned long long)gridDim.x * 8;
+    for (unsigned long long w = w0; w < nW; w += wstride) {
         const unsigned long long idx = w_idx[w];
         const float val = w_val[w];
-        if (!(val >= cutA) || idx < own_lo || idx >= own_hi) continue;      // block-uniform
-        if (threadIdx.x == 0) { found = 0; amb = 0; }
+        if (!(val >= cutA) || idx < own_lo || idx >= own_hi) continue;      // warp-uniform
         const int x = (int)(idx % (unsigned long long)d.X);
         const int y = (int)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
         const int z = (int)(idx / ((unsigned long long)d.X * d.Y));
         const float lo = val * kApxDn, hi = val * kApxUp;
-        const int nlist = approx_list_bricks(g, gy, gx, d, r, z, y, x, lo, s_list, &s_n);
-        for (int li = warp; li < nlist; li += nwarps) {
-            if (*(volatile int *)&found) break;
+        // bricks of the ball whose maximum reaches lo
+        const int bz0 = max(z - r, 0) / kBrick, bz1 = (int)(min((long long)z + r, d.Z - 1) / kBrick);
+        const int by0 = max(y - r, 0) / kBrick, by1 = (int)(min((long long)y + r, d.Y - 1) / kBrick);
+        const int bx0 = max(x - r, 0) / kBrick, bx1 = (int)(min((long long)x + r, d.X - 1) / kBrick);
+        const int nby = by1 - by0 + 1, nbx = bx1 - bx0 + 1, nb = (bz1 - bz0 + 1) * nby * nbx;
+        int nlist = 0;
+        for (int i0 = 0; i0 < nb; i0 += 32) {
+            const int i = i0 + lane;
+            bool take = false;
+            int code = 0;
+            if (i < nb) {
+                const int bx = bx0 + i % nbx, by = by0 + (i / nbx) % nby, bz = bz0 + i / (nbx * nby);
+                const float gm = __ldg(g + ((size_t)bz * gy + by) * gx + bx);
+                if (gm >= lo) {
+                    const int cz = min(max(z, bz * kBrick), bz * kBrick + kBrick - 1);
+                    const int cy = min(max(y, by * kBrick), by * kBrick + kBrick - 1);
+                    const int cx = min(max(x, bx * kBrick), bx * kBrick + kBrick - 1);
+                    take = (cz - z) * (cz - z) + (cy - y) * (cy - y) + (cx - x) * (cx - x) <= r2;
+                    code = (bz << 20) | (by << 10) | bx;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (take) { const int slot = nlist + __popc(m & ((1u << lane) - 1u)); if (slot < kBcListCap) s_list[slot] = code; }
+            nlist += __popc(m);
+        }
+        __syncwarp();
+        if (nlist > kBcListCap) { if (lane == 0) atomicAdd(&S->overflow, 1ULL); continue; }
+        bool found = false, amb = false;
+        for (int li = 0; li < nlist && !found; ++li) {
             const int code = s_list[li];
             const int bz = code >> 20, by = (code >> 10) & 1023, bx = code & 1023;
             bool hit = false, near = false;
@@ -599,11 +744,11 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
                     if (vq >= lo && q != idx && !is_suppressed(sup, q)) { if (vq > hi) hit = true; else near = true; }
                 }
             }
-            if (__any_sync(0xffffffffu, hit)) { if (lane == 0) found = 1; }
-            if (__any_sync(0xffffffffu, near)) { if (lane == 0) amb = 1; }
+            found = __any_sync(0xffffffffu, hit);
+            amb = amb || __any_sync(0xffffffffu, near);
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && !found) {
+        __syncwarp();
+        if (lane == 0 && !found) {
             if (amb) {
                 const unsigned long long a = atomicAdd(&S->n_amb, 1ULL);
                 if (a < (unsigned long long)kApxAmbCap) amb_idx[a] = idx;
@@ -615,7 +760,6 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
                 else atomicAdd(&cnt->overflow, 1ULL);
             }
         }
-        __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&cnt->ball_checks, nW);
 }
@@ -854,34 +998,50 @@ static size_t approx_workspace_bytes(int64_t Z, int64_t Y, int64_t X, long long 
     const size_t n = (size_t)Z * Y * X;
     const size_t ns = (size_t)((Z + kApxSampleStep - 1) / kApxSampleStep) * ((Y + 3) / 4) * ((X + 3) / 4);
     return n * 4 + ns * 4 + (size_t)band_cap * 12 + (size_t)narrow_cap * 12 + (size_t)kApxAmbCap * 8 +
-           sizeof(ApproxState) + sizeof(ApproxHost) + 16 * 256 + 4096;
+           sizeof(ApproxState) + sizeof(ApproxHost) + (size_t)kExactBatch * (21 * 21 + 21) * 4 + 16 * 256 + 4096;
 }
 
 // The two-tier path of fpl_voxel2obj.  *done = false (with FPL_OK) when the map or the parameters do not qualify, or
 // when a certificate fails: the caller then runs the exact path.  Never returns a result it has not certified.
+// why the two-tier path handed the call to the exact path (fpl_debug_v2o_decline_reason; 0 = it did not):
+// 1 parameters / shape, 2 taps, 3 percentile at or near zero, 4 rank beyond the interior, 5 sample band touches an end,
+// 6 inputs negative / non-finite / huge or cut-off too small or list overflow, 16 the sample predicts a band list
+// overflow (values crowd around the percentile within the bound), 7 band certificate, 8 narrow list
+// overflow, 9 narrow band leaves the listed band, 10 narrow rank certificate, 11 NaN threshold, 12.. overflow in a round
+static int decline(fpl_ctx *ctx, int code) {
+    ctx->v2o_decline = code;
+    const ApproxHost *h = (const ApproxHost *)ctx->h_pinned;     // last snapshot (diagnosis only)
+    ctx->v2o_info[0] = (long long)h->st.n_below; ctx->v2o_info[1] = (long long)h->st.n_band;
+    ctx->v2o_info[2] = (long long)h->st.n_narrow; ctx->v2o_info[3] = (long long)h->st.n_below_narrow;
+    ctx->v2o_info[4] = (long long)h->st.overflow; ctx->v2o_info[5] = (long long)h->cnt.overflow;
+    ctx->v2o_info[6] = (long long)h->st.bad_bits; ctx->v2o_info[7] = (long long)(h->st.cutA * 1e9f);
+    return FPL_OK;
+}
+
 static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X, const fpl_v2o_params *p,
                             SelectState *d_states, ThreshOut *d_tout, long long list_cap, double *d_dets,
                             int64_t capacity, int64_t *h_count, double *h_threshold, int64_t *h_stats,
                             cudaStream_t st, bool *done) {
     *done = false;
+    ctx->v2o_decline = 0;
     const long long n = Z * Y * X;
     const int r = p->obj_min_dist, lw = p->lw;
-    if (r <= 0 || r > 27 + 4 || lw < 0 || lw > r || !approx_lw_supported(lw) || n < 32768 || p->thd != p->thd) return FPL_OK;
+    if (r <= 0 || r > 27 + 4 || lw < 0 || lw > r || !approx_lw_supported(lw) || n < 32768 || p->thd != p->thd) return decline(ctx, 1);
     Taps taps;
     memset(&taps, 0, sizeof(taps));
     float w32[2 * kApxMaxLw + 1];
     for (int i = 0; i < 2 * lw + 1; ++i) {
         taps.w[i] = p->h_weights[i];
-        if (!(taps.w[i] >= 0.0) || !(taps.w[i] <= 1.0)) return FPL_OK;
+        if (!(taps.w[i] >= 0.0) || !(taps.w[i] <= 1.0)) return decline(ctx, 2);
         w32[i] = (float)taps.w[i];
     }
     const unsigned long long n_pad = (unsigned long long)(Z + 2 * r) * (Y + 2 * r) * (X + 2 * r);
     const unsigned long long extra = n_pad - (unsigned long long)n;
     const int ns = p->rank_hi != p->rank_lo ? 2 : 1;
     // ranks among the interior values (the border zeros are the smallest values of a non-negative map)
-    if ((unsigned long long)p->rank_lo < extra + 16) return FPL_OK;         // percentile at / near zero: exact path
+    if ((unsigned long long)p->rank_lo < extra + 16) return decline(ctx, 3);         // percentile at / near zero: exact path
     const unsigned long long k_lo = (unsigned long long)p->rank_lo - extra, k_hi = (unsigned long long)p->rank_hi - extra;
-    if (k_hi >= (unsigned long long)n) return FPL_OK;
+    if (k_hi >= (unsigned long long)n) return decline(ctx, 4);
     Dims d{Z, Y, X};
     const int sy = (int)((Y + 3) / 4), sx = (int)((X + 3) / 4);
     const long long n_s = ((Z + kApxSampleStep - 1) / kApxSampleStep) * (long long)sy * sx;
@@ -890,7 +1050,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
     const double sig = sqrt((double)n_s * frac_lo * (1.0 - frac_lo));
     long long r_lo = (long long)floor(frac_lo * (double)(n_s - 1) - 6.0 * sig - 4.0);
     long long r_hi = (long long)ceil(frac_hi * (double)(n_s - 1) + 6.0 * sig + 4.0);
-    if (r_lo < 1 || r_hi > n_s - 2) return FPL_OK;                           // band would touch an end of the sample
+    if (r_lo < 1 || r_hi > n_s - 2) return decline(ctx, 5);                           // band would touch an end of the sample
     long long band_cap = (long long)(4.0 * (double)(r_hi - r_lo + 1) / (double)n_s * (double)n) + 65536;
     if (band_cap > n) band_cap = n;
     const long long narrow_cap = 1 << 18;
@@ -905,7 +1065,10 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
     unsigned long long *amb_idx = (unsigned long long *)ctx->arena.take((size_t)kApxAmbCap * 8);
     ApproxState *S = (ApproxState *)ctx->arena.take(sizeof(ApproxState));
     ApproxHost *d_host = (ApproxHost *)ctx->arena.take(sizeof(ApproxHost));
-    FPL_REQUIRE(A && sample && band_idx && band_val && nar_idx && nar_val && amb_idx && S && d_host &&
+    const int W = 2 * lw + 1;
+    float *ex_t1 = (float *)ctx->arena.take((size_t)kExactBatch * W * W * 4);
+    float *ex_t2 = (float *)ctx->arena.take((size_t)kExactBatch * W * 4);
+    FPL_REQUIRE(A && sample && band_idx && band_val && nar_idx && nar_val && amb_idx && S && d_host && ex_t1 && ex_t2 &&
                 sizeof(ApproxHost) <= 1024, "voxel2obj: workspace sizing error (two-tier path)");
     DetectBuffers B;
     FPL_TRY(take_detect_buffers(ctx, Z, Y, X, list_cap, det_cap, B, st));
@@ -933,18 +1096,24 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         FPL_TRY(select_rank(ctx, sample, n_s, 0ULL, (unsigned long long)r_hi, &d_states[1], st));
         approx_band_kernel<<<1, 32, 0, st>>>(&d_states[0], &d_states[1], p->thd, S);
         FPL_LAUNCH_CHECK(ctx);
+        approx_sample_count_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(sample, n_s, S, &S->n_narrow);     // (n_narrow is unused until later)
+        FPL_LAUNCH_CHECK(ctx);
+        FPL_TRY(collect());
+        if (h->st.bad_bits >= kApxBadBits || !(h->st.cutA >= kApxMinCut)) return decline(ctx, 6);
+        if ((double)h->st.n_narrow * 64.0 * 1.5 > (double)band_cap) return decline(ctx, 16);     // band list would overflow
+        FPL_CUDA_CHECK(cudaMemsetAsync(&S->n_narrow, 0, sizeof(unsigned long long), st));
         FPL_CUDA_CHECK(cudaMemsetAsync(B.grid, 0, brick_grid_bytes(Z, Y, X), st));
-        const long long items = Z * ((Y + kP1Rows - 1) / kP1Rows);
+        const long long items = Z * ((Y + kP1Strip - 1) / kP1Strip) * ((X + kP1Cols - 1) / kP1Cols);
         long long g1 = (items + 3) / 4;
         if (g1 > (long long)ctx->sm_count * 64) g1 = (long long)ctx->sm_count * 64;
         approx_pass1_kernel<<<(unsigned)g1, 128, 0, st>>>(A, d, B.gy, B.gx, B.grid, S, band_idx, band_val, band_cap, B.w_idx,
-                                                          B.w_val, B.list_cap, B.cnt);
+                                                          B.w_val, B.list_cap, B.cnt, 0, (int)Z);
         FPL_LAUNCH_CHECK(ctx);
         FPL_TRY(collect());
     }
-    if (h->st.bad_bits >= kApxBadBits || !(h->st.cutA >= kApxMinCut) || h->st.overflow || h->cnt.overflow) return FPL_OK;
+    if (h->st.bad_bits >= kApxBadBits || !(h->st.cutA >= kApxMinCut) || h->st.overflow || h->cnt.overflow) return decline(ctx, 6);
     // certificate of the band: both ranks fall inside the listed voxels
-    if (k_lo < h->st.n_below || k_hi - h->st.n_below >= h->st.n_band) return FPL_OK;
+    if (k_lo < h->st.n_below || k_hi - h->st.n_below >= h->st.n_band) return decline(ctx, 7);
     const unsigned long long j_lo = k_lo - h->st.n_below, j_hi = k_hi - h->st.n_below;
     float s_lo = 0.f, s_hi = 0.f;
     {
@@ -960,14 +1129,13 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         int nb = (int)((h->st.n_band + 255) / 256); if (nb > grid_stream) nb = grid_stream; if (nb < 1) nb = 1;
         approx_narrow_kernel<<<nb, 256, 0, st>>>(band_idx, band_val, S, nar_idx, narrow_cap);
         FPL_LAUNCH_CHECK(ctx);
-        exact_list_kernel<<<ctx->sm_count * 4, 256, ex_smem, st>>>(d_pred, d, lw, taps, nar_idx, &S->n_narrow, nar_val);
-        FPL_LAUNCH_CHECK(ctx);
         FPL_TRY(collect());
-        if (h->st.overflow || h->st.n_narrow > (unsigned long long)narrow_cap) return FPL_OK;
+        if (h->st.overflow || h->st.n_narrow > (unsigned long long)narrow_cap) return decline(ctx, 8);
+        FPL_TRY(exact_list(ctx, d_pred, d, lw, taps, nar_idx, (long long)h->st.n_narrow, nar_val, ex_t1, ex_t2, st));
         // the narrow band must lie inside the listed band (else voxels outside the list could belong to it)
-        if (!(h->st.n_lo >= h->st.Lb) || !(h->st.n_hi <= h->st.Hb)) return FPL_OK;
+        if (!(h->st.n_lo >= h->st.Lb) || !(h->st.n_hi <= h->st.Hb)) return decline(ctx, 9);
         const unsigned long long below = h->st.n_below_narrow;
-        if (j_lo < below || j_hi - below >= h->st.n_narrow) return FPL_OK;
+        if (j_lo < below || j_hi - below >= h->st.n_narrow) return decline(ctx, 10);
         std::vector<float> vals((size_t)h->st.n_narrow);
         FPL_CUDA_CHECK(cudaMemcpyAsync(vals.data(), nar_val, sizeof(float) * vals.size(), cudaMemcpyDeviceToHost, st));
         FPL_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -976,7 +1144,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         s_hi = vals[(size_t)(j_hi - below)];
     }
     const double threshold = approx_threshold_value(s_lo, s_hi, p->gamma, p->thd);
-    if (threshold != threshold) return FPL_OK;
+    if (threshold != threshold) return decline(ctx, 11);
     if (h_threshold) *h_threshold = threshold;
     approx_set_thresh_kernel<<<1, 32, 0, st>>>(d_tout, threshold, s_lo, s_hi);
     FPL_LAUNCH_CHECK(ctx);
@@ -1019,13 +1187,13 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
                 FPL_CUDA_CHECK(cudaMemcpyAsync(&h->cnt.n_cand, &B.cnt->n_cand, 8, cudaMemcpyDeviceToHost, st));
                 FPL_CUDA_CHECK(cudaMemcpyAsync(&h->cnt.overflow, &B.cnt->overflow, 8, cudaMemcpyDeviceToHost, st));
                 FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-                if (h->st.overflow) return FPL_OK;
+                if (h->st.overflow) return decline(ctx, 12);
                 if (h->cnt.overflow) {
                     if (h->cnt.n_det > (unsigned long long)det_cap) {
                         fpl::set_error("voxel2obj: detection capacity %lld too small (need > %llu)", (long long)capacity, h->cnt.n_det);
                         return FPL_EOVERFLOW;
                     }
-                    return FPL_OK;
+                    return decline(ctx, 13);
                 }
                 n_first = h->cnt.n_det;
                 n_amb_total += h->st.n_amb;
@@ -1039,13 +1207,13 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
             FPL_LAUNCH_CHECK(ctx);
             FPL_CUDA_CHECK(cudaMemcpyAsync(h, d_host, sizeof(ApproxHost), cudaMemcpyDeviceToHost, st));
             FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-            if (h->st.overflow) return FPL_OK;
+            if (h->st.overflow) return decline(ctx, 14);
             if (h->cnt.overflow) {
                 if (h->cnt.n_det > (unsigned long long)det_cap) {
                     fpl::set_error("voxel2obj: detection capacity %lld too small (need > %llu)", (long long)capacity, h->cnt.n_det);
                     return FPL_EOVERFLOW;
                 }
-                return FPL_OK;
+                return decline(ctx, 15);
             }
             if (h->cnt.n_sel_round == 0 && h->cnt.n_next > 0) {
                 fpl::set_error("voxel2obj: NMS round made no progress (internal error, two-tier path)");
@@ -1059,10 +1227,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         }
         // tier 2 for the detections: exact confidences; finish_rows drops the selected points that are not above the threshold
         const unsigned long long n_det = h->cnt.n_det;
-        if (n_det > 0) {
-            exact_list_kernel<<<ctx->sm_count * 4, 256, ex_smem, st>>>(d_pred, d, lw, taps, B.det_idx, &B.cnt->n_det, B.det_val);
-            FPL_LAUNCH_CHECK(ctx);
-        }
+        if (n_det > 0) FPL_TRY(exact_list(ctx, d_pred, d, lw, taps, B.det_idx, (long long)n_det, B.det_val, ex_t1, ex_t2, st));
         unsigned long long n_rows = 0;
         FPL_TRY(finish_detections(ctx, B, n_det, d, p, d_dets, capacity, d_tout, &n_rows, st));
         if (h_count) *h_count = (int64_t)n_rows;

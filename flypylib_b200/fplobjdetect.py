@@ -124,8 +124,11 @@ def voxel2obj_device(pred_dev, obj_min_dist, smoothing_sigma, volume_offset=(0, 
     if return_stats:
         # stats[6]: which path of fpl_voxel2obj produced the result (all three are bit-identical by construction)
         path = {2: 'two-tier', 1: 'fused-exact'}.get(int(stats[6]), 'classic-exact')
+        lib = _lib.lib()
+        lib.fpl_debug_v2o_decline_reason.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        declined = int(lib.fpl_debug_v2o_decline_reason(ctx.handle, 0))
         return out, {'threshold': thresh.value, 'candidates': stats[0], 'rounds': stats[1],
-                     'ball_checks': stats[2], 'selected': stats[3], 'path': path,
+                     'ball_checks': stats[2], 'selected': stats[3], 'path': path, 'two_tier_declined': declined,
                      'exact_recomputed': int(stats[4]) if path == 'two-tier' else None,
                      'ambiguous_ball_checks': int(stats[7]) if path == 'two-tier' else None}
     return out

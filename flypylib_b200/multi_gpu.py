@@ -135,6 +135,14 @@ def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigm
     return merge_detections([p.cpu().numpy() for p in parts])
 
 
+def halo_planes(obj_min_dist, smoothing_sigma):
+    """Planes of the probability map a rank needs beyond its own on each side for the exact-global voxel2obj:
+    r (suppression ball) + lw (Gaussian half width)."""
+    from . import fplobjdetect as P
+    _, lw = P._gaussian_taps(smoothing_sigma)
+    return int(obj_min_dist) + max(int(lw), 0)
+
+
 def detect_volume_sharded(network, image_slab, Z, plans, normalize, obj_min_dist, smoothing_sigma,
                           volume_offset=(0, 0, 0), buffer_sz=0, thd=0, group=None, return_stats=False):
     """The whole T-bar path on ONE (Z,Y,X) volume sharded as z-slabs over the ranks of ``group`` (one process per
@@ -148,14 +156,21 @@ def detect_volume_sharded(network, image_slab, Z, plans, normalize, obj_min_dist
     rank = dist.get_rank(group)
     (in0, in1), (own0, own1) = plans[rank]
     Y, X = int(image_slab.shape[1]), int(image_slab.shape[2])
+    ext = None
     if in1 > in0:
-        pred, first, last = network.infer_slab_device(image_slab, Z, in0, normalize=normalize)
+        # the forward pass writes this rank's planes straight into the extended slab the detection works on (its halo
+        # margins are filled by the exchange): no staging copy of the probability map
+        h = halo_planes(obj_min_dist, smoothing_sigma)
+        e0, e1 = max(0, own0 - h), min(Z, own1 + h)
+        ext = torch.empty((e1 - e0, Y, X), dtype=torch.float32, device=image_slab.device)
+        _, first, last = network.infer_slab_device(image_slab, Z, in0, normalize=normalize, pred=ext, pred_z0=e0)
         assert (first, last) == (own0, own1), ((first, last), (own0, own1))
+        pred = ext[own0 - e0:own1 - e0]
     else:
         pred = torch.zeros((0, Y, X), dtype=torch.float32, device=image_slab.device)
     coll = _DistCollectives(group, all_ranges=[p[1] for p in plans])
     return voxel2obj_global([pred], [(own0, own1)], Z, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd,
-                            coll=coll, return_stats=return_stats)
+                            coll=coll, return_stats=return_stats, ext_slabs=[ext])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -182,7 +197,9 @@ class _DistCollectives(object):
         self.local_ranks = [self.rank]
         self.all_ranges = [tuple(r) for r in all_ranges] if all_ranges is not None else None
 
-    def halo(self, slabs, ranges, Z, h):
+    def halo(self, slabs, ranges, Z, h, ext=None):
+        """-> [(extended slab, its first plane)].  ``ext`` (optional): the extended slab preallocated by the caller with
+        the owned planes already in place (``slabs[0]`` is then a view of it) -- no staging copy."""
         import torch
         dist = self.dist
         slab, (z0, z1) = slabs[0], ranges[0]
@@ -190,12 +207,17 @@ class _DistCollectives(object):
         if all_ranges is None:                                  # callers that know the plan pass it (no collective)
             all_ranges = [None] * self.world
             dist.all_gather_object(all_ranges, (z0, z1), group=self.group)
+            self.all_ranges = [tuple(r) for r in all_ranges]
         assert tuple(all_ranges[self.rank]) == (z0, z1)
         if z1 <= z0:                                            # a rank without planes takes no part in the exchange
             return [(slab, z0)]
         e0, e1 = max(0, z0 - h), min(Z, z1 + h)
-        ext = torch.empty((e1 - e0,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
-        ext[z0 - e0:z1 - e0] = slab
+        if ext is not None and ext[0] is not None:
+            ext = ext[0]
+            assert int(ext.shape[0]) == e1 - e0
+        else:
+            ext = torch.empty((e1 - e0,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+            ext[z0 - e0:z1 - e0] = slab
         ops = []
         for peer, (p0, p1) in enumerate(all_ranges):
             if peer == self.rank or p1 <= p0:
@@ -211,6 +233,17 @@ class _DistCollectives(object):
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         return [(ext, e0)]
+
+    def known_ranges(self, ranges):
+        return self.all_ranges
+
+    def gather_blocks(self, blocks):
+        """One all-gather of equal-sized blocks -> [(world, *block.shape)]."""
+        import torch
+        b = blocks[0]
+        out = torch.empty(self.world * b.numel(), dtype=b.dtype, device=b.device)
+        self.dist.all_gather_into_tensor(out, b.reshape(-1), group=self.group)
+        return [out.view((self.world,) + tuple(b.shape))]
 
     def allreduce(self, tensors):
         self.dist.all_reduce(tensors[0], group=self.group)
@@ -246,7 +279,15 @@ class _LocalCollectives(object):
     def __init__(self, world):
         self.world, self.rank, self.local_ranks = world, 0, list(range(world))
 
-    def halo(self, slabs, ranges, Z, h):
+    def known_ranges(self, ranges):
+        return list(ranges)
+
+    def gather_blocks(self, blocks):
+        import torch
+        g = torch.stack(blocks, 0)
+        return [g for _ in blocks]
+
+    def halo(self, slabs, ranges, Z, h, ext=None):
         import torch
         full = torch.cat(slabs, 0)
         base = ranges[0][0]
@@ -288,7 +329,7 @@ def _scan_level(hist, rank, prefix, mask, shift, bins, extra_zeros):
 
 
 def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volume_offset=(0, 0, 0), buffer_sz=0,
-                     thd=0, coll=None, return_stats=False):
+                     thd=0, coll=None, return_stats=False, ext_slabs=None):
     """voxel2obj of the whole (Z,Y,X) map whose planes [z0,z1) are held by different ranks; bit-identical to
     the single call.  ``pred_slabs`` / ``ranges``: CUDA float32 slabs and their (z0,z1) for the LOCAL ranks
     (one entry with torch.distributed, all ranks with ``_LocalCollectives``).  Every rank returns the full
@@ -309,13 +350,27 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
     r, lw = int(p.obj_min_dist), max(int(p.lw), 0)
     empty = {'locs': np.zeros((0, 3)), 'conf': np.zeros(0)}
     stats = {'threshold': float('nan'), 'rounds': 0}
+    stages = stats.setdefault('stage_ms', {}) if return_stats == 'stages' else None
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def mark(name):
+        """stage timing (only with return_stats='stages': it synchronises the device at every stage boundary)"""
+        if stages is not None:
+            torch.cuda.synchronize()
+            now = _time.perf_counter()
+            stages[name] = stages.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
 
     def done(out):
         return (out, stats) if return_stats else out
 
     with torch.cuda.device(devi):
         # 1. halo exchange + exact smoothing of [z0-r, z1+r)
-        ext = coll.halo([s.contiguous() for s in pred_slabs], ranges, Z, r + lw)
+        mark('setup')
+        # (ext_slabs: extended slabs preallocated by the caller, owned planes already in place -- see halo_planes())
+        ext = coll.halo([s.contiguous() for s in pred_slabs], ranges, Z, r + lw, ext=ext_slabs)
+        mark('halo_exchange')
         smooth, s_lo = [], []
         for (e, e0), (z0, z1) in zip(ext, ranges):
             d_s = torch.empty_like(e)
@@ -325,6 +380,7 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
             s0, s1 = max(0, z0 - r), min(Z, z1 + r)
             smooth.append(d_s[s0 - e0:s1 - e0]); s_lo.append(s0)
         del ext
+        mark('smooth_exact')
         # 2. global percentile (np.percentile of the padded volume): three all-reduced radix levels
         n_pad = (Z + 2 * r) * (Y + 2 * r) * (X + 2 * r)
         extra = n_pad - Z * Y * X
@@ -359,6 +415,7 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
         pr = float(res)
         thresh = float('nan') if (pr != pr or p.thd != p.thd) else max(pr, float(p.thd))
         stats['threshold'] = thresh
+        mark('percentile_3_levels_allreduce')
         # 3. NMS rounds
         cand_bound = max(1, n_pad - targets[0])
         sessions, sel_bufs = [], []
@@ -372,30 +429,34 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
             _lib.check(lib.fpl_v2o_slab_begin(ctx.handle, sm.data_ptr(), ze, Y, X, ctypes.byref(p), thresh, z0 - lo, z1 - lo,
                                               int(min(ze * Y * X, cand_bound)), cap, ctypes.byref(h), ctypes.byref(ncand), st),
                        "fpl_v2o_slab_begin")
-            sessions.append(h); sel_bufs.append(torch.empty((cap, 3), dtype=torch.int64, device=dev))
+            sessions.append(h); sel_bufs.append(None)
+        mark('dense_pass_local_maxima')
+        # every round: decision half on every rank -> ONE all-gather of fixed-size blocks (header + selected points) ->
+        # update half; the host reads the gathered headers once per round (termination, overflow)
+        all_rng = coll.known_ranges(ranges)
+        max_planes = max([b_ - a_ for a_, b_ in all_rng] + [1])
+        sel_cap = P._default_capacity((max_planes + 2 * r, Y, X), r)
+        blocks = [torch.zeros((1 + sel_cap, 3), dtype=torch.int64, device=dev) for _ in sessions]
         while True:
-            sels, alive = [], []
-            for h, buf, lo in zip(sessions, sel_bufs, s_lo):
-                if h is None:
-                    sels.append(torch.zeros((0, 3), dtype=torch.int64, device=dev)); alive.append(0); continue
-                n_sel, n_alive = ctypes.c_int64(), ctypes.c_int64()
-                _lib.check(lib.fpl_v2o_slab_round(h, buf.data_ptr(), int(buf.shape[0]), ctypes.byref(n_sel),
-                                                  ctypes.byref(n_alive), st), "fpl_v2o_slab_round")
-                pts = buf[:n_sel.value].clone()
-                pts[:, 0] += lo                                         # global z
-                sels.append(pts); alive.append(n_alive.value)
-            gathered, tot_alive = coll.allgather(sels, scalars=alive)
-            if tot_alive == 0:
+            for h, blk, lo in zip(sessions, blocks, s_lo):
+                if h is not None:
+                    _lib.check(lib.fpl_v2o_slab_round_pack(h, blk.data_ptr(), sel_cap, lo, st), "fpl_v2o_slab_round_pack")
+            mark('round_decide')
+            gathered = coll.gather_blocks(blocks)
+            mark('round_allgather')
+            for h, lo, gb in zip(sessions, s_lo, gathered):
+                if h is not None:
+                    _lib.check(lib.fpl_v2o_slab_apply_blocks(h, gb.data_ptr(), int(gb.shape[0]), sel_cap, lo, st),
+                               "fpl_v2o_slab_apply_blocks")
+            heads = gathered[0][:, 0, :].cpu().numpy()              # the one host synchronisation of the round
+            mark('round_suppress')
+            if heads[:, 2].any():
+                raise RuntimeError("voxel2obj_global: list overflow in an NMS round (capacity %d)" % sel_cap)
+            if int(heads[:, 1].sum()) == 0:
                 break
             stats['rounds'] += 1
-            if int(gathered[0].shape[0]) == 0:
+            if int(heads[:, 0].sum()) == 0:
                 raise RuntimeError("voxel2obj_global: NMS round made no progress (internal error)")
-            for h, lo, pts in zip(sessions, s_lo, gathered):
-                if h is None:
-                    continue
-                loc = pts.clone()
-                loc[:, 0] -= lo
-                _lib.check(lib.fpl_v2o_slab_suppress(h, loc.data_ptr(), int(loc.shape[0]), st), "fpl_v2o_slab_suppress")
         # 4. owned detections -> global list
         rows = []
         for h, lo, sm in zip(sessions, s_lo, smooth):
@@ -410,6 +471,7 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
             o[:, 0] += lo
             rows.append(o)
         allrows = coll.allgather(rows)[0].cpu().numpy()
+        mark('final_allgather')
     if allrows.shape[0] == 0:
         return done(empty)
     z, y, x, c = allrows[:, 0], allrows[:, 1], allrows[:, 2], allrows[:, 3]

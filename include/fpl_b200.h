@@ -141,6 +141,15 @@ int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64
 /* Update half: suppress the balls of the points selected by ALL ranks (slab coordinates; points outside the
  * slab are legal, only the part of their ball inside counts). */
 int fpl_v2o_slab_suppress(void *session, const int64_t *d_zyx, int64_t n_pts, void *stream);
+/* The same round without a host round trip between its halves.  round_pack: decision half; d_block (device,
+ * (1 + sel_cap) x 3 int64) receives row 0 = (points selected, valid owned candidates at round start, overflow flag)
+ * and rows 1.. = (z + z_offset, y, x) of the selected points.  The caller all-gathers the blocks of all ranks (ONE
+ * collective per round) and passes them to apply_blocks, which suppresses every ball that reaches this slab
+ * (z_offset = global z of this slab's plane 0 in both calls).  Neither call synchronises; the caller reads the
+ * gathered header rows once per round to decide termination. */
+int fpl_v2o_slab_round_pack(void *session, int64_t *d_block, int64_t sel_cap, int64_t z_offset, void *stream);
+int fpl_v2o_slab_apply_blocks(void *session, const int64_t *d_blocks, int32_t n_blocks, int64_t sel_cap,
+                              int64_t z_offset, void *stream);
 /* Close: rows (z, y, x, conf) of the owned detections in slab coordinates, unordered. */
 int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h_count, int64_t *h_rounds,
                      void *stream);

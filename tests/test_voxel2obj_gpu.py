@@ -64,6 +64,17 @@ def test_stages_bit_exact_vs_oracle_and_golden(case, generic):
     assert np.array_equal(rows[:, 3], GOLD[name + "/conf"])
 
 
+@pytest.fixture(autouse=True)
+def _no_two_tier_backoff():
+    """fpl_voxel2obj backs off from the two-tier path after data-dependent declines (adaptive, per context); tests
+    must not inherit that state from the maps of the previous test."""
+    from flypylib_b200 import _lib
+    lib = _lib.lib()
+    lib.fpl_debug_v2o_decline_reason.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.fpl_debug_v2o_decline_reason(_lib.context(0).handle, 1)
+    yield
+
+
 @pytest.fixture(params=["default", "fused", "classic"])
 def v2o_path(request):
     """fpl_voxel2obj has three detection paths: the two-tier one (fp32 smoothing with a proven bound, exact values

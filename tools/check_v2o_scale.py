@@ -67,6 +67,8 @@ def compare(shape, kind, seed, r, sigma, buf, thd, classic=False, mode=None):
     lib.fpl_debug_v2o_classic.argtypes = [ctypes.c_int]
     mode = (1 if classic else 0) if mode is None else int(mode)
     lib.fpl_debug_v2o_classic(mode)
+    lib.fpl_debug_v2o_decline_reason.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.fpl_debug_v2o_decline_reason(_lib.context(0).handle, 1)          # no back-off inherited from earlier maps
     try:
         got, st = fplobjdetect.voxel2obj_device(pm, r, sigma, (0, 0, 0), buf, thd, return_stats=True)    # warm-up
         torch.cuda.synchronize()

@@ -1,0 +1,5 @@
+#!/bin/bash
+tag=${1:-r2m}
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-extras > gpurun_out/${tag}_bench_n2.json 2> gpurun_out/${tag}_bench_n2.err; echo "rc=$?" >> gpurun_out/${tag}_bench_n2.err
+exit 0
