@@ -377,14 +377,22 @@ static int infer_volume_impl(fpl_net *net, const void *d_image, int image_is_u8,
             TileGrid gs = g;
             gs.out_sz = nxy * g.out_sz; gs.in_sz = gs.out_sz + 2 * off;
             gs.ny = gs.nx = 1;
-            const int n_full = g.nz / mz, rem = g.nz % mz;
+            // full slabs of mz reference layers, then ONE tail slab that holds exactly the planes that are left, rounded
+            // up to the net stride (shift-equivariance: any thickness that is a multiple of rf_stride reproduces the
+            // reference values) -- a tail of whole layers would compute up to out_sz - 1 planes nobody reads, which is
+            // a quarter of the work of a rank that owns 128 planes of a sharded volume
+            const long long need = Z - 2LL * off;                        // prediction planes to produce
+            const long long slab_out = (long long)mz * g.out_sz;
+            const int n_full = (int)(need / slab_out);
+            const long long tail = need - (long long)n_full * slab_out;
+            const int stride = net->info.rf_stride;
             if (n_full > 0) {
-                gs.out_z = mz * g.out_sz; gs.in_z = gs.out_z + 2 * off; gs.nz = n_full; gs.z_base = 0;
+                gs.out_z = (int)slab_out; gs.in_z = gs.out_z + 2 * off; gs.nz = n_full; gs.z_base = 0;
                 phases.push_back({gs, (long long)n_full, 1, nullptr, 0});
             }
-            if (rem > 0) {
-                gs.out_z = rem * g.out_sz; gs.in_z = gs.out_z + 2 * off; gs.nz = 1;
-                gs.z_base = (long long)n_full * mz * g.out_sz;
+            if (tail > 0) {
+                gs.out_z = (int)((tail + stride - 1) / stride * stride); gs.in_z = gs.out_z + 2 * off; gs.nz = 1;
+                gs.z_base = (long long)n_full * slab_out;
                 phases.push_back({gs, 1, 1, nullptr, 0});
             }
         }

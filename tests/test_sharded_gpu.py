@@ -123,6 +123,13 @@ def test_bench_tile_schedule_equals_reference_grid():
     got = net.infer_device(u8, normalize=NORM)
     assert torch.equal(ref, got)
     assert float(got[10:-10, 10:-10, 10:-10].min()) > 0.0 and not got[:10].any()
+    # tail slab trimmed to the planes that are left (rounded up to rf_stride): 431 planes -> 320 + 92 (91 needed)
+    for zcut in (431, 346, 118):
+        sub = u8[:zcut].contiguous()
+        net.tile_multiplier = 1
+        ref = net.infer_device(sub, normalize=NORM)
+        net.tile_multiplier = 4
+        assert torch.equal(ref, net.infer_device(sub, normalize=NORM)), zcut
 
 
 def test_bf16_config_tile_and_slab_tile_vs_float64():
