@@ -312,27 +312,30 @@ def leg_cfg4(dev, sync, ctx, pk, size=2048):
 
 
 def leg_cfg3(dev, sync, world, rank, size=2048):
-    """BASELINE configs[2]: unet_like2 on ONE synthetic size^3 volume, z-slab sharded at tile-layer granularity with
-    receptive-field halos over the ranks, exact-global voxel2obj, detections on every rank."""
+    """BASELINE configs[2]: unet_like2 on ONE synthetic size^3 volume, sharded over the ranks with the (z, y) tile rows
+    of the reference grid dealt evenly (the U-Net can only be cut on the tile grid; rows a rank evaluates for a
+    neighbour's layer go to the plane owner over NCCL P2P), exact-global voxel2obj, detections on every rank."""
     import torch
     from flypylib_b200 import multi_gpu
     net = build_net("unet_like2", "bf16", 1)
-    plans = multi_gpu.shard_plan(size, int(net.rf_offset[0]), net.slab_granularity(), world)
-    (in0, in1), own = plans[rank]
+    off, out = int(net.rf_offset[0]), net.slab_granularity()
+    pieces, plans = multi_gpu.row_plan(size, size, off, out, world)
+    in0, in1 = multi_gpu.image_planes_for_pieces(pieces[rank], size, size, off, out)
     slab = synth_volume_planes(size, in0, in1, 4321, dev)
 
     def step():
-        return multi_gpu.detect_volume_sharded(net, slab, size, plans, NORM, DET["obj_min_dist"], DET["smoothing_sigma"],
-                                               (0, 0, 0), DET["buffer_sz"], DET["thd"])
+        return multi_gpu.detect_volume_rows_sharded(net, slab, in0, size, pieces, plans, NORM, DET["obj_min_dist"],
+                                                    DET["smoothing_sigma"], (0, 0, 0), DET["buffer_sz"], DET["thd"])
     step()
-    ms, _, out = timed(step, 1, sync)
+    ms, _, out_d = timed(step, 1, sync)
     t = torch.tensor([ms], device=dev)
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t)
-    return {"workload": "unet_like2 (bf16) inference + exact-global voxel2obj on ONE synthetic %d^3 uint8 volume, z-slab "
-                        "sharded over %d GPUs at tile-layer granularity (BASELINE configs[2])" % (size, world),
+    return {"workload": "unet_like2 (bf16) inference + exact-global voxel2obj on ONE synthetic %d^3 uint8 volume sharded over "
+                        "%d GPUs, tile rows of the reference grid dealt evenly (BASELINE configs[2])" % (size, world),
             "value": size ** 3 / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world,
-            "detections": int(out["conf"].size), "planes_per_rank": [p[1][1] - p[1][0] for p in plans]}
+            "detections": int(out_d["conf"].size), "tile_rows_per_rank": [sum(yb - ya for _, ya, yb, _ in m) for m in pieces],
+            "planes_owned_per_rank": [p[1][1] - p[1][0] for p in plans]}
 
 
 def main():
@@ -404,10 +407,12 @@ def main():
             # single-GPU detection list on every rank
             return multi_gpu.detect_volume_sharded(net, vol, size, plans, NORM, *det)
 
+    # the clock sampler (nvidia-smi -lms) is started BEFORE the warm-up: its start-up (NVML initialisation takes driver
+    # locks for ~1 s) must not fall into the timed region; it keeps sampling through the timed steps
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         out = step()
     sync()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count()
     ctx.profile_begin()
     ms_per_step, _, out = timed(step, args.steps, sync)
@@ -421,6 +426,9 @@ def main():
         _o, st_ = multi_gpu.detect_volume_sharded(net, vol, size, plans, NORM, *det, return_stats='stages')
         s2_stages = {k: round(v, 3) for k, v in st_['stage_ms'].items()}       # 'setup' = the forward pass of this rank
         s2_stages['rounds'] = st_['rounds']
+        per_rank = [None] * world                                               # load balance: forward ms / total of every rank
+        dist.all_gather_object(per_rank, (round(st_['stage_ms'].get('setup', 0.0), 2), round(sum(st_['stage_ms'].values()), 2)))
+        s2_stages['forward_and_total_ms_by_rank'] = per_rank
     n_det = int(out["conf"].size)
     import hashlib      # same list at every N (strong scaling on one volume, exact-global detection): compare across runs
     det_sha = hashlib.sha256(np.ascontiguousarray(out["locs"]).tobytes() + np.ascontiguousarray(out["conf"]).tobytes()).hexdigest()[:16]

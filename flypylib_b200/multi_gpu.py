@@ -135,6 +135,133 @@ def detect_substacks(network, image_dev, normalize, obj_min_dist, smoothing_sigm
     return merge_detections([p.cpu().numpy() for p in parts])
 
 
+# ---------------------------------------------------------------------------------------------------
+# Sub-layer load balance for the U-Nets (their output depends on the tile phase, so work can only be cut on the
+# reference tile grid): the (z, y) ROWS of tiles are dealt to the ranks instead of whole layers -- 25 layers on 8 ranks
+# balance 25/32 = 0.78, 625 rows balance 0.99 -- and the rows a rank computes for a neighbour's layer travel to the
+# plane owner over NCCL P2P (one partial layer per rank, ~1 GB at 2048^2 x 82 planes: ~2 ms on NVLink).
+# ---------------------------------------------------------------------------------------------------
+def row_plan(Z, Y, rf_offset, out_sz, world_size):
+    """Deal the tile rows of the reference grid.  Returns (pieces, plans): ``pieces[r]`` = list of
+    ``(kz, ya, yb, owner)`` -- rank r evaluates the tiles of layer kz, rows [ya, yb) (all x), and the prediction
+    planes of layer kz belong to rank ``owner``; ``plans`` = ``shard_plan`` (plane ownership by whole layers, what
+    ``voxel2obj_global`` works on)."""
+    nz, ny = tile_layers(Z, rf_offset, out_sz), tile_layers(Y, rf_offset, out_sz)
+    plans = shard_plan(Z, rf_offset, out_sz, world_size)
+    own_layers = partition_layers(nz, world_size)
+
+    def owner(kz):
+        for r, (a, b) in enumerate(own_layers):
+            if a <= kz < b:
+                return r
+        raise AssertionError(kz)
+
+    pieces = []
+    for a, b in partition_layers(nz * ny, world_size):
+        mine = []
+        if b > a:
+            for kz in range(a // ny, (b - 1) // ny + 1):
+                ya, yb = max(a, kz * ny) - kz * ny, min(b, (kz + 1) * ny) - kz * ny
+                mine.append((kz, ya, yb, owner(kz)))
+        pieces.append(mine)
+    return pieces, plans
+
+
+def piece_geometry(piece, Z, Y, rf_offset, out_sz):
+    """((z0, z1), (y0, y1)) image block a piece reads and ((pz0, pz1), (py0, py1)) prediction block it produces
+    (global coordinates; the far faces clip at the volume, like the reference's zero-padded edge tiles)."""
+    kz, ya, yb, _ = piece
+    off = rf_offset
+    z0, y0 = kz * out_sz, ya * out_sz
+    z1, y1 = min(Z, z0 + out_sz + 2 * off), min(Y, yb * out_sz + 2 * off)
+    pz0, py0 = z0 + off, y0 + off
+    pz1, py1 = min(Z - off, pz0 + out_sz), min(Y - off, y0 + off + (yb - ya) * out_sz)
+    return ((z0, z1), (y0, y1)), ((pz0, pz1), (py0, py1))
+
+
+def image_planes_for_pieces(my_pieces, Z, Y, rf_offset, out_sz):
+    """z-range of the image the pieces of one rank read (empty: (Z, Z))."""
+    if not my_pieces:
+        return (Z, Z)
+    g = [piece_geometry(p, Z, Y, rf_offset, out_sz)[0][0] for p in my_pieces]
+    return (min(a for a, _ in g), max(b for _, b in g))
+
+
+def infer_rows_sharded(compute_block, pieces, plans, rank, Z, Y, X, rf_offset, out_sz, halo, device, group=None,
+                       dtype=None):
+    """Forward pass of ONE volume with the tile rows dealt to the ranks.  ``compute_block((z0,z1),(y0,y1))`` returns
+    the prediction of that image block evaluated as an independent volume (``FplNetwork.infer_device`` on the block:
+    its origin lies on the reference tile grid, so every interior value equals the whole-volume one).  Returns
+    ``(ext, e0)``: this rank's extended slab [e0, e0+len) with its OWNED planes complete (``plans[rank][1]``) and the
+    ``halo`` margin planes still to be filled by the detection's halo exchange."""
+    import torch
+    import torch.distributed as dist
+    dtype = dtype or torch.float32
+    own0, own1 = plans[rank][1]
+    e0, e1 = (max(0, own0 - halo), min(Z, own1 + halo)) if own1 > own0 else (own0, own0)
+    ext = torch.zeros((e1 - e0, Y, X), dtype=dtype, device=device)
+    sends, keep = [], []
+    for piece in pieces[rank]:
+        (zr, yr), ((pz0, pz1), (py0, py1)) = piece_geometry(piece, Z, Y, rf_offset, out_sz)
+        if pz1 <= pz0 or py1 <= py0:
+            continue
+        sub = compute_block(zr, yr)                          # (z1-z0, y1-y0, X), border rf_offset wide = 0
+        part = sub[rf_offset:rf_offset + (pz1 - pz0), rf_offset:rf_offset + (py1 - py0)]
+        if piece[3] == rank:
+            ext[pz0 - e0:pz1 - e0, py0:py1] = part
+        else:
+            buf = part.contiguous()
+            keep.append(buf)
+            sends.append((piece[3], buf))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ops, recvs = [], []
+        for dst, buf in sends:
+            ops.append(dist.P2POp(dist.isend, buf, dst, group=group))
+        for src, theirs in enumerate(pieces):               # every rank knows the whole plan: post the matching receives
+            if src == rank:
+                continue
+            for piece in theirs:
+                if piece[3] != rank:
+                    continue
+                _, ((pz0, pz1), (py0, py1)) = piece_geometry(piece, Z, Y, rf_offset, out_sz)
+                if pz1 <= pz0 or py1 <= py0:
+                    continue
+                tmp = torch.empty((pz1 - pz0, py1 - py0, X), dtype=dtype, device=device)
+                recvs.append((tmp, (pz0, pz1, py0, py1)))
+                ops.append(dist.P2POp(dist.irecv, tmp, src, group=group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for tmp, (pz0, pz1, py0, py1) in recvs:
+            ext[pz0 - e0:pz1 - e0, py0:py1] = tmp
+    else:
+        assert not sends, "pieces for other ranks need torch.distributed"
+    return ext, e0
+
+
+def detect_volume_rows_sharded(network, image_slab, slab_z0, Z, pieces, plans, normalize, obj_min_dist, smoothing_sigma,
+                               volume_offset=(0, 0, 0), buffer_sz=0, thd=0, group=None, return_stats=False):
+    """``detect_volume_sharded`` with tile-row load balance (U-Nets): ``image_slab`` holds the image planes
+    [slab_z0, slab_z0+len) this rank's pieces read (``image_planes_for_pieces``)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    Y, X = int(image_slab.shape[1]), int(image_slab.shape[2])
+    off, out_sz = int(network.rf_offset[0]), int(network.infer_sz[0]) - 2 * int(network.rf_offset[0])
+
+    def compute_block(zr, yr):
+        blk = image_slab[zr[0] - slab_z0:zr[1] - slab_z0, yr[0]:yr[1]].contiguous()
+        return network.infer_device(blk, normalize=normalize)
+
+    h = halo_planes(obj_min_dist, smoothing_sigma)
+    ext, e0 = infer_rows_sharded(compute_block, pieces, plans, rank, Z, Y, X, off, out_sz, h, image_slab.device, group)
+    own0, own1 = plans[rank][1]
+    pred = ext[own0 - e0:own1 - e0]
+    coll = _DistCollectives(group, all_ranges=[p[1] for p in plans])
+    return voxel2obj_global([pred], [(own0, own1)], Z, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd,
+                            coll=coll, return_stats=return_stats, ext_slabs=[ext if own1 > own0 else None])
+
+
 def halo_planes(obj_min_dist, smoothing_sigma):
     """Planes of the probability map a rank needs beyond its own on each side for the exact-global voxel2obj:
     r (suppression ball) + lw (Gaussian half width)."""

@@ -177,3 +177,73 @@ def test_shard_plan_partitions_the_volume():
     # VGG on 1024^3: 251 groups of 4 planes -> 32/31 groups per rank (balance 0.98)
     plans = multi_gpu.shard_plan(1024, 10, 4, 8)
     assert sorted({p[1][1] - p[1][0] for p in plans[1:-1]}) == [124, 128]
+
+
+def test_row_plan_covers_every_tile_row_once():
+    """multi_gpu.row_plan: the (z, y) tile rows of the reference grid are dealt contiguously and evenly; every row
+    is evaluated by exactly one rank; the prediction blocks of the pieces tile [off, Z-off) x [off, Y-off)."""
+    for Z, Y, off, out, world in [(2048, 2048, 9, 82, 8), (270, 200, 9, 82, 3), (300, 120, 6, 90, 4), (100, 100, 9, 82, 2)]:
+        pieces, plans = multi_gpu.row_plan(Z, Y, off, out, world)
+        nz, ny = multi_gpu.tile_layers(Z, off, out), multi_gpu.tile_layers(Y, off, out)
+        seen = np.zeros((nz, ny), int)
+        cover = np.zeros((Z, Y), int)
+        counts = []
+        for r, mine in enumerate(pieces):
+            counts.append(sum(yb - ya for _, ya, yb, _ in mine))
+            for piece in mine:
+                kz, ya, yb, owner = piece
+                seen[kz, ya:yb] += 1
+                o0, o1 = plans[owner][1]
+                (zr, yr), ((pz0, pz1), (py0, py1)) = multi_gpu.piece_geometry(piece, Z, Y, off, out)
+                assert o0 <= pz0 and pz1 <= o1                      # the owner of the layer owns these planes
+                assert zr[0] == kz * out and yr[0] == ya * out and zr[1] <= Z and yr[1] <= Y
+                cover[pz0:pz1, py0:py1] += 1
+            lo, hi = multi_gpu.image_planes_for_pieces(mine, Z, Y, off, out)
+            assert all(lo <= multi_gpu.piece_geometry(p, Z, Y, off, out)[0][0][0] for p in mine)
+        assert (seen == 1).all()
+        assert max(counts) - min(counts) <= 1
+        assert (cover[off:Z - off, off:Y - off] == 1).all() and cover.sum() == (Z - 2 * off) * (Y - 2 * off)
+    pieces, _ = multi_gpu.row_plan(2048, 2048, 9, 82, 8)
+    assert [sum(yb - ya for _, ya, yb, _ in m) for m in pieces] == [79] + [78] * 7       # 625 rows: balance 0.99
+
+
+def _rows_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Z, Y, X, off, out, halo = 60, 50, 7, 2, 8, 3
+        full = torch.zeros((Z, Y, X))
+        full[off:Z - off, off:Y - off, off:X - off] = torch.arange((Z - 2 * off) * (Y - 2 * off) * (X - 2 * off),
+                                                                 dtype=torch.float32).view(Z - 2 * off, Y - 2 * off, X - 2 * off) + 1
+
+        def compute_block(zr, yr):            # "prediction of the block evaluated on its own": right values inside, 0 border
+            sub = full[zr[0]:zr[1], yr[0]:yr[1]].clone()
+            sub[:off] = 0; sub[:, :off] = 0
+            if zr[1] < Z: sub[-off:] = 0
+            if yr[1] < Y: sub[:, -off:] = 0
+            return sub
+        pieces, plans = multi_gpu.row_plan(Z, Y, off, out, world)
+        ext, e0 = multi_gpu.infer_rows_sharded(compute_block, pieces, plans, rank, Z, Y, X, off, out, halo, torch.device("cpu"))
+        own0, own1 = plans[rank][1]
+        ok = torch.equal(ext[own0 - e0:own1 - e0], full[own0:own1]) and e0 == max(0, own0 - halo)
+        q.put((rank, bool(ok), [len(m) for m in pieces]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_forward_exchange_gloo(world):
+    """infer_rows_sharded over gloo with a stand-in for the network: the rows a rank evaluates for a neighbour's layer
+    arrive at the plane owner; every rank ends up with exactly its owned planes of the whole-volume result."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30300 + os.getpid() % 300 + world
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res

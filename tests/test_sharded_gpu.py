@@ -157,3 +157,24 @@ def test_bf16_config_tile_and_slab_tile_vs_float64():
     want_v = M.infer_tiler(img, M.TorchNet(arch, w, dtype=torch.float64), net.infer_sz, net.rf_offset, n_gpu=1)
     e = np.abs(got_v.astype(np.float64) - want_v.astype(np.float64)).max()
     assert e < 2e-2, "bf16 slab tile vs float64 oracle tiling: %g" % e
+
+
+def test_row_sharded_unet_equals_whole_volume():
+    """U-Net with the (z, y) tile rows dealt to the ranks (multi_gpu.row_plan): every piece evaluated as an independent
+    block on the reference tile grid, assembled == whole-volume infer, bit for bit."""
+    import torch
+    from flypylib_b200 import multi_gpu
+    net = _net("unet_like2", "bf16", 7, 1)
+    shape = (270, 200, 190)                                  # 4 layers x 3 rows of tiles
+    u8 = torch.from_numpy(cases.em_volume(shape, seed=8)).cuda()
+    want = net.infer_device(u8, normalize=NORM)
+    Z, Y, X = shape
+    off, out = 9, 82
+    pieces, plans = multi_gpu.row_plan(Z, Y, off, out, 5)
+    got = torch.zeros(shape, dtype=torch.float32, device="cuda")
+    for mine in pieces:
+        for piece in mine:
+            (zr, yr), ((pz0, pz1), (py0, py1)) = multi_gpu.piece_geometry(piece, Z, Y, off, out)
+            sub = net.infer_device(u8[zr[0]:zr[1], yr[0]:yr[1]].contiguous(), normalize=NORM)
+            got[pz0:pz1, py0:py1] = sub[off:off + pz1 - pz0, off:off + py1 - py0]
+    assert torch.equal(got, want)
