@@ -1989,8 +1989,12 @@ int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int6
         const long long items = Ze * ((Y + kP1Strip - 1) / kP1Strip) * ((X + kP1Cols - 1) / kP1Cols);
         long long g1 = (items + 3) / 4;
         if (g1 > (long long)ctx->sm_count * 64) g1 = (long long)ctx->sm_count * 64;
-        approx_pass1_kernel<<<(unsigned)g1, 128, 0, st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid, S->state, nullptr, nullptr, 0,
-                                                          S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, (int)own_lo, (int)own_hi);
+        if ((X % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_smooth_ext) & 15) == 0))
+            approx_pass1_kernel<true><<<(unsigned)g1, 128, 0, st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid, S->state, nullptr, nullptr, 0,
+                                                                    S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, (int)own_lo, (int)own_hi);
+        else
+            approx_pass1_kernel<false><<<(unsigned)g1, 128, 0, st>>>(d_smooth_ext, S->d, S->B.gy, S->B.gx, S->B.grid, S->state, nullptr, nullptr, 0,
+                                                                     S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, (int)own_lo, (int)own_hi);
         FPL_LAUNCH_CHECK(ctx);
     }
     Counters *h_cnt = (Counters *)ctx->h_pinned;

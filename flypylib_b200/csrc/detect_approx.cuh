@@ -47,7 +47,8 @@ struct ApproxState {                                        // device
     float a_lo, a_hi;                                       // A values at the two ranks inside the band
     float n_lo, n_hi;                                       // narrow band (exact recompute) edges
     unsigned bad_bits;                                      // max of the raw input bits
-    unsigned long long n_below;                             // owned voxels with A < Lb
+    unsigned long long n_below;                             // owned voxels with A < Lb (= owned voxels - n_ge)
+    unsigned long long n_ge;                                // owned voxels with A >= Lb, counted by the dense pass
     unsigned long long n_band;                              // band list entries
     unsigned long long n_below_narrow;                      // band entries below the narrow band
     unsigned long long n_narrow;                            // narrow list entries
@@ -412,6 +413,8 @@ approx_sample_count_kernel(const float *__restrict__ sample, long long n_s, cons
 // integer atomicMax on the zero-initialised grid (the values are non-negative floats).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kP1Strip = 32, kP1Cols = 120, kP1Group = 4;
+__device__ __align__(16) unsigned g_nan_row[4] = {0x7fc00000u, 0x7fc00000u, 0x7fc00000u, 0x7fc00000u};   // what lanes outside the volume load
+template <bool VEC>
 __global__ void __launch_bounds__(128, 5)
 approx_pass1_kernel(const float *__restrict__ A, Dims d, int gy, int gx, float *__restrict__ g,
                     ApproxState *S, unsigned long long *band_idx, float *band_val, long long band_cap,
@@ -422,14 +425,13 @@ approx_pass1_kernel(const float *__restrict__ A, Dims d, int gy, int gx, float *
     const float lowA = fminf(Lb, cutA);                     // (a thd above the percentile lifts cutA over the band)
     const int lane = threadIdx.x & 31;
     const int X = (int)d.X, Y = (int)d.Y, Z = (int)d.Z;
-    const bool vec_ok = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const long long plane = d.Y * d.X;
     const int strips = (Y + kP1Strip - 1) / kP1Strip, xchunks = (X + kP1Cols - 1) / kP1Cols;
     const long long n_items = (long long)Z * strips * xchunks;
     const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
     const bool lane_owns = lane >= 1 && lane <= 30;
-    unsigned long long n_below = 0;
+    unsigned long long n_ge = 0;                            // owned voxels with A >= Lb (the host turns it into "below")
     for (long long it = warp0; it < n_items; it += n_warps) {
         // x chunk fastest, then strip, then plane: concurrently running warps share halo rows / planes in L1/L2
         const int xcI = (int)(it % xchunks);
@@ -440,80 +442,72 @@ approx_pass1_kernel(const float *__restrict__ A, Dims d, int gy, int gx, float *
         const float *pz = A + (long long)z * plane;
         const bool owned = z >= own_z0 && z < own_z1;       // warp-uniform
         const bool col_ok = x >= 0 && x < X;
+        const bool owns = owned && lane_owns;
+        // values outside the volume are NaN: every comparison with them is false (not counted, not a candidate, never
+        // "better") and fmaxf / FMNMX ignore them -- no per-voxel range tests in the hot loop.  Lanes whose columns lie
+        // outside read a NaN row (stride 0) instead of the map: the load itself needs no predicate either.
+        const float kOut = __int_as_float(0x7fc00000);
+        const float *lane_base = col_ok ? pz + x : reinterpret_cast<const float *>(g_nan_row);
+        const long long lane_stride = col_ok ? (long long)X : 0LL;
         auto load_row = [&](int yy, float (&o)[4]) {
-            if (yy >= 0 && yy < Y && col_ok) {
-                const float *rp = pz + (long long)yy * X + x;
-                if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4 *>(rp)); o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
+            if (yy >= 0 && yy < Y) {                            // warp-uniform
+                const float *rp = lane_base + (long long)yy * lane_stride;
+                if (VEC) { const float4 q = __ldg(reinterpret_cast<const float4 *>(rp)); o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
                 else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = x + e < X ? __ldg(rp + e) : -INFINITY;
+                    for (int e = 0; e < 4; ++e) o[e] = (!col_ok || x + e < X) ? __ldg(rp + e) : kOut;
                 }
-            } else { o[0] = o[1] = o[2] = o[3] = -INFINITY; }
+            } else { o[0] = o[1] = o[2] = o[3] = kOut; }
         };
-        float pv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};          // values of the previous row
-        float m3pp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, m3p[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float pv[4] = {kOut, kOut, kOut, kOut};             // values of the previous row
+        float m3pp[4] = {kOut, kOut, kOut, kOut}, m3p[4] = {kOut, kOut, kOut, kOut};
         float bm = 0.f;                                     // running brick maximum (8 rows)
-        float nxt[kP1Group][4];
-#pragma unroll
-        for (int k = 0; k < kP1Group; ++k) load_row(y0 - 1 + k, nxt[k]);
-        // rows y0-1 .. y_end (inclusive) are consumed; row yy-1 is produced when row yy arrives
-        for (int yb = y0 - 1; yb <= y_end; yb += kP1Group) {
-            float cur[kP1Group][4];
-#pragma unroll
-            for (int k = 0; k < kP1Group; ++k)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) cur[k][e] = nxt[k][e];
-            if (yb + kP1Group <= y_end) {
-#pragma unroll
-                for (int k = 0; k < kP1Group; ++k) load_row(yb + kP1Group + k, nxt[k]);
-            }
-            unsigned surv = 0, bandm = 0;                   // bit 4 k + e: output row yb + k - 1, column x + e
+        unsigned surv = 0, bandm = 0;                       // bit 4 k + e of the current group: output row yb + k - 1, column x + e
+        // one group = 4 consecutive rows; row yy - 1 is decided when row yy arrives.  Uniform control flow only (the
+        // shuffles must not sit behind divergent branches): rows past the strip are loaded as -inf / masked out.
+        auto process_group = [&](const float (&c)[kP1Group][4], int yb) {
 #pragma unroll
             for (int k = 0; k < kP1Group; ++k) {
-                const int yy = yb + k;                      // the row that arrives; row yy - 1 is decided now
-                if (yy > y_end) break;                      // warp-uniform
-                const float lf = __shfl_up_sync(0xffffffffu, cur[k][3], 1), rt = __shfl_down_sync(0xffffffffu, cur[k][0], 1);
+                const float lf = __shfl_up_sync(0xffffffffu, c[k][3], 1), rt = __shfl_down_sync(0xffffffffu, c[k][0], 1);
                 float m3c[4];
-                m3c[0] = fmaxf(fmaxf(lf, cur[k][0]), cur[k][1]);
-                m3c[1] = fmaxf(fmaxf(cur[k][0], cur[k][1]), cur[k][2]);
-                m3c[2] = fmaxf(fmaxf(cur[k][1], cur[k][2]), cur[k][3]);
-                m3c[3] = fmaxf(fmaxf(cur[k][2], cur[k][3]), rt);
-                const int yo = yy - 1;                      // output row
-                if (yo >= y0) {
-                    unsigned cand = 0, nb = 0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float f = pv[e];                  // -inf outside the volume
-                        bm = fmaxf(bm, f);
-                        nb += (f < Lb && f >= 0.f) ? 1u : 0u;
-                        cand |= (f >= lowA ? 1u : 0u) << e;
-                    }
-                    if (owned && lane_owns) {
-                        n_below += nb;
-                        if (cand) {
+                m3c[0] = fmaxf(fmaxf(lf, c[k][0]), c[k][1]);
+                m3c[1] = fmaxf(fmaxf(c[k][0], c[k][1]), c[k][2]);
+                m3c[2] = fmaxf(fmaxf(c[k][1], c[k][2]), c[k][3]);
+                m3c[3] = fmaxf(fmaxf(c[k][2], c[k][3]), rt);
+                const int yo = yb + k - 1;                  // output row
+                const bool row_out = yo >= y0 && yo < y_end;        // warp-uniform
+                if (row_out) {
+                    // common path, per row of 4 voxels: row maximum (brick maximum, "any candidate?") and the below-band count
+                    const float rmax = fmaxf(fmaxf(pv[0], pv[1]), fmaxf(pv[2], pv[3]));
+                    bm = fmaxf(bm, rmax);
+                    if (owns && rmax >= lowA) {                     // rare: some voxel of the row reaches the band / the cut-off
+                        {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float f = pv[e];
+                                n_ge += f >= Lb ? 1u : 0u;
                                 const float m9 = fmaxf(fmaxf(m3pp[e], m3p[e]), m3c[e]);
                                 // band member / nobody in the plane certainly beats it (near-equal neighbours are left to
                                 // the ball check): both are rare and handled after the group, out of the unrolled code
-                                if ((cand & (1u << e)) && f >= Lb && f <= Hb) bandm |= 1u << (4 * k + e);
-                                if ((cand & (1u << e)) && f >= cutA && !(m9 > f * kApxUp)) surv |= 1u << (4 * k + e);
+                                if (f >= Lb && f <= Hb) bandm |= 1u << (4 * k + e);
+                                if (f >= cutA && !(m9 > f * kApxUp)) surv |= 1u << (4 * k + e);
                             }
                         }
                     }
-                    // brick maximum: flushed every 8 rows (strips start on brick boundaries); lanes (odd, odd+1) share a brick
-                    if ((yo & (kBrick - 1)) == kBrick - 1 || yo == y_end - 1) {
-                        const float other = __shfl_down_sync(0xffffffffu, bm, 1);
-                        if ((lane & 1) && lane <= 29 && col_ok && fmaxf(bm, other) > 0.f)
-                            atomicMax(reinterpret_cast<int *>(g + ((size_t)(z / kBrick) * gy + yo / kBrick) * gx + x / kBrick),
-                                      __float_as_int(fmaxf(bm, other)));
-                        bm = 0.f;
-                    }
+                }
+                // brick maximum: flushed every 8 rows (strips start on brick boundaries); lanes (odd, odd+1) share a brick
+                if (row_out && ((yo & (kBrick - 1)) == kBrick - 1 || yo == y_end - 1)) {        // warp-uniform
+                    const float other = __shfl_down_sync(0xffffffffu, bm, 1);
+                    if ((lane & 1) && lane <= 29 && col_ok && fmaxf(bm, other) > 0.f)
+                        atomicMax(reinterpret_cast<int *>(g + ((size_t)(z / kBrick) * gy + yo / kBrick) * gx + x / kBrick),
+                                  __float_as_int(fmaxf(bm, other)));
+                    bm = 0.f;
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { pv[e] = cur[k][e]; m3pp[e] = m3p[e]; m3p[e] = m3c[e]; }
+                for (int e = 0; e < 4; ++e) { pv[e] = c[k][e]; m3pp[e] = m3p[e]; m3p[e] = m3c[e]; }
             }
+        };
+        auto rare = [&](int yb) {
 #pragma unroll 1
             while (bandm) {
                 const int b = __ffs((int)bandm) - 1;
@@ -554,11 +548,27 @@ approx_pass1_kernel(const float *__restrict__ A, Dims d, int gy, int gx, float *
                     else atomicAdd(&cnt->overflow, 1ULL);
                 }
             }
+        };
+        // rows y0-1 .. y_end are consumed in groups of 4; the loads of the next group are in flight while the current
+        // one is processed (one copy of the processing code: it must stay inside the instruction cache)
+        float cur[kP1Group][4], nxt[kP1Group][4];
+#pragma unroll
+        for (int k = 0; k < kP1Group; ++k) load_row(y0 - 1 + k, nxt[k]);
+#pragma unroll 1
+        for (int yb = y0 - 1; yb <= y_end; yb += kP1Group) {
+#pragma unroll
+            for (int k = 0; k < kP1Group; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cur[k][e] = nxt[k][e];
+#pragma unroll
+            for (int k = 0; k < kP1Group; ++k) load_row(yb + kP1Group + k <= y_end ? yb + kP1Group + k : -1, nxt[k]);
+            process_group(cur, yb);
+            rare(yb);
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) n_below += __shfl_xor_sync(0xffffffffu, n_below, off);
-    if (lane == 0 && n_below) atomicAdd(&S->n_below, n_below);
+    for (int off = 16; off > 0; off >>= 1) n_ge += __shfl_xor_sync(0xffffffffu, n_ge, off);
+    if (lane == 0 && n_ge) atomicAdd(&S->n_ge, n_ge);
 }
 
 // a_lo / a_hi (A at the two ranks, found by the radix select on the band list) -> narrow band edges
@@ -912,6 +922,64 @@ approx_compact_kernel(const float *__restrict__ v, Dims d, const float *__restri
     }
 }
 
+// Suppression balls, brick-guided: the validity bit of a voxel is only ever consulted for voxels with A >= cutA (1 - 4 eps)
+// (filter, ball check, resolve, compaction), and those live in bricks whose maximum reaches gcut = cutA (1 - 4 eps)^2.
+// A block first marks which of the <= 9^3 bricks around its point qualify (one bit each, shared memory); rows of the
+// ball whose 64-bit words only cover other bricks are skipped -- on sparse maps that is most of the 4 800 atomics a
+// ball of radius 27 would otherwise issue.
+__global__ void __launch_bounds__(256)
+approx_suppress_kernel(unsigned *sup, Dims d, int r, const float *__restrict__ g, int gy, int gx, const ApproxState *S,
+                       const unsigned long long *__restrict__ sel_idx, const Counters *cnt) {
+    __shared__ unsigned s_rowbits[10 * 10];                 // [brick z][brick y] -> bit per brick x (relative)
+    const unsigned long long nS = cnt->n_sel_round;
+    const int side = 2 * r + 1;
+    const float gcut = S->cutA * kApxDn * kApxDn;
+    for (unsigned long long s = blockIdx.x; s < nS; s += gridDim.x) {
+        const unsigned long long idx = sel_idx[s];
+        const long long x = (long long)(idx % (unsigned long long)d.X);
+        const long long y = (long long)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
+        const long long z = (long long)(idx / ((unsigned long long)d.X * d.Y));
+        const int bz0 = (int)(max(z - r, 0LL) / kBrick), by0 = (int)(max(y - r, 0LL) / kBrick), bx0 = (int)(max(x - r, 0LL) / kBrick);
+        const int bz1 = (int)(min(z + r, d.Z - 1) / kBrick), by1 = (int)(min(y + r, d.Y - 1) / kBrick), bx1 = (int)(min(x + r, d.X - 1) / kBrick);
+        const int nbz = bz1 - bz0 + 1, nby = by1 - by0 + 1, nbx = bx1 - bx0 + 1;      // <= 9 each for r <= 31
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbz * nby; i += blockDim.x) {
+            const int bz = bz0 + i / nby, by = by0 + i % nby;
+            unsigned bits = 0;
+            for (int k = 0; k < nbx; ++k)
+                if (__ldg(g + ((size_t)bz * gy + by) * gx + bx0 + k) >= gcut) bits |= 1u << k;
+            s_rowbits[(i / nby) * 10 + (i % nby)] = bits;
+        }
+        __syncthreads();
+        for (int row = threadIdx.x; row < side * side; row += blockDim.x) {
+            const int dz = row / side - r, dy = row % side - r;
+            const int rem = r * r - dz * dz - dy * dy;
+            if (rem < 0) continue;
+            const long long zz = z + dz, yy = y + dy;
+            if (zz < 0 || zz >= d.Z || yy < 0 || yy >= d.Y) continue;
+            const unsigned bits = s_rowbits[((int)(zz / kBrick) - bz0) * 10 + ((int)(yy / kBrick) - by0)];
+            if (!bits) continue;
+            const int hw = isqrt_floor(rem);
+            const long long x0 = x - hw < 0 ? 0 : x - hw;
+            const long long x1 = x + hw >= d.X ? d.X - 1 : x + hw;
+            const unsigned long long rowbase = ((unsigned long long)zz * d.Y + yy) * d.X;
+            const unsigned long long q0 = rowbase + x0, q1 = rowbase + x1;
+            unsigned long long *sup64 = reinterpret_cast<unsigned long long *>(sup);
+            for (unsigned long long wd = q0 >> 6; wd <= (q1 >> 6); ++wd) {
+                const unsigned long long lo = wd << 6;
+                const unsigned b0 = q0 > lo ? (unsigned)(q0 - lo) : 0u;
+                const unsigned b1 = q1 < lo + 63 ? (unsigned)(q1 - lo) : 63u;
+                // bricks (in x) this word segment covers
+                const int kx0 = (int)((lo + b0 - rowbase) / kBrick) - bx0, kx1 = (int)((lo + b1 - rowbase) / kBrick) - bx0;
+                const unsigned seg = ((kx1 >= 31 ? 0xffffffffu : ((1u << (kx1 + 1)) - 1u)) & ~((1u << kx0) - 1u));
+                if (!(bits & seg)) continue;
+                const unsigned long long mask = (b1 == 63u ? ~0ULL : ((1ULL << (b1 + 1)) - 1ULL)) & ~((1ULL << b0) - 1ULL);
+                atomicOr(&sup64[wd], mask);
+            }
+        }
+    }
+}
+
 __global__ void approx_round_reset_kernel(Counters *cnt, ApproxState *S) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         cnt->n_cand = cnt->n_next; cnt->n_next = 0; cnt->n_work = 0; cnt->n_sel_round = 0; cnt->n_alive_owned = 0;
@@ -1106,10 +1174,15 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         const long long items = Z * ((Y + kP1Strip - 1) / kP1Strip) * ((X + kP1Cols - 1) / kP1Cols);
         long long g1 = (items + 3) / 4;
         if (g1 > (long long)ctx->sm_count * 64) g1 = (long long)ctx->sm_count * 64;
-        approx_pass1_kernel<<<(unsigned)g1, 128, 0, st>>>(A, d, B.gy, B.gx, B.grid, S, band_idx, band_val, band_cap, B.w_idx,
-                                                          B.w_val, B.list_cap, B.cnt, 0, (int)Z);
+        if ((X % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0))
+            approx_pass1_kernel<true><<<(unsigned)g1, 128, 0, st>>>(A, d, B.gy, B.gx, B.grid, S, band_idx, band_val, band_cap, B.w_idx,
+                                                                    B.w_val, B.list_cap, B.cnt, 0, (int)Z);
+        else
+            approx_pass1_kernel<false><<<(unsigned)g1, 128, 0, st>>>(A, d, B.gy, B.gx, B.grid, S, band_idx, band_val, band_cap, B.w_idx,
+                                                                     B.w_val, B.list_cap, B.cnt, 0, (int)Z);
         FPL_LAUNCH_CHECK(ctx);
         FPL_TRY(collect());
+        h->st.n_below = (unsigned long long)n - h->st.n_ge;        // every interior voxel is either below the band or counted
     }
     if (h->st.bad_bits >= kApxBadBits || !(h->st.cutA >= kApxMinCut) || h->st.overflow || h->cnt.overflow) return decline(ctx, 6);
     // certificate of the band: both ranks fall inside the listed voxels
@@ -1173,7 +1246,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
             approx_resolve_kernel<<<ctx->sm_count * 2, 256, ex_smem, st>>>(d_pred, A, B.sup, d, r, lw, taps, B.grid, B.gy, B.gx, amb_idx,
                                                                            B.det_idx, B.det_val, B.sel_idx, B.det_cap, B.cnt, S);
             FPL_LAUNCH_CHECK(ctx);
-            nms_suppress_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(B.sup, d, r, B.sel_idx, B.cnt);
+            approx_suppress_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(B.sup, d, r, B.grid, B.gy, B.gx, S, B.sel_idx, B.cnt);
             FPL_LAUNCH_CHECK(ctx);
             if (first) {
                 approx_collect_kernel<<<1, 32, 0, st>>>(B.cnt, S, d_host);
