@@ -2249,6 +2249,9 @@ int fpl_debug_v2o_decline_reason(fpl_ctx *ctx, int reset_backoff) {
     return ctx->v2o_decline;
 }
 
+// test / experiment hook: 0 = the sigma-5 Gaussian uses the generic (uniform-register taps) instantiation too
+int fpl_debug_gauss_imm(int on) { fpl::v2o::g_gauss_imm = on; return FPL_OK; }
+
 int fpl_debug_v2o_decline_info(fpl_ctx *ctx, long long *out8) {
     if (!ctx || !out8) return -2;
     for (int i = 0; i < 8; ++i) out8[i] = ctx->v2o_info[i];

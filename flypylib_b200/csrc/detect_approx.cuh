@@ -206,7 +206,7 @@ struct GaussCfg {
     static constexpr int PITCH0 = PWV > 24 + WINV ? PWV : 24 + WINV;
     static constexpr int PITCH = ((PITCH0 / 4) % 2 == 1) ? PITCH0 : PITCH0 + 4;   // pitch / 4 odd: conflict-free LDS.128
     static constexpr int XS_PITCH = kGT;
-    static constexpr size_t SMEM = sizeof(float) * (size_t)(2 * PH * PITCH + PH * XS_PITCH);
+    static constexpr size_t SMEM = sizeof(float) * (size_t)(2 * PH * PITCH + 2 * PH * XS_PITCH);
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
@@ -225,14 +225,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // packed fp32: one FFMA2 issues two fused multiply-adds (sm_100 fma.rn.f32x2) -- the kernel is issue-bound
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-template <int LW>
+// float32 taps of sigma = 5, truncate 2.0 (lw = 10) -- the reference's smoothing_sigma everywhere (scripts/*.py,
+// fplobjdetect.py:844) -- as literals: the IMM instantiation multiplies by immediates (FFMA with an immediate operand
+// issues at twice the rate of the register form, /opt/skills/guides/B300_MICROARCH.md "Pipe rates").  The host selects
+// it only when the call's float32 taps equal this table bit for bit.
+__device__ constexpr float kTapsSigma5[21] = {1.1194727e-02f, 1.6369877e-02f, 2.299882e-02f, 3.1045157e-02f, 4.02634e-02f, 5.0171286e-02f, 6.0065933e-02f, 6.909227e-02f, 7.6358765e-02f, 8.108053e-02f, 8.271846e-02f, 8.108053e-02f, 7.6358765e-02f, 6.909227e-02f, 6.0065933e-02f, 5.0171286e-02f, 4.02634e-02f, 3.1045157e-02f, 2.299882e-02f, 1.6369877e-02f, 1.1194727e-02f};
+
+template <int LW, bool IMM>
 __global__ void __launch_bounds__(256)
 gauss32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__restrict__ sample, Dims d, int zc_len,
                int sy, int sx, int vec_ok, ApproxState *state) {
     using C = GaussCfg<LW>;
     extern __shared__ __align__(16) float g_sm[];
     float *patch = g_sm;                                   // [2][PH][PITCH]
-    float *xs = g_sm + 2 * C::PH * C::PITCH;               // [PH][32]
+    float *xs = g_sm + 2 * C::PH * C::PITCH;               // [2][PH][32]
     const int t = threadIdx.x;
     const int X = (int)d.X, Y = (int)d.Y, Z = (int)d.Z;    // (the host checks that the extents fit 32 bits)
     const int tx0 = blockIdx.x * kGT, ty0 = blockIdx.y * kGT;
@@ -292,6 +298,12 @@ gauss32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__r
     float2 w2[C::W];                                        // taps duplicated into both halves
 #pragma unroll
     for (int j = 0; j < C::W; ++j) w2[j] = make_float2(c_gw32[j], c_gw32[j]);
+    static_assert(!IMM || LW == 10, "immediate taps exist for lw = 10 (sigma 5) only");
+    // c + w[j] * a on both halves: packed FFMA2 with the tap in a uniform register, or two FFMA with the tap as an
+    // immediate (j is a compile-time constant after unrolling, so kTapsSigma5[j] folds into the instruction)
+#define FPL_MAC2(j, av, cv) (IMM ? make_float2(fmaf(kTapsSigma5[(j) < 21 ? (j) : 0], (av).x, (cv).x), \
+                                               fmaf(kTapsSigma5[(j) < 21 ? (j) : 0], (av).y, (cv).y)) \
+                                 : ffma2(w2[j], av, cv))
     unsigned bad = 0;
     // output / sample addressing of this thread (fixed in y and x)
     const int gx = tx0 + 2 * cx2, gy = ty0 + cy0;
@@ -299,14 +311,10 @@ gauss32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__r
     const bool row_ok0 = gy < Y && gx < X, row_ok1 = gy + 1 < Y && gx < X;
     float *optr = out + (long long)zc0 * plane + (long long)gy * X + gx;
 
-    issue(z_begin, 0);
-    for (int zi = z_begin; zi < z_end; ++zi) {
-        const int buf = (zi - z_begin) & 1;
-        cp_async_wait_all();
-        __syncthreads();                                   // patch[buf] complete; xs of the previous plane consumed
-        if (zi + 1 < z_end) issue(zi + 1, buf ^ 1);
+    // x pass of one staged plane: patch[pbuf] -> xs[xbuf]
+    auto x_pass = [&](int pbuf, int xbuf) {
         if (x_active) {
-            const float *prow = patch + buf * C::PH * C::PITCH + xrow * C::PITCH + 8 * xrun;
+            const float *prow = patch + pbuf * C::PH * C::PITCH + xrow * C::PITCH + 8 * xrun;
             float win[C::WINV + 1];
 #pragma unroll
             for (int k = 0; k < C::WINV / 4; ++k) {
@@ -324,27 +332,44 @@ gauss32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__r
                 float2 a = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < C::W; ++j)
-                    a = ffma2(w2[j], make_float2(win[C::XOFF + 2 * m + j], win[C::XOFF + 2 * m + j + 1]), a);
+                    a = FPL_MAC2(j, make_float2(win[C::XOFF + 2 * m + j], win[C::XOFF + 2 * m + j + 1]), a);
                 o2[m] = a;
             }
-            float4 *xo = reinterpret_cast<float4 *>(xs + xrow * C::XS_PITCH + 8 * xrun);
+            float4 *xo = reinterpret_cast<float4 *>(xs + xbuf * C::PH * C::XS_PITCH + xrow * C::XS_PITCH + 8 * xrun);
             xo[0] = make_float4(o2[0].x, o2[0].y, o2[1].x, o2[1].y);
             xo[1] = make_float4(o2[2].x, o2[2].y, o2[3].x, o2[3].y);
         }
-        __syncthreads();
+    };
+    // Software pipeline with ONE block barrier per plane: in phase zi the y/z pass of plane zi (from xs[i&1]) and the x
+    // pass of plane zi+1 (patch[(i+1)&1] -> xs[(i+1)&1]) run back to back, while cp.async stages plane zi+2.
+    issue(z_begin, 0);
+    if (z_begin + 1 < z_end) issue(z_begin + 1, 1);
+    if (z_begin + 1 < z_end) asm volatile("cp.async.wait_group 1;\n" ::: "memory"); else cp_async_wait_all();
+    __syncthreads();
+    x_pass(0, 0);
+    for (int zi = z_begin; zi < z_end; ++zi) {
+        const int i = zi - z_begin;
+        cp_async_wait_all();
+        __syncthreads();                                   // xs[i&1] complete; patch[(i+1)&1] staged; patch[i&1] free
+        if (zi + 2 < z_end) issue(zi + 2, i & 1);
         {
+            const float *xsb = xs + (i & 1) * C::PH * C::XS_PITCH;
             float2 win[2 + 2 * LW];
 #pragma unroll
-            for (int k = 0; k < 2 + 2 * LW; ++k) win[k] = *reinterpret_cast<const float2 *>(xs + (cy0 + k) * C::XS_PITCH + 2 * cx2);
+            for (int k = 0; k < 2 + 2 * LW; ++k) win[k] = *reinterpret_cast<const float2 *>(xsb + (cy0 + k) * C::XS_PITCH + 2 * cx2);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                float2 p = make_float2(0.f, 0.f);
+                // two independent partial sums (even / odd taps): twice the ILP of one 21-long dependent chain
+                float2 pe = make_float2(0.f, 0.f), po = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < C::W; ++j) p = ffma2(w2[j], win[c + j], p);
+                for (int j = 0; j < C::W; j += 2) pe = FPL_MAC2(j, win[c + j], pe);
+#pragma unroll
+                for (int j = 1; j < C::W; j += 2) po = FPL_MAC2(j, win[c + j], po);
+                const float2 p = __fadd2_rn(pe, po);
                 // running z accumulators: after this plane acc[c][k] belongs to output plane zi - LW + k
 #pragma unroll
-                for (int k = 0; k < C::W - 1; ++k) acc[c][k] = ffma2(w2[C::W - 1 - k], p, acc[c][k + 1]);
-                acc[c][C::W - 1] = make_float2(w2[0].x * p.x, w2[0].x * p.y);
+                for (int k = 0; k < C::W - 1; ++k) acc[c][k] = FPL_MAC2(C::W - 1 - k, p, acc[c][k + 1]);
+                acc[c][C::W - 1] = IMM ? make_float2(kTapsSigma5[0] * p.x, kTapsSigma5[0] * p.y) : make_float2(w2[0].x * p.x, w2[0].x * p.y);
             }
         }
         const int o = zi - LW;
@@ -365,12 +390,15 @@ gauss32_kernel(const float *__restrict__ in, float *__restrict__ out, float *__r
                     sample[((long long)(o / kApxSampleStep) * sy + (gy >> 2)) * sx + (gx >> 2)] = want == gy ? acc[0][0].x : acc[1][0].x;
             }
         }
+        if (zi + 1 < z_end) x_pass((i + 1) & 1, (i + 1) & 1);
     }
     // negative / non-finite / huge inputs disqualify the map (the bound needs non-negative finite terms)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) bad = max(bad, __shfl_xor_sync(0xffffffffu, bad, off));
     if ((t & 31) == 0 && bad >= kApxBadBits) atomicMax(&state->bad_bits, bad);
 }
+#undef FPL_MAC2
+
 
 // band [Lb, Hb] from the two sample order statistics; NMS cut-off
 __global__ void approx_band_kernel(const SelectState *lo, const SelectState *hi, double thd, ApproxState *s) {
@@ -1004,13 +1032,13 @@ __global__ void approx_collect_kernel(const Counters *cnt, const ApproxState *S,
     out->cnt = *cnt; out->st = *S;
 }
 
-template <int LW>
+template <int LW, bool IMM = false>
 static int launch_gauss32(fpl_ctx *ctx, const float *in, float *out, float *sample, Dims d, int sy, int sx,
                           ApproxState *state, cudaStream_t st) {
     using C = GaussCfg<LW>;
     static bool attr_done = false;
     if (!attr_done) {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(gauss32_kernel<LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(gauss32_kernel<LW, IMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_done = true;
     }
     const long long txn = (d.X + kGT - 1) / kGT, tyn = (d.Y + kGT - 1) / kGT;
@@ -1025,7 +1053,7 @@ static int launch_gauss32(fpl_ctx *ctx, const float *in, float *out, float *samp
     FPL_REQUIRE(tyn <= 65535 && nzc <= 65535 && txn < 2147483647LL && d.X < (1LL << 30) && d.Y < (1LL << 30) && d.Z < (1LL << 30),
                 "gauss32: volume too large for one launch");
     const int vec_ok = (d.X % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-    gauss32_kernel<LW><<<dim3((unsigned)txn, (unsigned)tyn, (unsigned)nzc), 256, C::SMEM, st>>>(in, out, sample, d, (int)zc, sy, sx,
+    gauss32_kernel<LW, IMM><<<dim3((unsigned)txn, (unsigned)tyn, (unsigned)nzc), 256, C::SMEM, st>>>(in, out, sample, d, (int)zc, sy, sx,
                                                                                          vec_ok, state);
     FPL_LAUNCH_CHECK(ctx);
     return FPL_OK;
@@ -1033,8 +1061,16 @@ static int launch_gauss32(fpl_ctx *ctx, const float *in, float *out, float *samp
 
 static bool approx_lw_supported(int lw) { return lw == 2 || lw == 3 || lw == 4 || lw == 8 || lw == 10; }
 
-static int launch_gauss32_any(fpl_ctx *ctx, int lw, const float *in, float *out, float *sample, Dims d, int sy, int sx,
-                              ApproxState *state, cudaStream_t st) {
+static int g_gauss_imm = 1;     // test / experiment hook (fpl_debug_gauss_imm): 0 = never use the immediate-tap instantiation
+
+static int launch_gauss32_any(fpl_ctx *ctx, int lw, const float *w32, const float *in, float *out, float *sample, Dims d,
+                              int sy, int sx, ApproxState *state, cudaStream_t st) {
+    static const int env_imm = getenv("FPL_GAUSS_IMM") ? atoi(getenv("FPL_GAUSS_IMM")) : -1;     // A/B measurements
+    if (lw == 10 && (env_imm >= 0 ? env_imm : g_gauss_imm)) {     // the reference's sigma = 5: taps as immediates, when they are exactly those
+        bool same = true;
+        for (int i = 0; i < 21; ++i) same = same && memcmp(&w32[i], &kTapsSigma5[i], 4) == 0;
+        if (same) return launch_gauss32<10, true>(ctx, in, out, sample, d, sy, sx, state, st);
+    }
     switch (lw) {
         case 2:  return launch_gauss32<2>(ctx, in, out, sample, d, sy, sx, state, st);
         case 3:  return launch_gauss32<3>(ctx, in, out, sample, d, sy, sx, state, st);
@@ -1156,7 +1192,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         fpl::ProfScope prof(ctx, st, fpl::PROF_GAUSS, 8.0 * (double)n);
         FPL_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(ApproxState), st));
         FPL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_gw32, w32, sizeof(float) * (2 * lw + 1), 0, cudaMemcpyHostToDevice, st));
-        FPL_TRY(launch_gauss32_any(ctx, lw, d_pred, A, sample, d, sy, sx, S, st));
+        FPL_TRY(launch_gauss32_any(ctx, lw, w32, d_pred, A, sample, d, sy, sx, S, st));
     }
     {
         fpl::ProfScope prof(ctx, st, fpl::PROF_SELECT, 4.0 * (double)n);
