@@ -1525,7 +1525,7 @@ __global__ void slab_pack_kernel(const unsigned long long *sel_idx, const Counte
     const unsigned long long n = cnt->n_sel_round;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         block[0] = (long long)n;
-        block[1] = first ? (long long)n_first : (long long)cnt->n_alive_owned;
+        block[1] = first ? (long long)cnt->n_work : (long long)cnt->n_alive_owned;      // round 1: owned local maxima
         block[2] = (long long)cnt->overflow + ((long long)n > sel_cap ? 1 : 0);
     }
     const unsigned long long m = n < (unsigned long long)sel_cap ? n : (unsigned long long)sel_cap;
@@ -1573,6 +1573,15 @@ nms_suppress_blocks_kernel(unsigned *sup, Dims d, int r, const long long *__rest
         }
     }
 }
+
+// warp-per-entry ball check (defined in detect_approx.cuh, which is included further down); EXACT = the reference's order
+struct ApproxState;
+template <bool EXACT>
+__global__ void approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d, int r,
+                                        const float *__restrict__ g, int gy, int gx, const unsigned long long *__restrict__ w_idx,
+                                        const float *__restrict__ w_val, unsigned long long *det_idx, float *det_val,
+                                        unsigned long long *sel_idx, long long det_capacity, Counters *cnt, ApproxState *S,
+                                        unsigned long long *amb_idx, unsigned long long own_lo, unsigned long long own_hi);
 
 struct DetectBuffers {
     unsigned *sup; size_t sup_words;
@@ -1657,6 +1666,8 @@ static int run_rounds(fpl_ctx *ctx, DetectBuffers &B, const float *d_smooth, Dim
         nms_filter_kernel<<<(unsigned)fblocks, 256, 0, st>>>(d_smooth, B.sup, d, a_idx, a_val, b_idx,
                                                             b_val, B.w_idx, B.w_val, B.list_cap, B.cnt);
         FPL_LAUNCH_CHECK(ctx);
+        // (block per entry: on dense maps a ball check scans hundreds of bricks -- eight warps with early exit beat the
+        // warp-per-entry kernel of the two-tier path, which wins on sparse maps; measured 5.9 vs 7.8 ms on the bench map)
         nms_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_smooth, B.sup, d, r, B.grid, B.gz, B.gy, B.gx, B.w_idx, B.w_val,
                                                                B.det_idx, B.det_val, B.sel_idx, B.det_cap,
                                                                B.cnt, nullptr);
@@ -1921,7 +1932,7 @@ int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefi
     FPL_REQUIRE(ctx && d_v && d_hist && n >= 0 && bins > 0 && bins <= 2048, "fpl_v2o_hist_level: bad argument");
     FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (ctx->arena.cap < sizeof(SelectState) + 4096) FPL_CUDA_CHECK(cudaStreamSynchronize(st));      // (the arena is about to be re-allocated)
     FPL_TRY(ctx->arena.reserve(sizeof(SelectState) + 4096));
     ctx->arena.reset();
     SelectState *s = (SelectState *)ctx->arena.take(sizeof(SelectState));
@@ -1936,8 +1947,7 @@ int fpl_v2o_hist_level(fpl_ctx *ctx, const float *d_v, int64_t n, uint32_t prefi
     hist_fold_kernel<<<8, 256, 0, st>>>(s, (unsigned long long *)d_hist);      // sum of the partial histograms
     FPL_LAUNCH_CHECK(ctx);
     if (d_nan) FPL_CUDA_CHECK(cudaMemcpyAsync(d_nan, &s->nan_count, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-    return FPL_OK;
+    return FPL_OK;                  // stream-ordered: the caller's read of d_hist synchronises
 }
 
 int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int64_t Y, int64_t X,
@@ -1997,19 +2007,13 @@ int fpl_v2o_slab_begin(fpl_ctx *ctx, const float *d_smooth_ext, int64_t Ze, int6
                                                                      S->B.w_idx, S->B.w_val, S->B.list_cap, S->B.cnt, (int)own_lo, (int)own_hi);
         FPL_LAUNCH_CHECK(ctx);
     }
-    Counters *h_cnt = (Counters *)ctx->h_pinned;
-    FPL_CUDA_CHECK(cudaMemcpyAsync(h_cnt, S->B.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (h_cnt->overflow) {
-        fpl::set_error("voxel2obj slab: worklist overflow (%llu > %lld)", h_cnt->n_work, (long long)list_cap);
-        cudaFree(S->mem); delete S;
-        return FPL_EOVERFLOW;
-    }
+    // no host round trip here: the size of the worklist (= "alive" of round 1) and a possible overflow travel in the
+    // header of the first exchange block (fpl_v2o_slab_round_pack) or are read by fpl_v2o_slab_round
     S->first = true;
-    S->n_first = h_cnt->n_work;
-    S->remaining = h_cnt->n_work;
+    S->n_first = ~0ULL;             // unknown on the host until the first round
+    S->remaining = 1;
     S->a_idx = S->B.a_idx; S->b_idx = S->B.b_idx; S->a_val = S->B.a_val; S->b_val = S->B.b_val;
-    if (h_n_candidates) *h_n_candidates = (int64_t)h_cnt->n_work;
+    if (h_n_candidates) *h_n_candidates = -1;
     *session = S;
     return FPL_OK;
 }
@@ -2062,7 +2066,7 @@ int fpl_v2o_slab_round(void *session, int64_t *d_sel_zyx, int64_t sel_cap, int64
     }
     *h_n_sel = (int64_t)h_cnt->n_sel_round;
     // round 1: "alive" = owned local maxima above the threshold (zero on every rank <=> there is no candidate at all)
-    *h_alive_owned = first ? (int64_t)S->n_first : (int64_t)h_cnt->n_alive_owned;
+    *h_alive_owned = first ? (int64_t)h_cnt->n_work : (int64_t)h_cnt->n_alive_owned;
     round_reset_kernel<<<1, 32, 0, st>>>(S->B.cnt);
     FPL_LAUNCH_CHECK(ctx);
     if (first) { S->first = false; return FPL_OK; }
@@ -2187,7 +2191,7 @@ int fpl_v2o_smooth(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int6
     FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)Z * Y * X;
-    FPL_CUDA_CHECK(cudaStreamSynchronize(st));   // arena may be re-allocated
+    if (ctx->arena.cap < n * sizeof(float) + 4096) FPL_CUDA_CHECK(cudaStreamSynchronize(st));   // the arena is about to be re-allocated
     FPL_TRY(ctx->arena.reserve(n * sizeof(float) + 4096));
     ctx->arena.reset();
     float *tmp = (float *)ctx->arena.take(n * sizeof(float));

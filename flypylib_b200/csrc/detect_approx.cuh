@@ -709,7 +709,10 @@ __device__ __forceinline__ int approx_list_bricks(const float *__restrict__ g, i
 // the ball certainly beats it -> nothing; every other valid voxel of the ball is certainly worse -> selected;
 // otherwise -> ambiguous list (exact resolve).  A voxel that matters has A >= A(p)(1 - 4 eps), so only bricks whose
 // maximum reaches that are scanned (the brick grid stays in L2); for an isolated peak that is its own blob.
+// EXACT: the same scan on an exact smoothed map with the reference's order (larger value, or equal value and lower flat
+// index) -- no margin, no ambiguous outcome; used by the exact rounds (single GPU and slab sessions).
 constexpr int kBcListCap = 768;                             // >= 9^3 bricks can touch a ball of radius <= 31
+template <bool EXACT>
 __global__ void __launch_bounds__(256)
 approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict__ sup, Dims d, int r,
                         const float *__restrict__ g, int gy, int gx, const unsigned long long *__restrict__ w_idx,
@@ -721,7 +724,7 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *s_list = s_list_all[warp];
     const int r2 = r * r;
-    const float cutA = S->cutA;
+    const float cutA = S ? S->cutA : -INFINITY;
     const unsigned long long w0 = (unsigned long long)blockIdx.x * 8 + warp, wstride = (unsigned long long)gridDim.x * 8;
     for (unsigned long long w = w0; w < nW; w += wstride) {
         const unsigned long long idx = w_idx[w];
@@ -730,7 +733,7 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
         const int x = (int)(idx % (unsigned long long)d.X);
         const int y = (int)((idx / (unsigned long long)d.X) % (unsigned long long)d.Y);
         const int z = (int)(idx / ((unsigned long long)d.X * d.Y));
-        const float lo = val * kApxDn, hi = val * kApxUp;
+        const float lo = EXACT ? val : val * kApxDn, hi = EXACT ? val : val * kApxUp;
         // bricks of the ball whose maximum reaches lo
         const int bz0 = max(z - r, 0) / kBrick, bz1 = (int)(min((long long)z + r, d.Z - 1) / kBrick);
         const int by0 = max(y - r, 0) / kBrick, by1 = (int)(min((long long)y + r, d.Y - 1) / kBrick);
@@ -757,7 +760,7 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
             nlist += __popc(m);
         }
         __syncwarp();
-        if (nlist > kBcListCap) { if (lane == 0) atomicAdd(&S->overflow, 1ULL); continue; }
+        if (nlist > kBcListCap) { if (lane == 0) atomicAdd(S ? &S->overflow : &cnt->overflow, 1ULL); continue; }
         bool found = false, amb = false;
         for (int li = 0; li < nlist && !found; ++li) {
             const int code = s_list[li];
@@ -779,7 +782,11 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
                     if (dzy + ddx * ddx > r2) continue;
                     const unsigned long long q = rowbase + xx;
                     const float vq = __ldg(v + q);
-                    if (vq >= lo && q != idx && !is_suppressed(sup, q)) { if (vq > hi) hit = true; else near = true; }
+                    if (vq >= lo && q != idx && !is_suppressed(sup, q)) {
+                        if (EXACT) { if (vq > val || q < idx) hit = true; }         // equal value: the lower flat index is better
+                        else if (vq > hi) hit = true;
+                        else near = true;
+                    }
                 }
             }
             found = __any_sync(0xffffffffu, hit);
@@ -787,7 +794,7 @@ approx_ballcheck_kernel(const float *__restrict__ v, const unsigned *__restrict_
         }
         __syncwarp();
         if (lane == 0 && !found) {
-            if (amb) {
+            if (!EXACT && amb) {
                 const unsigned long long a = atomicAdd(&S->n_amb, 1ULL);
                 if (a < (unsigned long long)kApxAmbCap) amb_idx[a] = idx;
                 else atomicAdd(&S->overflow, 1ULL);
@@ -1276,7 +1283,7 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
                                                                         B.list_cap, B.cnt);
                 FPL_LAUNCH_CHECK(ctx);
             }
-            approx_ballcheck_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(A, B.sup, d, r, B.grid, B.gy, B.gx, B.w_idx, B.w_val, B.det_idx,
+            approx_ballcheck_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(A, B.sup, d, r, B.grid, B.gy, B.gx, B.w_idx, B.w_val, B.det_idx,
                                                                        B.det_val, B.sel_idx, B.det_cap, B.cnt, S, amb_idx, 0ULL, ~0ULL);
             FPL_LAUNCH_CHECK(ctx);
             approx_resolve_kernel<<<ctx->sm_count * 2, 256, ex_smem, st>>>(d_pred, A, B.sup, d, r, lw, taps, B.grid, B.gy, B.gx, amb_idx,

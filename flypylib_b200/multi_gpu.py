@@ -448,8 +448,8 @@ def _scan_level(hist, rank, prefix, mask, shift, bins, extra_zeros):
     zkey = 0x80000000
     if (zkey & mask) == prefix:
         h[(zkey >> shift) & (bins - 1)] += np.uint64(extra_zeros)
-    cum = np.cumsum(h[:bins].astype(object))
-    sel = int(np.searchsorted(np.array([int(c) for c in cum], dtype=object), rank, side='right'))
+    cum = np.cumsum(h[:bins], dtype=np.uint64)                    # counts stay far below 2^64
+    sel = int(np.searchsorted(cum, np.uint64(rank), side='right'))
     sel = min(sel, bins - 1)
     before = int(cum[sel - 1]) if sel else 0
     return rank - before, prefix | (sel << shift), mask | ((bins - 1) << shift)

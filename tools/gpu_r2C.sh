@@ -1,0 +1,6 @@
+#!/bin/bash
+tag=${1:-r2C}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${tag}_tests.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" >> gpurun_out/${tag}_bench.err
+exit 0
