@@ -5,13 +5,15 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path over one synthetic EM volume that is already resident in HBM
-as uint8: FplNetwork.infer (tiled CNN forward, reference tile grid) -> voxel2obj (Gaussian
-smoothing, 97th-percentile threshold, greedy NMS) -> detection list.  Workload at N=1 is
-BASELINE.json configs[1]: vgg_like2 (scripts/fpl_cx1_0_vgg_4ss.py) on a synthetic 1024^3 volume,
-obj_min_dist=27, smoothing_sigma=5, buffer_sz=15.  With N>1 every rank owns one such substack
-(full_roi_inference semantics: independent substacks, flypylib/fplobjdetect.py:841-986) and the
-detection lists are all-gathered over NCCL inside the timed region ("weak" scaling).
+A "step" is one pass of the hot path over ONE synthetic EM volume (BASELINE.json configs[1]: vgg_like2,
+scripts/fpl_cx1_0_vgg_4ss.py, 1024^3 uint8, obj_min_dist=27, smoothing_sigma=5, buffer_sz=15): FplNetwork.infer (tiled CNN
+forward, reference tile grid) -> voxel2obj (Gaussian smoothing, 97th-percentile threshold, greedy NMS) -> detection list.
+N = 1: the volume is resident in HBM.  N > 1: the SAME volume is z-slab sharded over the ranks (strong scaling): every
+rank evaluates its slab + 2*rf_offset halo with no forward communication, then the exact-global voxel2obj
+(multi_gpu.voxel2obj_global) yields the single-GPU detection list on every rank -- `detections_sha256_16` is the same at
+every N.  Extra legs, each guarded so that it can never take the main line down: `e2e_dropin` (the literal reference call
+sequence with numpy arrays), `cfg1` and `cfg4` at N = 1 (BASELINE configs[0] and [3]), `cfg3` at N > 1 (configs[2]: the
+U-Net on a 2048^3 volume, tile rows dealt over the ranks).
 
 Prints ONE JSON line (rank 0).
 """
