@@ -1117,7 +1117,7 @@ static size_t approx_workspace_bytes(int64_t Z, int64_t Y, int64_t X, long long 
 // why the two-tier path handed the call to the exact path (fpl_debug_v2o_decline_reason; 0 = it did not):
 // 1 parameters / shape, 2 taps, 3 percentile at or near zero, 4 rank beyond the interior, 5 sample band touches an end,
 // 6 inputs negative / non-finite / huge or cut-off too small or list overflow, 16 the sample predicts a band list
-// overflow (values crowd around the percentile within the bound), 7 band certificate, 8 narrow list
+// overflow, 17 .. too many exact recomputations (values crowd around the percentile within the bound), 7 band certificate, 8 narrow list
 // overflow, 9 narrow band leaves the listed band, 10 narrow rank certificate, 11 NaN threshold, 12.. overflow in a round
 static int decline(fpl_ctx *ctx, int code) {
     ctx->v2o_decline = code;
@@ -1212,6 +1212,15 @@ static int voxel2obj_approx(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_
         FPL_TRY(collect());
         if (h->st.bad_bits >= kApxBadBits || !(h->st.cutA >= kApxMinCut)) return decline(ctx, 6);
         if ((double)h->st.n_narrow * 64.0 * 1.5 > (double)band_cap) return decline(ctx, 16);     // band list would overflow
+        {   // the voxels within 3 eps of the percentile are recomputed exactly (~25 ns each) and tight value distributions
+            // also mean many undecidable ball comparisons: predict the size of that narrow band from the sample (its share
+            // of the listed band = ratio of the widths) and leave maps that crowd around the percentile to the exact path
+            const double band_w = (double)h->st.Hb - (double)h->st.Lb;
+            const double narrow_w = 6.0 * (double)kApxEps * 0.5 * ((double)h->st.Hb + (double)h->st.Lb);
+            const double pred = (double)h->st.n_narrow * 64.0 * (band_w > 0.0 ? (narrow_w < band_w ? narrow_w / band_w : 1.0) : 1.0);
+            const double budget = (double)n / 16384.0 > 8192.0 ? (double)n / 16384.0 : 8192.0;
+            if (pred > budget) return decline(ctx, 17);
+        }
         FPL_CUDA_CHECK(cudaMemsetAsync(&S->n_narrow, 0, sizeof(unsigned long long), st));
         FPL_CUDA_CHECK(cudaMemsetAsync(B.grid, 0, brick_grid_bytes(Z, Y, X), st));
         const long long items = Z * ((Y + kP1Strip - 1) / kP1Strip) * ((X + kP1Cols - 1) / kP1Cols);

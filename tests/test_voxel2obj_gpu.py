@@ -236,7 +236,10 @@ def test_scale_runner_vs_c_oracle(shape, kind, mode):
     from tools import check_v2o_scale
     res = check_v2o_scale.compare(shape, kind, 7, 27, 5.0, 15, 0.0, mode=mode)
     assert res["detections_oracle"] > 20
-    assert res["gpu_path"] == {0: "two-tier", 1: "classic-exact", 2: "fused-exact"}[mode], res["gpu_path"]
+    if mode == 0 and kind == "uniform":     # i.i.d. noise smoothed with sigma 5 crowds within 1 % of its mean: the two-tier
+        assert res["gpu_path"] in ("two-tier", "fused-exact")     # path may hand it to the exact path (cost guard)
+    else:
+        assert res["gpu_path"] == {0: "two-tier", 1: "classic-exact", 2: "fused-exact"}[mode], res["gpu_path"]
     assert res["threshold_identical"] and res["locs_identical"] and res["conf_identical"], res
 
 
