@@ -84,6 +84,7 @@ _SIGNATURES = {
     "fpl_net_forward_tiles": (ctypes.c_int, [vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]),
     "fpl_train_create": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
     "fpl_train_destroy": (ctypes.c_int, [vp]),
+    "fpl_train_set_precision": (ctypes.c_int, [vp, ctypes.c_int]),
     "fpl_train_sizes": (ctypes.c_int, [vp, c_i64p, c_i64p]),
     "fpl_train_forward_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_uint64,
                                                   c_f64p, c_i64p, vp]),

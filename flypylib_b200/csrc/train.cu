@@ -11,10 +11,13 @@
 //   update                    : Adam (Keras defaults), moving averages of the BN statistics (momentum 0.99)
 // The gradients live in one flat buffer (Keras get_weights() order) owned by the caller, who
 // all-reduces it across ranks (NCCL, torch.distributed) between fpl_train_forward_backward and
-// fpl_train_apply.  Patches are tiny (64 x 24^3 per GPU, 1.1 GFLOP forward each): everything here is
-// plain fp32 CUDA-core code, correctness first; activations are (N,z,y,x,C) float32.
+// fpl_train_apply.  Activations are (N,z,y,x,C) float32.  The three contractions of every convolution (forward,
+// dgrad, wgrad) run on the tensor cores (train_tc.cuh: tcgen05 / TMEM, bf16 hi/lo split operands = fp32-class
+// results by default); the fp32 CUDA-core kernels below remain as the validation path (FPL_PREC_FP32).
 #include "net.cuh"
+#include "train_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace fpl {
 namespace train {
@@ -47,6 +50,10 @@ struct fpl_trainer {
     size_t off_final_kernel = 0, off_final_bias = 0, n_params = 0, n_bn = 0;
     int final_cin = 0;
     float *g0 = nullptr, *g1 = nullptr;       // gradient ping-pong (max activation size)
+    float *gpad = nullptr;                    // zero-padded dx of the layer whose dgrad runs (tensor-core path)
+    float *gemb = nullptr;                    // dx on the input grid of the layer whose wgrad runs (slab wgrad)
+    void *wimg = nullptr;                     // packed bf16 hi/lo weight image of the convolution that runs (slab conv)
+    int precision = FPL_PREC_TF32;            // FPL_PREC_TF32: bf16 hi/lo x3 on tcgen05; FPL_PREC_BF16; FPL_PREC_FP32: CUDA cores
     float *logit = nullptr, *dlogit = nullptr;
     double *loss_acc = nullptr;               // [0] sum of per-sample BCE, [1] correct count
     std::vector<void *> allocs;
@@ -90,18 +97,36 @@ conv_fwd_kernel(const float *__restrict__ in, const float *__restrict__ w, float
     }
 }
 
-// per-channel sum and sum of squares over `rows` rows of C channels (double accumulation)
+// per-channel sum and sum of squares over `rows` rows of C channels (double accumulation).  Each thread owns one
+// channel of `lanes` interleaved rows, keeps 8 independent loads in flight, the block reduces its row lanes in shared
+// memory and issues ONE atomic per channel and statistic.
+constexpr int kBnUnroll = 8;
 __global__ void __launch_bounds__(256)
 bn_sums_kernel(const float *__restrict__ x, long long rows, int c, double *__restrict__ stat) {
+    __shared__ double s_red[2][256];
     const int lanes = 256 / c;                 // row lanes per block
     const int ch = threadIdx.x % c, rl = threadIdx.x / c;
     double s = 0.0, ss = 0.0;
-    if (rl < lanes)
-        for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
-            const double v = (double)x[r * c + ch];
-            s += v; ss += v * v;
+    if (rl < lanes) {
+        const long long stride = (long long)gridDim.x * lanes;
+        for (long long r0 = (long long)blockIdx.x * lanes + rl; r0 < rows; r0 += stride * kBnUnroll) {
+            float v[kBnUnroll];
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const long long r = r0 + u * stride;
+                v[u] = r < rows ? __ldg(x + r * c + ch) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) { const double d = (double)v[u]; s += d; ss += d * d; }
         }
-    if (rl < lanes) { atomicAdd(&stat[ch], s); atomicAdd(&stat[c + ch], ss); }
+    }
+    s_red[0][threadIdx.x] = s; s_red[1][threadIdx.x] = ss;
+    __syncthreads();
+    if (threadIdx.x < c) {
+        double a = 0.0, b = 0.0;
+        for (int l = 0; l < lanes; ++l) { a += s_red[0][l * c + threadIdx.x]; b += s_red[1][l * c + threadIdx.x]; }
+        atomicAdd(&stat[threadIdx.x], a); atomicAdd(&stat[c + threadIdx.x], b);
+    }
 }
 
 __global__ void bn_finalize_kernel(const double *__restrict__ stat, long long rows, int c, float eps,
@@ -133,13 +158,27 @@ bn_relu_dropout_kernel(const float *__restrict__ x, long long total, int c, cons
                        const float *__restrict__ beta, const float *__restrict__ mean,
                        const float *__restrict__ invstd, float *__restrict__ y, float *__restrict__ yd,
                        unsigned long long seed, unsigned long long layer) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+    __shared__ float s_m[96], s_k[96], s_g[96], s_b[96];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) { s_m[i] = mean[i]; s_k[i] = invstd[i]; s_g[i] = gamma[i]; s_b[i] = beta[i]; }
+    __syncthreads();
+    const int c4 = c >> 2;
+    const long long total4 = total >> 2;            // C is a multiple of 4
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % c);
-        float v = (x[i] - mean[ch]) * invstd[ch] * gamma[ch] + beta[ch];
-        v = fmaxf(v, 0.f);
-        y[i] = v;
-        if (yd) yd[i] = keep_bit(seed, layer, (unsigned long long)i) ? v * 2.f : 0.f;
+        const int ch = (int)(i % c4) * 4;
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        const float in[4] = {xv.x, xv.y, xv.z, xv.w};
+        float o[4], od[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // same operation order as the scalar form: ((x - mean) * invstd) * gamma + beta
+            float v = (in[e] - s_m[ch + e]) * s_k[ch + e] * s_g[ch + e] + s_b[ch + e];
+            v = fmaxf(v, 0.f);
+            o[e] = v;
+            od[e] = (yd && !keep_bit(seed, layer, (unsigned long long)(i * 4 + e))) ? 0.f : v * 2.f;
+        }
+        reinterpret_cast<float4 *>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (yd) reinterpret_cast<float4 *>(yd)[i] = make_float4(od[0], od[1], od[2], od[3]);
     }
 }
 
@@ -233,20 +272,44 @@ bn_bwd_reduce_kernel(const float *__restrict__ dout, const float *__restrict__ x
                      long long rows, int c, const float *__restrict__ mean, const float *__restrict__ invstd,
                      int dropout, unsigned long long seed, unsigned long long layer, float *__restrict__ dz,
                      double *__restrict__ acc) {
+    __shared__ double s_red[2][256];
+    constexpr int U = 4;
     const int lanes = 256 / c;
     const int ch = threadIdx.x % c, rl = threadIdx.x / c;
     double dg = 0.0, db = 0.0;
-    if (rl < lanes)
-        for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
-            const long long i = r * c + ch;
-            float g = dout[i];
-            if (dropout) g = keep_bit(seed, layer, (unsigned long long)i) ? g * 2.f : 0.f;
-            g = y[i] > 0.f ? g : 0.f;
-            dz[i] = g;
-            const float xhat = (x[i] - mean[ch]) * invstd[ch];
-            dg += (double)g * (double)xhat; db += (double)g;
+    if (rl < lanes) {
+        const float m = mean[ch], is = invstd[ch];
+        const long long stride = (long long)gridDim.x * lanes;
+        for (long long r0 = (long long)blockIdx.x * lanes + rl; r0 < rows; r0 += stride * U) {
+            float gv[U], xv[U], yv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + u * stride;
+                const bool ok = r < rows;
+                const long long i = r * c + ch;
+                gv[u] = ok ? __ldg(dout + i) : 0.f; xv[u] = ok ? __ldg(x + i) : 0.f; yv[u] = ok ? __ldg(y + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + u * stride;
+                if (r >= rows) continue;
+                const long long i = r * c + ch;
+                float g = gv[u];
+                if (dropout) g = keep_bit(seed, layer, (unsigned long long)i) ? g * 2.f : 0.f;
+                g = yv[u] > 0.f ? g : 0.f;
+                dz[i] = g;
+                const float xhat = (xv[u] - m) * is;
+                dg += (double)g * (double)xhat; db += (double)g;
+            }
         }
-    if (rl < lanes) { atomicAdd(&acc[ch], dg); atomicAdd(&acc[c + ch], db); }
+    }
+    s_red[0][threadIdx.x] = dg; s_red[1][threadIdx.x] = db;
+    __syncthreads();
+    if (threadIdx.x < c) {
+        double a = 0.0, b = 0.0;
+        for (int l = 0; l < lanes; ++l) { a += s_red[0][l * c + threadIdx.x]; b += s_red[1][l * c + threadIdx.x]; }
+        atomicAdd(&acc[threadIdx.x], a); atomicAdd(&acc[c + threadIdx.x], b);
+    }
 }
 
 // dx = gamma*invstd * (dz - dbeta/M - xhat*dgamma/M); also emits dgamma/dbeta as float gradients
@@ -255,13 +318,28 @@ bn_bwd_apply_kernel(float *__restrict__ dz_dx, const float *__restrict__ x, long
                     const float *__restrict__ gamma, const float *__restrict__ mean,
                     const float *__restrict__ invstd, const double *__restrict__ acc,
                     float *__restrict__ g_gamma, float *__restrict__ g_beta) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+    __shared__ float s_m[96], s_is[96], s_k[96], s_dg[96], s_db[96];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        s_m[i] = mean[i]; s_is[i] = invstd[i]; s_k[i] = gamma[i] * invstd[i];
+        s_dg[i] = (float)(acc[i] / (double)rows); s_db[i] = (float)(acc[c + i] / (double)rows);
+        if (blockIdx.x == 0) { g_gamma[i] = (float)acc[i]; g_beta[i] = (float)acc[c + i]; }
+    }
+    __syncthreads();
+    const int c4 = c >> 2;
+    const long long total4 = total >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % c);
-        const float xhat = (x[i] - mean[ch]) * invstd[ch];
-        const float dg = (float)(acc[ch] / (double)rows), db = (float)(acc[c + ch] / (double)rows);
-        dz_dx[i] = gamma[ch] * invstd[ch] * (dz_dx[i] - db - xhat * dg);
-        if (i < c) { g_gamma[i] = (float)acc[i]; g_beta[i] = (float)acc[c + i]; }
+        const int ch = (int)(i % c4) * 4;
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        const float4 dv = reinterpret_cast<const float4 *>(dz_dx)[i];
+        const float xi[4] = {xv.x, xv.y, xv.z, xv.w}, di[4] = {dv.x, dv.y, dv.z, dv.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float xhat = (xi[e] - s_m[ch + e]) * s_is[ch + e];
+            o[e] = s_k[ch + e] * (di[e] - s_db[ch + e] - xhat * s_dg[ch + e]);
+        }
+        reinterpret_cast<float4 *>(dz_dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -388,9 +466,172 @@ static int blocks_for(fpl_ctx *ctx, long long total) {
 
 static int row_blocks(fpl_ctx *ctx, long long rows, int c) {     // grid for the (rows x C) reductions
     const long long lanes = 256 / c;
-    long long b = (rows + lanes - 1) / lanes, cap = (long long)ctx->sm_count * 16;
+    long long b = (rows + lanes - 1) / lanes, cap = (long long)ctx->sm_count * 8;
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core launches (train_tc.cuh)
+// ------------------------------------------------------------------------------------------------
+static bool tc_layer_ok(int k, int cin, int cout) {
+    const bool cin_ok = (cin == 1 && k == 3) || cin % 48 == 0;
+    return cin_ok && cout % 48 == 0 && cout <= kTcMaxN && cin <= kTcMaxN && (k == 1 || k == 3);
+}
+
+template <int NS>
+static int tc_set_smem() {
+    static bool done = false;
+    if (!done) {
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    return FPL_OK;
+}
+
+// valid convolution of `act` (n, din^3, ca) with the k^3 kernel `w`; flip = 0: forward (nn = cout, w read as
+// (tap, ca, nn)), flip = 1: dgrad on the zero-padded dx (nn = cin, w read as (T-1-tap, nn, ca)); out (n*dout^3, nn)
+static int launch_tc_conv(fpl_ctx *ctx, int prec, const float *act, const float *w, float *out, int n, int din, int k,
+                          int ca, int nn, int flip, cudaStream_t st) {
+    TcArgs a{};
+    a.act = act; a.mat = w; a.out = out;
+    a.n_img = n; a.din = din; a.dout = din - (k - 1); a.k = k; a.ca = ca; a.nn = nn; a.flip = flip;
+    a.K = k * k * k * ca;
+    a.rows = (long long)n * a.dout * a.dout * a.dout;
+    const int apc = ca == 1 ? 4 : 6;
+    a.a_bytes = (uint32_t)apc * 2048u; a.b_bytes = (uint32_t)apc * (uint32_t)nn * 16u;
+    const int np = prec == FPL_PREC_BF16 ? 1 : 2;
+    const size_t smem = 2 * (size_t)np * (a.a_bytes + a.b_bytes);
+    const long long tiles = (a.rows + 127) / 128;
+    const long long cap = (long long)ctx->sm_count * 3;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    if (prec == FPL_PREC_BF16) { FPL_TRY(tc_set_smem<1>()); tc_conv_kernel<1><<<grid, kTcThreads, smem, st>>>(a); }
+    else { FPL_TRY(tc_set_smem<3>()); tc_conv_kernel<3><<<grid, kTcThreads, smem, st>>>(a); }
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
+}
+
+// dW (k^3*cin, cout) += sum over the n*dout^3 output voxels of in[v + tap, ci] * dx[v, co]
+static int launch_tc_wgrad(fpl_ctx *ctx, int prec, const float *in, const float *dx, float *dw, int n, int din, int k,
+                           int cin, int cout, cudaStream_t st) {
+    TcArgs a{};
+    a.act = in; a.mat = dx; a.out = dw;
+    a.n_img = n; a.din = din; a.dout = din - (k - 1); a.k = k; a.ca = cin; a.nn = cout;
+    a.Mtot = k * k * k * cin;
+    a.rows = (long long)n * a.dout * a.dout * a.dout;
+    FPL_REQUIRE((long long)n * din * din * din * cin < (1ll << 31), "wgrad: activation tensor too large for 32-bit offsets");
+    a.a_bytes = 8u * 2048u; a.b_bytes = 8u * (uint32_t)cout * 16u;
+    const int np = prec == FPL_PREC_BF16 ? 1 : 2;
+    const size_t smem = 2 * (size_t)np * (a.a_bytes + a.b_bytes);
+    const int mtiles = (a.Mtot + 127) / 128;
+    const long long nchunks = (a.rows + 63) / 64;
+    long long ksplit = ((long long)ctx->sm_count * 3 + mtiles - 1) / mtiles;
+    if (ksplit > nchunks) ksplit = nchunks;
+    if (ksplit < 1) ksplit = 1;
+    a.chunks_per_cta = (int)((nchunks + ksplit - 1) / ksplit);
+    ksplit = (nchunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
+    dim3 grid((unsigned)mtiles, (unsigned)ksplit);
+    if (prec == FPL_PREC_BF16) { FPL_TRY(tc_set_smem<1>()); tc_wgrad_kernel<1><<<grid, kTcThreads, smem, st>>>(a); }
+    else { FPL_TRY(tc_set_smem<3>()); tc_wgrad_kernel<3><<<grid, kTcThreads, smem, st>>>(a); }
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
+}
+
+// ---- slab kernels (48 | Cin): see train_tc.cuh
+static int g_tc_gather = -1;     // FPL_TC_GATHER=1: A/B switch back to the per-tap gather kernels
+static bool slab_layer_ok(int k, int cin, int cout) {
+    if (g_tc_gather < 0) { const char *e = getenv("FPL_TC_GATHER"); g_tc_gather = (e && e[0] == '1') ? 1 : 0; }
+    return !g_tc_gather && cin % 48 == 0 && cout % 48 == 0 && cin <= 96 && cout <= 96 && (k == 1 || k == 3);
+}
+static size_t slab_wimg_bytes(int k, int ca, int nn) { return (size_t)k * k * k * (ca / 48) * 2 * 6 * nn * 16; }
+
+template <int NS>
+static int slab_set_smem() {
+    static bool done = false;
+    if (!done) {
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        done = true;
+    }
+    return FPL_OK;
+}
+
+// valid convolution (forward: flip 0, dgrad on the zero-padded dx: flip 1); wimg: scratch for the packed weights
+static int launch_slab_conv(fpl_ctx *ctx, int prec, const float *act, const float *w, void *wimg, float *out, int n,
+                            int din, int k, int ca, int nn, int flip, cudaStream_t st) {
+    const int ns = prec == FPL_PREC_BF16 ? 1 : 3, np = ns == 3 ? 2 : 1;
+    const int ntaps = k * k * k;
+    const int total = ntaps * (ca / 48) * 6 * nn;
+    if (ns == 1) tc_pack_w_kernel<1><<<(total + 255) / 256, 256, 0, st>>>(w, (uint8_t *)wimg, ntaps, ca, nn, flip);
+    else tc_pack_w_kernel<3><<<(total + 255) / 256, 256, 0, st>>>(w, (uint8_t *)wimg, ntaps, ca, nn, flip);
+    FPL_LAUNCH_CHECK(ctx);
+    SlabConvArgs a{};
+    a.act = act; a.wimg = (const __nv_bfloat16 *)wimg; a.out = out;
+    a.k = k; a.ca = ca; a.nn = nn;
+    const int dout = din - (k - 1);
+    if (k == 1) { a.flat = 1; a.n_img = 1; a.din = 1 << 14; a.dout = a.din; a.u_max = n * din * din * din; a.img_vox = a.u_max; }
+    else { a.flat = 0; a.n_img = n; a.din = din; a.dout = dout; a.u_max = ((dout - 1) * din + (dout - 1)) * din + dout;
+           a.img_vox = (long long)din * din * din; }
+    if (k == 1) FPL_REQUIRE((long long)n * din * din * din < (1ll << 30), "slab conv: too many rows");
+    const int halo = k == 1 ? 0 : (k - 1) * (din + 1);
+    const size_t b_ring = (size_t)kSlabRing * np * 6 * nn * 16;
+    size_t smem = 0;
+    for (int mt = 2; mt >= 1; --mt) {
+        int sp = mt * 128 + halo;
+        sp += (9 - sp % 8) % 8;                                   // == 1 (mod 8): staging stores spread over the banks
+        smem = (size_t)np * k * (ca / 8) * sp * 16 + b_ring;
+        a.mt = mt; a.s_pad = sp;
+        if (smem <= 227 * 1024 - 1024 && 2 * mt * nn <= 512) break;
+    }
+    FPL_REQUIRE(smem <= 227 * 1024 - 1024, "slab conv: layer does not fit shared memory");
+    const int rows_pass = a.mt * 128;
+    a.pairs_per_img = (a.u_max + rows_pass - 1) / rows_pass;
+    const long long passes = (long long)a.n_img * a.pairs_per_img;
+    const int grid = (int)(passes < ctx->sm_count ? passes : ctx->sm_count);
+    if (ns == 1) { FPL_TRY(slab_set_smem<1>()); tc_slab_conv_kernel<1><<<grid, kSlabThreads, smem, st>>>(a); }
+    else { FPL_TRY(slab_set_smem<3>()); tc_slab_conv_kernel<3><<<grid, kSlabThreads, smem, st>>>(a); }
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
+}
+
+// dW += in^T * dx; dxe: dx on the input grid (k == 3: zero-embedded copy; k == 1: dx itself)
+static int launch_slab_wgrad(fpl_ctx *ctx, int prec, const float *in, const float *dxe, float *dw, int n, int din, int k,
+                             int ci, int co, cudaStream_t st) {
+    const int ns = prec == FPL_PREC_BF16 ? 1 : 3, np = ns == 3 ? 2 : 1;
+    SlabWgradArgs a{};
+    a.act = in; a.dxe = dxe; a.dw = dw; a.k = k; a.ci = ci; a.co = co;
+    const int dout = din - (k - 1);
+    long long u_max;
+    if (k == 1) { a.n_img = 1; a.din = 1 << 14; a.dout = a.din; u_max = (long long)n * din * din * din; a.img_vox = u_max; }
+    else { a.n_img = n; a.din = din; a.dout = dout; u_max = ((long long)(dout - 1) * din + (dout - 1)) * din + dout;
+           a.img_vox = (long long)din * din * din; }
+    FPL_REQUIRE(u_max < (1ll << 30), "slab wgrad: too many voxels");
+    const int halo = k == 1 ? 0 : (k - 1) * (din + 1);
+    int sp = kWgKc + halo;
+    sp += (9 - sp % 8) % 8;
+    a.s_pad = sp;
+    a.chunks_per_img = (int)((u_max + kWgKc - 1) / kWgKc);
+    const size_t pa = (size_t)kWgAPad * 16, a_img = (size_t)(co / 8) * pa, x_img = (size_t)(ci / 8) * sp * 16;
+    const size_t stage = np * (a_img + x_img);
+    const size_t over = (np - 1) * a_img + 16 * pa;               // reach of the M = 128 read from the last A image
+    size_t smem = 2 * stage + (over > stage ? over - stage : 0);
+    smem = (smem + 15) & ~(size_t)15;
+    FPL_REQUIRE(smem <= 227 * 1024 - 1024, "slab wgrad: layer does not fit shared memory");
+    FPL_REQUIRE(k * k * ci <= 512, "slab wgrad: accumulators do not fit TMEM");
+    a.smem_bytes = (uint32_t)smem;
+    const long long n_units = (long long)a.n_img * a.chunks_per_img;
+    long long per_kd = ctx->sm_count / k;
+    if (per_kd < 1) per_kd = 1;
+    if (per_kd > n_units) per_kd = n_units;
+    a.units_per_cta = (int)((n_units + per_kd - 1) / per_kd);
+    per_kd = (n_units + a.units_per_cta - 1) / a.units_per_cta;
+    dim3 grid((unsigned)k, (unsigned)per_kd);
+    if (ns == 1) { FPL_TRY(slab_set_smem<1>()); tc_slab_wgrad_kernel<1><<<grid, kWgThreads, smem, st>>>(a); }
+    else { FPL_TRY(slab_set_smem<3>()); tc_slab_wgrad_kernel<3><<<grid, kWgThreads, smem, st>>>(a); }
+    FPL_LAUNCH_CHECK(ctx);
+    return FPL_OK;
 }
 
 }  // namespace train
@@ -471,6 +712,24 @@ int fpl_train_create(fpl_ctx *ctx, int arch, int patch_sz, int batch, fpl_traine
         mem_ok = mem_ok && L.x && L.y && L.yd && (!L.pool_after || L.yp) && L.stat && L.mean && L.invstd;
     }
     t->g0 = (float *)alloc(max_elems * 4); t->g1 = (float *)alloc(max_elems * 4);
+    size_t pad_elems = 16;
+    for (size_t li = 1; li < t->layers.size(); ++li) {
+        const Layer &L = t->layers[li];
+        const size_t dp = (size_t)L.dout + 2 * (L.k - 1);
+        if (L.k > 1 && (size_t)batch * dp * dp * dp * L.cout > pad_elems) pad_elems = (size_t)batch * dp * dp * dp * L.cout;
+    }
+    t->gpad = (float *)alloc(pad_elems * 4);
+    size_t emb_elems = 16, wimg_bytes = 16;
+    for (size_t li = 0; li < t->layers.size(); ++li) {
+        const Layer &L = t->layers[li];
+        if (L.cin % 48 || L.cout % 48) continue;
+        if (L.k > 1 && (size_t)batch * L.din * L.din * L.din * L.cout > emb_elems) emb_elems = (size_t)batch * L.din * L.din * L.din * L.cout;
+        if (slab_wimg_bytes(L.k, L.cin, L.cout) > wimg_bytes) wimg_bytes = slab_wimg_bytes(L.k, L.cin, L.cout);
+        if (slab_wimg_bytes(L.k, L.cout, L.cin) > wimg_bytes) wimg_bytes = slab_wimg_bytes(L.k, L.cout, L.cin);
+    }
+    t->gemb = (float *)alloc(emb_elems * 4);
+    t->wimg = alloc(wimg_bytes);
+    mem_ok = mem_ok && t->gpad && t->gemb && t->wimg;
     t->logit = (float *)alloc(batch * 4); t->dlogit = (float *)alloc(batch * 4);
     t->loss_acc = (double *)alloc(2 * sizeof(double));
     if (!mem_ok || !t->g0 || !t->g1 || !t->logit || !t->dlogit || !t->loss_acc) {
@@ -480,6 +739,70 @@ int fpl_train_create(fpl_ctx *ctx, int arch, int patch_sz, int batch, fpl_traine
     }
     *out = t;
     return FPL_OK;
+}
+
+int fpl_train_set_precision(fpl_trainer *t, int precision) {
+    FPL_REQUIRE(t, "fpl_train_set_precision: NULL trainer");
+    FPL_REQUIRE(precision == FPL_PREC_FP32 || precision == FPL_PREC_BF16 || precision == FPL_PREC_TF32,
+                "fpl_train_set_precision: unknown precision %d", precision);
+    t->precision = precision;
+    return FPL_OK;
+}
+
+// test hooks (not part of include/fpl_b200.h): the three tensor-core contractions on caller-provided device tensors
+// what = 0: forward conv (act (n,din^3,cin), w (k^3,cin,cout) -> out (n,dout^3,cout))
+// what = 1: dgrad       (act = dx (n,dout^3,cout), w -> out (n,din^3,cin)); scratch >= n*(dout+2(k-1))^3*cout floats
+// what = 2: wgrad       (act = layer input (n,din^3,cin), w = dx (n,dout^3,cout) -> out (k^3,cin,cout), overwritten)
+int fpl_debug_train_tc(fpl_ctx *ctx, int what, int precision, const float *act, const float *w, float *out,
+                       float *scratch, int n, int din, int k, int cin, int cout, void *stream) {
+    FPL_REQUIRE(ctx && act && w && out, "fpl_debug_train_tc: NULL argument");
+    FPL_REQUIRE(tc_layer_ok(k, cin, cout), "fpl_debug_train_tc: layer shape not covered by the tensor-core kernels");
+    FPL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int dout = din - (k - 1);
+    const bool slab = slab_layer_ok(k, cin, cout);
+    const int p = k - 1, dp = dout + 2 * p;
+    void *wimg = nullptr; float *emb = nullptr;
+    if (slab) {
+        const size_t wb = slab_wimg_bytes(k, cin, cout) > slab_wimg_bytes(k, cout, cin) ? slab_wimg_bytes(k, cin, cout) : slab_wimg_bytes(k, cout, cin);
+        FPL_CUDA_CHECK(cudaMalloc(&wimg, wb));
+        FPL_CUDA_CHECK(cudaMalloc((void **)&emb, (size_t)n * din * din * din * cout * sizeof(float)));
+    }
+    int rc = FPL_OK;
+    if (what == 0) {
+        rc = slab ? launch_slab_conv(ctx, precision, act, w, wimg, out, n, din, k, cin, cout, 0, st)
+                  : launch_tc_conv(ctx, precision, act, w, out, n, din, k, cin, cout, 0, st);
+    } else if (what == 1) {
+        const float *dxp = act;
+        if (k > 1) {
+            FPL_REQUIRE(scratch, "fpl_debug_train_tc: dgrad needs the scratch buffer");
+            tc_embed_kernel<<<blocks_for(ctx, (long long)n * dp * dp * dp * (cout / 4)), 256, 0, st>>>(
+                (const float4 *)act, (float4 *)scratch, n, dout, p, dp, cout / 4);
+            ctx->launches++;
+            dxp = scratch;
+        }
+        rc = slab ? launch_slab_conv(ctx, precision, dxp, w, wimg, out, n, dp, k, cout, cin, 1, st)
+                  : launch_tc_conv(ctx, precision, dxp, w, out, n, dp, k, cout, cin, 1, st);
+    } else {
+        cudaMemsetAsync(out, 0, (size_t)k * k * k * cin * cout * sizeof(float), st);
+        if (slab) {
+            const float *dxe = w;
+            if (k > 1) {
+                tc_embed_kernel<<<blocks_for(ctx, (long long)n * din * din * din * (cout / 4)), 256, 0, st>>>(
+                    (const float4 *)w, (float4 *)emb, n, dout, 0, din, cout / 4);
+                ctx->launches++;
+                dxe = emb;
+            }
+            rc = launch_slab_wgrad(ctx, precision, act, dxe, out, n, din, k, cin, cout, st);
+        } else {
+            rc = launch_tc_wgrad(ctx, precision, act, w, out, n, din, k, cin, cout, st);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (wimg) cudaFree(wimg);
+    if (emb) cudaFree(emb);
+    if (rc == FPL_OK && e != cudaSuccess) { fpl::set_error("fpl_debug_train_tc: %s", cudaGetErrorString(e)); rc = FPL_ECUDA; }
+    return rc;
 }
 
 int fpl_train_sizes(const fpl_trainer *t, int64_t *n_params, int64_t *n_bn) {
@@ -503,9 +826,13 @@ int fpl_train_forward_backward(fpl_trainer *t, const float *d_x, const uint8_t *
     for (size_t li = 0; li < t->layers.size(); ++li) {
         Layer &L = t->layers[li];
         const long long rows = (long long)n * L.dout * L.dout * L.dout, total = rows * L.cout;
-        if (L.k == 3) conv_fwd_kernel<3><<<blocks_for(ctx, total / 8), 256, 0, st>>>(cur, d_params + L.off_kernel, L.x, n, L.din, L.cin, L.cout);
+        const bool tc = t->precision != FPL_PREC_FP32 && tc_layer_ok(L.k, L.cin, L.cout);
+        if (tc && slab_layer_ok(L.k, L.cin, L.cout))
+            FPL_TRY(launch_slab_conv(ctx, t->precision, cur, d_params + L.off_kernel, t->wimg, L.x, n, L.din, L.k, L.cin, L.cout, 0, st));
+        else if (tc) FPL_TRY(launch_tc_conv(ctx, t->precision, cur, d_params + L.off_kernel, L.x, n, L.din, L.k, L.cin, L.cout, 0, st));
+        else if (L.k == 3) conv_fwd_kernel<3><<<blocks_for(ctx, total / 8), 256, 0, st>>>(cur, d_params + L.off_kernel, L.x, n, L.din, L.cin, L.cout);
         else conv_fwd_kernel<1><<<blocks_for(ctx, total / 8), 256, 0, st>>>(cur, d_params + L.off_kernel, L.x, n, L.din, L.cin, L.cout);
-        FPL_LAUNCH_CHECK(ctx);
+        if (!tc) FPL_LAUNCH_CHECK(ctx);
         FPL_CUDA_CHECK(cudaMemsetAsync(L.stat, 0, 4 * L.cout * sizeof(double), st));
         bn_sums_kernel<<<row_blocks(ctx, rows, L.cout), 256, 0, st>>>(L.x, rows, L.cout, L.stat);
         FPL_LAUNCH_CHECK(ctx);
@@ -548,19 +875,51 @@ int fpl_train_forward_backward(fpl_trainer *t, const float *d_x, const uint8_t *
         FPL_LAUNCH_CHECK(ctx);
         // gb now holds dx (gradient w.r.t. the conv output)
         const float *lin = li == 0 ? d_x : (t->layers[li - 1].pool_after ? t->layers[li - 1].yp : t->layers[li - 1].yd);
-        FPL_REQUIRE(L.cin * L.cout <= 256 * kWgAcc && L.cin <= 96 && L.cout <= 96, "wgrad: layer too wide");
-        const long long rpb = 2048;
-        dim3 wg(L.k * L.k * L.k, (unsigned)((rows + rpb - 1) / rpb));
-        if (L.k == 3) conv_wgrad_kernel<3><<<wg, 256, 0, st>>>(lin, gb, d_grads + L.off_kernel, n, L.din, L.cin, L.cout, rpb);
-        else conv_wgrad_kernel<1><<<wg, 256, 0, st>>>(lin, gb, d_grads + L.off_kernel, n, L.din, L.cin, L.cout, rpb);
-        FPL_LAUNCH_CHECK(ctx);
-        if (li > 0) {
-            const long long tin = (long long)n * L.din * L.din * L.din * L.cin;
-            if (L.k == 3) conv_dgrad_kernel<3><<<blocks_for(ctx, tin / 8), 256, 0, st>>>(gb, d_params + L.off_kernel, ga, n, L.din, L.cin, L.cout);
-            else conv_dgrad_kernel<1><<<blocks_for(ctx, tin / 8), 256, 0, st>>>(gb, d_params + L.off_kernel, ga, n, L.din, L.cin, L.cout);
+        const bool tc = t->precision != FPL_PREC_FP32 && tc_layer_ok(L.k, L.cin, L.cout);
+        if (tc) {
+            const bool slab = slab_layer_ok(L.k, L.cin, L.cout);
+            const int p = L.k - 1;
+            if (slab) {
+                const float *dxe = gb;                   // dx on the input grid (zeros where there is no output)
+                if (L.k > 1) {
+                    const long long te = (long long)n * L.din * L.din * L.din * (L.cout / 4);
+                    tc_embed_kernel<<<blocks_for(ctx, te), 256, 0, st>>>((const float4 *)gb, (float4 *)t->gemb, n, L.dout, 0, L.din, L.cout / 4);
+                    FPL_LAUNCH_CHECK(ctx);
+                    dxe = t->gemb;
+                }
+                FPL_TRY(launch_slab_wgrad(ctx, t->precision, lin, dxe, d_grads + L.off_kernel, n, L.din, L.k, L.cin, L.cout, st));
+            } else {
+                FPL_TRY(launch_tc_wgrad(ctx, t->precision, lin, gb, d_grads + L.off_kernel, n, L.din, L.k, L.cin, L.cout, st));
+            }
+            if (li > 0) {
+                // dgrad = valid convolution of the zero-padded dx with the flipped kernel (channels swapped)
+                const float *dxp = gb;
+                if (L.k > 1) {
+                    const int dp = L.dout + 2 * p;
+                    const long long tp = (long long)n * dp * dp * dp * (L.cout / 4);
+                    tc_embed_kernel<<<blocks_for(ctx, tp), 256, 0, st>>>((const float4 *)gb, (float4 *)t->gpad, n, L.dout, p, dp, L.cout / 4);
+                    FPL_LAUNCH_CHECK(ctx);
+                    dxp = t->gpad;
+                }
+                if (slab) FPL_TRY(launch_slab_conv(ctx, t->precision, dxp, d_params + L.off_kernel, t->wimg, ga, n, L.dout + 2 * p, L.k,
+                                                   L.cout, L.cin, 1, st));
+                else FPL_TRY(launch_tc_conv(ctx, t->precision, dxp, d_params + L.off_kernel, ga, n, L.dout + 2 * p, L.k, L.cout, L.cin, 1, st));
+            }
+        } else {
+            FPL_REQUIRE(L.cin * L.cout <= 256 * kWgAcc && L.cin <= 96 && L.cout <= 96, "wgrad: layer too wide");
+            const long long rpb = 2048;
+            dim3 wg(L.k * L.k * L.k, (unsigned)((rows + rpb - 1) / rpb));
+            if (L.k == 3) conv_wgrad_kernel<3><<<wg, 256, 0, st>>>(lin, gb, d_grads + L.off_kernel, n, L.din, L.cin, L.cout, rpb);
+            else conv_wgrad_kernel<1><<<wg, 256, 0, st>>>(lin, gb, d_grads + L.off_kernel, n, L.din, L.cin, L.cout, rpb);
             FPL_LAUNCH_CHECK(ctx);
-            // ga = gradient w.r.t. this layer's input = previous block's (pooled / dropped-out) output
+            if (li > 0) {
+                const long long tin = (long long)n * L.din * L.din * L.din * L.cin;
+                if (L.k == 3) conv_dgrad_kernel<3><<<blocks_for(ctx, tin / 8), 256, 0, st>>>(gb, d_params + L.off_kernel, ga, n, L.din, L.cin, L.cout);
+                else conv_dgrad_kernel<1><<<blocks_for(ctx, tin / 8), 256, 0, st>>>(gb, d_params + L.off_kernel, ga, n, L.din, L.cin, L.cout);
+                FPL_LAUNCH_CHECK(ctx);
+            }
         }
+        // ga = gradient w.r.t. this layer's input = previous block's (pooled / dropped-out) output
     }
     double *h = (double *)ctx->h_pinned;
     FPL_CUDA_CHECK(cudaMemcpyAsync(h, t->loss_acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));

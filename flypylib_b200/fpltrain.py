@@ -17,8 +17,14 @@ ADAM = dict(lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)     # Keras 'adam' 
 BN_MOMENTUM = 0.99
 
 
+PRECISIONS = {"fp32": 0, "bf16": 1, "tf32": 2}     # FPL_PREC_* of include/fpl_b200.h
+
+
 class Trainer(object):
-    def __init__(self, model, patch_sz, batch_size, device=None):
+    def __init__(self, model, patch_sz, batch_size, device=None, precision="tf32"):
+        """precision: arithmetic of the convolution contractions -- 'tf32' (default: tcgen05 tensor cores on bf16
+        hi/lo split operands, fp32-class results), 'bf16' (one bf16 contraction) or 'fp32' (CUDA-core validation
+        path)."""
         import torch
         self.model = model
         self.ctx = _lib.context(device)
@@ -29,6 +35,8 @@ class Trainer(object):
         _lib.check(_lib.lib().fpl_train_create(self.ctx.handle, model.spec["id"], self.patch, self.batch,
                                                ctypes.byref(h)), "fpl_train_create")
         self.handle = h
+        self.precision = precision
+        _lib.check(_lib.lib().fpl_train_set_precision(h, PRECISIONS[precision]), "fpl_train_set_precision")
         n_p, n_bn = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(_lib.lib().fpl_train_sizes(h, ctypes.byref(n_p), ctypes.byref(n_bn)))
         flat = np.concatenate([w.ravel() for w in model.get_weights()]).astype(np.float32)

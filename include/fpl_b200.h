@@ -244,6 +244,11 @@ typedef struct fpl_trainer fpl_trainer;
  * batch = patches per GPU (64 in scripts/fpl_cx1_0_vgg_4ss.py:11-17) */
 int fpl_train_create(fpl_ctx *ctx, int arch, int patch_sz, int batch, fpl_trainer **out);
 int fpl_train_destroy(fpl_trainer *t);
+/* Arithmetic of the convolution contractions (forward, dgrad, wgrad) of the step.  FPL_PREC_TF32 (default): tcgen05
+ * tensor cores on bf16 hi/lo split operands, three bf16 contractions with fp32 accumulation -- fp32-class results
+ * (the reference trains in float32); FPL_PREC_BF16: one bf16 contraction; FPL_PREC_FP32: fp32 CUDA-core kernels
+ * (validation path). */
+int fpl_train_set_precision(fpl_trainer *t, int precision);
 /* n_params: floats of the flat parameter vector (Keras get_weights() order, concatenated);
  * n_bn: floats of the batch-statistics vector (per BN layer: mean[C], biased var[C]) */
 int fpl_train_sizes(const fpl_trainer *t, int64_t *n_params, int64_t *n_bn);

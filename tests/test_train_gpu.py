@@ -9,44 +9,76 @@ from oracle import train_oracle as T
 pytestmark = pytest.mark.gpu
 
 
-def _setup(arch, batch, seed):
+def _setup(arch, batch, seed, precision="tf32"):
     from flypylib_b200 import fplmodels, fpltrain
     rf = M.ARCHS[arch][1][0]
     model, _, _, _ = getattr(fplmodels, arch)(rf)
     w = M.random_weights(arch, seed=seed)
     model.set_weights(w)
-    tr = fpltrain.Trainer(model, rf, batch)
+    tr = fpltrain.Trainer(model, rf, batch, precision=precision)
     rng = np.random.default_rng(seed + 1)
     x = rng.standard_normal((batch, rf, rf, rf)).astype(np.float32)
     y = (rng.random(batch) < 0.5).astype(np.uint8)
     return model, tr, w, x, y
 
 
+# Gradient criteria.  The step is badly conditioned at random initialisation (BN over a handful of samples, ReLU and
+# max-pool routing flips): the float64 oracle itself, with i.i.d. relative noise on every convolution output, moves
+# single gradient entries by 2e-6 of the array maximum at noise 1e-7 (fp32 arithmetic), by up to 3e-2 at 7e-6 (the
+# measured error of one bf16 hi/lo x3 contraction, tests/test_train_tc_gpu.py) and by 30-70 % at 2.5e-3 (one bf16
+# contraction); in L2 norm over all parameters 6e-3 / 3e-1, cosine 1 - 2e-5 / 1 - 6e-2 (tools/train_sensitivity.py).
+#   fp32 CUDA-core path : every entry within 2e-3 of the array maximum (the pin of the step's logic)
+#   tf32 (default) path : forward quantities as fp32; gradient within 2e-2 in L2 over all parameters, 5e-2 per array
+#   bf16 path           : forward quantities within 2e-2; gradient direction preserved (cosine > 0.8)
+# The contractions themselves are pinned one by one at 2e-5 / 2e-2 in tests/test_train_tc_gpu.py.
+GRAD_TOL = {"fp32": 2e-3}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32", "bf16"])
 @pytest.mark.parametrize("arch,batch", [("vgg_like", 8), ("vgg_like2", 6)])
-def test_forward_backward_and_adam_vs_oracle(arch, batch):
+def test_forward_backward_and_adam_vs_oracle(arch, batch, precision):
     import torch
-    model, tr, w, x, y = _setup(arch, batch, 17)
+    model, tr, w, x, y = _setup(arch, batch, 17, precision)
+    loose = precision == "bf16"
     seed, gb = 12345, batch * 4                      # as if 4 ranks contributed to the global mean
     loss, ok = tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), gb, seed)
     want_loss, want_ok, want_g, want_bn = T.forward_backward(arch, w, x, y, gb, seed)
-    assert abs(loss - want_loss) < 1e-4 * max(1.0, abs(want_loss))
-    assert ok == want_ok
+    assert abs(loss - want_loss) < (5e-2 if loose else 1e-4) * max(1.0, abs(want_loss))
+    assert loose or ok == want_ok
     got_g = T.split_params(arch, tr.grads.cpu().numpy())
-    for i, (g, wg) in enumerate(zip(got_g, want_g)):
-        scale = max(np.abs(wg).max(), 1e-6)
-        assert np.abs(g - wg).max() < 2e-3 * scale + 1e-7, "gradient %d: %g vs scale %g" % (i, np.abs(g - wg).max(), scale)
+    if precision == "fp32":
+        for i, (g, wg) in enumerate(zip(got_g, want_g)):
+            scale = max(np.abs(wg).max(), 1e-6)
+            assert np.abs(g - wg).max() < GRAD_TOL["fp32"] * scale + 1e-7, \
+                "gradient %d: %g vs scale %g" % (i, np.abs(g - wg).max(), scale)
+    else:
+        fa = np.concatenate([np.asarray(g, dtype=np.float64).ravel() for g in got_g])
+        fb = np.concatenate([np.asarray(g, dtype=np.float64).ravel() for g in want_g])
+        rel = np.linalg.norm(fa - fb) / np.linalg.norm(fb)
+        cos = float(fa @ fb / (np.linalg.norm(fa) * np.linalg.norm(fb)))
+        per = [np.linalg.norm(g - wg) / np.linalg.norm(wg) for g, wg in zip(got_g, want_g) if np.abs(wg).max() > 0]
+        print("%s %s: gradient rel L2 %.3g, 1-cos %.3g, worst array rel L2 %.3g" % (arch, precision, rel, 1 - cos, max(per)))
+        if loose:
+            assert cos > 0.8, cos
+        else:
+            assert rel < 2e-2 and max(per) < 5e-2, (rel, max(per))
     got_bn = tr.bn_batch.cpu().numpy()
     o = 0
     for mean, var in want_bn:
         c = mean.size
-        assert np.abs(got_bn[o:o + c] - mean).max() < 1e-4
-        assert np.abs(got_bn[o + c:o + 2 * c] - var).max() < 1e-4 * max(1.0, var.max())
+        assert np.abs(got_bn[o:o + c] - mean).max() < (5e-2 if loose else 1e-4)
+        assert np.abs(got_bn[o + c:o + 2 * c] - var).max() < (5e-2 if loose else 1e-4) * max(1.0, var.max())
         o += 2 * c
+    if loose:
+        return
     # Adam + moving statistics
     tr.apply()
     w64 = [np.asarray(a, dtype=np.float64) for a in w]
     m = [np.zeros_like(a) for a in w64]; v = [np.zeros_like(a) for a in w64]
-    want_w, _, _ = T.adam_step(w64, want_g, m, v, want_bn, 1)
+    # the first Adam step moves every weight by ~lr * sign(gradient): on the tensor-core path the update is checked
+    # against the oracle's Adam applied to the gradient the device produced (near-zero entries may differ in sign)
+    adam_g = want_g if precision == "fp32" else [np.asarray(g, dtype=np.float64) for g in got_g]
+    want_w, _, _ = T.adam_step(w64, adam_g, m, v, want_bn, 1)
     got_w = T.split_params(arch, tr.params.cpu().numpy())
     for i, (a, b) in enumerate(zip(got_w, want_w)):
         # first Adam step moves every trainable weight by ~lr regardless of gradient scale

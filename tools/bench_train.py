@@ -27,6 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="vgg_like2", choices=["vgg_like", "vgg_like2"])
     ap.add_argument("--batch", type=int, default=64, help="patches per GPU")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"],
+                    help="tf32 = tcgen05 on bf16 hi/lo split operands (fp32-class), bf16 = one contraction, fp32 = CUDA cores")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
@@ -44,7 +46,7 @@ def main():
     rf = builder()[1][0]
     model = builder(rf)[0]
     model.set_weights(bench.seeded_weights(a.model))
-    tr = fpltrain.Trainer(model, rf, a.batch)            # broadcasts rank 0's parameters
+    tr = fpltrain.Trainer(model, rf, a.batch, precision=a.precision)            # broadcasts rank 0's parameters
     g = torch.Generator(device=dev); g.manual_seed(77 + rank)
     x = torch.randn((a.batch, rf, rf, rf), generator=g, device=dev)
     y = (torch.rand(a.batch, generator=g, device=dev) < 0.5).to(torch.uint8)
@@ -107,7 +109,9 @@ def main():
                           "patches_per_gpu": a.batch, "patch": rf, "ms_per_step": ms, "patches_per_s": gb / (ms * 1e-3),
                           "ms_forward_backward": fb, "ms_grad_allreduce": ar, "ms_adam_bn_update": ad,
                           "allreduce_bytes": 4 * n_params, "e2e_ms_per_step_with_h2d": e_ms,
-                          "identical_parameters_on_all_ranks": same, "arithmetic": "fp32 CUDA-core kernels (csrc/train.cu)",
+                          "identical_parameters_on_all_ranks": same, "arithmetic": {"tf32": "tcgen05 bf16 hi/lo x3, fp32 accumulate (csrc/train_tc.cuh)",
+                                         "bf16": "tcgen05 bf16, fp32 accumulate (csrc/train_tc.cuh)",
+                                         "fp32": "fp32 CUDA-core kernels (csrc/train.cu)"}[a.precision],
                           "steps": a.steps, "warmup": a.warmup, "convs": len(spec["convs"])}))
     if world > 1:
         dist.destroy_process_group()
