@@ -254,9 +254,60 @@ class Model(object):
                     cb.on_epoch_end(epoch, logs)
         return history
 
+    def keras_layers(self):
+        """[(layer name, [(weight name, array), ...])] in Keras layer order: what Model.save writes under
+        /model_weights (conv3d_i: kernel [, bias]; batch_normalization_i: gamma, beta, moving_mean, moving_variance)."""
+        out, ws, ci, bi = [], list(self._weights), 0, 0
+        i = 0
+        while i < len(ws):
+            ci += 1
+            name = "conv3d_%d" % ci
+            entry = [("%s/kernel:0" % name, ws[i])]
+            i += 1
+            if i < len(ws) and ws[i].ndim == 1 and ws[i].shape[0] == entry[0][1].shape[4] and \
+                    (i + 1 == len(ws) or ws[i + 1].ndim == 5):
+                entry.append(("%s/bias:0" % name, ws[i]))          # the final convolution's bias
+                i += 1
+                out.append((name, entry))
+                continue
+            out.append((name, entry))
+            if i + 3 < len(ws) and all(w.ndim == 1 for w in ws[i:i + 4]):
+                bi += 1
+                bn = "batch_normalization_%d" % bi
+                out.append((bn, [("%s/%s:0" % (bn, n), ws[i + j])
+                                 for j, n in enumerate(("gamma", "beta", "moving_mean", "moving_variance"))]))
+                i += 4
+        return out
+
     def save(self, path):
-        """Keras Model.save stand-in (h5py is unavailable): weights in get_weights() order as .npz."""
-        np.savez(path if str(path).endswith(".npz") else str(path) + ".npz", *self._weights)
+        """Keras ``Model.save`` (flypylib/fplnetwork.py:17,83): an HDF5 file with the weights in the Keras layout
+        (``/model_weights/<layer>/<layer>/<weight>:0``, attributes ``layer_names`` / ``weight_names``) written by
+        flypylib_b200.h5lite; ``*.npz`` paths keep the array-list container of round 1."""
+        if str(path).endswith(".npz"):
+            np.savez(path, *self._weights)
+            return
+        from . import h5lite
+        h5lite.write_keras_weights(str(path), self.keras_layers(), full_model=True,
+                                   model_config='{"class_name": "Model", "config": {"name": "%s"}}' % self.arch)
+
+    def save_weights(self, path):
+        from . import h5lite
+        h5lite.write_keras_weights(str(path), self.keras_layers(), full_model=False)
+
+    def load_weights(self, path):
+        """Weights from a Keras ``.h5`` file (``Model.save`` or ``save_weights`` layout; layer order of the file =
+        ``get_weights()`` order) or from an ``.npz`` array list."""
+        if str(path).endswith(".npz"):
+            with np.load(path) as z:
+                self.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
+            return
+        from . import h5lite
+        arrays, names = h5lite.read_keras_weights(str(path))
+        shapes = self.weight_shapes()
+        if len(arrays) != len(shapes) or any(tuple(a.shape) != tuple(s) for a, s in zip(arrays, shapes)):
+            raise ValueError("%s does not hold the weights of %s: got %s" % (path, self.arch,
+                                                                             [tuple(a.shape) for a in arrays]))
+        self.set_weights(arrays)
 
     def close(self):
         if getattr(self, "_trainer", None) is not None:

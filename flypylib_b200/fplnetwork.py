@@ -57,16 +57,31 @@ def get_custom_objects(compile_args):
 
 
 def _weights_path(filepath):
-    """Weight container next to the pickled network.  The reference writes ``<filepath>.keras.h5`` through
-    Keras/h5py (fplnetwork.py:82-83); h5py is not available here, so the same arrays (Model.get_weights()
-    order) go to ``<filepath>.keras.npz``."""
+    """Weight file next to the pickled network: ``<filepath>.keras.h5`` as in the reference (fplnetwork.py:82-83),
+    read and written by flypylib_b200.h5lite (h5py is not needed).  ``<filepath>.keras.npz`` (round-1 container) is
+    still read when no .h5 file exists."""
+    import os
+    h5 = filepath + '.keras.h5'
+    if os.path.exists(h5) or not os.path.exists(filepath + '.keras.npz'):
+        return h5
     return filepath + '.keras.npz'
 
 
+class _RefUnpickler(pickle.Unpickler):
+    """Network pickles written by the reference name ``flypylib.fplnetwork.FplNetwork`` and the builder / loss
+    functions of ``flypylib.fplmodels``: resolve them to this package."""
+
+    def find_class(self, module, name):
+        if module == 'flypylib' or module.startswith('flypylib.'):
+            module = 'flypylib_b200' + module[len('flypylib'):]
+        return super().find_class(module, name)
+
+
 def load_network(filepath):
-    """fplnetwork.py:32-44: un-pickle an FplNetwork written by ``save_network`` and restore its weights."""
+    """fplnetwork.py:32-44: un-pickle an FplNetwork written by ``save_network`` (this package's or the reference's)
+    and restore its weights from ``<filepath>.keras.h5``."""
     with open(filepath, 'rb') as fn:
-        network = pickle.load(fn)
+        network = _RefUnpickler(fn).load()
     network._restore_models(_weights_path(filepath))
     return network
 
@@ -105,7 +120,7 @@ class FplNetwork:
     def save_network(self, filepath):
         """fplnetwork.py:81-97: weights to the side file, the network object (builder, receptive-field info,
         compile_args, ...) pickled to ``filepath``; the live networks are kept."""
-        self.train_single.save(_weights_path(filepath))
+        self.train_single.save(filepath + '.keras.h5')
         with open(filepath, 'wb') as fn:
             pickle.dump(self, fn)
 
@@ -118,12 +133,12 @@ class FplNetwork:
 
     def _restore_models(self, weights_file):
         precision = self.__dict__.pop('_precision', None)
+        self.__dict__.setdefault('tile_multiplier', 1)      # absent from pickles written by the reference
         self.train_single, _, _, _ = self.model()
         self.train_network = self.train_single
         if precision:
             self.train_single.set_precision(precision)
-        with np.load(weights_file) as z:
-            self.train_single.set_weights([z['arr_%d' % i] for i in range(len(z.files))])
+        self.train_single.load_weights(weights_file)
         self.train_network.compile(**self.compile_args)
         self._set_infer()
 
@@ -290,8 +305,9 @@ class FplNetwork:
         rank evaluates its z-slab and the prediction planes are all-gathered, so every rank returns the whole map
         -- bit-identical to the single-GPU result."""
         import torch
-        if isinstance(image, str):
-            raise NotImplementedError("h5 file input needs h5py, which is not available; pass an array")
+        if isinstance(image, str):                       # fplnetwork.py:137-139: h5 file with the volume in /main
+            from . import h5lite
+            image = h5lite.File(image)['/main'][:]
         self._check_built()
         world = self._world()
         if isinstance(image, torch.Tensor):

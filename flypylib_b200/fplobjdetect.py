@@ -151,8 +151,9 @@ def voxel2obj(pred, obj_min_dist, smoothing_sigma,
     import torch
     if seg is not None or seg_dilate is not None or seg_sz_thd is not None or seg_force:
         raise NotImplementedError("segmentation-aware suppression is not part of the B200 hot path")
-    if isinstance(pred, str):
-        raise NotImplementedError("h5 file input needs h5py, which is not available; pass an array")
+    if isinstance(pred, str):                            # fplobjdetect.py:154-156: h5 file with the map in /main
+        from . import h5lite
+        pred = h5lite.File(pred)['/main'][:]
     if isinstance(pred, torch.Tensor):
         dev = pred if pred.is_cuda else pred.cuda()
         if dev.dtype != torch.float32:

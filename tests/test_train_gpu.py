@@ -107,7 +107,7 @@ def test_fplnetwork_train_dropin(tmp_path):
     assert rows[0] == "epoch,acc,loss" and len(rows) == 3
     l0, l1 = float(rows[1].split(",")[2]), float(rows[2].split(",")[2])
     assert l1 < l0
-    assert (tmp_path / "ckpt_000.h5.npz").exists() and (tmp_path / "ckpt_001.h5.npz").exists()
+    assert (tmp_path / "ckpt_000.h5").exists() and (tmp_path / "ckpt_001.h5").exists()
     w1 = net.train_single.get_weights()
     assert any(np.abs(a - b).max() > 0 for a, b in zip(w0, w1))
     assert net.infer_network is not None

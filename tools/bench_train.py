@@ -105,6 +105,15 @@ def main():
     if rank == 0:
         spec = fplmodels._ARCH[a.model]
         n_params = int(sum(int(np.prod(s)) for s in model.weight_shapes()))
+        # algorithmic work of one step: forward + dgrad + wgrad = 3 x 2*k^3*Cin*Cout*out^3 per convolution and patch
+        # (max-pooling after the 2nd and 4th convolution of both VGG builders, flypylib/fplmodels.py:102-172)
+        d, fl = rf, 0.0
+        for ci, (k, cin, cout) in enumerate(spec["convs"]):
+            d -= k - 1
+            fl += 2.0 * k ** 3 * cin * cout * d ** 3
+            if ci in (1, 3):
+                d //= 2
+        flops_step = 3.0 * fl * gb
         print(json.dumps({"metric": "ms per data-parallel training step (config 5)", "model": a.model, "n_gpus": world,
                           "patches_per_gpu": a.batch, "patch": rf, "ms_per_step": ms, "patches_per_s": gb / (ms * 1e-3),
                           "ms_forward_backward": fb, "ms_grad_allreduce": ar, "ms_adam_bn_update": ad,
@@ -112,7 +121,9 @@ def main():
                           "identical_parameters_on_all_ranks": same, "arithmetic": {"tf32": "tcgen05 bf16 hi/lo x3, fp32 accumulate (csrc/train_tc.cuh)",
                                          "bf16": "tcgen05 bf16, fp32 accumulate (csrc/train_tc.cuh)",
                                          "fp32": "fp32 CUDA-core kernels (csrc/train.cu)"}[a.precision],
-                          "steps": a.steps, "warmup": a.warmup, "convs": len(spec["convs"])}))
+                          "steps": a.steps, "warmup": a.warmup, "convs": len(spec["convs"]),
+                          "algorithmic_gflop_per_step": flops_step / 1e9,
+                          "algorithmic_tflops": flops_step / (ms * 1e-3) / 1e12}))
     if world > 1:
         dist.destroy_process_group()
 
