@@ -12,7 +12,7 @@ N = 1: the volume is resident in HBM.  N > 1: the SAME volume is z-slab sharded 
 rank evaluates its slab + 2*rf_offset halo with no forward communication, then the exact-global voxel2obj
 (multi_gpu.voxel2obj_global) yields the single-GPU detection list on every rank -- `detections_sha256_16` is the same at
 every N.  Extra legs, each guarded so that it can never take the main line down: `e2e_dropin` (the literal reference call
-sequence with numpy arrays), `cfg1` and `cfg4` at N = 1 (BASELINE configs[0] and [3]), `cfg3` at N > 1 (configs[2]: the
+sequence with numpy arrays), `cfg1`, `cfg4` and `cfg5` at N = 1 (BASELINE configs[0], [3], [4]; `cfg5` also at N > 1), `cfg3` at N > 1 (configs[2]: the
 U-Net on a 2048^3 volume, tile rows dealt over the ranks).
 
 Prints ONE JSON line (rank 0).
@@ -340,6 +340,49 @@ def leg_cfg3(dev, sync, world, rank, size=2048):
             "planes_owned_per_rank": [p[1][1] - p[1][0] for p in plans]}
 
 
+def leg_cfg5(dev, sync, world, rank, batch=64, steps=10):
+    """BASELINE configs[4]: one data-parallel training step of vgg_like2 on synthetic minibatches (64 patches of 24^3 per
+    GPU, already in HBM): forward / dgrad / wgrad on the tensor cores (bf16 hi/lo x3, fp32 accumulation), gradient
+    all-reduce over NCCL at N > 1, Adam.  tools/bench_train.py is the stand-alone form with the stage split."""
+    import torch
+    from flypylib_b200 import fplmodels, fpltrain
+    rf = 24
+    model = fplmodels.vgg_like2(rf)[0]
+    model.set_weights(seeded_weights("vgg_like2"))
+    tr = fpltrain.Trainer(model, rf, batch, precision="tf32")
+    g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+    x = torch.randn((batch, rf, rf, rf), generator=g, device=dev)
+    y = (torch.rand(batch, generator=g, device=dev) < 0.5).to(torch.uint8)
+    gb = batch * world
+    it = [0]
+
+    def step():
+        it[0] += 1
+        loss, _ = tr.forward_backward(x, y, gb, 1000 + it[0])
+        tr.allreduce()
+        tr.apply()
+        return loss
+    for _ in range(3):
+        step()
+    ms, _, loss = timed(step, steps, sync)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    d, fl = rf, 0.0
+    for ci, (k, cin, cout) in enumerate(fplmodels._ARCH["vgg_like2"]["convs"]):
+        d -= k - 1
+        fl += 2.0 * k ** 3 * cin * cout * d ** 3
+        if ci in (1, 3):
+            d //= 2
+    tr.close()
+    return {"workload": "data-parallel training step, vgg_like2, %d patches of 24^3 per GPU, %d GPU(s) (BASELINE configs[4])"
+                        % (batch, world), "ms_per_step": ms, "value": gb / (ms * 1e-3), "unit": "patches/s",
+            "arithmetic": "tcgen05 bf16 hi/lo x3, fp32 accumulate", "n_gpus": world, "loss_sum_last_step": float(loss),
+            "algorithmic_tflops": 3.0 * fl * gb / (ms * 1e-3) / 1e12,
+            "round1_fp32_cuda_core_ms_per_step": 76.0}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -548,8 +591,11 @@ def main():
                 line["cfg1"] = leg_cfg1(dev, sync)
                 ctx.release_workspace(); torch.cuda.empty_cache()
                 line["cfg4"] = leg_cfg4(dev, sync, ctx, pk)
+                ctx.release_workspace(); torch.cuda.empty_cache()
+                line["cfg5"] = leg_cfg5(dev, sync, world, rank)
             else:
                 line["cfg3"] = leg_cfg3(dev, sync, world, rank)
+                line["cfg5"] = leg_cfg5(dev, sync, world, rank)
         except Exception as e:      # noqa: BLE001
             line["extras_error"] = repr(e)[:300]
         watchdog.cancel()

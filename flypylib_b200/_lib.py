@@ -63,6 +63,9 @@ _SIGNATURES = {
     "fpl_voxel2obj": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.POINTER(V2OParams), vp, ctypes.c_int64, c_i64p, c_f64p,
                                      c_i64p, vp]),
+    "fpl_v2o_detect_seg": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.POINTER(V2OParams), ctypes.c_int32, ctypes.c_int32,
+                                          vp, ctypes.c_int64, vp, vp]),
     "fpl_v2o_hist_level": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                           ctypes.c_int, vp, vp, vp]),
     "fpl_v2o_slab_begin": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

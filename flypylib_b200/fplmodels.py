@@ -27,6 +27,10 @@ _ARCH = {
                               (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
     "baseline_model": dict(id=_lib.ARCH_BASELINE, rf=(18, 7, 4), infer_sz=102, final_bias=True,
                            convs=[(3, 1, 32), (3, 32, 32), (3, 32, 32), (1, 32, 64)], final_cin=64),
+    # fplmodels.py:174-208; a 4th entry False marks a convolution without BatchNormalization (the shortcut)
+    "resnet_like": dict(id=_lib.ARCH_RESNET_LIKE, rf=(18, 7, 4), infer_sz=102, final_bias=True,
+                        convs=[(3, 1, 32), (3, 32, 32), (1, 32, 32), (3, 32, 64), (1, 32, 64, False), (1, 64, 64)],
+                        final_cin=64),
     "unet_like": dict(id=_lib.ARCH_UNET_LIKE, rf=(18, 6, 1), infer_sz=102, final_bias=False,
                       convs=[(3, 1, 32), (1, 32, 32), (3, 32, 64), (1, 64, 64), (1, 64, 128), (3, 192, 64),
                              (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
@@ -89,9 +93,11 @@ class Model(object):
     # ---- Keras-like surface ------------------------------------------------------------------
     def weight_shapes(self):
         shapes = []
-        for k, cin, cout in self.spec["convs"]:
+        for cv in self.spec["convs"]:
+            k, cin, cout = cv[:3]
             shapes.append((k, k, k, cin, cout))
-            shapes += [(cout,)] * 4
+            if len(cv) < 4 or cv[3]:
+                shapes += [(cout,)] * 4
         shapes.append((1, 1, 1, self.spec["final_cin"], 1))
         if self.spec["final_bias"]:
             shapes.append((1,))
@@ -100,11 +106,13 @@ class Model(object):
     def _initial_weights(self):
         """Keras defaults: glorot_uniform kernels, BN gamma=1 beta=0 mean=0 var=1, zero bias."""
         ws = []
-        for k, cin, cout in self.spec["convs"]:
+        for cv in self.spec["convs"]:
+            k, cin, cout = cv[:3]
             lim = np.sqrt(6.0 / (k ** 3 * cin + k ** 3 * cout))
             ws.append(np.random.uniform(-lim, lim, (k, k, k, cin, cout)).astype(np.float32))
-            ws += [np.ones(cout, np.float32), np.zeros(cout, np.float32), np.zeros(cout, np.float32),
-                   np.ones(cout, np.float32)]
+            if len(cv) < 4 or cv[3]:
+                ws += [np.ones(cout, np.float32), np.zeros(cout, np.float32), np.zeros(cout, np.float32),
+                       np.ones(cout, np.float32)]
         cin = self.spec["final_cin"]
         lim = np.sqrt(6.0 / (cin + 1))
         ws.append(np.random.uniform(-lim, lim, (1, 1, 1, cin, 1)).astype(np.float32))
@@ -349,6 +357,11 @@ def masked_binary_crossentropy(y_true, y_pred):     # fplmodels.py:52-60, named 
 def baseline_model(in_sz=None):
     """returns simple baseline model (flypylib/fplmodels.py:73-100)"""
     return Model("baseline_model", in_sz), (18, 7, 4), 102, None
+
+
+def resnet_like(in_sz=None):
+    """fplmodels.py:174-208: residual blocks (add of a cropped shortcut, BN before the add, ReLU after it)."""
+    return Model("resnet_like", in_sz), (18, 7, 4), 102, None
 
 
 def unet_like(in_sz=18):

@@ -146,11 +146,15 @@ def voxel2obj(pred, obj_min_dist, smoothing_sigma,
     which detections are dropped, ``thd`` lower bound on the threshold.  Returns
     ``{'locs': (N,3) float64 (x,y,z), 'conf': (N,) float64}`` in the reference's emission order.
 
-    The segmentation-aware branch (seg*, :161-165,177-181,192-195,213-224) is out of scope.
+    With ``seg`` (label volume of ``pred``'s shape, array or h5 path) the segmentation-aware branch runs
+    (:161-165,177-181,192-195,213-224): ``seg_sz_thd`` zeroes the smoothed map inside segments smaller than that many
+    voxels, a selected point suppresses only ball voxels inside its own segment dilated ``seg_dilate`` times
+    (6-connected), ``seg_force`` always suppresses an inner ball -- see ``voxel2obj_seg_device``.
     """
     import torch
     if seg is not None or seg_dilate is not None or seg_sz_thd is not None or seg_force:
-        raise NotImplementedError("segmentation-aware suppression is not part of the B200 hot path")
+        return _voxel2obj_seg(pred, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd, seg, seg_dilate,
+                              seg_sz_thd, seg_force)
     if isinstance(pred, str):                            # fplobjdetect.py:154-156: h5 file with the map in /main
         from . import h5lite
         pred = h5lite.File(pred)['/main'][:]
@@ -168,6 +172,103 @@ def voxel2obj(pred, obj_min_dist, smoothing_sigma,
         _lib.context()          # raises when there is no GPU: no CPU fallback
         dev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
     return voxel2obj_device(dev, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+
+
+def _voxel2obj_seg(pred, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd, seg, seg_dilate, seg_sz_thd,
+                   seg_force):
+    import torch
+    from . import h5lite
+    if isinstance(pred, str):
+        pred = h5lite.File(pred)['/main'][:]
+    if isinstance(seg, str):                             # fplobjdetect.py:162-164
+        seg = h5lite.File(seg)['/main'][:]
+    _lib.context()                                       # raises when there is no GPU: no CPU fallback
+    if isinstance(pred, torch.Tensor):
+        pdev = pred if pred.is_cuda else pred.cuda()
+    else:
+        a = np.asarray(pred)
+        if a.ndim != 3:
+            raise ValueError("pred must be 3-D")
+        if a.dtype != np.float32:
+            raise TypeError("the B200 voxel2obj path is the float32 path FplNetwork.infer produces; got dtype %s" % a.dtype)
+        pdev = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sdev = None
+    if seg is not None:
+        if isinstance(seg, torch.Tensor):
+            sdev = seg.to(device=pdev.device, dtype=torch.int64)
+        else:
+            s = np.asarray(seg)
+            if s.dtype == np.uint64:
+                s = s.view(np.int64)                     # labels are only compared for equality
+            sdev = torch.from_numpy(np.ascontiguousarray(s.astype(np.int64, copy=False))).to(pdev.device)
+        if tuple(sdev.shape) != tuple(pdev.shape):
+            raise ValueError("seg must have the shape of pred")
+    elif seg_sz_thd is not None:
+        raise TypeError("seg_sz_thd needs a segmentation")           # np.unique(None) in the reference
+    return voxel2obj_seg_device(pdev, obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd, sdev, seg_dilate,
+                                seg_sz_thd, seg_force)
+
+
+def voxel2obj_seg_device(pred_dev, obj_min_dist, smoothing_sigma, volume_offset=(0, 0, 0), buffer_sz=0, thd=0,
+                         seg_dev=None, seg_dilate=None, seg_sz_thd=None, seg_force=None):
+    """Segmentation-aware voxel2obj on device tensors (pred float32 (Z,Y,X), seg int64 (Z,Y,X) or None).
+
+    Stages: exact smoothing (``fpl_v2o_smooth``) -> optional size filter (:177-181: label counts of the zero-PADDED
+    segmentation; device-side ``torch.unique``) -> threshold (``fpl_v2o_threshold``) -> candidates sorted by (value desc,
+    index asc) -> ``fpl_v2o_detect_seg``: the reference's sequential loop with the segment-shaped suppression masks,
+    in one persistent CTA.  Everything stays on the GPU; bit-exact against the unmodified reference
+    (tests/golden/voxel2obj_seg_golden.npz)."""
+    import torch
+    if seg_dilate is not None and int(seg_dilate) < 1:
+        raise ValueError("seg_dilate must be >= 1 (SciPy's iterations < 1 means 'until convergence')")
+    pred_dev = pred_dev.contiguous()
+    dev = pred_dev.device.index
+    ctx = _lib.context(dev)
+    lib = _lib.lib()
+    Z, Y, X = (int(v) for v in pred_dev.shape)
+    p, _keepalive = _make_params((Z, Y, X), obj_min_dist, smoothing_sigma, volume_offset, buffer_sz, thd)
+    r = int(p.obj_min_dist)
+    with torch.cuda.device(dev):
+        st = _lib.current_stream_ptr(dev)
+        smooth = torch.empty_like(pred_dev)
+        _lib.check(lib.fpl_v2o_smooth(ctx.handle, pred_dev.data_ptr(), Z, Y, X, ctypes.byref(p), smooth.data_ptr(), st),
+                   "fpl_v2o_smooth")
+        if seg_sz_thd is not None:
+            ids, inv, counts = torch.unique(seg_dev, return_inverse=True, return_counts=True)
+            counts = counts.clone()
+            pad_vox = (Z + 2 * r) * (Y + 2 * r) * (X + 2 * r) - Z * Y * X
+            counts[ids == 0] += pad_vox                  # the zero padding belongs to label 0
+            small = counts < int(seg_sz_thd)
+            smooth[small[inv]] = 0.0
+            del ids, inv, counts, small
+        h = (ctypes.c_double * 4)()
+        _lib.check(lib.fpl_v2o_threshold(ctx.handle, smooth.data_ptr(), Z, Y, X, ctypes.byref(p), h, st),
+                   "fpl_v2o_threshold")
+        thr = float(h[0])
+        # float32 v > thr (float64)  <=>  v > (largest float32 <= thr)
+        t32 = np.float32(thr)
+        if float(t32) > thr:
+            t32 = np.nextafter(t32, np.float32(-np.inf))
+        flat = smooth.reshape(-1)
+        idx = torch.nonzero(flat > float(t32)).reshape(-1)
+        vals, order = torch.sort(flat[idx], descending=True, stable=True)     # ties keep ascending index order
+        idx = idx[order].contiguous()
+        n = Z * Y * X
+        supp = torch.zeros(((n + 31) // 32,), dtype=torch.int32, device=pred_dev.device)
+        # with a segmentation two detections may be neighbours (different segments): every candidate can be selected
+        cap = max(int(idx.numel()), 1) if seg_dev is not None else min(_default_capacity((Z, Y, X), r), max(int(idx.numel()), 1))
+        rows = torch.empty((cap, 4), dtype=torch.float64, device=pred_dev.device)
+        count = torch.zeros((3,), dtype=torch.int64, device=pred_dev.device)
+        _lib.check(lib.fpl_v2o_detect_seg(ctx.handle, vals.data_ptr(), idx.data_ptr(), int(idx.numel()),
+                                          seg_dev.data_ptr() if seg_dev is not None else None, supp.data_ptr(), Z, Y, X,
+                                          ctypes.byref(p), -1 if seg_dilate is None else int(seg_dilate),
+                                          int(seg_force) if seg_force else 0, rows.data_ptr(), cap, count.data_ptr(), st),
+                   "fpl_v2o_detect_seg")
+        c = count.cpu().numpy()
+        if c[2]:
+            raise _lib.FplError("voxel2obj (seg): detection list overflow (%d rows)" % cap)
+        out = rows[:int(c[0])].cpu().numpy()
+    return {'locs': out[:, :3].copy(), 'conf': out[:, 3].copy()}
 
 
 # ---------------------------------------------------------------------------------------------

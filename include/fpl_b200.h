@@ -111,6 +111,18 @@ int fpl_v2o_detect(fpl_ctx *ctx, const float *d_smooth, int64_t Z, int64_t Y, in
                    const fpl_v2o_params *p, double threshold, double *d_dets, int64_t capacity,
                    int64_t *h_count, int64_t *h_stats, void *stream);
 
+/* Stage C with a segmentation: the seg / seg_dilate / seg_force branch of voxel2obj (fplobjdetect.py:192-195, 213-224).
+ * The suppression set of a selected point is  ball AND dilate_D(seg cube == seg[point])  (OR the forced inner ball of
+ * radius seg_force); the loop runs sequentially on the device in one persistent CTA.  d_val / d_idx: the candidates
+ * (smoothed value > threshold) sorted by (value desc, flat interior index asc); d_seg: (Z,Y,X) int64 labels (voxels
+ * outside the volume count as label 0, the reference's zero padding) or NULL; d_supp: ceil(Z*Y*X/32) zeroed uint32
+ * words; seg_dilate < 0: no dilation (None); seg_force <= 0: none; obj_min_dist <= 31.  d_rows: capacity x 4 doubles
+ * (x, y, z, conf) after un-padding, buffer crop and offset; d_count: 3 int64 (rows written, points selected before the
+ * crop, overflow flag).  Does not synchronise. */
+int fpl_v2o_detect_seg(fpl_ctx *ctx, const float *d_val, const int64_t *d_idx, int64_t n_cand, const int64_t *d_seg,
+                       uint32_t *d_supp, int64_t Z, int64_t Y, int64_t X, const fpl_v2o_params *p, int32_t seg_dilate,
+                       int32_t seg_force, double *d_rows, int64_t capacity, int64_t *d_count, void *stream);
+
 /* A+B+C in one call: the replacement for fplobjdetect.voxel2obj(pred, ...) on a device-resident
  * float32 probability map.  h_threshold (optional) receives the threshold used. */
 int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64_t X,

@@ -26,7 +26,9 @@ import torch.nn.functional as F
 
 BN_EPS = 1e-3
 
-# (kind, k, cin, cout) chains; 'P' pool, 'U' up-sample+concat with a stored skip (crop), 'S' store skip
+# (kind, k, cin, cout) chains; 'P' pool, 'U' up-sample+concat with a stored skip (crop), 'S' store skip;
+# resnet_like adds: 'CB' conv + BN without ReLU, 'CS' plain conv (no BN, no activation) applied to a stored skip,
+# 'A' add the symmetrically cropped skip, then ReLU
 ARCHS = {
     # name: (ops, (rf_size, rf_offset, rf_stride), infer_sz, final_has_bias)
     "vgg_like": ([("C", 3, 1, 48), ("C", 1, 48, 48), ("P",), ("C", 3, 48, 48), ("C", 1, 48, 48), ("P",),
@@ -41,6 +43,12 @@ ARCHS = {
                     ("C", 3, 192, 64), ("C", 1, 64, 64), ("U", "conv1", 6),
                     ("C", 3, 96, 32), ("C", 1, 32, 32), ("F", 32)],
                    (24, 9, 1), 100, False),
+    # fplmodels.py:174-208.  Weight order = Keras model.layers order: the shortcut convolution (created after conv3b, but
+    # reached first when Keras walks the graph back from the output: add([crop_pool2, conv3])) precedes conv3b.
+    "resnet_like": ([("C", 3, 1, 32), ("P",), ("S", "pool1"),
+                     ("C", 3, 32, 32), ("CB", 1, 32, 32), ("A", "pool1", 1), ("P",), ("S", "pool2"),
+                     ("C", 3, 32, 64), ("CS", 1, 32, 64, "pool2"), ("CB", 1, 64, 64), ("A", "pool2", 1), ("F", 64)],
+                    (18, 7, 4), 102, True),
     # further builders with the same layer vocabulary: fplmodels.py:73-100, :206-256, :306-357, :359-410, :412-467
     "baseline_model": ([("C", 3, 1, 32), ("P",), ("C", 3, 32, 32), ("P",), ("C", 3, 32, 32), ("C", 1, 32, 64), ("F", 64)],
                        (18, 7, 4), 102, True),
@@ -77,10 +85,12 @@ def weight_shapes(arch):
     ops, _, _, final_bias = ARCHS[arch]
     shapes = []
     for op in ops:
-        if op[0] == "C":
+        if op[0] in ("C", "CB"):
             _, k, cin, cout = op
             shapes.append((k, k, k, cin, cout))
             shapes += [(cout,)] * 4
+        elif op[0] == "CS":
+            shapes.append((op[1],) * 3 + (op[2], op[3]))
         elif op[0] == "F":
             shapes.append((1, 1, 1, op[1], 1))
             if final_bias:
@@ -94,7 +104,11 @@ def random_weights(arch, seed=4321, trained_like=True):
     ops, _, _, final_bias = ARCHS[arch]
     ws = []
     for op in ops:
-        if op[0] == "C":
+        if op[0] == "CS":
+            k, cin, cout = op[1], op[2], op[3]
+            lim = np.sqrt(6.0 / (k ** 3 * cin + k ** 3 * cout))
+            ws.append(rng.uniform(-lim, lim, (k, k, k, cin, cout)).astype(np.float32))
+        elif op[0] in ("C", "CB"):
             _, k, cin, cout = op
             lim = np.sqrt(6.0 / (k ** 3 * cin + k ** 3 * cout))
             ws.append(rng.uniform(-lim, lim, (k, k, k, cin, cout)).astype(np.float32))
@@ -124,14 +138,25 @@ def forward(arch, weights, x, dtype=torch.float64, upsample=True):
     wi = 0
     skips = {}
     for op in ops:
-        if op[0] == "C":
+        if op[0] in ("C", "CB"):
             kern = torch.as_tensor(weights[wi]).to(dtype).permute(4, 3, 0, 1, 2)
             gamma, beta, mean, var = (torch.as_tensor(w).to(dtype) for w in weights[wi + 1:wi + 5])
             wi += 5
             t = F.conv3d(t, kern)
             t = (t - mean.view(1, -1, 1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1, 1) + BN_EPS) \
                 * gamma.view(1, -1, 1, 1, 1) + beta.view(1, -1, 1, 1, 1)
-            t = torch.relu(t)
+            if op[0] == "C":
+                t = torch.relu(t)
+        elif op[0] == "CS":                       # plain convolution of a stored tensor (resnet shortcut)
+            kern = torch.as_tensor(weights[wi]).to(dtype).permute(4, 3, 0, 1, 2)
+            wi += 1
+            skips[op[4]] = F.conv3d(skips[op[4]], kern)
+        elif op[0] == "A":                        # add([Cropping3D(skip), t]) -> ReLU
+            sk = skips[op[1]]
+            c = op[2]
+            if c:
+                sk = sk[:, :, c:-c, c:-c, c:-c]
+            t = torch.relu(sk + t)
         elif op[0] == "P":
             t = F.max_pool3d(t, 2)
         elif op[0] == "S":

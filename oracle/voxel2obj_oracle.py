@@ -205,6 +205,55 @@ def greedy_nms_sorted(s, thresh, r):
     return rows
 
 
+def greedy_nms_seg(s, thresh, r, seg_padded, seg_dilate=None, seg_force=None):
+    """fplobjdetect.py:187-231 with a segmentation (:192-195, :213-224), restated literally: the suppression mask of a
+    selected point is ball AND dilate(seg cube == seg[point]) (OR the forced inner ball)."""
+    from scipy import ndimage
+    flat = s.ravel()
+    cand = np.flatnonzero(flat > thresh)
+    dist_flt = ~ball_mask(r)
+    if seg_force:
+        cn = ~np.pad(ball_mask(seg_force), r - seg_force, 'constant')
+    valid = np.ones(s.shape, dtype=bool)
+    vflat = valid.reshape(-1)
+    rows = []
+    while cand.size:
+        vals = flat[cand]
+        j = int(np.argmax(vals))
+        if vals[j] <= 0:
+            break
+        z, y, x = np.unravel_index(cand[j], s.shape)
+        rows.append((x, y, z, vals[j]))
+        keep = dist_flt
+        if seg_padded is not None:
+            m = seg_padded[z - r:z + r + 1, y - r:y + r + 1, x - r:x + r + 1] == seg_padded[z, y, x]
+            if seg_dilate is not None:
+                m = ndimage.binary_dilation(m, iterations=seg_dilate)
+            keep = np.logical_not(m) | dist_flt
+            if seg_force:
+                keep = keep & cn
+        valid[z - r:z + r + 1, y - r:y + r + 1, x - r:x + r + 1] &= keep
+        cand = cand[vflat[cand]]
+    return rows
+
+
+def voxel2obj_seg(pred, obj_min_dist, smoothing_sigma, volume_offset=(0, 0, 0), buffer_sz=0, thd=0,
+                  seg=None, seg_dilate=None, seg_sz_thd=None, seg_force=None):
+    """Oracle for the segmentation-aware call of fplobjdetect.voxel2obj (:161-165, 177-181, 192-195, 213-224)."""
+    r = obj_min_dist
+    pred = np.asarray(pred)
+    s = smooth_padded(pred, r, smoothing_sigma)
+    segp = np.pad(np.asarray(seg), r, 'constant') if seg is not None else None
+    if seg_sz_thd is not None:
+        ids, counts = np.unique(segp, return_counts=True)
+        for i, c in zip(ids, counts):
+            if c < seg_sz_thd:
+                s[segp == i] = False
+    t = threshold(s, thd)
+    rows = greedy_nms_seg(s, t, r, segp, seg_dilate, seg_force)
+    return finish(rows, r, pred.shape, buffer_sz, volume_offset)
+
+
 def finish(rows, r, pred_sz, buffer_sz, volume_offset):
     """fplobjdetect.py:233-257: to (K,4) float64, un-pad, buffer crop, offset, split."""
     b = to3d(buffer_sz)

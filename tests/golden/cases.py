@@ -120,3 +120,35 @@ def blob_volume(shape, n_side, seed=5, amp=100.0, sigma=4.0, margin=34, noise=0.
                 vol[z - w:z + w + 1, y - w:y + w + 1, x - w:x + w + 1] += amp * bump
                 centres.append((x, y, z))
     return np.clip(vol, 0, 255).astype(np.uint8), np.asarray(centres, dtype=np.float64)
+
+
+def segmentation(shape, seed, n_seeds=40):
+    """Synthetic label volume (Z,Y,X) int64: nearest-seed (Voronoi) cells with a few tiny extra segments and some
+    background (label 0)."""
+    rng = np.random.default_rng(seed)
+    Z, Y, X = shape
+    pts = np.stack([rng.integers(0, Z, n_seeds), rng.integers(0, Y, n_seeds), rng.integers(0, X, n_seeds)], axis=1)
+    zz, yy, xx = np.meshgrid(np.arange(Z), np.arange(Y), np.arange(X), indexing="ij")
+    best = np.full(shape, np.inf)
+    lab = np.zeros(shape, dtype=np.int64)
+    for i, (pz, py, px) in enumerate(pts):
+        d = (zz - pz) ** 2 + 1.7 * (yy - py) ** 2 + 0.6 * (xx - px) ** 2
+        m = d < best
+        best[m] = d[m]
+        lab[m] = 1000 + 7 * i
+    lab[best > (0.35 * max(shape)) ** 2] = 0                      # background far from every seed
+    for k in range(6):                                           # tiny segments (below any size threshold)
+        z, y, x = rng.integers(1, Z - 2), rng.integers(1, Y - 2), rng.integers(1, X - 2)
+        lab[z:z + 2, y:y + 2, x:x + 2] = 50 + k
+    return lab
+
+
+# name, shape, seed, kind, r, sigma, thd, buffer, offset, seg_dilate, seg_sz_thd, seg_force
+VOXEL2OBJ_SEG_CASES = [
+    ("seg_blobs_56_r6_d3",     (56, 56, 56), 21, "blobs",   6, 1.5, 0, 2, (0, 0, 0),    3,    None, None),
+    ("seg_uniform_48_r7_d8",   (48, 52, 60), 22, "uniform", 7, 2.0, 0, 0, (5, 6, 7),    8,    None, None),
+    ("seg_uniform_48_r5_none", (48, 48, 48), 23, "uniform", 5, 1.0, 0, 0, (0, 0, 0),    None, None, None),
+    ("seg_uniform_48_r6_f3",   (48, 48, 48), 24, "uniform", 6, 1.5, 0, 3, (0, 0, 0),    2,    None, 3),
+    ("seg_blobs_64_r8_sz",     (64, 64, 64), 25, "blobs",   8, 2.0, 0, 4, (0, 0, 0),    4,    20,   None),
+    ("seg_uniform_40_r27_d8",  (70, 64, 66), 26, "uniform", 27, 5.0, 0, 5, (0, 0, 0),   8,    None, 4),
+]

@@ -7,6 +7,8 @@ Outputs (committed):
                                       ``cases.VOXEL2OBJ_CASES`` + sha256 of the smoothed padded map
                                       and the threshold, obtained with the very calls the reference
                                       makes (fplobjdetect.py:159-183) on SciPy/NumPy of this image
+  tests/golden/voxel2obj_seg_golden.npz  reference ``voxel2obj`` with seg / seg_dilate / seg_sz_thd / seg_force
+                                      (fplobjdetect.py:161-224) run unmodified on ``cases.VOXEL2OBJ_SEG_CASES``
   tests/golden/infer_tiler_golden.npz reference ``FplNetwork.infer`` tiling/scatter run unmodified
                                       with a deterministic fake ``infer_network`` (fplnetwork.py:136-189)
   tests/golden/substack_golden.npz    reference ``fri_get_image`` (fplobjdetect.py:1021-1112) run unmodified on an
@@ -53,6 +55,23 @@ def golden_voxel2obj(ref):
             hashlib.sha256(np.ascontiguousarray(s).tobytes()).digest(), dtype=np.uint8)
         print("%-26s dets=%5d thresh=%r" % (name, res["conf"].size, t))
     np.savez_compressed(os.path.join(HERE, "voxel2obj_golden.npz"), **out)
+
+
+def golden_voxel2obj_seg(ref):
+    """reference voxel2obj run unmodified with seg / seg_dilate / seg_sz_thd / seg_force (fplobjdetect.py:161-224)"""
+    out = {}
+    for name, shape, seed, kind, r, sigma, thd, buf, off, dil, szt, force in cases.VOXEL2OBJ_SEG_CASES:
+        pred = cases.prob_map(shape, seed, kind)
+        seg = cases.segmentation(shape, seed + 100)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = ref.fplobjdetect.voxel2obj(pred.copy(), r, sigma, off, buf, thd, seg=seg.copy(), seg_dilate=dil,
+                                             seg_sz_thd=szt, seg_force=force)
+            plain = ref.fplobjdetect.voxel2obj(pred.copy(), r, sigma, off, buf, thd)
+        out[name + "/locs"] = res["locs"]
+        out[name + "/conf"] = res["conf"]
+        print("%-26s dets=%5d (without seg: %d)" % (name, res["conf"].size, plain["conf"].size))
+    np.savez_compressed(os.path.join(HERE, "voxel2obj_seg_golden.npz"), **out)
 
 
 _FakeNet = cases.FakeNet
@@ -229,7 +248,11 @@ def golden_gen_batches(ref):
 
 if __name__ == "__main__":
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "seg":           # only the segmentation-aware goldens
+        golden_voxel2obj_seg(ref)
+        sys.exit(0)
     golden_voxel2obj(ref)
+    golden_voxel2obj_seg(ref)
     golden_infer_tiler(ref)
     golden_eval(ref)
     golden_substack_images(ref)

@@ -107,8 +107,9 @@ def test_error_behaviour_of_the_python_shims():
         fplobjdetect.voxel2obj(np.zeros((4, 4), np.float32), 3, 1.0)
     with pytest.raises(TypeError):
         fplobjdetect.voxel2obj(np.zeros((4, 4, 4), np.float64), 3, 1.0)
-    with pytest.raises(NotImplementedError):
-        fplobjdetect.voxel2obj(np.zeros((4, 4, 4), np.float32), 3, 1.0, seg=np.zeros((4, 4, 4)))
+    from flypylib_b200._lib import FplError
+    with pytest.raises((FplError, ValueError)):          # no GPU here: no CPU fallback; on a GPU box: shape mismatch
+        fplobjdetect.voxel2obj(np.zeros((4, 4, 4), np.float32), 3, 1.0, seg=np.zeros((4, 4, 5)))
     with pytest.raises(ValueError):
         fplmodels.vgg_like()[0].set_weights([np.zeros(3, np.float32)])
     m = fplmodels.vgg_like2()[0]

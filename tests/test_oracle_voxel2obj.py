@@ -70,3 +70,15 @@ def test_product_host_scalars_match_oracle():
     assert P._promote_thd(0) == 0.0
     assert P._promote_thd(0.05) == float(np.float32(0.05))
     assert P._promote_thd(np.float64(0.05)) == 0.05
+
+
+def test_seg_branch_of_the_oracle_matches_the_unmodified_reference():
+    """oracle.voxel2obj_seg (seg / seg_dilate / seg_sz_thd / seg_force, fplobjdetect.py:161-224) == goldens produced by
+    the unmodified reference (tests/golden/make_golden.py seg)."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxel2obj_seg_golden.npz"))
+    for name, shape, seed, kind, r, sigma, thd, buf, off, dil, szt, force in cases.VOXEL2OBJ_SEG_CASES[:5]:
+        pred = cases.prob_map(shape, seed, kind)
+        seg = cases.segmentation(shape, seed + 100)
+        out = O.voxel2obj_seg(pred, r, sigma, off, buf, thd, seg=seg, seg_dilate=dil, seg_sz_thd=szt, seg_force=force)
+        assert np.array_equal(out["locs"], gold[name + "/locs"]), name
+        assert np.array_equal(out["conf"], gold[name + "/conf"]), name
