@@ -77,6 +77,7 @@ struct fpl_ctx {
     int v2o_decline = 0;                  // why the last fpl_voxel2obj left the two-tier path (0 = it did not)
     long long v2o_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // counters behind the decline (diagnosis)
     int v2o_skip = 0, v2o_fail_streak = 0; // adaptive: calls that go straight to the exact path after declines
+    long long v2o_key[5] = {-1, -1, -1, -1, -1};       // (Z, Y, X, r, lw) of the calls the back-off state belongs to
     std::vector<fpl::PoolBuf> slab_cache; // workspace blocks of finished voxel2obj slab sessions, reused by the next
 };
 

@@ -219,6 +219,20 @@ static int launch_conv(fpl_ctx *ctx, const float *in, const ConvParams &c, float
     return FPL_OK;
 }
 
+// out[i] = relu(cur[i] + skip[cropped index]) in place on cur: (d^3, c) channels-last float32, skip (ds^3, c)
+__global__ void __launch_bounds__(256)
+add_fp32_kernel(float *__restrict__ cur, int d, int c, const float *__restrict__ skip, int ds, int crop) {
+    const long long total = (long long)d * d * d * c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c); long long v = i / c;
+        const int x = (int)(v % d); v /= d;
+        const int y = (int)(v % d); const int z = (int)(v / d);
+        const float s = skip[((((size_t)(z + crop) * ds + y + crop) * ds) + x + crop) * c + ch];
+        cur[i] = fmaxf(cur[i] + s, 0.f);
+    }
+}
+
 int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
     fpl_ctx *ctx = net->ctx;
     // activations of one tile at a time (the fp32 tensors are large: 98^3 x 48 x 4 B = 181 MB)
@@ -227,6 +241,7 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         int d = in_sz, c = 1;
         int sc[4] = {0, 0, 0, 0};
         for (const Op &o : net->ops) {
+            if (o.kind == OP_CONV && o.src_slot >= 0) { sc[o.src_slot] = o.cout; continue; }
             if (o.kind == OP_CONV) { d -= o.k - 1; c = o.cout; }
             else if (o.kind == OP_POOL) d /= 2;
             else if (o.kind == OP_SAVE) sc[o.slot] = c;
@@ -235,9 +250,10 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             if (e > max_elems) max_elems = e;
         }
     }
-    // buffers: ping, pong, two skip slots
-    float *bufs[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < 4; ++i) {
+    // buffers: ping, pong, two skip slots, one for a convolved skip (resnet_like shortcut)
+    constexpr int kBufs = 5;
+    float *bufs[kBufs] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < kBufs; ++i) {
         cudaError_t e = cudaMalloc((void **)&bufs[i], max_elems * sizeof(float));
         if (e != cudaSuccess) {
             for (int j = 0; j < i; ++j) cudaFree(bufs[j]);
@@ -257,12 +273,20 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         int skip_d[2] = {0, 0}, skip_c[2] = {0, 0};
         int skip_buf_used = 0;
         for (const Op &o : net->ops) {
-            if (o.kind == OP_CONV) {
+            if (o.kind == OP_CONV && o.src_slot >= 0) {
+                const ConvParams &cp = net->convs[o.conv_index];
+                rc = launch_conv<1>(ctx, skip_ptr[o.src_slot], cp, bufs[4], 1, skip_d[o.src_slot], o.relu ? 1 : 0, st);
+                if (rc != FPL_OK) break;
+                skip_ptr[o.src_slot] = bufs[4]; skip_c[o.src_slot] = o.cout;
+            } else if (o.kind == OP_ADD) {
+                add_fp32_kernel<<<stream_blocks, 256, 0, st>>>(const_cast<float *>(cur), d, c, skip_ptr[o.slot], skip_d[o.slot], o.crop);
+                ctx->launches++;
+            } else if (o.kind == OP_CONV) {
                 const ConvParams &cp = net->convs[o.conv_index];
                 float *dst = bufs[which];
                 if (cur == dst) { which ^= 1; dst = bufs[which]; }
-                rc = (o.k == 3) ? launch_conv<3>(ctx, cur, cp, dst, 1, d, 1, st)
-                                : launch_conv<1>(ctx, cur, cp, dst, 1, d, 1, st);
+                rc = (o.k == 3) ? launch_conv<3>(ctx, cur, cp, dst, 1, d, o.relu ? 1 : 0, st)
+                                : launch_conv<1>(ctx, cur, cp, dst, 1, d, o.relu ? 1 : 0, st);
                 if (rc != FPL_OK) break;
                 d -= o.k - 1; c = o.cout; cur = dst; which ^= 1;
             } else if (o.kind == OP_POOL) {
@@ -292,7 +316,7 @@ int forward_fp32(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
         }
     }
     cudaError_t e = cudaStreamSynchronize(st);
-    for (int i = 0; i < 4; ++i) cudaFree(bufs[i]);
+    for (int i = 0; i < kBufs; ++i) cudaFree(bufs[i]);
     if (rc != FPL_OK) return rc;
     FPL_CUDA_CHECK(e);
     FPL_CUDA_CHECK(cudaGetLastError());

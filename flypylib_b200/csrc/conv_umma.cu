@@ -1008,6 +1008,31 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
 // TMEM: second-layer accumulators 2 M-tile regions x 4 blocks x C2 columns (384); first-layer tiles rotate
 // through 2 slots at 384 + 48 s.
 // ------------------------------------------------------------------------------------------------
+// resnet_like: cur = relu(cur + crop(skip)) on C8-blocked bf16 tensors (tile, C/8, z, y, x, 8), in place on cur
+__global__ void __launch_bounds__(256)
+add_blocked_kernel(uint4 *__restrict__ cur, int d, int dz, const uint4 *__restrict__ skip, int ds, int dsz, int crop,
+                   long long n_groups) {
+    const long long per = (long long)dz * d * d, total = n_groups * per;
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / per; long long v = i - g * per;
+        const int x = (int)(v % d); v /= d;
+        const int y = (int)(v % d); const int z = (int)(v / d);
+        uint4 a = cur[i];
+        const uint4 b = skip[((g * dsz + z + crop) * ds + y + crop) * (long long)ds + x + crop];
+        __nv_bfloat162 *pa = reinterpret_cast<__nv_bfloat162 *>(&a);
+        const __nv_bfloat162 *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // sum in fp32, one rounding (the operands are bf16 values)
+            const float2 fa = __bfloat1622float2(pa[j]), fb = __bfloat1622float2(pb[j]);
+            pa[j] = __hmax2(__floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y), zero);
+        }
+        cur[i] = a;
+    }
+}
+
 constexpr int kFusedThreads = 576;
 struct FusedArgs {
     const float *in;                 // (tile, din_z, din, din) float32 raw tiles
@@ -2173,6 +2198,9 @@ static int launch_conv_hilo(fpl_ctx *ctx, const ConvParams &c, const __nv_bfloat
 
 static int forward_hilo(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, float *d_out, cudaStream_t st) {
     fpl_ctx *ctx = net->ctx;
+    for (const Op &o : net->ops)
+        FPL_REQUIRE(o.kind != OP_ADD && !(o.kind == OP_CONV && (!o.relu || !o.bn || o.src_slot >= 0)),
+                    "precision 'tf32' (hi/lo path) does not cover the residual blocks of resnet_like: use 'bf16' or 'fp32'");
     std::vector<PoolBuf> &g_bufs = ctx->act_pool;
     for (PoolBuf &b : g_bufs) b.busy = false;
     auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
@@ -2262,7 +2290,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
     for (PoolBuf &b : g_bufs) b.busy = false;
     auto release = [&](int i) { if (i >= 0) g_bufs[i].busy = false; };
     int cur = -1;                 // pool buffer holding the current activation (-1: the fp32 input tiles)
-    int skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
+    int skip_buf[4] = {-1, -1, -1, -1}, skip_d[4] = {0, 0, 0, 0}, skip_dz[4] = {0, 0, 0, 0}, skip_c[4] = {0, 0, 0, 0};
     bool cur_is_skip = false;
     int d = in_sz, dzv = in_z, c = 1;          // x/y extent, z extent, channels of the current activation
     const int stream_blocks = ctx->sm_count * 8;
@@ -2324,6 +2352,35 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
                 continue;
             }
         }
+        if (o.kind == OP_CONV && o.src_slot >= 0) {
+            // resnet_like shortcut: 1x1x1 convolution of a stored tensor, which it replaces
+            const ConvParams &cp = net->convs[o.conv_index];
+            const int sl = o.src_slot, sd = skip_d[sl], sdz = skip_dz[sl];
+            const int nb = pool_take(ctx, (size_t)n_tiles * sdz * sd * sd * cp.cout * 2, st);
+            if (nb < 0) return FPL_ENOMEM;
+            const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_bufs[skip_buf[sl]].p;
+            if (umma_supported(cp) && !g_force_direct)
+                FPL_TRY(launch_conv_umma(ctx, cp, src, (__nv_bfloat16 *)g_bufs[nb].p, n_tiles, sd, sdz, o.relu ? 1 : 0, 0, st));
+            else {
+                FPL_REQUIRE(sdz == sd, "forward_umma: CUDA-core convolution handles cubic tiles only");
+                FPL_TRY(launch_conv_direct(ctx, cp, src, (__nv_bfloat16 *)g_bufs[nb].p, n_tiles, sd, o.relu ? 1 : 0, st));
+            }
+            if (skip_buf[sl] != cur) release(skip_buf[sl]);
+            else cur_is_skip = false;                 // the stored tensor was also the current one: it stays alive as cur only
+            skip_buf[sl] = nb; skip_c[sl] = cp.cout;
+            continue;
+        }
+        if (o.kind == OP_ADD) {
+            const int sl = o.slot;
+            FPL_REQUIRE(cur >= 0 && !cur_is_skip && skip_c[sl] == c && skip_d[sl] - 2 * o.crop == d && skip_dz[sl] - 2 * o.crop == dzv,
+                        "forward_umma: add: shapes do not match");
+            add_blocked_kernel<<<stream_blocks, 256, 0, st>>>((uint4 *)g_bufs[cur].p, d, dzv, (const uint4 *)g_bufs[skip_buf[sl]].p,
+                                                             skip_d[sl], skip_dz[sl], o.crop, (long long)n_tiles * (c / 8));
+            FPL_LAUNCH_CHECK(ctx);
+            release(skip_buf[sl]);
+            skip_buf[sl] = -1;
+            continue;
+        }
         if (o.kind == OP_CONV) {
             const ConvParams &cp = net->convs[o.conv_index];
             const int dout = d - (o.k - 1), dout_z = dzv - (o.k - 1);
@@ -2375,10 +2432,10 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             } else {
                 const __nv_bfloat16 *src = (const __nv_bfloat16 *)g_bufs[cur].p;
                 if (umma_supported(cp) && !g_force_direct)
-                    FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, dzv, 1, fuse_pool ? 1 : 0, st));
+                    FPL_TRY(launch_conv_umma(ctx, cp, src, dst, n_tiles, d, dzv, o.relu ? 1 : 0, fuse_pool ? 1 : 0, st));
                 else {
                     FPL_REQUIRE(dzv == d, "forward_umma: CUDA-core convolution handles cubic tiles only");
-                    FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, 1, st));
+                    FPL_TRY(launch_conv_direct(ctx, cp, src, dst, n_tiles, d, o.relu ? 1 : 0, st));
                 }
             }
             if (!cur_is_skip) release(cur);
@@ -2397,7 +2454,7 @@ int forward_umma(fpl_net *net, const float *d_tiles, int n_tiles, int in_sz, flo
             cur = nb; cur_is_skip = false;
             d /= 2; dzv /= 2;
         } else if (o.kind == OP_SAVE) {
-            skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_c[o.slot] = c;
+            skip_buf[o.slot] = cur; skip_d[o.slot] = d; skip_dz[o.slot] = dzv; skip_c[o.slot] = c;
             cur_is_skip = true;
         } else if (o.kind == OP_UPCAT) {
             FPL_REQUIRE(dzv == d, "forward_umma: the U-Net runs on cubic tiles");

@@ -2289,6 +2289,11 @@ int fpl_voxel2obj(fpl_ctx *ctx, const float *d_pred, int64_t Z, int64_t Y, int64
     if (try_approx) need += (size_t)n / 16 + ((size_t)1 << 24) + ((size_t)128 << 20);     // lattice sample, band / narrow / ambiguity lists, exact-value scratch
     FPL_TRY(ctx->arena.reserve(need));
     ctx->arena.reset();
+    // the back-off belongs to one kind of map: a call on a volume of another shape / with other parameters starts afresh
+    if (ctx->v2o_key[0] != Z || ctx->v2o_key[1] != Y || ctx->v2o_key[2] != X || ctx->v2o_key[3] != r || ctx->v2o_key[4] != p->lw) {
+        ctx->v2o_key[0] = Z; ctx->v2o_key[1] = Y; ctx->v2o_key[2] = X; ctx->v2o_key[3] = r; ctx->v2o_key[4] = p->lw;
+        ctx->v2o_skip = 0; ctx->v2o_fail_streak = 0;
+    }
     if (try_approx && ctx->v2o_skip > 0) {
         // adaptive: the last call(s) on this context did not qualify (a kind of map whose certificates fail, e.g. a value
         // distribution so tight that too many voxels sit within the bound of the percentile) -- do not pay for the

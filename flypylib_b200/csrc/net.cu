@@ -14,6 +14,9 @@ static Op conv(int k, int cin, int cout) { Op o; o.kind = OP_CONV; o.k = k; o.ci
 static Op pool() { Op o; o.kind = OP_POOL; return o; }
 static Op save(int slot) { Op o; o.kind = OP_SAVE; o.slot = slot; return o; }
 static Op upcat(int slot, int crop) { Op o; o.kind = OP_UPCAT; o.slot = slot; o.crop = crop; return o; }
+static Op conv_bn_only(int k, int cin, int cout) { Op o = conv(k, cin, cout); o.relu = false; return o; }
+static Op conv_on_skip(int slot, int cin, int cout) { Op o = conv(1, cin, cout); o.relu = false; o.bn = false; o.src_slot = slot; return o; }
+static Op add(int slot, int crop) { Op o; o.kind = OP_ADD; o.slot = slot; o.crop = crop; return o; }
 static Op final_(int cin) { Op o; o.kind = OP_FINAL; o.k = 1; o.cin = cin; o.cout = 1; return o; }
 
 static int build_graph(fpl_net *n) {
@@ -64,6 +67,11 @@ static int build_graph(fpl_net *n) {
                  conv(1, 32, 32), final_(32)};
             n->info = {40, 17, 1, 100, false};
             break;
+        case FPL_ARCH_RESNET_LIKE:   // fplmodels.py:174-208 (weight order = Keras model.layers order: the shortcut convolution precedes conv3b)
+            g = {conv(3, 1, 32), pool(), save(0), conv(3, 32, 32), conv_bn_only(1, 32, 32), add(0, 1), pool(), save(1),
+                 conv(3, 32, 64), conv_on_skip(1, 32, 64), conv_bn_only(1, 64, 64), add(1, 1), final_(64)};
+            n->info = {18, 7, 4, 102, true};
+            break;
         default:
             set_error("fpl_net_create: unknown architecture %d", n->arch);
             return FPL_EINVAL;
@@ -84,7 +92,10 @@ static int walk_sizes(const fpl_net *n, int in_sz, std::vector<int> *sizes_out =
     int skip_d[4] = {0, 0, 0, 0};
     for (const Op &o : n->ops) {
         switch (o.kind) {
-            case OP_CONV: case OP_FINAL: d -= (o.k - 1); if (d <= 0) return -1; break;
+            case OP_CONV: case OP_FINAL:
+                if (o.kind == OP_CONV && o.src_slot >= 0) break;         // 1x1x1 convolution of a stored tensor
+                d -= (o.k - 1); if (d <= 0) return -1; break;
+            case OP_ADD: if (skip_d[o.slot] - 2 * o.crop != d) return -1; break;
             case OP_POOL: if (d % 2) return -1; d /= 2; if (d <= 0) return -1; break;
             case OP_SAVE: skip_d[o.slot] = d; break;
             case OP_UPCAT: d *= 2; if (skip_d[o.slot] - 2 * o.crop != d) return -1; break;
@@ -221,7 +232,7 @@ int fpl_net_num_weights(const fpl_net *net, int32_t *n) {
     FPL_REQUIRE(net && n, "fpl_net_num_weights: NULL argument");
     int c = 0;
     for (const Op &o : net->ops) {
-        if (o.kind == OP_CONV) c += 5;
+        if (o.kind == OP_CONV) c += o.bn ? 5 : 1;
         if (o.kind == OP_FINAL) c += net->info.final_bias ? 2 : 1;
     }
     *n = c;
@@ -234,8 +245,8 @@ int fpl_net_weight_size(const fpl_net *net, int32_t index, int64_t *elems) {
     for (const Op &o : net->ops) {
         if (o.kind == OP_CONV) {
             if (index == c) { *elems = (int64_t)o.k * o.k * o.k * o.cin * o.cout; return FPL_OK; }
-            if (index > c && index < c + 5) { *elems = o.cout; return FPL_OK; }
-            c += 5;
+            if (o.bn && index > c && index < c + 5) { *elems = o.cout; return FPL_OK; }
+            c += o.bn ? 5 : 1;
         } else if (o.kind == OP_FINAL) {
             if (index == c) { *elems = o.cin; return FPL_OK; }
             if (net->info.final_bias && index == c + 1) { *elems = 1; return FPL_OK; }
@@ -274,7 +285,9 @@ int fpl_net_set_weights(fpl_net *net, const float *const *h_arrays, int32_t n, i
         c.kernel.assign(h_arrays[w], h_arrays[w] + ke);
         c.scale.assign(o.cout, 1.f);
         c.bias.assign(o.cout, 0.f);
-        if (o.kind == OP_CONV) {
+        if (o.kind == OP_CONV && !o.bn) {
+            w += 1;
+        } else if (o.kind == OP_CONV) {
             const float *gamma = h_arrays[w + 1], *beta = h_arrays[w + 2], *mean = h_arrays[w + 3],
                         *var = h_arrays[w + 4];
             for (int j = 0; j < o.cout; ++j) {   // BatchNormalization(eps=1e-3) inference, folded in double

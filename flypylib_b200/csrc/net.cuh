@@ -9,13 +9,16 @@ namespace net {
 
 // One step of the (static) graph.  Mirrors the Keras functional graphs of
 // flypylib/fplmodels.py:102-136 / :138-172 / :258-304.
-enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_SAVE = 2, OP_UPCAT = 3, OP_FINAL = 4 };
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_SAVE = 2, OP_UPCAT = 3, OP_FINAL = 4, OP_ADD = 5 };
 
 struct Op {
     OpKind kind;
     int k = 0, cin = 0, cout = 0;   // OP_CONV / OP_FINAL (cout == 1)
     int slot = -1;                  // OP_SAVE: skip slot to store; OP_UPCAT: skip slot to read
-    int crop = 0;                   // OP_UPCAT: symmetric crop of the skip tensor
+    int crop = 0;                   // OP_UPCAT / OP_ADD: symmetric crop of the skip tensor
+    bool relu = true;               // OP_CONV: ReLU after the (folded) BatchNormalization (false: resnet_like's BN-only convs)
+    bool bn = true;                 // OP_CONV: followed by BatchNormalization (false: plain convolution, one weight array)
+    int src_slot = -1;              // OP_CONV: >= 0 convolves the stored skip tensor in place of the current one (1x1x1 only)
     int conv_index = -1;            // index into ConvParams
 };
 

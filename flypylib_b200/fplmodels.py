@@ -154,9 +154,11 @@ class Model(object):
 
     def summary(self):
         print("Model %s  input %s  precision %s" % (self.arch, self.input_shape, self.precision))
-        for i, (k, cin, cout) in enumerate(self.spec["convs"]):
-            print("  conv%d  Conv3D(%d,(%d,%d,%d)) + BN + relu   in=%d  params=%d"
-                  % (i, cout, k, k, k, cin, k ** 3 * cin * cout + 4 * cout))
+        for i, cv in enumerate(self.spec["convs"]):
+            k, cin, cout = cv[:3]
+            bn = len(cv) < 4 or cv[3]
+            print("  conv%d  Conv3D(%d,(%d,%d,%d))%s   in=%d  params=%d"
+                  % (i, cout, k, k, k, " + BN" if bn else "", cin, k ** 3 * cin * cout + (4 * cout if bn else 0)))
         print("  predictions Conv3D(1,(1,1,1)) sigmoid  in=%d" % self.spec["final_cin"])
         if self.upsample_output and self.spec["rf"][2] != 1:
             print("  UpSampling3D(%d)" % self.spec["rf"][2])

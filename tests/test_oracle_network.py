@@ -66,12 +66,20 @@ def _forward_scipy(arch, weights, x, upsample=True):
     t = np.asarray(x, np.float64)[..., None]
     wi, skips = 0, {}
     for op in ops:
-        if op[0] == "C":
+        if op[0] in ("C", "CB"):
             kern = np.asarray(weights[wi], np.float64)
             gamma, beta, mean, var = (np.asarray(w, np.float64) for w in weights[wi + 1:wi + 5])
             wi += 5
             t = _conv3d_valid(t, kern)
-            t = np.maximum(gamma * (t - mean) / np.sqrt(var + 1e-3) + beta, 0.0)
+            t = gamma * (t - mean) / np.sqrt(var + 1e-3) + beta
+            if op[0] == "C":
+                t = np.maximum(t, 0.0)
+        elif op[0] == "CS":                       # resnet_like shortcut: plain 1x1x1 convolution of a stored tensor
+            skips[op[4]] = skips[op[4]] @ np.asarray(weights[wi], np.float64)[0, 0, 0]
+            wi += 1
+        elif op[0] == "A":
+            sk, c = skips[op[1]], op[2]
+            t = np.maximum(sk[c:-c, c:-c, c:-c] + t, 0.0)
         elif op[0] == "P":
             d, h, w = (s // 2 for s in t.shape[:3])
             t = t[:2 * d, :2 * h, :2 * w].reshape(d, 2, h, 2, w, 2, -1).max(axis=(1, 3, 5))
@@ -97,7 +105,7 @@ def _forward_scipy(arch, weights, x, upsample=True):
     return t
 
 
-@pytest.mark.parametrize("arch,s", [("vgg_like", 22), ("vgg_like2", 28), ("unet_like2", 28)])
+@pytest.mark.parametrize("arch,s", [("vgg_like", 22), ("vgg_like2", 28), ("unet_like2", 28), ("resnet_like", 26)])
 def test_forward_restatements_agree(arch, s):
     w = M.random_weights(arch, seed=17)
     x = np.random.default_rng(3).standard_normal((s, s, s))

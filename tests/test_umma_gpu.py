@@ -29,7 +29,7 @@ def _predict(arch, s, w, x, precision, force_direct=False):
 @pytest.mark.parametrize("arch,s,n", [("vgg_like2", 36, 2), ("vgg_like2", 52, 3), ("vgg_like", 38, 2),
                                       ("unet_like2", 36, 2), ("vgg_like2", 100, 1), ("baseline_model", 38, 2),
                                       ("unet_like", 30, 2), ("unet_like3", 44, 2), ("unet_like4", 52, 1),
-                                      ("unet_like4b", 52, 1)])
+                                      ("unet_like4b", 52, 1), ("resnet_like", 34, 2), ("resnet_like", 50, 1)])
 def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
     w = M.random_weights(arch, seed=11)
     x = np.random.default_rng(s).standard_normal((n, s, s, s)).astype(np.float32)
@@ -42,6 +42,25 @@ def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
         want = M.forward(arch, w, x)
         e = np.abs(got.astype(np.float64) - want).max()
         assert e < 2e-2, "bf16 path vs float64 oracle: %g" % e
+
+
+def test_resnet_like_volume_bf16_slab_tiles_equal_reference_grid():
+    """resnet_like (residual adds on z-slab tiles): tile_multiplier 3 == reference grid bit for bit; 'tf32' raises."""
+    import torch
+    from flypylib_b200 import fplmodels, fplnetwork, _lib
+    net = fplnetwork.FplNetwork(fplmodels.resnet_like)
+    net.train_single.set_weights(M.random_weights("resnet_like", seed=5))
+    net.set_precision("bf16")
+    net._set_infer()
+    u8 = torch.from_numpy(cases.em_volume((290, 190, 200), seed=9)).cuda()
+    net.tile_multiplier = 1
+    a = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+    net.tile_multiplier = 3
+    b = net.infer_device(u8, normalize=(128.0, 33.0)).cpu().numpy()
+    assert np.array_equal(a, b) and a.max() > 0
+    net.set_precision("tf32")
+    with pytest.raises(_lib.FplError):
+        net.infer_device(u8[:110, :110, :110].contiguous(), normalize=(128.0, 33.0))
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
