@@ -406,9 +406,11 @@ __global__ void __launch_bounds__(kSlabThreads, 1)
 tc_slab_conv_kernel(const SlabConvArgs a) {
     constexpr int NP = NS == 3 ? 2 : 1;
     extern __shared__ __align__(128) uint8_t tc_smem[];
-    __shared__ uint64_t bars[2 + 2 * kSlabRing];
+    __shared__ uint64_t bars[7 + 2 * kSlabRing];
     __shared__ uint32_t tmem_slot;
-    uint64_t *a_full = &bars[0], *mma_done = &bars[1], *b_full = &bars[2], *b_empty = &bars[2 + kSlabRing];
+    // per kd slice of the A image: full (workers -> MMA issuer) and free (tcgen05.commit after the slice's last MMA), so
+    // the workers re-stage slice kd for the next pass while the MMAs of the other slices still run
+    uint64_t *slice_full = &bars[0], *slice_free = &bars[3], *mma_done = &bars[6], *b_full = &bars[7], *b_empty = &bars[7 + kSlabRing];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int apv = a.ca / 8;                                    // channel atoms per voxel
     const uint32_t pitch = (uint32_t)a.s_pad * 16u;              // bytes between channel atoms
@@ -420,7 +422,8 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
     const uint32_t acc_cols = (uint32_t)(a.mt * a.nn);
     const uint32_t tmem_cols = 2 * acc_cols <= 256 ? 256u : 512u;
     if (tid == 0) {
-        mbar_init(a_full, 1); mbar_init(mma_done, 1);
+        mbar_init(mma_done, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&slice_full[i], 1); mbar_init(&slice_free[i], 1); }
         for (int i = 0; i < kSlabRing; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         fence_barrier_init();
     }
@@ -466,18 +469,20 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
             tc_fence_before();
         };
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pl) {
-            if (pl >= 1) { mbar_wait(mma_done, (pl - 1u) & 1u); tc_fence_after(); }   // A image free, accumulators of pl-1 ready
             const int img = pair / a.pairs_per_img, u0 = (pair - img * a.pairs_per_img) * rows_pass;
             const int nvox = rows_pass + halo;
             for (int kd = 0; kd < a.k; ++kd) {
+                if (pl >= 1) mbar_wait(&slice_free[kd], (pl - 1u) & 1u);          // the MMAs of the previous pass are done with it
                 const long long e0 = (long long)img * img_elems + ((long long)u0 + (long long)kd * a.din * a.din) * a.ca;
                 slab_stage<NS>(a.act + e0, tot_elems - e0, nvox, apv, sA + kd * slice_bytes, a_img_bytes, pitch, tid,
                                kSlabWorkers);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 0) mbar_arrive(&slice_full[kd]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid == 0) mbar_arrive(a_full);
-            if (prev_pair >= 0) epilogue(prev_pair, (pl - 1u) & 1u);
+            // the last slice_free wait above implies mma_done of the previous pass: drain its accumulators now, under
+            // the MMAs of this pass
+            if (prev_pair >= 0) { mbar_wait(mma_done, (pl - 1u) & 1u); tc_fence_after(); epilogue(prev_pair, (pl - 1u) & 1u); }
             prev_pair = pair;
         }
         if (prev_pair >= 0) {
@@ -501,11 +506,11 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
             const bool two = a.mt == 2;
             uint32_t pl = 0, g = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pl) {
-                mbar_wait(a_full, pl & 1u);
-                tc_fence_after();
                 const uint32_t d0 = tmem_base + (pl & 1u) * acc_cols, d1 = d0 + (uint32_t)a.nn;
                 uint32_t first = 0u;                                         // 0 on the first chunk: overwrite the accumulator
-                for (int kd = 0; kd < a.k; ++kd)
+                for (int kd = 0; kd < a.k; ++kd) {
+                    mbar_wait(&slice_full[kd], pl & 1u);
+                    tc_fence_after();
                     for (int kh = 0; kh < a.k; ++kh)
                         for (int kw = 0; kw < a.k; ++kw)
                             for (int hf = 0; hf < cpt; ++hf, ++g) {
@@ -534,6 +539,8 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
                                 first = 1u;
                                 umma_commit(&b_empty[slot]);
                             }
+                    umma_commit(&slice_free[kd]);
+                }
                 umma_commit(mma_done);
             }
         }
