@@ -15,6 +15,7 @@ PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
 ARCH_VGG_LIKE, ARCH_VGG_LIKE2, ARCH_UNET_LIKE2 = 1, 2, 3
 ARCH_BASELINE, ARCH_UNET_LIKE, ARCH_UNET_LIKE3, ARCH_UNET_LIKE4, ARCH_UNET_LIKE4B = 4, 5, 6, 7, 8
 ARCH_RESNET_LIKE = 9
+ARCH_UNET_LIKE_VOL = 10
 
 
 class FplError(RuntimeError):

@@ -14,6 +14,7 @@ static Op conv(int k, int cin, int cout) { Op o; o.kind = OP_CONV; o.k = k; o.ci
 static Op pool() { Op o; o.kind = OP_POOL; return o; }
 static Op save(int slot) { Op o; o.kind = OP_SAVE; o.slot = slot; return o; }
 static Op upcat(int slot, int crop) { Op o; o.kind = OP_UPCAT; o.slot = slot; o.crop = crop; return o; }
+static Op conv_no_bn(int k, int cin, int cout) { Op o = conv(k, cin, cout); o.bn = false; return o; }
 static Op conv_bn_only(int k, int cin, int cout) { Op o = conv(k, cin, cout); o.relu = false; return o; }
 static Op conv_on_skip(int slot, int cin, int cout) { Op o = conv(1, cin, cout); o.relu = false; o.bn = false; o.src_slot = slot; return o; }
 static Op add(int slot, int crop) { Op o; o.kind = OP_ADD; o.slot = slot; o.crop = crop; return o; }
@@ -66,6 +67,12 @@ static int build_graph(fpl_net *n) {
                  conv(1, 128, 48), upcat(1, 4), conv(3, 112, 64), conv(1, 64, 64), upcat(0, 14), conv(3, 96, 32),
                  conv(1, 32, 32), final_(32)};
             n->info = {40, 17, 1, 100, false};
+            break;
+        case FPL_ARCH_UNET_LIKE_VOL: // fplmodels.py:470-526: Conv3D(activation='relu', use_bias=False), no BatchNormalization
+            g = {conv_no_bn(3, 1, 16), conv_no_bn(1, 16, 16), save(0), pool(), conv_no_bn(3, 16, 32), conv_no_bn(1, 32, 32),
+                 save(1), pool(), conv_no_bn(1, 32, 64), upcat(1, 0), conv_no_bn(3, 96, 64), conv_no_bn(1, 64, 64),
+                 upcat(0, 4), conv_no_bn(3, 80, 32), conv_no_bn(1, 32, 32), final_(32)};
+            n->info = {62, 6, 1, 102, false};
             break;
         case FPL_ARCH_RESNET_LIKE:   // fplmodels.py:174-208 (weight order = Keras model.layers order: the shortcut convolution precedes conv3b)
             g = {conv(3, 1, 32), pool(), save(0), conv(3, 32, 32), conv_bn_only(1, 32, 32), add(0, 1), pool(), save(1),

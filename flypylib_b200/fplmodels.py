@@ -31,6 +31,11 @@ _ARCH = {
     "resnet_like": dict(id=_lib.ARCH_RESNET_LIKE, rf=(18, 7, 4), infer_sz=102, final_bias=True,
                         convs=[(3, 1, 32), (3, 32, 32), (1, 32, 32), (3, 32, 64), (1, 32, 64, False), (1, 64, 64)],
                         final_cin=64),
+    # fplmodels.py:470-526: no BatchNormalization (all convolutions marked False)
+    "unet_like_vol": dict(id=_lib.ARCH_UNET_LIKE_VOL, rf=(62, 6, 1), infer_sz=102, final_bias=False,
+                          convs=[(3, 1, 16, False), (1, 16, 16, False), (3, 16, 32, False), (1, 32, 32, False),
+                                 (1, 32, 64, False), (3, 96, 64, False), (1, 64, 64, False), (3, 80, 32, False),
+                                 (1, 32, 32, False)], final_cin=32),
     "unet_like": dict(id=_lib.ARCH_UNET_LIKE, rf=(18, 6, 1), infer_sz=102, final_bias=False,
                       convs=[(3, 1, 32), (1, 32, 32), (3, 32, 64), (1, 64, 64), (1, 64, 128), (3, 192, 64),
                              (1, 64, 64), (3, 96, 32), (1, 32, 32)], final_cin=32),
@@ -359,6 +364,16 @@ def masked_binary_crossentropy(y_true, y_pred):     # fplmodels.py:52-60, named 
 def baseline_model(in_sz=None):
     """returns simple baseline model (flypylib/fplmodels.py:73-100)"""
     return Model("baseline_model", in_sz), (18, 7, 4), 102, None
+
+
+def masked_weighted_binary_crossentropy(y_true, y_pred):     # fplmodels.py, named for compile_args only
+    raise NotImplementedError("training losses are outside the B200 inference hot path")
+
+
+def unet_like_vol(in_sz=62):
+    """fplmodels.py:470-526: U-Net without BatchNormalization (16/32/64 channels), volume-to-volume training."""
+    compile_args = {'loss': masked_weighted_binary_crossentropy, 'optimizer': 'adam', 'metrics': ['masked_accuracy']}
+    return Model("unet_like_vol", in_sz), (62, 6, 1), 102, compile_args
 
 
 def resnet_like(in_sz=None):

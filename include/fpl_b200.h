@@ -182,6 +182,8 @@ int fpl_v2o_slab_end(void *session, double *d_rows, int64_t capacity, int64_t *h
 #define FPL_ARCH_UNET_LIKE4B 8
 /* flypylib/fplmodels.py:174-208: residual blocks (add of a cropped shortcut); bf16 and fp32 precisions */
 #define FPL_ARCH_RESNET_LIKE 9
+/* flypylib/fplmodels.py:470-526: U-Net without BatchNormalization */
+#define FPL_ARCH_UNET_LIKE_VOL 10
 
 /* arithmetic of the conv stack */
 #define FPL_PREC_FP32  0   /* CUDA-core fp32 direct convolution (validation path)            */

@@ -27,6 +27,7 @@ import torch.nn.functional as F
 BN_EPS = 1e-3
 
 # (kind, k, cin, cout) chains; 'P' pool, 'U' up-sample+concat with a stored skip (crop), 'S' store skip;
+# unet_like_vol: 'CN' conv + ReLU without BatchNormalization;
 # resnet_like adds: 'CB' conv + BN without ReLU, 'CS' plain conv (no BN, no activation) applied to a stored skip,
 # 'A' add the symmetrically cropped skip, then ReLU
 ARCHS = {
@@ -49,6 +50,14 @@ ARCHS = {
                      ("C", 3, 32, 32), ("CB", 1, 32, 32), ("A", "pool1", 1), ("P",), ("S", "pool2"),
                      ("C", 3, 32, 64), ("CS", 1, 32, 64, "pool2"), ("CB", 1, 64, 64), ("A", "pool2", 1), ("F", 64)],
                     (18, 7, 4), 102, True),
+    # fplmodels.py:470-526: no BatchNormalization anywhere (Conv3D(activation='relu', use_bias=False)); trains volume to
+    # volume, rf tuple (62, 6, 1) as the builder returns it
+    "unet_like_vol": ([("CN", 3, 1, 16), ("CN", 1, 16, 16), ("S", "conv1"), ("P",),
+                       ("CN", 3, 16, 32), ("CN", 1, 32, 32), ("S", "conv2"), ("P",),
+                       ("CN", 1, 32, 64), ("U", "conv2", 0),
+                       ("CN", 3, 96, 64), ("CN", 1, 64, 64), ("U", "conv1", 4),
+                       ("CN", 3, 80, 32), ("CN", 1, 32, 32), ("F", 32)],
+                      (62, 6, 1), 102, False),
     # further builders with the same layer vocabulary: fplmodels.py:73-100, :206-256, :306-357, :359-410, :412-467
     "baseline_model": ([("C", 3, 1, 32), ("P",), ("C", 3, 32, 32), ("P",), ("C", 3, 32, 32), ("C", 1, 32, 64), ("F", 64)],
                        (18, 7, 4), 102, True),
@@ -89,7 +98,7 @@ def weight_shapes(arch):
             _, k, cin, cout = op
             shapes.append((k, k, k, cin, cout))
             shapes += [(cout,)] * 4
-        elif op[0] == "CS":
+        elif op[0] in ("CS", "CN"):
             shapes.append((op[1],) * 3 + (op[2], op[3]))
         elif op[0] == "F":
             shapes.append((1, 1, 1, op[1], 1))
@@ -104,7 +113,7 @@ def random_weights(arch, seed=4321, trained_like=True):
     ops, _, _, final_bias = ARCHS[arch]
     ws = []
     for op in ops:
-        if op[0] == "CS":
+        if op[0] in ("CS", "CN"):
             k, cin, cout = op[1], op[2], op[3]
             lim = np.sqrt(6.0 / (k ** 3 * cin + k ** 3 * cout))
             ws.append(rng.uniform(-lim, lim, (k, k, k, cin, cout)).astype(np.float32))
@@ -147,6 +156,10 @@ def forward(arch, weights, x, dtype=torch.float64, upsample=True):
                 * gamma.view(1, -1, 1, 1, 1) + beta.view(1, -1, 1, 1, 1)
             if op[0] == "C":
                 t = torch.relu(t)
+        elif op[0] == "CN":                       # Conv3D(activation='relu', use_bias=False), no BatchNormalization
+            kern = torch.as_tensor(weights[wi]).to(dtype).permute(4, 3, 0, 1, 2)
+            wi += 1
+            t = torch.relu(F.conv3d(t, kern))
         elif op[0] == "CS":                       # plain convolution of a stored tensor (resnet shortcut)
             kern = torch.as_tensor(weights[wi]).to(dtype).permute(4, 3, 0, 1, 2)
             wi += 1

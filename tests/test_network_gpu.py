@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 2e-3      # north_star: prob maps within 2e-3 max-abs on the fp32/TF32 path
 SMALL = {"vgg_like": 30, "vgg_like2": 36, "unet_like2": 36, "baseline_model": 30, "unet_like": 30, "unet_like3": 44,
-         "unet_like4": 52, "unet_like4b": 52, "resnet_like": 34}
+         "unet_like4": 52, "unet_like4b": 52, "resnet_like": 34, "unet_like_vol": 34}
 
 
 def _builder(arch):
@@ -20,7 +20,7 @@ def _builder(arch):
 
 
 @pytest.mark.parametrize("arch", ["vgg_like", "vgg_like2", "unet_like2", "baseline_model", "unet_like", "unet_like3",
-                                  "unet_like4", "unet_like4b", "resnet_like"])
+                                  "unet_like4", "unet_like4b", "resnet_like", "unet_like_vol"])
 def test_forward_tiles_fp32_vs_float64_oracle(arch):
     s = SMALL[arch]
     model, rf, infer_sz, _ = _builder(arch)(s)

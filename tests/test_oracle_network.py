@@ -74,6 +74,9 @@ def _forward_scipy(arch, weights, x, upsample=True):
             t = gamma * (t - mean) / np.sqrt(var + 1e-3) + beta
             if op[0] == "C":
                 t = np.maximum(t, 0.0)
+        elif op[0] == "CN":
+            t = np.maximum(_conv3d_valid(t, np.asarray(weights[wi], np.float64)), 0.0)
+            wi += 1
         elif op[0] == "CS":                       # resnet_like shortcut: plain 1x1x1 convolution of a stored tensor
             skips[op[4]] = skips[op[4]] @ np.asarray(weights[wi], np.float64)[0, 0, 0]
             wi += 1
@@ -105,7 +108,8 @@ def _forward_scipy(arch, weights, x, upsample=True):
     return t
 
 
-@pytest.mark.parametrize("arch,s", [("vgg_like", 22), ("vgg_like2", 28), ("unet_like2", 28), ("resnet_like", 26)])
+@pytest.mark.parametrize("arch,s", [("vgg_like", 22), ("vgg_like2", 28), ("unet_like2", 28), ("resnet_like", 26),
+                                    ("unet_like_vol", 30)])
 def test_forward_restatements_agree(arch, s):
     w = M.random_weights(arch, seed=17)
     x = np.random.default_rng(3).standard_normal((s, s, s))
