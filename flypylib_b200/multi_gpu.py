@@ -597,13 +597,18 @@ def voxel2obj_global(pred_slabs, ranges, Z, obj_min_dist, smoothing_sigma, volum
             o = out[:cnt.value].clone()
             o[:, 0] += lo
             rows.append(o)
-        allrows = coll.allgather(rows)[0].cpu().numpy()
+        ar = coll.allgather(rows)[0]
+        if ar.shape[0] > 1:
+            # emission order of the greedy loop = (conf desc, flat index asc): two stable sorts on the device (a host
+            # np.lexsort of the 7e4 detections of a 1024^3 volume costs 5 ms -- a sixth of the 8-GPU step)
+            flat = (ar[:, 0] * Y + ar[:, 1]) * X + ar[:, 2]            # exact in float64 (< 2^53)
+            ar = ar[torch.argsort(flat, stable=True)]
+            ar = ar[torch.argsort(ar[:, 3], descending=True, stable=True)]
+        allrows = ar.cpu().numpy()
         mark('final_allgather')
     if allrows.shape[0] == 0:
         return done(empty)
     z, y, x, c = allrows[:, 0], allrows[:, 1], allrows[:, 2], allrows[:, 3]
-    order = np.lexsort((x, y, z, -c))                                   # conf desc, flat index asc
-    z, y, x, c = z[order], y[order], x[order], c[order]
     bx, by, bz = (int(p.buffer_xyz[i]) for i in range(3))
     keep = (x >= bx) & (y >= by) & (z >= bz) & (x < X - bx) & (y < Y - by) & (z < Z - bz)
     locs = np.stack([x[keep] + p.offset_xyz[0], y[keep] + p.offset_xyz[1], z[keep] + p.offset_xyz[2]], 1)
