@@ -492,9 +492,11 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
         }
     } else if (warp == 8) {
         // ======================= MMA issuer =======================
-        // One thread issues every MMA: its instruction stream is the limit (a dependent chain runs at one instruction
-        // per ~4 clocks), so the descriptors are kept as 32-bit words that differ by precomputed constants.
-        if (lane == 0) {
+        // The whole warp walks the (warp-uniform) loops and one elected lane issues: with `if (lane == 0)` around the loops
+        // the compiler cannot keep the descriptors in uniform registers and wraps EVERY tcgen05.mma in an ELECT / R2UR /
+        // BRA.U.ANY sequence (~86 clocks per MMA measured, against 24 clocks of tensor-pipe time at N = 48).
+        const bool leader = elect_one();
+        {
             const uint32_t idesc = make_idesc_bf16(128, a.nn);
             const uint32_t b_lbo = (uint32_t)a.nn * 16u;
             const uint32_t hi_w = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
@@ -523,25 +525,30 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
                                 for (int ks = 0; ks < 3; ++ks) {
                                     const uint32_t al = ac + (uint32_t)ks * a_ks, bl = bc + (uint32_t)ks * b_ks;
                                     const uint32_t acc = ks == 0 ? first : 1u;
-                                    umma_bf16(d0, desc64(al, hi_w), desc64(bl, hi_w), idesc, acc);
-                                    if (NS == 3) {
-                                        umma_bf16(d0, desc64(al + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
-                                        umma_bf16(d0, desc64(al, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
-                                    }
-                                    if (two) {
-                                        umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl, hi_w), idesc, acc);
+                                    if (leader) {
+                                        umma_bf16(d0, desc64(al, hi_w), desc64(bl, hi_w), idesc, acc);
                                         if (NS == 3) {
-                                            umma_bf16(d1, desc64(al + 128u + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
-                                            umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
+                                            umma_bf16(d0, desc64(al + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
+                                            umma_bf16(d0, desc64(al, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
+                                        }
+                                        if (two) {
+                                            umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl, hi_w), idesc, acc);
+                                            if (NS == 3) {
+                                                umma_bf16(d1, desc64(al + 128u + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
+                                                umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
+                                            }
                                         }
                                     }
                                 }
                                 first = 1u;
-                                umma_commit(&b_empty[slot]);
+                                if (leader) umma_commit(&b_empty[slot]);
+                                __syncwarp();
                             }
-                    umma_commit(&slice_free[kd]);
+                    if (leader) umma_commit(&slice_free[kd]);
+                    __syncwarp();
                 }
-                umma_commit(mma_done);
+                if (leader) umma_commit(mma_done);
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -684,8 +691,9 @@ tc_slab_wgrad_kernel(const SlabWgradArgs a) {
                 }
             }
         }
-    } else if (lane == 0) {
-        // ======================= MMA issuer =======================
+    } else {
+        // ======================= MMA issuer (whole warp in the loops, one elected lane issues) =======================
+        const bool leader = elect_one();
         // both operands MN-major, no swizzle: SBO = pitch between 8-channel atoms, LBO = 128 B between 8-voxel groups
         const uint32_t idesc = make_idesc_bf16(128, a.ci) | (1u << 15) | (1u << 16);
         const uint32_t hi_a = (pa >> 4) | (1u << 14), hi_b = (px >> 4) | (1u << 14);
@@ -707,14 +715,17 @@ tc_slab_wgrad_kernel(const SlabWgradArgs a) {
 #pragma unroll
                     for (int ks = 0; ks < kWgKc / 16; ++ks) {
                         const uint32_t al = al0 + (uint32_t)ks * 16u, bl = xt + (uint32_t)ks * 16u;    // 16 voxels = 256 B
-                        umma_bf16(d, desc64(al, hi_a), desc64(bl, hi_b), idesc, ks == 0 ? first : 1u);
-                        if (NS == 3) {
-                            umma_bf16(d, desc64(al + a_lo_img, hi_a), desc64(bl, hi_b), idesc, 1u);
-                            umma_bf16(d, desc64(al, hi_a), desc64(bl + x_lo_img, hi_b), idesc, 1u);
+                        if (leader) {
+                            umma_bf16(d, desc64(al, hi_a), desc64(bl, hi_b), idesc, ks == 0 ? first : 1u);
+                            if (NS == 3) {
+                                umma_bf16(d, desc64(al + a_lo_img, hi_a), desc64(bl, hi_b), idesc, 1u);
+                                umma_bf16(d, desc64(al, hi_a), desc64(bl + x_lo_img, hi_b), idesc, 1u);
+                            }
                         }
                     }
                 }
-            umma_commit(&empty[s]);
+            if (leader) umma_commit(&empty[s]);
+            __syncwarp();
         }
     }
     __syncwarp();
