@@ -677,13 +677,16 @@ tc_slab_wgrad_kernel(const SlabWgradArgs a) {
             mbar_wait(&empty[last & 1u], (last >> 1) & 1u);
             tc_fence_after();
             const int q = warp & 3, half = warp >> 2;
-            const int co = q * 32 + lane;
+            const bool stacked = NS == 3 && 2 * a.co <= 128;        // rows Cout..2*Cout-1 hold the lo*hi products
+            int co = q * 32 + lane;
+            const bool row_ok = co < a.co || (stacked && co < 2 * a.co);
+            if (co >= a.co) co -= a.co;
             const int ncb = taps * a.ci / 16;
             for (int cb = half; cb < ncb; cb += 2) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + (uint32_t)(cb * 16) + ((uint32_t)(q * 32) << 16), r);
                 tmem_ld_wait();
-                if (co < a.co) {
+                if (row_ok) {
                     const int col0 = cb * 16, tl = col0 / a.ci, ci0 = col0 - tl * a.ci;      // 16 | ci: one tap per block
                     float *o = a.dw + ((size_t)(kd * taps + tl) * a.ci + ci0) * a.co + co;
 #pragma unroll
@@ -699,6 +702,7 @@ tc_slab_wgrad_kernel(const SlabWgradArgs a) {
         const uint32_t hi_a = (pa >> 4) | (1u << 14), hi_b = (px >> 4) | (1u << 14);
         const uint32_t lbo = (128u >> 4) << 16;
         const uint32_t a_lo_img = a_img >> 4, x_lo_img = x_img >> 4;
+        const bool stacked = NS == 3 && 2 * a.co <= 128;
         uint32_t it = 0;
         for (int unit = unit0; unit < unit1; ++unit, ++it) {
             const uint32_t s = it & 1u, use = it >> 1;
@@ -716,9 +720,12 @@ tc_slab_wgrad_kernel(const SlabWgradArgs a) {
                     for (int ks = 0; ks < kWgKc / 16; ++ks) {
                         const uint32_t al = al0 + (uint32_t)ks * 16u, bl = xt + (uint32_t)ks * 16u;    // 16 voxels = 256 B
                         if (leader) {
+                            // NS = 3, Cout = 48: the lo image of dx follows the hi image at the same atom pitch, so the
+                            // M = 128 read of the first MMA already covers [hi rows 0..47 | lo rows 48..95]: lo*hi lands
+                            // in accumulator rows 48..95 for free (the epilogue adds them) and its own MMA is dropped
                             umma_bf16(d, desc64(al, hi_a), desc64(bl, hi_b), idesc, ks == 0 ? first : 1u);
                             if (NS == 3) {
-                                umma_bf16(d, desc64(al + a_lo_img, hi_a), desc64(bl, hi_b), idesc, 1u);
+                                if (!stacked) umma_bf16(d, desc64(al + a_lo_img, hi_a), desc64(bl, hi_b), idesc, 1u);
                                 umma_bf16(d, desc64(al, hi_a), desc64(bl + x_lo_img, hi_b), idesc, 1u);
                             }
                         }
