@@ -583,9 +583,9 @@ static int launch_slab_conv(fpl_ctx *ctx, int prec, const float *act, const floa
         sp += (9 - sp % 8) % 8;                                   // == 1 (mod 8): staging stores spread over the banks
         smem = (size_t)np * k * (ca / 8) * sp * 16 + b_ring;
         a.mt = mt; a.s_pad = sp;
-        if (smem <= 227 * 1024 - 1024 && 2 * mt * nn <= 512) break;
+        if (smem <= 227 * 1024 - 1024 && 2 * mt * np * nn <= 512) break;
     }
-    FPL_REQUIRE(smem <= 227 * 1024 - 1024, "slab conv: layer does not fit shared memory");
+    FPL_REQUIRE(smem <= 227 * 1024 - 1024 && 2 * a.mt * np * nn <= 512, "slab conv: layer does not fit shared memory / TMEM");
     const int rows_pass = a.mt * 128;
     a.pairs_per_img = (a.u_max + rows_pass - 1) / rows_pass;
     const long long passes = (long long)a.n_img * a.pairs_per_img;

@@ -419,7 +419,8 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
     const uint32_t b_half = 6u * (uint32_t)a.nn * 16u;           // hi part of one K chunk
     const uint32_t b_slot = NP * b_half;
     uint8_t *sA = tc_smem, *sB = tc_smem + NP * a_img_bytes;
-    const uint32_t acc_cols = (uint32_t)(a.mt * a.nn);
+    const uint32_t ncol = (uint32_t)NP * (uint32_t)a.nn;          // accumulator columns per M tile: [hi*hi + lo*hi | hi*lo]
+    const uint32_t acc_cols = (uint32_t)a.mt * ncol;
     const uint32_t tmem_cols = 2 * acc_cols <= 256 ? 256u : 512u;
     if (tid == 0) {
         mbar_init(mma_done, 1);
@@ -454,15 +455,23 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
                 const bool ok = a.flat ? u < a.u_max : (z < a.dout && y < a.dout && x < a.dout);
                 float *o = a.out + (a.flat ? (size_t)u : (((size_t)img * a.dout + z) * a.dout + y) * a.dout + x) * a.nn;
                 for (int cb = half; cb < a.nn / 16; cb += 2) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + buf * acc_cols + (uint32_t)(t * a.nn + cb * 16) + ((uint32_t)(q * 32) << 16), r);
+                    uint32_t r[16], r2[16];
+                    const uint32_t tcol = tmem_base + buf * acc_cols + (uint32_t)t * ncol + (uint32_t)(cb * 16) + ((uint32_t)(q * 32) << 16);
+                    tmem_ld16(tcol, r);
+                    if (NS == 3) tmem_ld16(tcol + (uint32_t)a.nn, r2);
                     tmem_ld_wait();
                     if (ok) {
                         float4 *o4 = reinterpret_cast<float4 *>(o + cb * 16);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            o4[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
-                                                __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+                        for (int e = 0; e < 4; ++e) {
+                            float4 v = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                                   __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+                            if (NS == 3) {
+                                v.x += __uint_as_float(r2[4 * e]); v.y += __uint_as_float(r2[4 * e + 1]);
+                                v.z += __uint_as_float(r2[4 * e + 2]); v.w += __uint_as_float(r2[4 * e + 3]);
+                            }
+                            o4[e] = v;
+                        }
                     }
                 }
             }
@@ -497,18 +506,18 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
         // BRA.U.ANY sequence (~86 clocks per MMA measured, against 24 clocks of tensor-pipe time at N = 48).
         const bool leader = elect_one();
         {
-            const uint32_t idesc = make_idesc_bf16(128, a.nn);
-            const uint32_t b_lbo = (uint32_t)a.nn * 16u;
+            const uint32_t idesc = make_idesc_bf16(128, a.nn), idesc2 = make_idesc_bf16(128, NP * a.nn);
+            const uint32_t b_lbo = (uint32_t)NP * (uint32_t)a.nn * 16u;      // atom pitch of the (stacked) weight image
             const uint32_t hi_w = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
             const uint32_t lo_a0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | ((pitch >> 4) << 16);     // LBO = atom pitch
             const uint32_t lo_b0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((b_lbo >> 4) << 16);
             const uint32_t a_ks = (2u * pitch) >> 4, a_lo_img = a_img_bytes >> 4, a_slice = slice_bytes >> 4;
-            const uint32_t b_ks = (2u * b_lbo) >> 4, b_lo_half = b_half >> 4, b_slot16 = b_slot >> 4;
+            const uint32_t b_ks = (2u * b_lbo) >> 4, b_slot16 = b_slot >> 4;
             const uint32_t a_half = (6u * pitch) >> 4;
             const bool two = a.mt == 2;
             uint32_t pl = 0, g = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pl) {
-                const uint32_t d0 = tmem_base + (pl & 1u) * acc_cols, d1 = d0 + (uint32_t)a.nn;
+                const uint32_t d0 = tmem_base + (pl & 1u) * acc_cols, d1 = d0 + ncol;
                 uint32_t first = 0u;                                         // 0 on the first chunk: overwrite the accumulator
                 for (int kd = 0; kd < a.k; ++kd) {
                     mbar_wait(&slice_full[kd], pl & 1u);
@@ -526,17 +535,13 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
                                     const uint32_t al = ac + (uint32_t)ks * a_ks, bl = bc + (uint32_t)ks * b_ks;
                                     const uint32_t acc = ks == 0 ? first : 1u;
                                     if (leader) {
-                                        umma_bf16(d0, desc64(al, hi_w), desc64(bl, hi_w), idesc, acc);
-                                        if (NS == 3) {
-                                            umma_bf16(d0, desc64(al + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
-                                            umma_bf16(d0, desc64(al, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
-                                        }
+                                        // hi activations x [hi | lo] weights (N = 2*nn), then lo activations x hi weights (N = nn,
+                                        // same image: its first nn rows) into the first column block
+                                        umma_bf16(d0, desc64(al, hi_w), desc64(bl, hi_w), idesc2, acc);
+                                        if (NS == 3) umma_bf16(d0, desc64(al + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
                                         if (two) {
-                                            umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl, hi_w), idesc, acc);
-                                            if (NS == 3) {
-                                                umma_bf16(d1, desc64(al + 128u + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
-                                                umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl + b_lo_half, hi_w), idesc, 1u);
-                                            }
+                                            umma_bf16(d1, desc64(al + 128u, hi_w), desc64(bl, hi_w), idesc2, acc);
+                                            if (NS == 3) umma_bf16(d1, desc64(al + 128u + a_lo_img, hi_w), desc64(bl, hi_w), idesc, 1u);
                                         }
                                     }
                                 }
@@ -573,7 +578,7 @@ tc_slab_conv_kernel(const SlabConvArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// packed operand-B images of one layer: chunk c = (tap, 48-channel half); [hi: [atom][n][8 bf16]] [lo]
+// packed operand-B images of one layer: chunk c = (tap, 48-channel half); [atom][hi rows | lo rows][8 bf16]
 //   flip = 0 (forward): B[n, (tap, c)] = W[tap][c][n]       (W is (tap, ca, nn))
 //   flip = 1 (dgrad):   B[n, (tap, c)] = W[T-1-tap][n][c]   (W is (tap, nn, ca))
 template <int NS>
@@ -581,7 +586,10 @@ __global__ void __launch_bounds__(256)
 tc_pack_w_kernel(const float *__restrict__ w, uint8_t *__restrict__ img, int ntaps, int ca, int nn, int flip) {
     const int cpt = ca / 48;
     const int total = ntaps * cpt * 6 * nn;
-    const uint32_t b_half = 6u * (uint32_t)nn * 16u, b_slot = (NS == 3 ? 2u : 1u) * b_half;
+    // NS = 3: per atom the hi rows are followed by the lo rows ([atom][hi 0..nn-1 | lo nn..2nn-1][16 B]): ONE N = 2*nn MMA
+    // of the hi activations then yields hi*hi and hi*lo side by side (the epilogue adds the two column blocks)
+    constexpr uint32_t NPK = NS == 3 ? 2u : 1u;
+    const uint32_t b_slot = NPK * 6u * (uint32_t)nn * 16u;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i % nn; int r = i / nn;
         const int at = r % 6; r /= 6;
@@ -593,9 +601,9 @@ tc_pack_w_kernel(const float *__restrict__ w, uint8_t *__restrict__ img, int nta
             v[e] = flip ? w[((size_t)(ntaps - 1 - tap) * nn + n) * ca + c0 + e] : w[((size_t)tap * ca + c0 + e) * nn + n];
         uint4 hi, lo;
         tc_pack8<NS>(v, hi, lo);
-        uint8_t *dst = img + (size_t)(tap * cpt + hf) * b_slot + (size_t)at * nn * 16 + (size_t)n * 16;
+        uint8_t *dst = img + (size_t)(tap * cpt + hf) * b_slot + (size_t)at * NPK * nn * 16 + (size_t)n * 16;
         *reinterpret_cast<uint4 *>(dst) = hi;
-        if (NS == 3) *reinterpret_cast<uint4 *>(dst + b_half) = lo;
+        if (NS == 3) *reinterpret_cast<uint4 *>(dst + (size_t)nn * 16) = lo;
     }
 }
 
