@@ -204,11 +204,7 @@ int fpl_v2o_detect_seg(fpl_ctx *ctx, const float *d_val, const int64_t *d_idx, i
     a.rows = d_rows; a.cap = capacity; a.out_count = (long long *)d_count;
     const int S = 2 * a.r + 1;
     const size_t smem = (size_t)2 * S * S * sizeof(unsigned long long);
-    static bool attr_done = false;
-    if (!attr_done) {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(fpl::v2oseg::seg_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 63 * 63 * 8));
-        attr_done = true;
-    }
+    FPL_CUDA_CHECK(cudaFuncSetAttribute(fpl::v2oseg::seg_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 63 * 63 * 8));
     cudaStream_t st = (cudaStream_t)stream;
     FPL_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 3 * sizeof(int64_t), st));
     fpl::v2oseg::seg_greedy_kernel<<<1, fpl::v2oseg::kThreads, smem, st>>>(a);

@@ -481,13 +481,9 @@ static bool tc_layer_ok(int k, int cin, int cout) {
 }
 
 template <int NS>
-static int tc_set_smem() {
-    static bool done = false;
-    if (!done) {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        done = true;
-    }
+static int tc_set_smem() {        // per launch: the attribute belongs to the current device
+    FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return FPL_OK;
 }
 
@@ -548,13 +544,9 @@ static bool slab_layer_ok(int k, int cin, int cout) {
 static size_t slab_wimg_bytes(int k, int ca, int nn) { return (size_t)k * k * k * (ca / 48) * 2 * 6 * nn * 16; }
 
 template <int NS>
-static int slab_set_smem() {
-    static bool done = false;
-    if (!done) {
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        done = true;
-    }
+static int slab_set_smem() {      // per launch: the attribute belongs to the current device
+    FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_conv_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    FPL_CUDA_CHECK(cudaFuncSetAttribute(tc_slab_wgrad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     return FPL_OK;
 }
 
@@ -762,6 +754,7 @@ int fpl_debug_train_tc(fpl_ctx *ctx, int what, int precision, const float *act, 
     const int dout = din - (k - 1);
     const bool slab = slab_layer_ok(k, cin, cout);
     const int p = k - 1, dp = dout + 2 * p;
+    FPL_REQUIRE(what != 1 || k == 1 || scratch, "fpl_debug_train_tc: dgrad needs the scratch buffer");
     void *wimg = nullptr; float *emb = nullptr;
     if (slab) {
         const size_t wb = slab_wimg_bytes(k, cin, cout) > slab_wimg_bytes(k, cout, cin) ? slab_wimg_bytes(k, cin, cout) : slab_wimg_bytes(k, cout, cin);
@@ -775,7 +768,6 @@ int fpl_debug_train_tc(fpl_ctx *ctx, int what, int precision, const float *act, 
     } else if (what == 1) {
         const float *dxp = act;
         if (k > 1) {
-            FPL_REQUIRE(scratch, "fpl_debug_train_tc: dgrad needs the scratch buffer");
             tc_embed_kernel<<<blocks_for(ctx, (long long)n * dp * dp * dp * (cout / 4)), 256, 0, st>>>(
                 (const float4 *)act, (float4 *)scratch, n, dout, p, dp, cout / 4);
             ctx->launches++;
