@@ -149,14 +149,14 @@ def test_bf16_config_tile_and_slab_tile_vs_float64():
     want = M.forward(arch, w, x)
     assert got.shape == want.shape == (1, 80, 80, 80)
     e = np.abs(got.astype(np.float64) - want).max()
-    assert e < 2e-2, "bf16 100^3 tile vs float64 oracle: %g" % e
+    assert e < 4e-3, "bf16 100^3 tile vs float64 oracle: %g" % e
     # slab-shaped tile through the volume API
     net = _net(arch, "bf16", 11, 4)
     img = ((cases.em_volume((44, 120, 120), seed=4).astype(np.float32) - 128.0) / 33.0).astype(np.float32)
     got_v = net.infer_device(torch.from_numpy(img).cuda()).cpu().numpy()
     want_v = M.infer_tiler(img, M.TorchNet(arch, w, dtype=torch.float64), net.infer_sz, net.rf_offset, n_gpu=1)
     e = np.abs(got_v.astype(np.float64) - want_v.astype(np.float64)).max()
-    assert e < 2e-2, "bf16 slab tile vs float64 oracle tiling: %g" % e
+    assert e < 4e-3, "bf16 slab tile vs float64 oracle tiling: %g" % e
 
 
 def test_row_sharded_unet_equals_whole_volume():

@@ -10,6 +10,11 @@ from tests.golden import cases
 
 pytestmark = pytest.mark.gpu
 
+# bf16 probability maps against the float64 restatement, random-init weights.  Measured max |error| over the builders:
+# 4.3e-4 (vgg_like2) .. 1.45e-3 (unet_like3) -- inside the 2e-3 the north_star asks of the fp32/TF32 path; the bound
+# below keeps a 2.7x margin.  (The north_star's criterion for bf16 itself is the detection F1, tested further down.)
+BF16_TOL = 4e-3
+
 
 def _predict(arch, s, w, x, precision, force_direct=False):
     from flypylib_b200 import fplmodels, _lib
@@ -38,7 +43,8 @@ def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
     if arch == "unet_like_vol":                    # 16-channel first layer: tensor-core first-layer kernel only
         want = M.forward(arch, w, x)
         e = np.abs(got.astype(np.float64) - want).max()
-        assert e < 2e-2, "bf16 path vs float64 oracle: %g" % e
+        print("bf16 vs float64 oracle %s %d: %.3g" % (arch, s, e))
+        assert e < BF16_TOL, "bf16 path vs float64 oracle: %g" % e
         return
     ref_direct = _predict(arch, s, w, x, "bf16", force_direct=True)
     assert got.shape == ref_direct.shape
@@ -49,7 +55,8 @@ def test_bf16_umma_vs_direct_and_oracle(arch, s, n):
     if s <= 52:
         want = M.forward(arch, w, x)
         e = np.abs(got.astype(np.float64) - want).max()
-        assert e < 2e-2, "bf16 path vs float64 oracle: %g" % e
+        print("bf16 vs float64 oracle %s %d: %.3g (tcgen05 vs direct %.3g)" % (arch, s, e, d))
+        assert e < BF16_TOL, "bf16 path vs float64 oracle: %g" % e
 
 
 def test_resnet_like_volume_bf16_slab_tiles_equal_reference_grid():
