@@ -897,25 +897,28 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 // MaxPooling3D((2,2,2)); one thread = one output atom (8 channels of one voxel)
 __global__ void __launch_bounds__(256)
 pool_blocked_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long n_cg_total, int din, int din_z) {
-    const int dout = din / 2, dout_z = din_z / 2;
-    const long long total = n_cg_total * dout_z * dout * dout;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long v = i;
-        const int x = (int)(v % dout); v /= dout;
-        const int y = (int)(v % dout); v /= dout;
-        const int z = (int)(v % dout_z); v /= dout_z;   // v = tile*CG + cg
-        const uint4 *ip = in + ((size_t)v * din_z + 2 * z) * din * din;
-        uint4 m = __ldg(ip + (size_t)(2 * y) * din + 2 * x);
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x + 1));
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x));
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x + 1));
-        ip += (size_t)din * din;
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x));
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y) * din + 2 * x + 1));
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x));
-        m = bf16x8_max(m, __ldg(ip + (size_t)(2 * y + 1) * din + 2 * x + 1));
-        out[i] = m;
+    // one (tile * channel group, z) output plane per block iteration; 32-bit index math inside the plane
+    const int dout = din / 2, dout_z = din_z / 2, plane = dout * dout;
+    const long long n_planes = n_cg_total * dout_z;
+    for (long long p = blockIdx.x; p < n_planes; p += gridDim.x) {
+        const int z = (int)(p % dout_z);
+        const long long v = p / dout_z;                 // tile*CG + cg
+        const uint4 *ip0 = in + ((size_t)v * din_z + 2 * z) * din * din;
+        const uint4 *ip1 = ip0 + (size_t)din * din;
+        uint4 *dst = out + (size_t)p * plane;
+        for (int i = threadIdx.x; i < plane; i += (int)blockDim.x) {
+            const int y = i / dout, x = i - y * dout;
+            const int o0 = (2 * y) * din + 2 * x, o1 = o0 + din;
+            uint4 m = __ldg(ip0 + o0);
+            m = bf16x8_max(m, __ldg(ip0 + o0 + 1));
+            m = bf16x8_max(m, __ldg(ip0 + o1));
+            m = bf16x8_max(m, __ldg(ip0 + o1 + 1));
+            m = bf16x8_max(m, __ldg(ip1 + o0));
+            m = bf16x8_max(m, __ldg(ip1 + o0 + 1));
+            m = bf16x8_max(m, __ldg(ip1 + o1));
+            m = bf16x8_max(m, __ldg(ip1 + o1 + 1));
+            dst[i] = m;
+        }
     }
 }
 
@@ -923,26 +926,35 @@ pool_blocked_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long 
 __global__ void __launch_bounds__(256)
 upcat_blocked_kernel(const uint4 *__restrict__ a, int da, int cga, const uint4 *__restrict__ skip, int ds, int cgs,
                      int crop, uint4 *__restrict__ out, int n_tiles) {
-    const int dout = 2 * da, cg_out = cga + cgs;
-    const long long total = (long long)n_tiles * cg_out * dout * dout * dout;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    auto src = [&](long long i) -> const uint4 * {
-        long long v = i;
-        const int x = (int)(v % dout); v /= dout;
-        const int y = (int)(v % dout); v /= dout;
-        const int z = (int)(v % dout); v /= dout;
-        const int cg = (int)(v % cg_out);
-        const int t = (int)(v / cg_out);
-        if (cg < cga) return a + ((((size_t)t * cga + cg) * da + z / 2) * da + y / 2) * da + x / 2;
-        return skip + ((((size_t)t * cgs + (cg - cga)) * ds + z + crop) * ds + y + crop) * ds + x + crop;
-    };
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < total; i += 4 * stride) {           // four 16-byte loads in flight per thread
-        const uint4 r0 = __ldg(src(i)), r1 = __ldg(src(i + stride)), r2 = __ldg(src(i + 2 * stride)),
-                    r3 = __ldg(src(i + 3 * stride));
-        out[i] = r0; out[i + stride] = r1; out[i + 2 * stride] = r2; out[i + 3 * stride] = r3;
+    // One (tile, channel group, z) output plane per block iteration: the plane is decoded once (the flat form paid five
+    // 64-bit divisions per 16-byte element and ran at a sixth of the HBM rate), the voxels of the plane use 32-bit math.
+    const int dout = 2 * da, cg_out = cga + cgs, plane = dout * dout;
+    const long long n_planes = (long long)n_tiles * cg_out * dout;
+    for (long long p = blockIdx.x; p < n_planes; p += gridDim.x) {
+        const int z = (int)(p % dout);
+        const long long tc = p / dout;
+        const int cg = (int)(tc % cg_out), t = (int)(tc / cg_out);
+        const bool up = cg < cga;
+        const uint4 *src = up ? a + (((size_t)t * cga + cg) * da + (z >> 1)) * da * da
+                              : skip + ((((size_t)t * cgs + (cg - cga)) * ds + z + crop) * ds + crop) * ds + crop;
+        const int pitch = up ? da : ds;
+        uint4 *dst = out + (size_t)p * plane;
+        int i = threadIdx.x;
+        for (; i + 3 * (int)blockDim.x < plane; i += 4 * (int)blockDim.x) {      // four 16-byte loads in flight per thread
+            uint4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = i + j * (int)blockDim.x, y = e / dout, x = e - y * dout;
+                r[j] = __ldg(src + (up ? (y >> 1) * pitch + (x >> 1) : y * pitch + x));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[i + j * (int)blockDim.x] = r[j];
+        }
+        for (; i < plane; i += (int)blockDim.x) {
+            const int y = i / dout, x = i - y * dout;
+            dst[i] = __ldg(src + (up ? (y >> 1) * pitch + (x >> 1) : y * pitch + x));
+        }
     }
-    for (; i < total; i += stride) out[i] = __ldg(src(i));
 }
 
 // final Conv3D(1,(1,1,1)) + sigmoid (+ nearest up-sampling by `stride`, fplnetwork.py:99-105) -> float32 tile
@@ -955,7 +967,7 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i / vox);
-        const long long v = i - (long long)t * vox;
+        const int v = (int)(i - (long long)t * vox);            // voxel inside the tile: 32-bit math from here on
         float acc = bias;
         for (int cg = 0; cg < cg_in; ++cg) {
             uint4 q = __ldg(in + ((size_t)t * cg_in + cg) * vox + v);
@@ -968,7 +980,7 @@ final_blocked_kernel(const uint4 *__restrict__ in, const float *__restrict__ w, 
             }
         }
         const float pr = 1.f / (1.f + expf(-acc));
-        const int x = (int)(v % d), y = (int)((v / d) % d), z = (int)(v / ((long long)d * d));
+        const int z = v / (d * d), rem = v - z * d * d, y = rem / d, x = rem - y * d;
         if (vio.pred) {
             // scatter of fplnetwork.py:180-187: pred[off + origin + (0..ext)) <- tile output
             const TileGrid &g = vio.g;
