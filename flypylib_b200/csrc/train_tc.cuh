@@ -7,10 +7,16 @@
 //             (a valid convolution of the zero-padded dx with the flipped, transposed kernel)
 //   wgrad     dW[tap, ci, co] = sum_v in[v + tap, ci] * dx[v, co]                     M = k^3*Cin, N = Cout, K = voxels
 // run as tcgen05.mma.cta_group::1.kind::f16 with fp32 accumulators in TMEM.  The training tensors stay float32 in
-// HBM ((N,z,y,x,C), the layout of the CUDA-core path); all threads of a CTA gather one K chunk
-// of both operands, convert it and write it to shared memory in the UMMA K-major no-swizzle canonical layout
-// (core matrix = 8 rows x 16 B; the layout conv_umma.cu validates), one thread issues the MMAs of the chunk while
-// the CTA builds the next chunk into the other stage (two stages, one mbarrier each, armed by tcgen05.commit).
+// HBM ((N,z,y,x,C), the layout of the CUDA-core path); they are converted to bf16 (hi / lo) operand images in shared
+// memory in the UMMA no-swizzle canonical layout (core matrix = 8 rows x 16 B; the layout conv_umma.cu validates).
+// Two kernel families:
+//   * slab kernels (second half of this file; every layer with 48 | Cin): rows are enumerated on the input grid so that
+//     a tap is a constant shift -- one contiguous voxel run is staged per kd and the taps are start addresses of the
+//     same image (K-major for forward / dgrad, MN-major for wgrad), weights streamed with cp.async.bulk, dedicated MMA
+//     issuer warp;
+//   * gather kernels (first half; the Cin = 1 first layer, and everything with FPL_TC_GATHER=1): all threads of a CTA
+//     gather one K chunk of both operands per tap, one thread issues the MMAs of the chunk while the CTA builds the
+//     next chunk into the other stage (two stages, one mbarrier each, armed by tcgen05.commit).
 //
 // Precision: NS = 3 (default) splits every operand into bf16 hi + bf16 lo (v = hi + lo + O(2^-17 v)) and
 // accumulates hi*hi + lo*hi + hi*lo in fp32: products of bf16 pairs are exact in fp32, so the result carries
